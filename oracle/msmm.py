@@ -1,0 +1,117 @@
+"""oracle/msmm.py -- TEST INFRASTRUCTURE ONLY (parity oracle / CPU baseline).
+
+Functional CPU restatement of the Multi-Scale Mamba Module in the skip connections:
+  * `SS2D_skip.forward` / `forward_corev0`  (reference MambaSkip.py:405-473, :515-543)
+  * `ConvolutionalGLU`, `DWConv`            (MambaSkip.py:545-577)
+  * `VSS_Conv_Block.forward`                (MambaSkip.py:720-753)
+Written from the math in SURVEY.md App. A.3 (index maps instead of stack/transpose/flip/cat),
+so it is an independent restatement, not the reference's op sequence.  Parameters are passed as
+a flat dict with the reference's state_dict key names.
+
+Pinned against the reference module source executed in this container:
+tests/golden/make_golden.py -> tests/golden/msmm_*.pt -> tests/test_oracle_golden.py.
+Nothing under mlagg-unet_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .scan import selective_scan_oracle
+
+
+def cross_scan_maps(hw):
+    """Source index of every scan position, per direction (App. A.3).
+
+    hw: list of (H_s, W_s), fine -> coarse.  Returns LongTensor (4, L_cat): position l of
+    direction k reads token idx[k, l] of the row-major, stage-concatenated sequence.
+    """
+    maps = [[], [], [], []]
+    off = 0
+    for (H, W) in hw:
+        n = H * W
+        l = torch.arange(n)
+        row_major = l
+        col_major = (l % H) * W + (l // H)  # l-th element of the W x H transposed view
+        maps[0].append(off + row_major)
+        maps[1].append(off + col_major)
+        maps[2].append(off + row_major.flip(0))
+        maps[3].append(off + col_major.flip(0))
+        off += n
+    return torch.stack([torch.cat(m) for m in maps])
+
+
+def dwconv3x3_tokens(x, weight, bias, H, W):
+    """Depthwise 3x3, pad 1, on tokens-major (B, H*W, C) input; weight (C,1,3,3)."""
+    Bn, Ntok, C = x.shape
+    y = F.conv2d(x.transpose(1, 2).reshape(Bn, C, H, W), weight, bias, padding=1, groups=C)
+    return y.flatten(2).transpose(1, 2)
+
+
+def ss2d_skip_forward(p, x, hw, scan=selective_scan_oracle, prefix=""):
+    """x (B, L_cat, d_model) -> (B, L_cat, d_model).  p[prefix + name] are the SS2D_skip tensors."""
+    g = lambda k: p[prefix + k]
+    Bn, L, _ = x.shape
+    K = 4
+    Wx, Wdt = g("x_proj_weight"), g("dt_projs_weight")
+    d_inner, R = Wdt.shape[1], Wdt.shape[2]
+    N = g("A_logs").shape[1]
+    x = x @ g("in_proj.weight").t()
+    parts, off = [], 0
+    for s, (H, W) in enumerate(hw):
+        xs = x[:, off:off + H * W]
+        xs = dwconv3x3_tokens(xs, g(f"conv2d.{s}.weight"), g(f"conv2d.{s}.bias"), H, W)
+        parts.append(F.silu(xs))
+        off += H * W
+    xc = torch.cat(parts, dim=1).transpose(1, 2)  # (B, d_inner, L) row-major per stage
+    idx = cross_scan_maps(hw).to(x.device)
+    xs = torch.stack([xc[:, :, idx[k]] for k in range(K)], dim=1)  # (B, K, d_inner, L)
+    x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, Wx)
+    dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+    dts = torch.einsum("bkrl,kdr->bkdl", dts, Wdt)
+    out = scan(
+        xs.reshape(Bn, K * d_inner, L).float().contiguous(),
+        dts.reshape(Bn, K * d_inner, L).float().contiguous(),
+        -torch.exp(g("A_logs").float()),
+        Bs.float().contiguous(), Cs.float().contiguous(),
+        g("Ds").float(), z=None, delta_bias=g("dt_projs_bias").float().reshape(-1),
+        delta_softplus=True,
+    ).view(Bn, K, d_inner, L)
+    y = torch.zeros_like(out[:, 0])
+    for k in range(K):
+        inv = torch.empty_like(idx[k])
+        inv[idx[k]] = torch.arange(L, device=idx.device)
+        y = y + out[:, k][:, :, inv]
+    y = F.layer_norm(y.transpose(1, 2), (d_inner,), g("out_norm.weight"), g("out_norm.bias"), 1e-5)
+    return y.to(x.dtype) @ g("out_proj.weight").t()
+
+
+def conv_glu_forward(p, x, H, W, prefix=""):
+    """ConvolutionalGLU with SiLU (MambaSkip.py:559-577): fc1 -> (a | v); silu(dw(a)) * v; fc2."""
+    g = lambda k: p[prefix + k]
+    a, v = F.linear(x, g("fc1.weight"), g("fc1.bias")).chunk(2, dim=-1)
+    a = F.silu(dwconv3x3_tokens(a, g("dwconv.dwconv.weight"), g("dwconv.dwconv.bias"), H, W))
+    return F.linear(a * v, g("fc2.weight"), g("fc2.bias"))
+
+
+def vss_conv_block_forward(p, inputs, hidden_dim, scan=selective_scan_oracle, prefix="", ln_eps=1e-5):
+    """inputs: list of (B, C_s, H_s, W_s) -> list of same shapes (eval mode: DropPath = identity)."""
+    g = lambda k: p[prefix + k]
+    hw = [(t.shape[2], t.shape[3]) for t in inputs]
+    m = torch.cat([t[:, :hidden_dim].flatten(2) for t in inputs], dim=-1).transpose(1, 2)
+    h = F.layer_norm(m, (hidden_dim,), g("ln_1.weight"), g("ln_1.bias"), ln_eps)
+    m = m + ss2d_skip_forward(p, h, hw, scan, prefix + "self_attention.")
+    m = F.layer_norm(m, (hidden_dim,), g("norm2.weight"), g("norm2.bias"), ln_eps)
+    outs, off = [], 0
+    for s, t in enumerate(inputs):
+        H, W = hw[s]
+        ms = m[:, off:off + H * W]
+        off += H * W
+        ms = ms + conv_glu_forward(p, ms, H, W, prefix + f"mlps.{s}.")
+        ms = ms.transpose(1, 2).reshape(t.shape[0], hidden_dim, H, W)
+        c = t[:, hidden_dim:]
+        c = F.conv2d(c, g(f"conv_branches.{s}.0.weight"), g(f"conv_branches.{s}.0.bias"), padding=1)
+        c = F.instance_norm(c, weight=g(f"conv_branches.{s}.1.weight"), bias=g(f"conv_branches.{s}.1.bias"),
+                            eps=1e-5)
+        outs.append(torch.cat([ms, F.silu(c)], dim=1))
+    return outs

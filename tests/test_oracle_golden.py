@@ -1,0 +1,113 @@
+"""CPU: the oracle (oracle/*.py, oracle/scan_ref.c) against the golden vectors produced by running the
+reference's own module source (tests/golden/make_golden.py).  Tolerance 2e-5 relative (fp32 op-order noise;
+the oracle uses index maps / neighbour gathers where the reference uses stack/flip/unfold)."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import mlagg as o_mlagg
+from oracle import mlla as o_mlla
+from oracle import msmm as o_msmm
+
+TOL = 2e-5
+
+
+def _leafs(state):
+    return {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in state.items()}
+
+
+def _loss(out):
+    torch.manual_seed(99)
+    if isinstance(out, (list, tuple)):
+        return sum((o * torch.randn_like(o)).sum() for o in out)
+    return (out * torch.randn_like(out)).sum()
+
+
+def test_cross_scan_maps_are_permutations():
+    idx = o_msmm.cross_scan_maps([(6, 5), (3, 4), (2, 2)])
+    L = 30 + 12 + 4
+    assert idx.shape == (4, L)
+    for k in range(4):
+        assert sorted(idx[k].tolist()) == list(range(L))
+    # direction 1 walks the first stage column by column: (0,0),(1,0),(2,0)...
+    assert idx[1, :3].tolist() == [0, 5, 10]
+    # reversal is per stage: direction 2 starts at the last token of stage 0, not of the sequence
+    assert idx[2, 0].item() == 29 and idx[2, 30].item() == 41
+
+
+def test_ss2d_skip_matches_reference():
+    g = load_golden("msmm_ss2d_skip.pt")
+    p = _leafs(g["state"])
+    x = g["input"].clone().requires_grad_()
+    y = o_msmm.ss2d_skip_forward(p, x, g["hw"])
+    assert rel_err(y, g["output"]) < TOL
+    (gx,) = torch.autograd.grad(_loss(y), [x])
+    assert rel_err(gx, g["grad_input"]) < TOL
+
+
+def test_vss_conv_layer_matches_reference():
+    g = load_golden("msmm_vss_conv_layer.pt")
+    p = _leafs(g["state"])
+    xs = [x.clone().requires_grad_() for x in g["inputs"]]
+    outs = o_msmm.vss_conv_block_forward(p, xs, g["hidden"], prefix="blocks.0.")
+    for o, ref in zip(outs, g["outputs"]):
+        assert rel_err(o, ref) < TOL
+    names = list(g["grad_params"])
+    grads = torch.autograd.grad(_loss(outs), xs + [p[n] for n in names], allow_unused=True)
+    for gi, ref in zip(grads[: len(xs)], g["grad_inputs"]):
+        assert rel_err(gi, ref) < TOL
+    for n, gp in zip(names, grads[len(xs):]):
+        if g["grad_params"][n] is None:
+            continue
+        assert rel_err(gp, g["grad_params"][n]) < 5e-5, n
+
+
+@pytest.mark.parametrize("kind", ["local", "pooled"])
+def test_aggregated_attention_matches_reference(kind):
+    g = load_golden(f"mlagg_attention_{kind}.pt")
+    p = _leafs(g["state"])
+    x = g["input"].clone().requires_grad_()
+    y = o_mlagg.aggregated_attention_forward(p, x, g["H"], g["W"], g["num_heads"], g["local"], g["sr_ratio"])
+    assert rel_err(y, g["output"]) < TOL
+    names = [n for n, v in g["grad_params"].items() if v is not None]
+    grads = torch.autograd.grad(_loss(y), [x] + [p[n] for n in names])
+    assert rel_err(grads[0], g["grad_input"]) < TOL
+    for n, gp in zip(names, grads[1:]):
+        assert rel_err(gp, g["grad_params"][n]) < 5e-5, n
+
+
+def test_mlagg_block_matches_reference():
+    g = load_golden("mlagg_block.pt")
+    p = _leafs(g["state"])
+    x = g["input"].clone().requires_grad_()
+    y = o_mlagg.mlla_block_forward(p, x, g["num_heads"], g["sr_ratio"])
+    assert rel_err(y, g["output"]) < TOL
+    names = [n for n, v in g["grad_params"].items() if v is not None]
+    grads = torch.autograd.grad(_loss(y), [x] + [p[n] for n in names])
+    assert rel_err(grads[0], g["grad_input"]) < TOL
+    for n, gp in zip(names, grads[1:]):
+        assert rel_err(gp, g["grad_params"][n]) < 5e-5, n
+
+
+def test_rope_and_linear_attention_match_reference():
+    g = load_golden("mlla_linear_attention.pt")
+    assert rel_err(o_mlla.rope(g["rope_in"], g["H"], g["W"]), g["rope_out"]) < TOL
+    p = _leafs(g["state"])
+    x = g["input"].clone().requires_grad_()
+    y = o_mlla.linear_attention_forward(p, x, g["H"], g["W"], g["num_heads"])
+    assert rel_err(y, g["output"]) < TOL
+    names = [n for n, v in g["grad_params"].items() if v is not None]
+    grads = torch.autograd.grad(_loss(y), [x] + [p[n] for n in names])
+    assert rel_err(grads[0], g["grad_input"]) < TOL
+    for n, gp in zip(names, grads[1:]):
+        assert rel_err(gp, g["grad_params"][n]) < 5e-5, n
+
+
+def test_mlla_block_matches_reference():
+    g = load_golden("mlla_block.pt")
+    p = _leafs(g["state"])
+    x = g["input"].clone().requires_grad_()
+    y = o_mlla.mlla_block_v1_forward(p, x, g["H"], g["W"], g["num_heads"])
+    assert rel_err(y, g["output"]) < TOL
+    (gx,) = torch.autograd.grad(_loss(y), [x])
+    assert rel_err(gx, g["grad_input"]) < TOL
