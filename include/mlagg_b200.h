@@ -1,0 +1,83 @@
+/*
+ * mlagg_b200.h -- C ABI of libmlagg_b200.so (sm_100a kernels for the MLAgg + MSMM hot path).
+ *
+ * Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the CALLER owns every buffer, including workspaces; nothing is allocated, no global state is
+ *     kept, no implicit synchronisation: work is enqueued on `stream` and the call returns;
+ *   - return value 0 = enqueued; negative = MLAGG_ERR_* (nothing was enqueued);
+ *   - all tensors are contiguous in the layout stated; "nullable" pointers may be NULL;
+ *   - reentrant and thread-safe (autograd calls the *_bwd entry points from its own thread).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo,
+ * mlagg/nnunetv2/training/nnUNetTrainer/...).
+ */
+#ifndef MLAGG_B200_H
+#define MLAGG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *mlagg_stream_t; /* cudaStream_t */
+
+enum {
+    MLAGG_OK = 0,
+    MLAGG_ERR_BAD_SHAPE = -1,   /* non-positive size, dim % ngroups != 0, ... */
+    MLAGG_ERR_UNSUPPORTED = -2, /* e.g. dstate not in {16}, unknown dtype code */
+    MLAGG_ERR_NULL = -3,        /* required pointer is NULL */
+    MLAGG_ERR_LAUNCH = -4,      /* cudaGetLastError() != cudaSuccess after the launch */
+    MLAGG_ERR_ALIGN = -5        /* pointer not aligned to the element size */
+};
+
+/* element type codes for activations */
+enum { MLAGG_F32 = 0, MLAGG_BF16 = 1 };
+
+int mlagg_version(void);
+const char *mlagg_error_string(int code);
+/* text of the last CUDA error seen by the calling thread inside this library ("" if none) */
+const char *mlagg_last_cuda_error(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Selective scan (S6), forward.
+ * Replaces selective_scan_cuda.fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
+ *   -- FFI shape documented at variants/mamba/vmamba/csms6s.py:224, called through
+ *      mamba_ssm's selective_scan_fn at variants/mamba/MambaSkip.py:445-451 (and :191-197).
+ *   u, delta, out : (batch, dim, seqlen) fp32        A : (dim, dstate) fp32 (real, = -exp(A_log))
+ *   B, C          : (batch, ngroups, dstate, seqlen) fp32; channel d uses group d / (dim/ngroups)
+ *   D, delta_bias : (dim) fp32, nullable
+ *   ckpt          : nullable.  When given, the running state is saved every MLAGG_SCAN_CHUNK steps for
+ *                   the backward pass: mlagg_scan_ckpt_bytes(...) bytes.  Pass NULL for inference.
+ *   last_state    : nullable, (batch, dim, dstate) fp32 -- h after the final step.
+ * ------------------------------------------------------------------------------------------ */
+#define MLAGG_SCAN_CHUNK 16
+size_t mlagg_scan_ckpt_bytes(int batch, int dim, int seqlen, int dstate);
+
+int mlagg_selective_scan_fwd(const float *u, const float *delta, const float *A, const float *B,
+                             const float *C, const float *D, const float *delta_bias, float *out,
+                             float *ckpt, float *last_state, int batch, int dim, int seqlen, int dstate,
+                             int ngroups, int delta_softplus, mlagg_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Selective scan, backward.
+ * Replaces selective_scan_cuda.bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, out, dz,
+ *                                  delta_softplus, recompute_out_z)  -- csms6s.py:235-238.
+ *   dout, du, ddelta : (batch, dim, seqlen) fp32
+ *   dA (dim, dstate), dD (dim, nullable iff D NULL), ddelta_bias (dim, nullable iff delta_bias NULL):
+ *       fp32, ACCUMULATED INTO with atomics -- the caller zero-fills them (or passes running sums).
+ *   dB, dC : (batch, ngroups, dstate, seqlen) fp32, ACCUMULATED INTO likewise (zero-fill first).
+ *   ckpt   : the buffer the forward call filled.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_selective_scan_bwd(const float *u, const float *delta, const float *A, const float *B,
+                             const float *C, const float *D, const float *delta_bias, const float *dout,
+                             const float *ckpt, float *du, float *ddelta, float *dA, float *dB, float *dC,
+                             float *dD, float *ddelta_bias, int batch, int dim, int seqlen, int dstate,
+                             int ngroups, int delta_softplus, mlagg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLAGG_B200_H */

@@ -1,0 +1,69 @@
+"""ctypes binding of libmlagg_b200.so (C ABI: include/mlagg_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a CUDA tensor is not given,
+the call raises.  `build()` compiles the library in-tree with nvcc for sm_100a."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmlagg_b200.so")
+_lib = None
+
+c_p, c_i, c_f, c_sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/mlagg_b200.h declares
+SIGNATURES = {
+    "mlagg_version": (c_i, []),
+    "mlagg_error_string": (ctypes.c_char_p, [c_i]),
+    "mlagg_last_cuda_error": (ctypes.c_char_p, []),
+    "mlagg_scan_ckpt_bytes": (c_sz, [c_i] * 4),
+    "mlagg_selective_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 6 + [c_p]),
+    "mlagg_selective_scan_bwd": (c_i, [c_p] * 16 + [c_i] * 6 + [c_p]),
+}
+
+
+class MlaggError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> mlagg-unet_b200/libmlagg_b200.so"""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise MlaggError("building libmlagg_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MlaggError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU / PyTorch fallback for the hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        L = lib()
+        raise MlaggError(f"{what}: {L.mlagg_error_string(rc).decode()} (code {rc}) "
+                         f"{L.mlagg_last_cuda_error().decode()}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,112 @@
+// capi.cu -- extern "C" entry points of libmlagg_b200.so (declared in include/mlagg_b200.h).
+// Argument validation only; all work is enqueued on the caller's stream by the *_dispatch functions.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mlagg_b200.h"
+#include "scan_common.cuh"
+
+namespace mlagg {
+cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
+cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
+
+static thread_local char g_last_err[256] = "";
+
+static int fail_cuda(cudaError_t e) {
+    snprintf(g_last_err, sizeof(g_last_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return MLAGG_ERR_LAUNCH;
+}
+static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+// consumer warps per CTA: 8 channels per warp; keep CTAs inside one group and fill >= 148 SMs when possible
+static int pick_warps(int batch, int G, int dpg) {
+    const char *env = getenv("MLAGG_SCAN_WARPS");
+    if (env && *env) return atoi(env);
+    if (dpg >= 32) return 4;
+    if (dpg >= 16) return 2;
+    return 1;
+}
+}  // namespace mlagg
+
+using namespace mlagg;
+
+extern "C" int mlagg_version(void) { return 100; }
+
+extern "C" const char *mlagg_error_string(int code) {
+    switch (code) {
+        case MLAGG_OK: return "ok";
+        case MLAGG_ERR_BAD_SHAPE: return "bad shape";
+        case MLAGG_ERR_UNSUPPORTED: return "unsupported configuration";
+        case MLAGG_ERR_NULL: return "required pointer is NULL";
+        case MLAGG_ERR_LAUNCH: return "CUDA launch failed";
+        case MLAGG_ERR_ALIGN: return "pointer not aligned to element size";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char *mlagg_last_cuda_error(void) { return g_last_err; }
+
+extern "C" size_t mlagg_scan_ckpt_bytes(int batch, int dim, int seqlen, int dstate) {
+    if (batch <= 0 || dim <= 0 || seqlen <= 0 || dstate <= 0) return 0;
+    const size_t nchunks = ((size_t)seqlen + MLAGG_SCAN_CHUNK - 1) / MLAGG_SCAN_CHUNK;
+    return (size_t)batch * nchunks * dim * dstate * sizeof(float);
+}
+
+static int scan_check(const void *u, const void *delta, const void *A, const void *B, const void *C, int batch,
+                      int dim, int seqlen, int dstate, int ngroups) {
+    if (!u || !delta || !A || !B || !C) return MLAGG_ERR_NULL;
+    if (batch <= 0 || dim <= 0 || seqlen <= 0 || ngroups <= 0 || dim % ngroups != 0) return MLAGG_ERR_BAD_SHAPE;
+    if (batch > 65535 || ngroups > 65535) return MLAGG_ERR_BAD_SHAPE;
+    if (dstate != kN) return MLAGG_ERR_UNSUPPORTED;
+    if (!aligned(u, 4) || !aligned(delta, 4) || !aligned(A, 4) || !aligned(B, 4) || !aligned(C, 4))
+        return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_selective_scan_fwd(const float *u, const float *delta, const float *A, const float *B,
+                                        const float *C, const float *D, const float *delta_bias, float *out,
+                                        float *ckpt, float *last_state, int batch, int dim, int seqlen,
+                                        int dstate, int ngroups, int delta_softplus, mlagg_stream_t stream) {
+    int rc = scan_check(u, delta, A, B, C, batch, dim, seqlen, dstate, ngroups);
+    if (rc) return rc;
+    if (!out) return MLAGG_ERR_NULL;
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.u = u; p.delta = delta; p.A = A; p.B = B; p.C = C; p.D = D; p.bias = delta_bias;
+    p.out = out; p.ckpt = ckpt; p.last_state = last_state;
+    p.batch = batch; p.dim = dim; p.L = seqlen; p.G = ngroups; p.dpg = dim / ngroups;
+    p.nchunks = (seqlen + kChunk - 1) / kChunk; p.softplus = delta_softplus;
+    const bool bulk = seqlen % 4 == 0 && aligned(u, 16) && aligned(delta, 16) && aligned(B, 16) &&
+                      aligned(C, 16) && aligned(out, 16) && (!ckpt || aligned(ckpt, 16)) &&
+                      !getenv("MLAGG_SCAN_NO_BULK");
+    if (ckpt && !aligned(ckpt, 16)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = scan_fwd_dispatch(p, bulk, pick_warps(batch, ngroups, p.dpg), (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_selective_scan_bwd(const float *u, const float *delta, const float *A, const float *B,
+                                        const float *C, const float *D, const float *delta_bias,
+                                        const float *dout, const float *ckpt, float *du, float *ddelta,
+                                        float *dA, float *dB, float *dC, float *dD, float *ddelta_bias,
+                                        int batch, int dim, int seqlen, int dstate, int ngroups,
+                                        int delta_softplus, mlagg_stream_t stream) {
+    int rc = scan_check(u, delta, A, B, C, batch, dim, seqlen, dstate, ngroups);
+    if (rc) return rc;
+    if (!dout || !ckpt || !du || !ddelta || !dA || !dB || !dC) return MLAGG_ERR_NULL;
+    if ((D && !dD) || (delta_bias && !ddelta_bias)) return MLAGG_ERR_NULL;
+    if (!aligned(ckpt, 16)) return MLAGG_ERR_ALIGN;
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.u = u; p.delta = delta; p.A = A; p.B = B; p.C = C; p.D = D; p.bias = delta_bias;
+    p.dout = dout; p.ckpt_in = ckpt;
+    p.du = du; p.ddelta = ddelta; p.dA = dA; p.dB = dB; p.dC = dC; p.dD = D ? dD : nullptr;
+    p.dbias = delta_bias ? ddelta_bias : nullptr;
+    p.batch = batch; p.dim = dim; p.L = seqlen; p.G = ngroups; p.dpg = dim / ngroups;
+    p.nchunks = (seqlen + kChunk - 1) / kChunk; p.softplus = delta_softplus;
+    const bool bulk = seqlen % 4 == 0 && aligned(u, 16) && aligned(delta, 16) && aligned(B, 16) &&
+                      aligned(C, 16) && aligned(dout, 16) && aligned(du, 16) && aligned(ddelta, 16) &&
+                      !getenv("MLAGG_SCAN_NO_BULK");
+    cudaError_t e = scan_bwd_dispatch(p, bulk, pick_warps(batch, ngroups, p.dpg), (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}

@@ -1,0 +1,93 @@
+"""Drop-in for `mamba_ssm.ops.selective_scan_interface.selective_scan_fn` backed by the sm_100a kernels.
+
+Reference call site: mlagg/nnunetv2/training/nnUNetTrainer/variants/mamba/MambaSkip.py:445-451
+(`selective_scan_fn(xs, dts, As, Bs, Cs, Ds, z=None, delta_bias=..., delta_softplus=True,
+return_last_state=False)`); FFI being replaced: selective_scan_cuda.fwd / .bwd (vmamba/csms6s.py:224, :235).
+
+Same positional/keyword signature and the same conventions: u, delta (B, D, L); A (D, N) real; B, C
+(B, N, L) or (B, G, N, L); D, delta_bias (D,) fp32; the scan runs in fp32 and returns u.dtype.
+CUDA only -- there is no CPU path here (the CPU restatement lives in oracle/ and is test-only).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def _f32c(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+        if not u.is_cuda:
+            raise _lib.MlaggError("selective_scan_fn: CUDA tensors required (no CPU fallback in the product path)")
+        if A.is_complex() or B.dim() not in (3, 4) or C.dim() != B.dim():
+            raise _lib.MlaggError("selective_scan_fn: real A and time-varying B, C of rank 3 or 4 are supported")
+        ctx.in_dtypes = (u.dtype, delta.dtype, A.dtype, B.dtype, C.dtype,
+                         None if D is None else D.dtype, None if delta_bias is None else delta_bias.dtype)
+        ctx.squeeze = B.dim() == 3
+        u32, dl32, A32, B32, C32, D32, b32 = map(_f32c, (u, delta, A, B, C, D, delta_bias))
+        if ctx.squeeze:
+            B32, C32 = B32.unsqueeze(1), C32.unsqueeze(1)
+        Bn, Dm, L = u32.shape
+        N, G = A32.shape[1], B32.shape[1]
+        need_grad = any(t is not None and t.requires_grad for t in (u, delta, A, B, C, D, delta_bias))
+        L_ = _lib.lib()
+        out = torch.empty_like(u32)
+        ckpt = None
+        if need_grad:
+            ckpt = torch.empty(L_.mlagg_scan_ckpt_bytes(Bn, Dm, L, N) // 4, device=u.device, dtype=torch.float32)
+        last = torch.empty(Bn, Dm, N, device=u.device, dtype=torch.float32) if return_last_state else None
+        with torch.cuda.device(u.device):
+            rc = L_.mlagg_selective_scan_fwd(_lib.ptr(u32), _lib.ptr(dl32), _lib.ptr(A32), _lib.ptr(B32),
+                                             _lib.ptr(C32), _lib.ptr(D32), _lib.ptr(b32), _lib.ptr(out),
+                                             _lib.ptr(ckpt), _lib.ptr(last), Bn, Dm, L, N, G,
+                                             int(bool(delta_softplus)), _lib.stream_ptr())
+        _lib.check(rc, "mlagg_selective_scan_fwd")
+        ctx.delta_softplus = bool(delta_softplus)
+        ctx.has = (D is not None, delta_bias is not None)
+        ctx.save_for_backward(u32, dl32, A32, B32, C32, D32, b32, ckpt)
+        out = out.to(u.dtype)
+        if return_last_state:
+            ctx.mark_non_differentiable(last)
+            return out, last
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *unused):
+        u, delta, A, B, C, D, bias, ckpt = ctx.saved_tensors
+        Bn, Dm, L = u.shape
+        N, G = A.shape[1], B.shape[1]
+        dout = dout.float().contiguous()
+        du, dd = torch.empty_like(u), torch.empty_like(u)
+        dA, dB, dC = torch.zeros_like(A), torch.zeros_like(B), torch.zeros_like(C)
+        dD = torch.zeros_like(D) if D is not None else None
+        db = torch.zeros_like(bias) if bias is not None else None
+        L_ = _lib.lib()
+        with torch.cuda.device(u.device):
+            rc = L_.mlagg_selective_scan_bwd(_lib.ptr(u), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(B), _lib.ptr(C),
+                                             _lib.ptr(D), _lib.ptr(bias), _lib.ptr(dout), _lib.ptr(ckpt),
+                                             _lib.ptr(du), _lib.ptr(dd), _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dC),
+                                             _lib.ptr(dD), _lib.ptr(db), Bn, Dm, L, N, G,
+                                             int(ctx.delta_softplus), _lib.stream_ptr())
+        _lib.check(rc, "mlagg_selective_scan_bwd")
+        if ctx.squeeze:
+            dB, dC = dB.squeeze(1), dC.squeeze(1)
+        dt = ctx.in_dtypes
+        cast = lambda g, d: None if g is None else g.to(d)
+        return (cast(du, dt[0]), cast(dd, dt[1]), cast(dA, dt[2]), cast(dB, dt[3]), cast(dC, dt[4]),
+                cast(dD, dt[5]), cast(db, dt[6]), None, None)
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """out = S6 scan of u (plus D*u), optionally gated by silu(z); see module docstring."""
+    res = SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, return_last_state)
+    out, last = res if return_last_state else (res, None)
+    if z is not None:
+        out = out * F.silu(z)
+    return (out, last) if return_last_state else out
