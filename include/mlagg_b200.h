@@ -77,6 +77,37 @@ int mlagg_selective_scan_bwd(const float *u, const float *delta, const float *A,
                              float *dD, float *ddelta_bias, int batch, int dim, int seqlen, int dstate,
                              int ngroups, int delta_softplus, mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Depthwise 3x3 convolution, padding 1, on TOKENS-MAJOR activations x (batch, H, W, C)  [= (B, N, C)].
+ * Replaces nn.Conv2d(C, C, 3, padding=1, groups=C) (+ the permute copies around it, + the SiLU after it) at
+ *   nnUNetTrainer_MLAgg_2D_dt_MS.py:851,890 (dwc) and :680,782 (lepe); variants/mamba/MambaSkip.py:302-312,
+ *   :521-523 (SS2D_skip.conv2d[i] + act) and :545-556 (DWConv); nnUNetTrainer_MLLA_UNet.py:279,289,215.
+ *   x, y, dy, dx, dz_ws : (batch, H, W, C), element type `dtype` (MLAGG_F32 | MLAGG_BF16); C % 4 == 0 takes the
+ *                         128-bit vector path, other C a scalar-channel path
+ *   weight (C, 9) fp32 [the (C,1,3,3) parameter], bias (C) fp32 nullable
+ *   act_silu != 0 : y = silu(conv(x) + bias)
+ * Backward: dz_ws is a caller-owned scratch of x's size; dweight (C,9) / dbias (C) fp32 are ACCUMULATED
+ * INTO (zero-fill first); dbias nullable.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_dwconv3x3_fwd(const void *x, const float *weight, const float *bias, void *y, int batch, int H, int W,
+                        int C, int act_silu, int dtype, mlagg_stream_t stream);
+int mlagg_dwconv3x3_bwd(const void *x, const float *weight, const float *bias, const void *dy, void *dz_ws,
+                        void *dx, float *dweight, float *dbias, int batch, int H, int W, int C, int act_silu,
+                        int dtype, mlagg_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d: y[b,c,t] = bias[c] + sum_j weight[c,j] * x[b,c,t-(K-1)+j]  (+ SiLU), K <= 4.
+ * Replaces causal_conv1d_fn(x, weight, bias, activation) of the causal-conv1d package (a pip dependency of
+ * mamba_ssm, reference README.md:49; named by north_star, not called by nnUNetTrainer_MLAgg_2D_dt_MS: F3).
+ *   x, y, dy, dx : (batch, C, L) fp32;  weight (C, K) fp32;  bias (C) fp32 nullable
+ *   dweight / dbias are ACCUMULATED INTO (zero-fill first).
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_causal_conv1d_fwd(const float *x, const float *weight, const float *bias, float *y, int batch, int C,
+                            int L, int K, int act_silu, mlagg_stream_t stream);
+int mlagg_causal_conv1d_bwd(const float *x, const float *weight, const float *bias, const float *dy, float *dx,
+                            float *dweight, float *dbias, int batch, int C, int L, int K, int act_silu,
+                            mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,10 @@ SIGNATURES = {
     "mlagg_scan_ckpt_bytes": (c_sz, [c_i] * 4),
     "mlagg_selective_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 6 + [c_p]),
     "mlagg_selective_scan_bwd": (c_i, [c_p] * 16 + [c_i] * 6 + [c_p]),
+    "mlagg_dwconv3x3_fwd": (c_i, [c_p] * 4 + [c_i] * 6 + [c_p]),
+    "mlagg_dwconv3x3_bwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
+    "mlagg_causal_conv1d_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),
+    "mlagg_causal_conv1d_bwd": (c_i, [c_p] * 7 + [c_i] * 5 + [c_p]),
 }
 
 
@@ -58,6 +62,32 @@ def check(rc: int, what: str):
         L = lib()
         raise MlaggError(f"{what}: {L.mlagg_error_string(rc).decode()} (code {rc}) "
                          f"{L.mlagg_last_cuda_error().decode()}")
+
+
+# ---- bookkeeping for bench.py: how many of OUR kernels were launched, and (optionally) per-kernel CUDA-event timing
+STATS = {"launches": 0, "events": None}
+
+
+class timed:
+    """with timed("scan_bwd", n_kernels): ...  -- counts launches; records CUDA events on the current stream when
+    STATS["events"] is a dict (bench.py turns that on for the timed region)."""
+
+    def __init__(self, name, n_kernels=1):
+        self.name, self.n = name, n_kernels
+
+    def __enter__(self):
+        STATS["launches"] += self.n
+        if STATS["events"] is not None:
+            import torch
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if STATS["events"] is not None:
+            self.e1.record()
+            STATS["events"].setdefault(self.name, []).append((self.e0, self.e1))
+        return False
 
 
 def ptr(t):

@@ -11,6 +11,17 @@ namespace mlagg {
 cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
 
+cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, void *y, int Bn, int H, int W,
+                                   int C, int act, int dtype, cudaStream_t st);
+cudaError_t dwconv3x3_bwd_dispatch(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
+                                   float *dw, float *db, int Bn, int H, int W, int C, int act, int dtype,
+                                   cudaStream_t st);
+cudaError_t causal_conv1d_fwd_dispatch(const float *x, const float *w, const float *b, float *y, int rows, int C,
+                                       int L, int K, int act, cudaStream_t st);
+cudaError_t causal_conv1d_bwd_dispatch(const float *x, const float *w, const float *b, const float *dy, float *dx,
+                                       float *dw, float *db, int rows, int C, int L, int K, int act,
+                                       cudaStream_t st);
+
 static thread_local char g_last_err[256] = "";
 
 static int fail_cuda(cudaError_t e) {
@@ -108,5 +119,56 @@ extern "C" int mlagg_selective_scan_bwd(const float *u, const float *delta, cons
                       aligned(C, 16) && aligned(dout, 16) && aligned(du, 16) && aligned(ddelta, 16) &&
                       !getenv("MLAGG_SCAN_NO_BULK");
     cudaError_t e = scan_bwd_dispatch(p, bulk, pick_warps(batch, ngroups, p.dpg), (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+static int dwconv_check(const void *x, const float *w, const void *y, int batch, int H, int W, int C, int dtype) {
+    if (!x || !w || !y) return MLAGG_ERR_NULL;
+    if (batch <= 0 || H <= 0 || W <= 0 || C <= 0 || C > 1024) return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    const size_t a = C % 4 != 0 ? (dtype == MLAGG_F32 ? 4 : 2) : (dtype == MLAGG_F32 ? 16 : 8);
+    if (!aligned(x, a) || !aligned(y, a) || !aligned(w, 4)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_dwconv3x3_fwd(const void *x, const float *weight, const float *bias, void *y, int batch, int H,
+                                   int W, int C, int act_silu, int dtype, mlagg_stream_t stream) {
+    int rc = dwconv_check(x, weight, y, batch, H, W, C, dtype);
+    if (rc) return rc;
+    if (bias && !aligned(bias, C % 4 ? 4 : 16)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = dwconv3x3_fwd_dispatch(x, weight, bias, y, batch, H, W, C, act_silu, dtype, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_dwconv3x3_bwd(const void *x, const float *weight, const float *bias, const void *dy,
+                                   void *dz_ws, void *dx, float *dweight, float *dbias, int batch, int H, int W,
+                                   int C, int act_silu, int dtype, mlagg_stream_t stream) {
+    int rc = dwconv_check(x, weight, dx, batch, H, W, C, dtype);
+    if (rc) return rc;
+    if (!dy || !dz_ws || !dweight) return MLAGG_ERR_NULL;
+    const size_t a = C % 4 != 0 ? (dtype == MLAGG_F32 ? 4 : 2) : (dtype == MLAGG_F32 ? 16 : 8);
+    if (!aligned(dy, a) || !aligned(dz_ws, a) || (bias && !aligned(bias, C % 4 ? 4 : 16))) return MLAGG_ERR_ALIGN;
+    cudaError_t e = dwconv3x3_bwd_dispatch(x, weight, bias, dy, dz_ws, dx, dweight, dbias, batch, H, W, C, act_silu,
+                                           dtype, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_causal_conv1d_fwd(const float *x, const float *weight, const float *bias, float *y, int batch,
+                                       int C, int L, int K, int act_silu, mlagg_stream_t stream) {
+    if (!x || !weight || !y) return MLAGG_ERR_NULL;
+    if (batch <= 0 || C <= 0 || L <= 0 || (long long)batch * C > 65535) return MLAGG_ERR_BAD_SHAPE;
+    if (K < 1 || K > 4) return MLAGG_ERR_UNSUPPORTED;
+    cudaError_t e = causal_conv1d_fwd_dispatch(x, weight, bias, y, batch * C, C, L, K, act_silu, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_causal_conv1d_bwd(const float *x, const float *weight, const float *bias, const float *dy,
+                                       float *dx, float *dweight, float *dbias, int batch, int C, int L, int K,
+                                       int act_silu, mlagg_stream_t stream) {
+    if (!x || !weight || !dy || !dx || !dweight) return MLAGG_ERR_NULL;
+    if (batch <= 0 || C <= 0 || L <= 0 || (long long)batch * C > 65535) return MLAGG_ERR_BAD_SHAPE;
+    if (K < 1 || K > 4) return MLAGG_ERR_UNSUPPORTED;
+    cudaError_t e = causal_conv1d_bwd_dispatch(x, weight, bias, dy, dx, dweight, dbias, batch * C, C, L, K, act_silu,
+                                               (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

@@ -1,0 +1,415 @@
+// dwconv.cu -- depthwise 3x3 convolution (pad 1, bias, optional fused SiLU) on TOKENS-MAJOR data, and the
+// depthwise causal conv1d.  Replaces, without the NCHW<->tokens permute copies the reference needs,
+//   nn.Conv2d(groups=C) at nnUNetTrainer_MLAgg_2D_dt_MS.py:851,890 (dwc), :680,782 (lepe);
+//   MambaSkip.py:302-312,521-523 (SS2D_skip.conv2d[i] + SiLU), :545-556 (DWConv in ConvolutionalGLU);
+//   nnUNetTrainer_MLLA_UNet.py:279,289 (cpe1/2), :215,248 (lepe);
+//   causal_conv1d_fn of the un-vendored causal-conv1d package (north_star; not on the trainer's path, F3).
+// HBM-bound stencils: every thread owns 4 consecutive channels of one pixel (128-bit fp32 / 64-bit bf16
+// accesses, coalesced across the channel dimension); neighbour rows come from L1/L2.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mlagg {
+
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T *p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float *p) {
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&raw.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&raw.y);
+    const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T>
+__device__ __forceinline__ void st4(T *p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float *p, float4 v) {
+    *reinterpret_cast<float4 *>(p) = v;
+}
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t *>(&a);
+    raw.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = raw;
+}
+
+__device__ __forceinline__ float silu_grad(float z) {  // d/dz [z * sigmoid(z)]
+    const float s = rcp_approx(1.f + ex2_approx(-z * kLog2e));
+    return s * (1.f + z * (1.f - s));
+}
+
+// weights as (C, 9) fp32 (the nn.Conv2d (C,1,3,3) tensor, contiguous); tap p = 3*(dr+1) + (dc+1).
+// FLIP=false: y[pix] = b + sum_p w[p] x[pix + off_p]           (forward)
+// FLIP=true : y[pix] =     sum_p w[p] x[pix - off_p]           (input gradient)
+template <typename T, bool FLIP, int ACT>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                        const float *__restrict__ bias, T *__restrict__ y, int Bn,
+                                                        int H, int W, int C) {
+    const int cv = C >> 2;
+    const long long total = (long long)Bn * H * W * cv;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cv) << 2;
+        const long long pix = idx / cv;
+        const int wc = (int)(pix % W);
+        const int hr = (int)((pix / W) % H);
+        const T *xb = x + (pix - (long long)hr * W - wc) * C + c;  // image base + channel
+        float4 acc = (!FLIP && bias) ? __ldg(reinterpret_cast<const float4 *>(bias + c)) : make_float4(0, 0, 0, 0);
+        float wr[4][9];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int p = 0; p < 9; ++p) wr[k][p] = __ldg(w + (c + k) * 9 + p);
+#pragma unroll
+        for (int dr = -1; dr <= 1; ++dr) {
+            const int rr = hr + dr;
+            if (rr < 0 || rr >= H) continue;
+#pragma unroll
+            for (int dc = -1; dc <= 1; ++dc) {
+                const int cc = wc + dc;
+                if (cc < 0 || cc >= W) continue;
+                const float4 v = ld4<T>(xb + ((long long)rr * W + cc) * C);
+                const int p = FLIP ? (3 * (1 - dr) + (1 - dc)) : (3 * (dr + 1) + (dc + 1));
+                acc.x = fmaf(wr[0][p], v.x, acc.x);
+                acc.y = fmaf(wr[1][p], v.y, acc.y);
+                acc.z = fmaf(wr[2][p], v.z, acc.z);
+                acc.w = fmaf(wr[3][p], v.w, acc.w);
+            }
+        }
+        if (ACT == 1) {
+            acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
+        }
+        st4<T>(y + pix * C + c, acc);
+    }
+}
+
+
+// ---- C % 4 != 0 (narrow test configurations): one channel per thread, same arithmetic.
+template <typename T>
+__device__ __forceinline__ float ld1(const T *p);
+template <>
+__device__ __forceinline__ float ld1<float>(const float *p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void st1(T *p, float v);
+template <>
+__device__ __forceinline__ void st1<float>(float *p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// mode 0: y = act(conv(x)+b); mode 1 (FLIP): y = conv_flipped(x); mode 2: dz = dy * act'(conv(x)+b) and dw/db atomics
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                               const float *__restrict__ bias,
+                                                               const T *__restrict__ dy, T *__restrict__ y,
+                                                               float *__restrict__ dw, float *__restrict__ db, int Bn,
+                                                               int H, int W, int C, int mode) {
+    const long long total = (long long)Bn * H * W * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const long long pix = idx / C;
+        const int wc = (int)(pix % W), hr = (int)((pix / W) % H);
+        const T *xb = x + (pix - (long long)hr * W - wc) * C + c;
+        float acc = (mode != 1 && bias) ? __ldg(bias + c) : 0.f;
+        float xn[9];
+#pragma unroll
+        for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+            for (int dc = -1; dc <= 1; ++dc) {
+                const int p = 3 * (dr + 1) + (dc + 1);
+                const int rr = hr + dr, cc = wc + dc;
+                const bool ok = rr >= 0 && rr < H && cc >= 0 && cc < W;
+                xn[p] = ok ? ld1<T>(xb + ((long long)rr * W + cc) * C) : 0.f;
+                acc = fmaf(__ldg(w + c * 9 + (mode == 1 ? 8 - p : p)), xn[p], acc);
+            }
+        if (mode == 2) {
+            float g = ld1<T>(dy + pix * C + c);
+            if (ACT == 1) g *= silu_grad(acc);
+            st1<T>(y + pix * C + c, g);
+#pragma unroll
+            for (int p = 0; p < 9; ++p) atomicAdd(dw + c * 9 + p, g * xn[p]);
+            if (db) atomicAdd(db + c, g);
+        } else {
+            st1<T>(y + pix * C + c, (ACT == 1 && mode == 0) ? silu_f(acc) : acc);
+        }
+    }
+}
+
+// Backward, pass 1: recompute z = conv(x) + b, dz = dy * act'(z); store dz; accumulate
+// dw[c, p] += sum_pix dz[pix] x[pix + off_p] and db[c] += sum_pix dz[pix] (registers -> smem -> atomics).
+// Block = (C/4 channel vectors) x PP pixel lanes; each block walks `pix_per_block` pixels.
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                              const float *__restrict__ bias,
+                                                              const T *__restrict__ dy, T *__restrict__ dz,
+                                                              float *__restrict__ dw, float *__restrict__ db,
+                                                              int Bn, int H, int W, int C, int pix_per_block) {
+    extern __shared__ float red[];  // [PP][cv][40]
+    const int cv = C >> 2;
+    const int PP = blockDim.x / cv;
+    const int cvi = threadIdx.x % cv, pl = threadIdx.x / cv;
+    const int c = cvi << 2;
+    const long long npix = (long long)Bn * H * W;
+    float aw[4][9], ab[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        ab[k] = 0.f;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) aw[k][p] = 0.f;
+    }
+    if (pl < PP) {
+        float wr[4][9];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int p = 0; p < 9; ++p) wr[k][p] = __ldg(w + (c + k) * 9 + p);
+        const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias + c)) : make_float4(0, 0, 0, 0);
+        const long long p0 = (long long)blockIdx.x * pix_per_block;
+        const long long p1 = min(npix, p0 + pix_per_block);
+        for (long long pix = p0 + pl; pix < p1; pix += PP) {
+            const int wc = (int)(pix % W);
+            const int hr = (int)((pix / W) % H);
+            const T *xb = x + (pix - (long long)hr * W - wc) * C + c;
+            float4 xn[9];
+            float4 z = bv;
+#pragma unroll
+            for (int dr = -1; dr <= 1; ++dr)
+#pragma unroll
+                for (int dc = -1; dc <= 1; ++dc) {
+                    const int p = 3 * (dr + 1) + (dc + 1);
+                    const int rr = hr + dr, cc = wc + dc;
+                    const bool ok = rr >= 0 && rr < H && cc >= 0 && cc < W;
+                    xn[p] = ok ? ld4<T>(xb + ((long long)rr * W + cc) * C) : make_float4(0, 0, 0, 0);
+                    z.x = fmaf(wr[0][p], xn[p].x, z.x);
+                    z.y = fmaf(wr[1][p], xn[p].y, z.y);
+                    z.z = fmaf(wr[2][p], xn[p].z, z.z);
+                    z.w = fmaf(wr[3][p], xn[p].w, z.w);
+                }
+            float4 g = ld4<T>(dy + pix * C + c);
+            if (ACT == 1) {
+                g.x *= silu_grad(z.x); g.y *= silu_grad(z.y); g.z *= silu_grad(z.z); g.w *= silu_grad(z.w);
+            }
+            st4<T>(dz + pix * C + c, g);
+            ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w;
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+                aw[0][p] = fmaf(g.x, xn[p].x, aw[0][p]);
+                aw[1][p] = fmaf(g.y, xn[p].y, aw[1][p]);
+                aw[2][p] = fmaf(g.z, xn[p].z, aw[2][p]);
+                aw[3][p] = fmaf(g.w, xn[p].w, aw[3][p]);
+            }
+        }
+        float *mine = red + ((size_t)pl * cv + cvi) * 40;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int p = 0; p < 9; ++p) mine[k * 10 + p] = aw[k][p];
+            mine[k * 10 + 9] = ab[k];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cv * 40; i += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < PP; ++l) s += red[(size_t)l * cv * 40 + i];
+        const int ch = (i / 40) * 4 + (i % 40) / 10, p = i % 10;
+        if (p < 9) atomicAdd(dw + ch * 9 + p, s);
+        else if (db) atomicAdd(db + ch, s);
+    }
+}
+
+// ------------------------------------------------------------------ causal conv1d, x (B, C, L) row-major
+// y[b,c,t] = bias[c] + sum_j w[c,j] x[b,c,t-(K-1)+j], optional SiLU.  One warp-row per (b,c); 4 steps per thread.
+template <int ACT>
+__global__ void __launch_bounds__(256) causal_conv1d_fwd_kernel(const float *__restrict__ x,
+                                                                const float *__restrict__ w,
+                                                                const float *__restrict__ bias,
+                                                                float *__restrict__ y, int rows, int C, int L, int K) {
+    const int row = blockIdx.y;
+    const int c = row % C;
+    float wk[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < K; ++j) wk[4 - K + j] = __ldg(w + c * K + j);  // right-aligned: wk[3] multiplies x[t]
+    const float bv = bias ? __ldg(bias + c) : 0.f;
+    const float *xr = x + (size_t)row * L;
+    float *yr = y + (size_t)row * L;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L; t += gridDim.x * blockDim.x) {
+        float acc = bv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int tt = t - 3 + j;
+            if (tt >= 0) acc = fmaf(wk[j], __ldg(xr + tt), acc);
+        }
+        yr[t] = ACT == 1 ? silu_f(acc) : acc;
+    }
+}
+
+// backward: dz = dy * act'(z); dx[t] = sum_j w[j] dz[t + (K-1) - j]; dw[c,j] += sum_t dz[t] x[t-(K-1)+j]; db += sum dz
+template <int ACT>
+__global__ void __launch_bounds__(256) causal_conv1d_bwd_kernel(const float *__restrict__ x,
+                                                                const float *__restrict__ w,
+                                                                const float *__restrict__ bias,
+                                                                const float *__restrict__ dy, float *__restrict__ dx,
+                                                                float *__restrict__ dw, float *__restrict__ db,
+                                                                int rows, int C, int L, int K) {
+    __shared__ float red[8][5];
+    const int row = blockIdx.y;
+    const int c = row % C;
+    float wk[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < K; ++j) wk[4 - K + j] = __ldg(w + c * K + j);
+    const float bv = bias ? __ldg(bias + c) : 0.f;
+    const float *xr = x + (size_t)row * L;
+    const float *gr = dy + (size_t)row * L;
+    float *dxr = dx + (size_t)row * L;
+    float aw[4] = {0.f, 0.f, 0.f, 0.f}, ab = 0.f;
+    auto dz_at = [&](int t) -> float {  // dy[t] * act'(z[t]); 0 outside [0, L)
+        if (t < 0 || t >= L) return 0.f;
+        float g = __ldg(gr + t);
+        if (ACT == 1) {
+            float z = bv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int tt = t - 3 + j;
+                if (tt >= 0) z = fmaf(wk[j], __ldg(xr + tt), z);
+            }
+            g *= silu_grad(z);
+        }
+        return g;
+    };
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < L; t += gridDim.x * blockDim.x) {
+        const float g0 = dz_at(t);
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // x[t] enters z[t + 3 - j] through wk[j]
+            acc = fmaf(wk[j], j == 3 ? g0 : dz_at(t + 3 - j), acc);
+            const int tt = t - 3 + j;
+            if (tt >= 0) aw[j] = fmaf(g0, __ldg(xr + tt), aw[j]);
+        }
+        dxr[t] = acc;
+        ab += g0;
+    }
+    // block reduction of the 5 partial sums
+    float vals[5] = {aw[0], aw[1], aw[2], aw[3], ab};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vals[k] += __shfl_xor_sync(0xffffffffu, vals[k], o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 5; ++k) red[warp][k] = vals[k];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        float s = 0.f;
+        for (int wdx = 0; wdx < (int)(blockDim.x >> 5); ++wdx) s += red[wdx][threadIdx.x];
+        if (threadIdx.x < 4) {
+            const int j = threadIdx.x - (4 - K);
+            if (j >= 0) atomicAdd(dw + c * K + j, s);
+        } else if (db) {
+            atomicAdd(db + c, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host launchers
+template <typename T>
+static cudaError_t dwconv_fwd_t(const void *x, const float *w, const float *b, void *y, int Bn, int H, int W, int C,
+                                int act, bool flip, cudaStream_t st) {
+    const T *xp0 = static_cast<const T *>(x);
+    T *yp0 = static_cast<T *>(y);
+    if (C % 4 != 0) {
+        long long nb1 = ((long long)Bn * H * W * C + 255) / 256;
+        if (nb1 > 148LL * 32) nb1 = 148LL * 32;
+        if (act && !flip) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xp0, w, b, nullptr, yp0, nullptr, nullptr, Bn, H, W, C, 0);
+        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xp0, w, b, nullptr, yp0, nullptr, nullptr, Bn, H, W, C, flip ? 1 : 0);
+        return cudaGetLastError();
+    }
+    const long long total = (long long)Bn * H * W * (C / 4);
+    long long nb = (total + 255) / 256;
+    if (nb > 148LL * 32) nb = 148LL * 32;
+    const int blocks = (int)nb;
+    const T *xp = static_cast<const T *>(x);
+    T *yp = static_cast<T *>(y);
+    if (flip) dwconv3x3_kernel<T, true, 0><<<blocks, 256, 0, st>>>(xp, w, nullptr, yp, Bn, H, W, C);
+    else if (act) dwconv3x3_kernel<T, false, 1><<<blocks, 256, 0, st>>>(xp, w, b, yp, Bn, H, W, C);
+    else dwconv3x3_kernel<T, false, 0><<<blocks, 256, 0, st>>>(xp, w, b, yp, Bn, H, W, C);
+    return cudaGetLastError();
+}
+
+cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, void *y, int Bn, int H, int W,
+                                   int C, int act, int dtype, cudaStream_t st) {
+    return dtype == 0 ? dwconv_fwd_t<float>(x, w, b, y, Bn, H, W, C, act, false, st)
+                      : dwconv_fwd_t<__nv_bfloat16>(x, w, b, y, Bn, H, W, C, act, false, st);
+}
+
+template <typename T>
+static cudaError_t dwconv_bwd_t(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
+                                float *dw, float *db, int Bn, int H, int W, int C, int act, cudaStream_t st) {
+    if (C % 4 != 0) {
+        long long nb1 = ((long long)Bn * H * W * C + 255) / 256;
+        if (nb1 > 148LL * 32) nb1 = 148LL * 32;
+        const T *xq = static_cast<const T *>(x), *gq = static_cast<const T *>(dy);
+        T *zq = static_cast<T *>(dz);
+        if (act) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2);
+        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2);
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return e1;
+        return dwconv_fwd_t<T>(dz, w, nullptr, dx, Bn, H, W, C, 0, true, st);
+    }
+    const int cv = C / 4;
+    const int PP = max(1, 256 / cv);
+    const int threads = cv * PP;  // <= 256 when cv <= 256
+    const long long npix = (long long)Bn * H * W;
+    const int ppb = PP * 32;  // pixels per block
+    const int blocks = (int)((npix + ppb - 1) / ppb);
+    const size_t smem = (size_t)PP * cv * 40 * sizeof(float);
+    const T *xp = static_cast<const T *>(x), *gp = static_cast<const T *>(dy);
+    T *zp = static_cast<T *>(dz);
+    cudaError_t e;
+    if (act) {
+        auto k = dwconv3x3_bwd_w_kernel<T, 1>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb);
+    } else {
+        auto k = dwconv3x3_bwd_w_kernel<T, 0>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return dwconv_fwd_t<T>(dz, w, nullptr, dx, Bn, H, W, C, 0, true, st);
+}
+
+cudaError_t dwconv3x3_bwd_dispatch(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
+                                   float *dw, float *db, int Bn, int H, int W, int C, int act, int dtype,
+                                   cudaStream_t st) {
+    return dtype == 0 ? dwconv_bwd_t<float>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, st)
+                      : dwconv_bwd_t<__nv_bfloat16>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, st);
+}
+
+cudaError_t causal_conv1d_fwd_dispatch(const float *x, const float *w, const float *b, float *y, int rows, int C,
+                                       int L, int K, int act, cudaStream_t st) {
+    dim3 grid(min((L + 255) / 256, 64), rows);
+    if (act) causal_conv1d_fwd_kernel<1><<<grid, 256, 0, st>>>(x, w, b, y, rows, C, L, K);
+    else causal_conv1d_fwd_kernel<0><<<grid, 256, 0, st>>>(x, w, b, y, rows, C, L, K);
+    return cudaGetLastError();
+}
+
+cudaError_t causal_conv1d_bwd_dispatch(const float *x, const float *w, const float *b, const float *dy, float *dx,
+                                       float *dw, float *db, int rows, int C, int L, int K, int act,
+                                       cudaStream_t st) {
+    dim3 grid(min((L + 255) / 256, 64), rows);
+    if (act) causal_conv1d_bwd_kernel<1><<<grid, 256, 0, st>>>(x, w, b, dy, dx, dw, db, rows, C, L, K);
+    else causal_conv1d_bwd_kernel<0><<<grid, 256, 0, st>>>(x, w, b, dy, dx, dw, db, rows, C, L, K);
+    return cudaGetLastError();
+}
+
+}  // namespace mlagg

@@ -171,13 +171,14 @@ __global__ void __launch_bounds__(2 * W * 32, 1) scan_bwd_kernel(const ScanParam
             const int gc = (t0 + tb) / kChunk;   // global chunk index
             const float4 h0v = hnext;
             hnext = load_ckpt(gc - 1);
-            float hprev[4];
+            float hprev[4], h0[4];
             {
                 const float hv[4] = {h0v.x, h0v.y, h0v.z, h0v.w};
 #pragma unroll
                 for (int s4 = 0; s4 < 4; ++s4) {  // checkpoint is stored in natural slot order
                     const int src = s4 ^ x;
                     hprev[s4] = src == 0 ? hv[0] : src == 1 ? hv[1] : src == 2 ? hv[2] : hv[3];
+                    h0[s4] = hprev[s4];
                 }
             }
             float hh[kChunk][4], aa[kChunk][4];
@@ -240,7 +241,8 @@ __global__ void __launch_bounds__(2 * W * 32, 1) scan_bwd_kernel(const ScanParam
                         Q[s4] = dy * ht;          // dC contribution
                         P[s4] = on ? gn * du : 0.f;  // dB contribution
                         s1 = fmaf(gn, Bji, s1);
-                        const float tmp = gn * fmaf(-du, Bji, ht);  // g * a_t * h_{t-1}
+                        const float hm1 = (i4 + i > 0) ? hh[(i4 + i > 0) ? i4 + i - 1 : 0][s4] : h0[s4];
+                        const float tmp = gn * (aa[i4 + i][s4] * hm1);  // g * a_t * h_{t-1}
                         if (on) {
                             dAacc[s4] = fmaf(tmp, dd[i], dAacc[s4]);
                             s2 = fmaf(tmp, A2[s4], s2);

@@ -1,0 +1,103 @@
+"""torch.autograd.Function wrappers over the C ABI (include/mlagg_b200.h) for the stencil ops of the hot path.
+
+All functions take TOKENS-MAJOR activations (B, N, C) with N = H*W row-major -- the layout the reference's
+blocks already use between their Linear layers -- so none of the reference's `permute(...).contiguous()`
+round trips around nn.Conv2d are needed.  CUDA only; no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _io(x):
+    """kernels take fp32 or bf16 activations; fp16 (reference autocast dtype) is widened to fp32"""
+    return x if x.dtype in _DT else x.float()
+
+
+class _DWConv3x3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, H, W, silu):
+        if not x.is_cuda:
+            raise _lib.MlaggError("dwconv3x3_tokens: CUDA tensor required (no CPU fallback in the product path)")
+        Bn, N, C = x.shape
+        assert N == H * W and weight.shape == (C, 1, 3, 3)
+        xin = _io(x).contiguous()
+        w32 = weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty_like(xin)
+        with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd"):
+            rc = _lib.lib().mlagg_dwconv3x3_fwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), Bn, H, W, C,
+                                                int(silu), _DT[xin.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dwconv3x3_fwd")
+        ctx.save_for_backward(xin, w32, b32)
+        ctx.meta = (H, W, bool(silu), x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xin, w32, b32 = ctx.saved_tensors
+        H, W, silu, xdt, wdt, bdt = ctx.meta
+        Bn, N, C = xin.shape
+        dy = dy.to(xin.dtype).contiguous()
+        dz, dx = torch.empty_like(xin), torch.empty_like(xin)
+        dw = torch.zeros(C, 9, device=xin.device, dtype=torch.float32)
+        db = torch.zeros(C, device=xin.device, dtype=torch.float32) if b32 is not None else None
+        with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2):
+            rc = _lib.lib().mlagg_dwconv3x3_bwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy), _lib.ptr(dz),
+                                                _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), Bn, H, W, C, int(silu),
+                                                _DT[xin.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dwconv3x3_bwd")
+        return (dx.to(xdt), dw.view(C, 1, 3, 3).to(wdt), None if db is None else db.to(bdt), None, None, None)
+
+
+def dwconv3x3_tokens(x, weight, bias, H, W, silu=False):
+    """x (B, H*W, C) -> depthwise 3x3 (pad 1) [+ SiLU]; weight is the nn.Conv2d(C, C, 3, groups=C) parameter."""
+    return _DWConv3x3.apply(x, weight, bias, H, W, silu)
+
+
+class _CausalConv1d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu):
+        if not x.is_cuda:
+            raise _lib.MlaggError("causal_conv1d_fn: CUDA tensor required (no CPU fallback in the product path)")
+        Bn, C, L = x.shape
+        K = weight.shape[1]
+        x32, w32 = x.float().contiguous(), weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty_like(x32)
+        with torch.cuda.device(x.device), _lib.timed("causal_conv1d_fwd"):
+            rc = _lib.lib().mlagg_causal_conv1d_fwd(_lib.ptr(x32), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), Bn, C, L,
+                                                    K, int(silu), _lib.stream_ptr())
+        _lib.check(rc, "mlagg_causal_conv1d_fwd")
+        ctx.save_for_backward(x32, w32, b32)
+        ctx.meta = (bool(silu), x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x32, w32, b32 = ctx.saved_tensors
+        silu, xdt, wdt, bdt = ctx.meta
+        Bn, C, L = x32.shape
+        K = w32.shape[1]
+        dy = dy.float().contiguous()
+        dx = torch.empty_like(x32)
+        dw = torch.zeros_like(w32)
+        db = torch.zeros(C, device=x32.device, dtype=torch.float32) if b32 is not None else None
+        with torch.cuda.device(x32.device), _lib.timed("causal_conv1d_bwd"):
+            rc = _lib.lib().mlagg_causal_conv1d_bwd(_lib.ptr(x32), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy),
+                                                    _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), Bn, C, L, K, int(silu),
+                                                    _lib.stream_ptr())
+        _lib.check(rc, "mlagg_causal_conv1d_bwd")
+        return dx.to(xdt), dw.to(wdt), None if db is None else db.to(bdt), None
+
+
+def causal_conv1d_fn(x, weight, bias=None, activation=None):
+    """Same call shape as causal_conv1d.causal_conv1d_fn: x (B, C, L), weight (C, K<=4), activation in
+    {None, 'silu', 'swish'}."""
+    if activation not in (None, "silu", "swish"):
+        raise NotImplementedError("activation must be None, silu, or swish")
+    return _CausalConv1d.apply(x, weight, bias, activation is not None)

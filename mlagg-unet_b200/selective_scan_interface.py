@@ -42,7 +42,7 @@ class SelectiveScanFn(torch.autograd.Function):
         if need_grad:
             ckpt = torch.empty(L_.mlagg_scan_ckpt_bytes(Bn, Dm, L, N) // 4, device=u.device, dtype=torch.float32)
         last = torch.empty(Bn, Dm, N, device=u.device, dtype=torch.float32) if return_last_state else None
-        with torch.cuda.device(u.device):
+        with torch.cuda.device(u.device), _lib.timed("scan_fwd"):
             rc = L_.mlagg_selective_scan_fwd(_lib.ptr(u32), _lib.ptr(dl32), _lib.ptr(A32), _lib.ptr(B32),
                                              _lib.ptr(C32), _lib.ptr(D32), _lib.ptr(b32), _lib.ptr(out),
                                              _lib.ptr(ckpt), _lib.ptr(last), Bn, Dm, L, N, G,
@@ -68,7 +68,7 @@ class SelectiveScanFn(torch.autograd.Function):
         dD = torch.zeros_like(D) if D is not None else None
         db = torch.zeros_like(bias) if bias is not None else None
         L_ = _lib.lib()
-        with torch.cuda.device(u.device):
+        with torch.cuda.device(u.device), _lib.timed("scan_bwd"):
             rc = L_.mlagg_selective_scan_bwd(_lib.ptr(u), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(B), _lib.ptr(C),
                                              _lib.ptr(D), _lib.ptr(bias), _lib.ptr(dout), _lib.ptr(ckpt),
                                              _lib.ptr(du), _lib.ptr(dd), _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dC),

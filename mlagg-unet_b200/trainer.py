@@ -1,0 +1,205 @@
+"""Trainer-level boundary: `nnUNetTrainer_MLAgg_2D_dt_MS` with the reference's static
+`build_network_architecture(plans_manager, dataset_json, configuration_manager, num_input_channels,
+enable_deep_supervision)` (reference nnUNetTrainer_MLAgg_2D_dt_MS.py:62-92), `configure_optimizers` (:137-147),
+`_get_deep_supervision_scales` (:101-104), `_build_loss` (:106-129), `set_deep_supervision_enabled` (:94-99) and
+a `train_step` that mirrors nnUNetTrainer.train_step (nnUNetTrainer.py:833-863).
+
+nnunetv2 itself cannot be imported in this image, so this class stands alone: the plans /
+configuration / label managers are duck-typed (`.patch_size`, `.batch_dice`, `.get_label_manager(...)`), and a
+synthetic stand-in (`SyntheticPlan`) provides them for benchmarks.  With a real nnunetv2 install, the overlay
+`nnunetv2/training/nnUNetTrainer/nnUNetTrainer_MLAgg_2D_dt_MS.py` subclasses the real
+nnUNetTrainer and delegates here.
+
+Deviations from the reference, all from SURVEY.md F5/F6: bf16 autocast without GradScaler (fp16+GradScaler is
+the reference default; selectable), `dummy_tensor` frozen, deep-supervision flag set on `.module` under DDP.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .mlagg import MLLA_Uper
+from .thirdparty_shims import CosineLRScheduler
+
+
+# ------------------------------------------------------------------ loss (reference training/loss/*, off the hot path)
+class _AllGatherGrad(torch.autograd.Function):
+    """all_gather forward, all_reduce backward (reference utilities/ddp_allgather.py:25-49)."""
+
+    @staticmethod
+    def forward(ctx, t):
+        out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t.contiguous())
+        return torch.stack(out, dim=0)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return g[dist.get_rank()]
+
+
+def soft_dice_loss(logits, target, batch_dice=True, do_bg=False, smooth=1e-5, ddp=False):
+    """MemoryEfficientSoftDiceLoss with softmax non-linearity (reference training/loss/dice.py:58-112)."""
+    x = torch.softmax(logits.float(), dim=1)
+    with torch.no_grad():
+        onehot = torch.zeros_like(x, dtype=torch.bool).scatter_(1, target.long(), 1)
+    if not do_bg:
+        x, onehot = x[:, 1:], onehot[:, 1:]
+    axes = tuple(range(2, x.dim()))
+    inter, spred, sgt = (x * onehot).sum(axes), x.sum(axes), onehot.sum(axes).float()
+    if ddp and batch_dice:
+        inter, spred, sgt = (_AllGatherGrad.apply(t).sum(0) for t in (inter, spred, sgt))
+    if batch_dice:
+        inter, spred, sgt = inter.sum(0), spred.sum(0), sgt.sum(0)
+    return -((2 * inter + smooth) / torch.clip(sgt + spred + smooth, 1e-8)).mean()
+
+
+class DeepSupervisionDiceCE(nn.Module):
+    """DeepSupervisionWrapper(DC_and_CE_loss(weight_ce=1, weight_dice=1)) with weights 1/2**i, normalised."""
+
+    def __init__(self, n_scales=5, batch_dice=True, ddp=False):
+        super().__init__()
+        w = np.array([1 / (2 ** i) for i in range(n_scales)])
+        self.weights = (w / w.sum()).tolist()
+        self.batch_dice, self.ddp = batch_dice, ddp
+
+    def one(self, logits, target):
+        ce = F.cross_entropy(logits.float(), target[:, 0].long())
+        return ce + soft_dice_loss(logits, target, self.batch_dice, False, 1e-5, self.ddp)
+
+    def forward(self, outputs, targets):
+        if not isinstance(outputs, (list, tuple)):
+            return self.one(outputs, targets[0] if isinstance(targets, (list, tuple)) else targets)
+        return sum(w * self.one(o, t) for w, o, t in zip(self.weights, outputs, targets))
+
+
+# ------------------------------------------------------------------ synthetic plans
+@dataclass
+class _LabelManager:
+    num_segmentation_heads: int
+    has_regions: bool = False
+    ignore_label: int | None = None
+
+
+@dataclass
+class SyntheticPlan:
+    """Stands in for PlansManager + ConfigurationManager + dataset_json of a `2d_bs10`-style plan."""
+    patch_size: tuple = (320, 320)
+    batch_size: int = 10
+    num_classes: int = 14
+    num_input_channels: int = 1
+    batch_dice: bool = True
+    dataset_json: dict = field(default_factory=dict)
+
+    def get_label_manager(self, dataset_json=None):
+        return _LabelManager(self.num_classes)
+
+
+def split_batch(global_batch: int, world_size: int):
+    """Per-rank batch sizes exactly as nnUNetTrainer._set_batch_size_and_oversample computes them
+    (reference nnUNetTrainer.py:295-307).  NOTE: for 10 images on 8 ranks this yields
+    [2,2,2,2,2,0,-2,-4] -- callers must reject non-positive entries."""
+    assert global_batch >= world_size, "Cannot run DDP if the batch size is smaller than the number of GPUs"
+    per = int(np.ceil(global_batch / world_size))
+    return [per - ((r + 1) * per - global_batch) if (r + 1) * per > global_batch else per for r in range(world_size)]
+
+
+class nnUNetTrainer_MLAgg_2D_dt_MS:
+    def __init__(self, plans: SyntheticPlan | None = None, configuration: str = "2d_bs10", fold: int = 0,
+                 dataset_json: dict | None = None, unpack_dataset: bool = True,
+                 device: torch.device = torch.device("cuda"), amp_dtype=torch.bfloat16):
+        self.plans = plans or SyntheticPlan()
+        self.plans_manager = self.configuration_manager = self.plans
+        self.dataset_json = dataset_json or self.plans.dataset_json
+        self.label_manager = self.plans.get_label_manager(self.dataset_json)
+        self.device = torch.device(device)
+        self.initial_lr, self.weight_decay = 5e-4, 3e-5
+        self.oversample_foreground_percent = 0.33
+        self.num_iterations_per_epoch, self.num_val_iterations_per_epoch = 250, 50
+        self.num_epochs, self.current_epoch = 500, 0
+        self.is_ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.amp_dtype = amp_dtype
+        self.grad_scaler = torch.amp.GradScaler("cuda") if (amp_dtype == torch.float16 and self.device.type == "cuda") else None
+        self.network = self.optimizer = self.lr_scheduler = self.loss = None
+
+    # ---- reference static API
+    @staticmethod
+    def build_network_architecture(plans_manager, dataset_json, configuration_manager, num_input_channels,
+                                   enable_deep_supervision: bool = True) -> nn.Module:
+        label_manager = plans_manager.get_label_manager(dataset_json)
+        return MLLA_Uper(img_size=configuration_manager.patch_size, patch_size=2, in_channels=num_input_channels,
+                         out_channels=label_manager.num_segmentation_heads, embed_dim=96, depths=[2, 2, 2, 2],
+                         num_heads=[2, 4, 8, 16], mlp_ratio=2, qkv_bias=True, drop_rate=0., dropout_path_rate=0.1,
+                         sr_ratio=[16, 8, 4, 2], norm_layer=nn.LayerNorm, ape=False, use_checkpoint=False,
+                         deep_supervision=enable_deep_supervision)
+
+    def set_deep_supervision_enabled(self, enabled: bool):
+        net = self.network.module if hasattr(self.network, "module") else self.network
+        net.deep_supervision = enabled
+
+    def _get_deep_supervision_scales(self):
+        return [list(i) for i in 1 / np.cumprod(np.vstack([[1, 1], [2, 2], [2, 2], [2, 2], [2, 2]]), axis=0)]
+
+    def _build_loss(self):
+        return DeepSupervisionDiceCE(len(self._get_deep_supervision_scales()), self.plans.batch_dice, self.is_ddp)
+
+    def configure_optimizers(self):
+        params = [p for p in self.network.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, self.initial_lr, weight_decay=self.weight_decay, eps=1e-4)
+        sched = CosineLRScheduler(opt, t_initial=self.num_epochs, lr_min=1e-6, warmup_t=10, warmup_lr_init=1e-4)
+        return opt, sched
+
+    # ---- lifecycle (nnUNetTrainer.initialize, :193-212)
+    def initialize(self):
+        self.network = self.build_network_architecture(self.plans_manager, self.dataset_json,
+                                                       self.configuration_manager, self.plans.num_input_channels,
+                                                       True).to(self.device)
+        self.optimizer, self.lr_scheduler = self.configure_optimizers()
+        if self.is_ddp:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            ids = [self.device.index] if self.device.type == "cuda" else None
+            self.network = DDP(self.network, device_ids=ids)
+        self.loss = self._build_loss()
+        return self
+
+    def synthetic_batch(self, batch_size=None, seed=0, device=None, pin=False):
+        """{'data': (B,C,H,W) float, 'target': [ (B,1,H/s,W/s) ] x 5} -- the shape the reference's augmenter yields
+        (pattern: nnUNetTrainerBenchmark_5epochs_noDataLoading.py:16-22)."""
+        g = torch.Generator().manual_seed(seed)
+        B = batch_size or self.plans.batch_size
+        H, W = self.plans.patch_size
+        data = torch.randn(B, self.plans.num_input_channels, H, W, generator=g)
+        target = [torch.round(torch.rand(B, 1, int(H * s[0]), int(W * s[1]), generator=g) * (self.plans.num_classes - 1))
+                  for s in self._get_deep_supervision_scales()]
+        if pin:
+            data, target = data.pin_memory(), [t.pin_memory() for t in target]
+        if device is not None:
+            data, target = data.to(device), [t.to(device) for t in target]
+        return {"data": data, "target": target}
+
+    def train_step(self, batch: dict, sync: bool = True) -> dict:
+        data = batch["data"].to(self.device, non_blocking=True)
+        target = [t.to(self.device, non_blocking=True) for t in batch["target"]]
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
+            output = self.network(data)
+            l = self.loss(output, target)
+        params = [p for p in self.network.parameters() if p.requires_grad]
+        if self.grad_scaler is not None:
+            self.grad_scaler.scale(l).backward()
+            self.grad_scaler.unscale_(self.optimizer)
+            torch.nn.utils.clip_grad_norm_(params, 12)
+            self.grad_scaler.step(self.optimizer)
+            self.grad_scaler.update()
+        else:
+            l.backward()
+            torch.nn.utils.clip_grad_norm_(params, 12)
+            self.optimizer.step()
+        return {"loss": l.detach().cpu().numpy() if sync else l.detach()}

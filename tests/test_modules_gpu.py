@@ -1,0 +1,168 @@
+"""GPU parity of the drop-in modules (mlagg-unet_b200/*.py over the C ABI) against the golden vectors produced
+by running the reference's own module source (tests/golden/make_golden.py) and against the CPU oracle.
+fp32: 1e-4 relative; bf16: 2e-2 relative (BASELINE.json:north_star)."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL32, TOL16 = 1e-4, 2e-2
+
+
+def _loss(out):
+    torch.manual_seed(99)
+    if isinstance(out, (list, tuple)):
+        return sum((o * torch.randn_like(o.cpu()).to(o.device)).sum() for o in out)
+    return (out * torch.randn_like(out.cpu()).to(out.device)).sum()
+
+
+def _check_param_grads(module, golden_grads, tol=TOL32):
+    for n, p in module.named_parameters():
+        ref = golden_grads.get(n)
+        if ref is None:
+            continue
+        assert p.grad is not None, n
+        assert rel_err(p.grad.cpu(), ref) < tol, n
+
+
+def test_ss2d_skip_matches_reference():
+    from mlagg_unet_b200.mamba_skip import SS2D_skip
+    g = load_golden("msmm_ss2d_skip.pt")
+    hw = g["hw"]
+    m = SS2D_skip(len(hw), 8).cuda().eval()
+    m.load_state_dict(g["state"], strict=True)
+    x = g["input"].cuda().requires_grad_()
+    y = m(x, 2, [h for h, _ in hw], [w for _, w in hw], [h * w for h, w in hw])
+    assert rel_err(y.cpu(), g["output"]) < TOL32
+    _loss(y).backward()
+    assert rel_err(x.grad.cpu(), g["grad_input"]) < TOL32
+
+
+def test_vss_conv_layer_matches_reference():
+    from mlagg_unet_b200.mamba_skip import VSS_Conv_Layer
+    g = load_golden("msmm_vss_conv_layer.pt")
+    m = VSS_Conv_Layer(g["dims"], g["hidden"], depth=1, drop_path=0.1).cuda().eval()
+    m.load_state_dict(g["state"], strict=True)
+    xs = [x.cuda().requires_grad_() for x in g["inputs"]]
+    outs = m(xs)
+    for o, ref in zip(outs, g["outputs"]):
+        assert rel_err(o.cpu(), ref) < TOL32
+    _loss(outs).backward()
+    for x, ref in zip(xs, g["grad_inputs"]):
+        assert rel_err(x.grad.cpu(), ref) < TOL32
+    _check_param_grads(m, g["grad_params"])
+
+
+@pytest.mark.parametrize("kind", ["local", "pooled"])
+def test_aggregated_attention_matches_reference(kind):
+    from mlagg_unet_b200.mlagg import AggregatedAttention
+    g = load_golden(f"mlagg_attention_{kind}.pt")
+    m = AggregatedAttention(g["dim"], (g["H"], g["W"]), num_heads=g["num_heads"], local=g["local"],
+                            sr_ratio=g["sr_ratio"]).cuda().eval()
+    m.load_state_dict(g["state"], strict=True)
+    x = g["input"].cuda().requires_grad_()
+    y = m(x, g["H"], g["W"])
+    assert rel_err(y.cpu(), g["output"]) < TOL32
+    _loss(y).backward()
+    assert rel_err(x.grad.cpu(), g["grad_input"]) < TOL32
+    _check_param_grads(m, g["grad_params"])
+
+
+def test_mlagg_block_matches_reference_fp32_and_bf16():
+    from mlagg_unet_b200.mlagg import MLLABlock
+    g = load_golden("mlagg_block.pt")
+    m = MLLABlock(g["dim"], (g["H"], g["W"]), g["num_heads"], mlp_ratio=2, sr_ratio=g["sr_ratio"], drop_path=0.05)
+    m = m.cuda().eval()
+    m.load_state_dict(g["state"], strict=True)
+    x = g["input"].cuda().requires_grad_()
+    y = m(x)
+    assert y.shape == g["output"].shape
+    assert rel_err(y.cpu(), g["output"]) < TOL32
+    _loss(y).backward()
+    assert rel_err(x.grad.cpu(), g["grad_input"]) < TOL32
+    _check_param_grads(m, g["grad_params"])
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = m(g["input"].cuda())
+    assert rel_err(y16.float().cpu(), g["output"]) < TOL16
+
+
+def test_linear_attention_and_mlla_block_match_reference():
+    from mlagg_unet_b200 import mlla
+    g = load_golden("mlla_linear_attention.pt")
+    m = mlla.LinearAttention(g["dim"], (g["H"], g["W"]), g["num_heads"]).cuda().eval()
+    m.load_state_dict(g["state"], strict=False)
+    assert rel_err(m.rope(g["rope_in"].cuda().reshape(2, g["H"], g["W"], g["dim"])).reshape(g["rope_out"].shape).cpu(),
+                   g["rope_out"]) < TOL32
+    x = g["input"].cuda().requires_grad_()
+    y = m(x)
+    assert rel_err(y.cpu(), g["output"]) < TOL32
+    _loss(y).backward()
+    assert rel_err(x.grad.cpu(), g["grad_input"]) < TOL32
+    _check_param_grads(m, g["grad_params"])
+    g = load_golden("mlla_block.pt")
+    b = mlla.MLLABlock(g["dim"], (g["H"], g["W"]), g["num_heads"], mlp_ratio=2.0, drop_path=0.05).cuda().eval()
+    b.load_state_dict(g["state"], strict=False)
+    x = g["input"].cuda().requires_grad_()
+    y = b(x)
+    assert rel_err(y.cpu(), g["output"]) < TOL32
+    _loss(y).backward()
+    assert rel_err(x.grad.cpu(), g["grad_input"]) < TOL32
+
+
+def test_full_network_logits_and_argmax_masks_identical():
+    """fp32 forward of the whole MLLA_Uper (narrow fixture): logits within 1e-4, argmax masks IDENTICAL."""
+    from mlagg_unet_b200.mlagg import MLLA_Uper
+    g = load_golden("mlla_uper_embed8.pt")
+    net = MLLA_Uper(img_size=[64, 64], patch_size=2, in_channels=1, out_channels=5, embed_dim=8, depths=[2, 2, 2, 2],
+                    num_heads=[2, 4, 8, 16], mlp_ratio=2, qkv_bias=True, drop_rate=0., dropout_path_rate=0.1,
+                    sr_ratio=[16, 8, 4, 2], deep_supervision=True).cuda().eval()
+    net.load_state_dict(g["state"], strict=True)
+    with torch.no_grad():
+        outs = net(g["input"].cuda())
+    assert [tuple(o.shape) for o in outs] == g["ds_shapes"]
+    assert rel_err(outs[0].cpu(), g["logits0"]) < TOL32
+    assert torch.equal(outs[0].argmax(1).to(torch.uint8).cpu(), g["argmax0"])
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, TOL16)])
+@pytest.mark.parametrize("shape,silu", [((2, 7, 5, 8), True), ((1, 1, 1, 4), False), ((2, 5, 4, 21), True), ((3, 16, 12, 96), True),
+                                        ((2, 20, 20, 128), False)])
+def test_dwconv3x3_tokens_matches_oracle(shape, silu, dtype, tol):
+    from mlagg_unet_b200.ops import dwconv3x3_tokens
+    from oracle.convs import dwconv3x3_tokens_act
+    Bn, H, W, C = shape
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(Bn, H * W, C, generator=g)
+    w = torch.randn(C, 1, 3, 3, generator=g) * 0.3
+    b = torch.randn(C, generator=g)
+    xr, wr, br = (t.clone().double().requires_grad_() for t in (x, w, b))
+    ref = dwconv3x3_tokens_act(xr, wr, br, H, W, silu)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    xc, wc, bc = x.cuda().to(dtype).requires_grad_(), w.cuda().requires_grad_(), b.cuda().requires_grad_()
+    y = dwconv3x3_tokens(xc, wc, bc, H, W, silu)
+    assert y.dtype == dtype
+    assert rel_err(y.float().cpu(), ref) < tol
+    y.backward(dy.cuda().to(dtype))
+    assert rel_err(xc.grad.float().cpu(), xr.grad) < tol
+    assert rel_err(wc.grad.cpu(), wr.grad) < tol * 2
+    assert rel_err(bc.grad.cpu(), br.grad) < tol * 2
+
+
+@pytest.mark.parametrize("K,silu,L", [(4, True, 100), (3, False, 37), (2, True, 1), (4, False, 2048)])
+def test_causal_conv1d_matches_oracle(K, silu, L):
+    from mlagg_unet_b200.ops import causal_conv1d_fn
+    from oracle.convs import causal_conv1d
+    g = torch.Generator().manual_seed(2)
+    x, w, b = torch.randn(2, 6, L, generator=g), torch.randn(6, K, generator=g), torch.randn(6, generator=g)
+    xr, wr, br = (t.clone().double().requires_grad_() for t in (x, w, b))
+    ref = causal_conv1d(xr, wr, br, silu)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    xc, wc, bc = (t.cuda().requires_grad_() for t in (x, w, b))
+    y = causal_conv1d_fn(xc, wc, bc, "silu" if silu else None)
+    assert rel_err(y.cpu(), ref) < 1e-5
+    y.backward(dy.cuda())
+    for a, r_ in ((xc, xr), (wc, wr), (bc, br)):
+        assert rel_err(a.grad.cpu(), r_.grad) < 1e-5
