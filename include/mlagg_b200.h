@@ -108,6 +108,30 @@ int mlagg_causal_conv1d_bwd(const float *x, const float *weight, const float *bi
                             float *dweight, float *dbias, int batch, int C, int L, int K, int act_silu,
                             mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Local (3x3 window) differential softmax attention + sub-LN, tokens-major, fused.
+ * Replaces the op chain of AggregatedAttention.forward, local branch, nnUNetTrainer_MLAgg_2D_dt_MS.py:698-717
+ * (nn.Unfold x2, q@k, masked_fill, softmax, lambda-combine, attn@v, RMSNorm(subln), * (1 - lambda_init)).
+ *   heads = h (the module's num_heads), head_dim = hd in {2,4,8,16,24,32}; C = 2*h*hd
+ *   q   : (batch, H*W, 2h, hd)  RAW projection output; row stride ldq elements; `scale` (= hd**-0.5) applied inside
+ *   k   : (batch, H*W, 2h, hd), v : (batch, H*W, h, 2hd); common row stride ldkv (the halves of the kv Linear)
+ *   out : (batch, H*W, h, 2hd)  row stride ldo
+ *   subln_w (2hd) fp32; lam = DEVICE pointer to the fp32 scalar lambda_full (no host sync); eps = 1e-5; post_scale = 1 - lambda_init
+ *   dtype: MLAGG_F32 | MLAGG_BF16 for q, k, v, out, dout, dq, dk, dv.
+ * Backward: dk / dv share row stride lddkv; d_subln_w (2hd) and d_lambda (1) fp32 are ACCUMULATED INTO;
+ *   ws: caller-owned scratch of mlagg_local_diffattn_ws_bytes(...) bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t mlagg_local_diffattn_ws_bytes(int batch, int H, int W, int heads, int head_dim);
+int mlagg_local_diffattn_fwd(const void *q, const void *k, const void *v, const float *subln_w, void *out,
+                             int batch, int H, int W, int heads, int head_dim, long long ldq, long long ldkv,
+                             long long ldo, float scale, const float *lam, float eps, float post_scale, int dtype,
+                             mlagg_stream_t stream);
+int mlagg_local_diffattn_bwd(const void *q, const void *k, const void *v, const float *subln_w, const void *dout,
+                             void *dq, void *dk, void *dv, float *d_subln_w, float *d_lambda, void *ws, int batch,
+                             int H, int W, int heads, int head_dim, long long ldq, long long ldkv, long long lddo,
+                             long long lddq, long long lddkv, float scale, const float *lam, float eps, float post_scale,
+                             int dtype, mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

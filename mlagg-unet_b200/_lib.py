@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmlagg_b200.so")
 _lib = None
 
-c_p, c_i, c_f, c_sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+c_p, c_i, c_f, c_sz, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_longlong
 
 # name -> (restype, argtypes); must list every symbol include/mlagg_b200.h declares
 SIGNATURES = {
@@ -26,6 +26,9 @@ SIGNATURES = {
     "mlagg_dwconv3x3_bwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
     "mlagg_causal_conv1d_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),
     "mlagg_causal_conv1d_bwd": (c_i, [c_p] * 7 + [c_i] * 5 + [c_p]),
+    "mlagg_local_diffattn_ws_bytes": (c_sz, [c_i] * 5),
+    "mlagg_local_diffattn_fwd": (c_i, [c_p] * 5 + [c_i] * 5 + [c_ll] * 3 + [c_f, c_p, c_f, c_f] + [c_i, c_p]),
+    "mlagg_local_diffattn_bwd": (c_i, [c_p] * 11 + [c_i] * 5 + [c_ll] * 5 + [c_f, c_p, c_f, c_f] + [c_i, c_p]),
 }
 
 

@@ -7,17 +7,20 @@
                          INCLUDING flash-attn's second head_dim**-0.5 scale
   linear_attention_core  elu+1 / RoPE / per-head K^T V state / normaliser (nnUNetTrainer_MLLA_UNet.py:234-246)
 
-STATUS (round 1): these three are compositions of torch CUDA ops (cuBLAS batched GEMM + elementwise), written
-from the math in App. A.4/A.5 rather than from the reference's op sequence.  They are the slots the fused
-sm_100a kernels `local_diffattn`, `pooled_diffattn`, `linattn_state/apply` (SURVEY.md 2.2 K7-K9) plug into;
-DESIGN.md lists them as "not yet native".  Depthwise convs and the scan around them already are native.
+STATUS (round 1): `local_diff_attention` is the fused sm_100a kernel (csrc/local_attn.cu).  The other two are
+still compositions of torch CUDA ops (cuBLAS batched GEMM + elementwise), written from the math in App. A.4/A.5
+rather than from the reference's op sequence; they are the slots `pooled_diffattn` and `linattn_state/apply`
+ plug into and DESIGN.md lists them as "not yet native".
 """
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
 
+from . import _lib
+
 LAMBDA_INIT = 0.8
+_DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
 def rmsnorm_affine(x, weight, eps):
@@ -30,42 +33,54 @@ def diff_lambda(lq1, lk1, lq2, lk2):
     return torch.exp(torch.sum(lq1 * lk1).float()) - torch.exp(torch.sum(lq2 * lk2).float()) + LAMBDA_INIT
 
 
-def _shifted_neighbours(t, H, W):
-    """t (B, H*W, ...) -> (B, H*W, 9, ...): the 3x3 neighbourhood, row-major over (dr, dc); zeros outside."""
-    Bn = t.shape[0]
-    rest = t.shape[2:]
-    img = t.reshape(Bn, H, W, -1)
-    pad = F.pad(img, (0, 0, 1, 1, 1, 1))
-    nb = torch.stack([pad[:, 1 + dr:1 + dr + H, 1 + dc:1 + dc + W] for dr in (-1, 0, 1) for dc in (-1, 0, 1)], dim=3)
-    return nb.reshape(Bn, H * W, 9, *rest)
+class _LocalDiffAttn(torch.autograd.Function):
+    """C ABI: mlagg_local_diffattn_fwd / _bwd (csrc/local_attn.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, lam, subln_w, H, W, h, hd, scale):
+        if not q.is_cuda:
+            raise _lib.MlaggError("local_diff_attention: CUDA tensors required (no CPU fallback in the product path)")
+        Bn, N, C = q.shape
+        dt = q.dtype if q.dtype in _DT else torch.float32
+        q_, kv_ = q.to(dt).contiguous(), kv.to(dt).contiguous()
+        lam_ = lam.detach().float().reshape(1).contiguous()
+        w_ = subln_w.detach().float().contiguous()
+        out = torch.empty_like(q_)
+        es = q_.element_size()
+        with torch.cuda.device(q.device), _lib.timed("local_diffattn_fwd"):
+            rc = _lib.lib().mlagg_local_diffattn_fwd(q_.data_ptr(), kv_.data_ptr(), kv_.data_ptr() + C * es, w_.data_ptr(),
+                                                     out.data_ptr(), Bn, H, W, h, hd, C, 2 * C, C, scale,
+                                                     lam_.data_ptr(), 1e-5, 1.0 - LAMBDA_INIT, _DT[dt], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_local_diffattn_fwd")
+        ctx.save_for_backward(q_, kv_, lam_, w_)
+        ctx.meta = (H, W, h, hd, scale, q.dtype, kv.dtype, lam.dtype, subln_w.dtype)
+        return out.to(q.dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q_, kv_, lam_, w_ = ctx.saved_tensors
+        H, W, h, hd, scale, qdt, kvdt, lamdt, wdt = ctx.meta
+        Bn, N, C = q_.shape
+        dt, es = q_.dtype, q_.element_size()
+        dout = dout.to(dt).contiguous()
+        dq, dkv = torch.empty_like(q_), torch.empty_like(kv_)
+        dw = torch.zeros_like(w_)
+        dlam = torch.zeros(1, device=q_.device, dtype=torch.float32)
+        L = _lib.lib()
+        ws = torch.empty(L.mlagg_local_diffattn_ws_bytes(Bn, H, W, h, hd) // 4, device=q_.device, dtype=torch.float32)
+        with torch.cuda.device(q_.device), _lib.timed("local_diffattn_bwd", 2):
+            rc = L.mlagg_local_diffattn_bwd(q_.data_ptr(), kv_.data_ptr(), kv_.data_ptr() + C * es, w_.data_ptr(),
+                                            dout.data_ptr(), dq.data_ptr(), dkv.data_ptr(), dkv.data_ptr() + C * es,
+                                            dw.data_ptr(), dlam.data_ptr(), ws.data_ptr(), Bn, H, W, h, hd, C, 2 * C, C, C,
+                                            2 * C, scale, lam_.data_ptr(), 1e-5, 1.0 - LAMBDA_INIT, _DT[dt],
+                                            _lib.stream_ptr())
+        _lib.check(rc, "mlagg_local_diffattn_bwd")
+        return dq.to(qdt), dkv.to(kvdt), dlam.reshape(()).to(lamdt), dw.to(wdt), None, None, None, None, None
 
 
-_MASKS = {}
-
-
-def _border_mask(H, W, device):
-    key = (H, W, str(device))
-    if key not in _MASKS:
-        r = torch.arange(H, device=device).view(H, 1, 1, 1) + torch.tensor([-1, 0, 1], device=device).view(1, 1, 3, 1)
-        c = torch.arange(W, device=device).view(1, W, 1, 1) + torch.tensor([-1, 0, 1], device=device).view(1, 1, 1, 3)
-        ok = (r >= 0) & (r < H) & (c >= 0) & (c < W)
-        _MASKS[key] = ~ok.reshape(H * W, 9)
-    return _MASKS[key]
-
-
-def local_diff_attention(q, k, v, lam, subln_w, H, W):
-    """q (B,N,2h,hd) pre-scaled by hd**-0.5; k (B,N,2h,hd); v (B,N,h,2hd) -> (B,N,h*2hd)."""
-    Bn, N, h2, hd = q.shape
-    h = h2 // 2
-    kn = _shifted_neighbours(k, H, W)                    # (B,N,9,2h,hd)
-    vn = _shifted_neighbours(v, H, W)                    # (B,N,9,h,2hd)
-    logits = torch.einsum("bnjd,bnpjd->bnjp", q, kn)
-    logits = logits.masked_fill(_border_mask(H, W, q.device)[None, :, None, :], float("-inf"))
-    a = logits.softmax(-1).view(Bn, N, h, 2, 9)
-    a = a[:, :, :, 0] - lam.to(a.dtype) * a[:, :, :, 1]
-    o = torch.einsum("bnmp,bnpmd->bnmd", a, vn)
-    o = rmsnorm_affine(o, subln_w, 1e-5) * (1 - LAMBDA_INIT)
-    return o.reshape(Bn, N, h * 2 * hd)
+def local_diff_attention(q, kv, lam, subln_w, H, W, h, hd, scale):
+    """q (B,N,C) RAW projection (scale applied in-kernel); kv (B,N,2C) = [k | v]; C = 2*h*hd -> (B,N,C)."""
+    return _LocalDiffAttn.apply(q, kv, lam, subln_w, H, W, h, hd, scale)
 
 
 def pooled_diff_attention(q, kp, vp, lam, subln_w):

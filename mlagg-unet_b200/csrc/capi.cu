@@ -22,6 +22,19 @@ cudaError_t causal_conv1d_bwd_dispatch(const float *x, const float *w, const flo
                                        float *dw, float *db, int rows, int C, int L, int K, int act,
                                        cudaStream_t st);
 
+struct LocalAttnParams {
+    const void *q, *k, *v, *dout;
+    void *out, *dq, *dk, *dv;
+    const float *subln_w;
+    float *d_subln_w, *d_lambda, *ws_dO, *ws_abar, *ws_dlog;
+    long long ldq, ldkv, ldo, lddo, lddq, lddkv;
+    int Bn, H, W, h;
+    const float *lamp;
+    float scale, eps, post;
+};
+bool local_attn_hd_supported(int hd);
+cudaError_t local_attn_dispatch(const LocalAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
+
 static thread_local char g_last_err[256] = "";
 
 static int fail_cuda(cudaError_t e) {
@@ -170,5 +183,64 @@ extern "C" int mlagg_causal_conv1d_bwd(const float *x, const float *weight, cons
     if (K < 1 || K > 4) return MLAGG_ERR_UNSUPPORTED;
     cudaError_t e = causal_conv1d_bwd_dispatch(x, weight, bias, dy, dx, dweight, dbias, batch * C, C, L, K, act_silu,
                                                (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" size_t mlagg_local_diffattn_ws_bytes(int batch, int H, int W, int heads, int head_dim) {
+    if (batch <= 0 || H <= 0 || W <= 0 || heads <= 0 || head_dim <= 0) return 0;
+    return (size_t)batch * H * W * heads * (2 * head_dim + 9 + 18) * sizeof(float);
+}
+
+static int local_check(const void *q, const void *k, const void *v, const float *w, int batch, int H, int W, int heads,
+                       int head_dim, int dtype) {
+    if (!q || !k || !v || !w) return MLAGG_ERR_NULL;
+    if (batch <= 0 || H <= 0 || W <= 0 || heads <= 0) return MLAGG_ERR_BAD_SHAPE;
+    if (!local_attn_hd_supported(head_dim) || (dtype != MLAGG_F32 && dtype != MLAGG_BF16)) return MLAGG_ERR_UNSUPPORTED;
+    const size_t a = dtype == MLAGG_F32 ? 16 : 8;
+    if (!aligned(q, a) || !aligned(k, a) || !aligned(v, a)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_local_diffattn_fwd(const void *q, const void *k, const void *v, const float *subln_w, void *out,
+                                        int batch, int H, int W, int heads, int head_dim, long long ldq,
+                                        long long ldkv, long long ldo, float scale, const float *lam, float eps,
+                                        float post_scale, int dtype, mlagg_stream_t stream) {
+    int rc = local_check(q, k, v, subln_w, batch, H, W, heads, head_dim, dtype);
+    if (rc) return rc;
+    if (!out || !lam) return MLAGG_ERR_NULL;
+    if (ldq % 4 || ldkv % 4 || ldo % 4) return MLAGG_ERR_ALIGN;
+    LocalAttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = q; p.k = k; p.v = v; p.out = out; p.subln_w = subln_w;
+    p.ldq = ldq; p.ldkv = ldkv; p.ldo = ldo;
+    p.Bn = batch; p.H = H; p.W = W; p.h = heads;
+    p.scale = scale; p.lamp = lam; p.eps = eps; p.post = post_scale;
+    cudaError_t e = local_attn_dispatch(p, head_dim, dtype, 0, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_local_diffattn_bwd(const void *q, const void *k, const void *v, const float *subln_w,
+                                        const void *dout, void *dq, void *dk, void *dv, float *d_subln_w,
+                                        float *d_lambda, void *ws, int batch, int H, int W, int heads, int head_dim,
+                                        long long ldq, long long ldkv, long long lddo, long long lddq,
+                                        long long lddkv, float scale, const float *lam, float eps, float post_scale,
+                                        int dtype, mlagg_stream_t stream) {
+    int rc = local_check(q, k, v, subln_w, batch, H, W, heads, head_dim, dtype);
+    if (rc) return rc;
+    if (!dout || !dq || !dk || !dv || !d_subln_w || !d_lambda || !ws || !lam) return MLAGG_ERR_NULL;
+    if (ldq % 4 || ldkv % 4 || lddo % 4 || lddq % 4 || lddkv % 4 || !aligned(ws, 16)) return MLAGG_ERR_ALIGN;
+    LocalAttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = q; p.k = k; p.v = v; p.dout = dout; p.dq = dq; p.dk = dk; p.dv = dv; p.subln_w = subln_w;
+    p.d_subln_w = d_subln_w; p.d_lambda = d_lambda;
+    const size_t ntok = (size_t)batch * H * W * heads;
+    p.ws_dO = static_cast<float *>(ws);
+    p.ws_abar = p.ws_dO + ntok * 2 * head_dim;
+    p.ws_dlog = p.ws_abar + ntok * 9;
+    p.ldq = ldq; p.ldkv = ldkv; p.lddo = lddo; p.lddq = lddq; p.lddkv = lddkv;
+    p.Bn = batch; p.H = H; p.W = W; p.h = heads;
+    p.scale = scale; p.lamp = lam; p.eps = eps; p.post = post_scale;
+    cudaError_t e = local_attn_dispatch(p, head_dim, dtype, 1, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = local_attn_dispatch(p, head_dim, dtype, 2, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

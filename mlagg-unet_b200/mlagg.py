@@ -105,13 +105,14 @@ class AggregatedAttention(nn.Module):
         Bn, N, C = x.shape
         assert N == H * W
         h, hd = self.num_heads, self.head_dim
-        q = self.q(x) * self.scale
-        k_local, v_local = self.kv(x).chunk(2, dim=-1)
+        q = self.q(x)
+        kv = self.kv(x)
+        v_local = kv[..., C:]
         lam = att.diff_lambda(self.lambda_q1, self.lambda_k1, self.lambda_q2, self.lambda_k2)
         if self.local:
-            o = att.local_diff_attention(q.view(Bn, N, 2 * h, hd), k_local.reshape(Bn, N, 2 * h, hd),
-                                         v_local.reshape(Bn, N, h, 2 * hd), lam, self.subln.weight, H, W)
+            o = att.local_diff_attention(q, kv, lam, self.subln.weight, H, W, h, hd, self.scale)
         else:
+            q = q * self.scale
             # pooled tokens: 1x1 conv == per-token Linear; pooling on the tokens-major image view
             t = F.gelu(F.linear(x, self.sr.weight.view(C, C), self.sr.bias))
             t = self.pool(t.transpose(1, 2).reshape(Bn, C, H, W)).flatten(2).transpose(1, 2)
