@@ -132,6 +132,30 @@ int mlagg_local_diffattn_bwd(const void *q, const void *k, const void *v, const 
                              long long lddq, long long lddkv, float scale, const float *lam, float eps, float post_scale,
                              int dtype, mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Pooled-token differential softmax attention + sub-LN, tokens-major, fused.
+ * Replaces AggregatedAttention.forward, pooled branch, nnUNetTrainer_MLAgg_2D_dt_MS.py:734-760: the four
+ * flash_attn_func(q_j, k_j, v_i) calls (:745-751), both torch.cat, the lambda-combine (:756), RMSNorm (:759) and
+ * * (1 - lambda_init) (:760).  The shipped DOUBLE scaling is reproduced: logits = (q . k) * scale * scale where
+ * `scale` = hd**-0.5 (once at :688, once more as flash-attn's default softmax_scale).
+ *   q   : (batch, N, h, 2, hd) RAW projection, row stride ldq
+ *   kp  : (batch, P, h, 2, hd), vp : (batch, P, h, 2hd); common row stride ldkv; P <= 256, P*hd*16 B of shared memory
+ *   out : (batch, N, h, 2hd) row stride ldo;   lse : (batch, N, h, 2) fp32, nullable (needed by the backward)
+ * Backward: dkp / dvp are fp32 (batch, P, h, 2hd) with common row stride ldd, ACCUMULATED INTO (zero-fill);
+ *   d_subln_w (2hd), d_lambda (1) ACCUMULATED INTO; ws: mlagg_pooled_diffattn_ws_bytes(...) bytes of scratch.
+ * ------------------------------------------------------------------------------------------ */
+size_t mlagg_pooled_diffattn_ws_bytes(int batch, int N, int heads, int head_dim);
+int mlagg_pooled_diffattn_fwd(const void *q, const void *kp, const void *vp, const float *subln_w, void *out,
+                              float *lse, int batch, int N, int P, int heads, int head_dim, long long ldq,
+                              long long ldkv, long long ldo, float scale, const float *lam, float eps,
+                              float post_scale, int dtype, mlagg_stream_t stream);
+int mlagg_pooled_diffattn_bwd(const void *q, const void *kp, const void *vp, const float *subln_w,
+                              const float *lse, const void *dout, void *dq, float *dkp, float *dvp,
+                              float *d_subln_w, float *d_lambda, void *ws, int batch, int N, int P, int heads,
+                              int head_dim, long long ldq, long long ldkv, long long lddo, long long lddq,
+                              long long ldd, float scale, const float *lam, float eps, float post_scale,
+                              int dtype, mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

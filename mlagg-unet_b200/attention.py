@@ -7,10 +7,10 @@
                          INCLUDING flash-attn's second head_dim**-0.5 scale
   linear_attention_core  elu+1 / RoPE / per-head K^T V state / normaliser (nnUNetTrainer_MLLA_UNet.py:234-246)
 
-STATUS (round 1): `local_diff_attention` is the fused sm_100a kernel (csrc/local_attn.cu).  The other two are
-still compositions of torch CUDA ops (cuBLAS batched GEMM + elementwise), written from the math in App. A.4/A.5
-rather than from the reference's op sequence; they are the slots `pooled_diffattn` and `linattn_state/apply`
- plug into and DESIGN.md lists them as "not yet native".
+STATUS (round 1): `local_diff_attention` and `pooled_diff_attention` are fused sm_100a kernels
+(csrc/local_attn.cu, csrc/pooled_attn.cu).  `linear_attention_core` is still a composition of torch CUDA ops
+(cuBLAS batched GEMM + elementwise) written from the math in App. A.5; it is the slot `linattn_state/apply`
+ plugs into and DESIGN.md lists it as "not yet native".
 """
 from __future__ import annotations
 
@@ -83,15 +83,60 @@ def local_diff_attention(q, kv, lam, subln_w, H, W, h, hd, scale):
     return _LocalDiffAttn.apply(q, kv, lam, subln_w, H, W, h, hd, scale)
 
 
-def pooled_diff_attention(q, kp, vp, lam, subln_w):
-    """q (B,N,h,2,hd) pre-scaled once; kp (B,P,h,2,hd); vp (B,P,h,2hd) -> (B,N,h*2hd)."""
-    Bn, N, h, _, hd = q.shape
-    logits = torch.einsum("bnmjd,bpmjd->bmjnp", q, kp) * (hd ** -0.5)   # flash_attn's own scale (F4)
-    a = logits.float().softmax(-1).to(q.dtype)
-    o = torch.einsum("bmjnp,bpmd->bnmjd", a, vp)
-    o = o[:, :, :, 0] - lam.to(o.dtype) * o[:, :, :, 1]
-    o = rmsnorm_affine(o, subln_w, 1e-5) * (1 - LAMBDA_INIT)
-    return o.reshape(Bn, N, h * 2 * hd)
+class _PooledDiffAttn(torch.autograd.Function):
+    """C ABI: mlagg_pooled_diffattn_fwd / _bwd (csrc/pooled_attn.cu)."""
+
+    @staticmethod
+    def forward(ctx, q, kvp, lam, subln_w, h, hd, scale):
+        if not q.is_cuda:
+            raise _lib.MlaggError("pooled_diff_attention: CUDA tensors required (no CPU fallback in the product path)")
+        Bn, N, C = q.shape
+        P = kvp.shape[1]
+        dt = q.dtype if q.dtype in _DT else torch.float32
+        q_, kv_ = q.to(dt).contiguous(), kvp.to(dt).contiguous()
+        lam_ = lam.detach().float().reshape(1).contiguous()
+        w_ = subln_w.detach().float().contiguous()
+        out = torch.empty_like(q_)
+        lse = torch.empty(Bn, N, h, 2, device=q.device, dtype=torch.float32)
+        es = q_.element_size()
+        with torch.cuda.device(q.device), _lib.timed("pooled_diffattn_fwd"):
+            rc = _lib.lib().mlagg_pooled_diffattn_fwd(q_.data_ptr(), kv_.data_ptr(), kv_.data_ptr() + C * es,
+                                                      w_.data_ptr(), out.data_ptr(), lse.data_ptr(), Bn, N, P, h, hd, C,
+                                                      2 * C, C, scale, lam_.data_ptr(), 1e-5, 1.0 - LAMBDA_INIT,
+                                                      _DT[dt], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_pooled_diffattn_fwd")
+        ctx.save_for_backward(q_, kv_, lam_, w_, lse)
+        ctx.meta = (h, hd, scale, q.dtype, kvp.dtype, lam.dtype, subln_w.dtype)
+        return out.to(q.dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q_, kv_, lam_, w_, lse = ctx.saved_tensors
+        h, hd, scale, qdt, kvdt, lamdt, wdt = ctx.meta
+        Bn, N, C = q_.shape
+        P = kv_.shape[1]
+        dt, es = q_.dtype, q_.element_size()
+        dout = dout.to(dt).contiguous()
+        dq = torch.empty_like(q_)
+        dkv = torch.zeros(Bn, P, 2 * C, device=q_.device, dtype=torch.float32)
+        dw = torch.zeros_like(w_)
+        dlam = torch.zeros(1, device=q_.device, dtype=torch.float32)
+        L = _lib.lib()
+        ws = torch.empty(L.mlagg_pooled_diffattn_ws_bytes(Bn, N, h, hd) // 4, device=q_.device, dtype=torch.float32)
+        with torch.cuda.device(q_.device), _lib.timed("pooled_diffattn_bwd", 2):
+            rc = L.mlagg_pooled_diffattn_bwd(q_.data_ptr(), kv_.data_ptr(), kv_.data_ptr() + C * es, w_.data_ptr(),
+                                             lse.data_ptr(), dout.data_ptr(), dq.data_ptr(), dkv.data_ptr(),
+                                             dkv.data_ptr() + C * 4, dw.data_ptr(), dlam.data_ptr(), ws.data_ptr(), Bn, N,
+                                             P, h, hd, C, 2 * C, C, C, 2 * C, scale, lam_.data_ptr(), 1e-5,
+                                             1.0 - LAMBDA_INIT, _DT[dt], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_pooled_diffattn_bwd")
+        return dq.to(qdt), dkv.to(kvdt), dlam.reshape(()).to(lamdt), dw.to(wdt), None, None, None
+
+
+def pooled_diff_attention(q, kvp, lam, subln_w, h, hd, scale):
+    """q (B,N,C) RAW projection; kvp (B,P,2C) = [k_pool | v_pool]; C = 2*h*hd -> (B,N,C).  Both hd**-0.5 scalings
+    of the shipped reference are applied in-kernel."""
+    return _PooledDiffAttn.apply(q, kvp, lam, subln_w, h, hd, scale)
 
 
 _ROPE = {}

@@ -35,6 +35,19 @@ struct LocalAttnParams {
 bool local_attn_hd_supported(int hd);
 cudaError_t local_attn_dispatch(const LocalAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
 
+struct PooledAttnParams {
+    const void *q, *kp, *vp, *dout;
+    void *out, *dq;
+    float *lse, *dkp, *dvp;
+    const float *subln_w;
+    float *d_subln_w, *d_lambda, *ws_dO, *ws_D;
+    const float *lamp;
+    long long ldq, ldkv, ldo, lddo, lddq, ldd;
+    int Bn, N, P, h;
+    float scale2, eps, post;
+};
+cudaError_t pooled_attn_dispatch(const PooledAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
+
 static thread_local char g_last_err[256] = "";
 
 static int fail_cuda(cudaError_t e) {
@@ -242,5 +255,59 @@ extern "C" int mlagg_local_diffattn_bwd(const void *q, const void *k, const void
     p.scale = scale; p.lamp = lam; p.eps = eps; p.post = post_scale;
     cudaError_t e = local_attn_dispatch(p, head_dim, dtype, 1, (cudaStream_t)stream);
     if (e == cudaSuccess) e = local_attn_dispatch(p, head_dim, dtype, 2, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" size_t mlagg_pooled_diffattn_ws_bytes(int batch, int N, int heads, int head_dim) {
+    if (batch <= 0 || N <= 0 || heads <= 0 || head_dim <= 0) return 0;
+    return (size_t)batch * N * heads * (2 * head_dim + 2) * sizeof(float);
+}
+
+static int pooled_check(const void *q, const void *kp, const void *vp, const float *w, const float *lam, int batch,
+                        int N, int P, int heads, int head_dim, int dtype) {
+    if (!q || !kp || !vp || !w || !lam) return MLAGG_ERR_NULL;
+    if (batch <= 0 || N <= 0 || P <= 0 || heads <= 0 || batch > 65535 || heads > 65535) return MLAGG_ERR_BAD_SHAPE;
+    if (!local_attn_hd_supported(head_dim) || (dtype != MLAGG_F32 && dtype != MLAGG_BF16)) return MLAGG_ERR_UNSUPPORTED;
+    if (P > 256 || (size_t)P * head_dim * 16 > 200 * 1024) return MLAGG_ERR_UNSUPPORTED;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_pooled_diffattn_fwd(const void *q, const void *kp, const void *vp, const float *subln_w,
+                                         void *out, float *lse, int batch, int N, int P, int heads, int head_dim,
+                                         long long ldq, long long ldkv, long long ldo, float scale, const float *lam,
+                                         float eps, float post_scale, int dtype, mlagg_stream_t stream) {
+    int rc = pooled_check(q, kp, vp, subln_w, lam, batch, N, P, heads, head_dim, dtype);
+    if (rc) return rc;
+    if (!out) return MLAGG_ERR_NULL;
+    PooledAttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = q; p.kp = kp; p.vp = vp; p.out = out; p.lse = lse; p.subln_w = subln_w; p.lamp = lam;
+    p.ldq = ldq; p.ldkv = ldkv; p.ldo = ldo;
+    p.Bn = batch; p.N = N; p.P = P; p.h = heads;
+    p.scale2 = scale * scale; p.eps = eps; p.post = post_scale;
+    cudaError_t e = pooled_attn_dispatch(p, head_dim, dtype, 0, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_pooled_diffattn_bwd(const void *q, const void *kp, const void *vp, const float *subln_w,
+                                         const float *lse, const void *dout, void *dq, float *dkp, float *dvp,
+                                         float *d_subln_w, float *d_lambda, void *ws, int batch, int N, int P,
+                                         int heads, int head_dim, long long ldq, long long ldkv, long long lddo,
+                                         long long lddq, long long ldd, float scale, const float *lam, float eps,
+                                         float post_scale, int dtype, mlagg_stream_t stream) {
+    int rc = pooled_check(q, kp, vp, subln_w, lam, batch, N, P, heads, head_dim, dtype);
+    if (rc) return rc;
+    if (!lse || !dout || !dq || !dkp || !dvp || !d_subln_w || !d_lambda || !ws) return MLAGG_ERR_NULL;
+    PooledAttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = q; p.kp = kp; p.vp = vp; p.dout = dout; p.dq = dq; p.lse = const_cast<float *>(lse);
+    p.dkp = dkp; p.dvp = dvp; p.subln_w = subln_w; p.d_subln_w = d_subln_w; p.d_lambda = d_lambda; p.lamp = lam;
+    p.ws_dO = static_cast<float *>(ws);
+    p.ws_D = p.ws_dO + (size_t)batch * N * heads * 2 * head_dim;
+    p.ldq = ldq; p.ldkv = ldkv; p.lddo = lddo; p.lddq = lddq; p.ldd = ldd;
+    p.Bn = batch; p.N = N; p.P = P; p.h = heads;
+    p.scale2 = scale * scale; p.eps = eps; p.post = post_scale;
+    cudaError_t e = pooled_attn_dispatch(p, head_dim, dtype, 1, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = pooled_attn_dispatch(p, head_dim, dtype, 2, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

@@ -137,7 +137,12 @@ class SS2D_skip(nn.Module):
         idx, inv = cross_scan_maps(hw, xc.device)
         x_dbl = F.linear(xc, self.x_proj_weight.view(K * (R + 2 * N), Di)).view(Bn, L, K, R + 2 * N)
         dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=-1)
-        dts = torch.einsum("blkr,kdr->bkdl", dts_r, self.dt_projs_weight)          # (B, 4, Di, L) un-permuted
+        # dt projection has inner dimension R = dt_rank (3): as a GEMM it is degenerate (K=3), so it is written as
+        # R broadcast multiply-adds; result (B, 4, Di, L) un-permuted, channels-major like the scan wants it
+        dts = None
+        for r_ in range(R):
+            term = dts_r[..., r_].permute(0, 2, 1).unsqueeze(2) * self.dt_projs_weight[:, :, r_].to(dts_r.dtype)[None, :, :, None]
+            dts = term if dts is None else dts + term
         u = xc.transpose(1, 2)                                                      # (B, Di, L) view
         Bs, Cs = Bs.permute(0, 2, 3, 1), Cs.permute(0, 2, 3, 1)                     # (B, 4, N, L) views
         gather = lambda t, k: t.index_select(-1, idx[k]).float()

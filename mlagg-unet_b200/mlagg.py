@@ -112,13 +112,10 @@ class AggregatedAttention(nn.Module):
         if self.local:
             o = att.local_diff_attention(q, kv, lam, self.subln.weight, H, W, h, hd, self.scale)
         else:
-            q = q * self.scale
             # pooled tokens: 1x1 conv == per-token Linear; pooling on the tokens-major image view
             t = F.gelu(F.linear(x, self.sr.weight.view(C, C), self.sr.bias))
             t = self.pool(t.transpose(1, 2).reshape(Bn, C, H, W)).flatten(2).transpose(1, 2)
-            kp, vp = self.kv(self.norm(t)).chunk(2, dim=-1)
-            o = att.pooled_diff_attention(q.view(Bn, N, h, 2, hd), kp.reshape(Bn, self.pool_len, h, 2, hd),
-                                          vp.reshape(Bn, self.pool_len, h, 2 * hd), lam, self.subln.weight)
+            o = att.pooled_diff_attention(q, self.kv(self.norm(t)), lam, self.subln.weight, h, hd, self.scale)
         return o + dwconv3x3_tokens(v_local.contiguous(), self.lepe.weight, self.lepe.bias, H, W)
 
 
