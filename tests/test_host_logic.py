@@ -1,0 +1,150 @@
+"""CPU: host-side logic of the product (no kernels are launched): C-ABI symbols, index maps, state_dict / API
+compatibility with the reference, scheduler + DropPath semantics, batch split, and that the product path refuses to
+run on CPU tensors (there is no fallback)."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from mlagg_unet_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    hdr = open(os.path.join(ROOT, "include", "mlagg_b200.h")).read()
+    declared = set(re.findall(r"\b(mlagg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.mlagg_version() >= 100
+    assert L.mlagg_scan_ckpt_bytes(10, 384, 34000, 16) == 10 * 2125 * 384 * 16 * 4
+    assert L.mlagg_error_string(-2).decode() == "unsupported configuration"
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    from mlagg_unet_b200 import _lib
+    L = _lib.lib()
+    assert L.mlagg_selective_scan_fwd(None, None, None, None, None, None, None, None, None, None,
+                                      1, 8, 16, 16, 1, 1, None) == -3          # NULL
+    assert L.mlagg_dwconv3x3_fwd(None, None, None, None, 1, 4, 4, 8, 0, 0, None) == -3
+    assert L.mlagg_local_diffattn_ws_bytes(2, 4, 4, 1, 24) == 2 * 16 * (48 + 27) * 4
+
+
+def test_cross_scan_maps_agree_with_oracle_and_are_inverse():
+    from mlagg_unet_b200.mamba_skip import _scan_maps_cpu
+    from oracle.msmm import cross_scan_maps
+    hw = ((6, 5), (3, 4), (2, 2))
+    idx, inv = _scan_maps_cpu(hw)
+    assert torch.equal(idx, cross_scan_maps(list(hw)))
+    L = idx.shape[1]
+    for k in range(4):
+        assert torch.equal(idx[k][inv[k]], torch.arange(L))
+
+
+def test_state_dict_compatibility_with_reference():
+    from mlagg_unet_b200 import mlla
+    from mlagg_unet_b200.mamba_skip import VSS_Conv_Layer
+    from mlagg_unet_b200.mlagg import MLLA_Uper, MLLABlock
+    g = load_golden("mlla_uper_embed8.pt")
+    net = MLLA_Uper(img_size=[64, 64], patch_size=2, in_channels=1, out_channels=5, embed_dim=8, depths=[2, 2, 2, 2],
+                    num_heads=[2, 4, 8, 16], mlp_ratio=2, sr_ratio=[16, 8, 4, 2], dropout_path_rate=0.1)
+    net.load_state_dict(g["state"], strict=True)
+    assert sum(p.numel() for p in net.parameters()) == g["n_params"]
+    assert not net.dummy_tensor.requires_grad  # F6: unused parameter must not take part in DDP reduction
+    g = load_golden("msmm_vss_conv_layer.pt")
+    VSS_Conv_Layer(g["dims"], g["hidden"], depth=1, drop_path=0.1).load_state_dict(g["state"], strict=True)
+    g = load_golden("mlagg_block.pt")
+    MLLABlock(g["dim"], (g["H"], g["W"]), g["num_heads"], mlp_ratio=2, sr_ratio=g["sr_ratio"]).load_state_dict(
+        g["state"], strict=True)
+    g = load_golden("mlla_block.pt")
+    res = mlla.MLLABlock(g["dim"], (g["H"], g["W"]), g["num_heads"], mlp_ratio=2.0).load_state_dict(g["state"], strict=False)
+    assert res.unexpected_keys == [] and res.missing_keys == ["attn.rope.rotations"]
+
+
+def test_full_size_network_has_reference_parameter_count():
+    from mlagg_unet_b200.trainer import SyntheticPlan, nnUNetTrainer_MLAgg_2D_dt_MS
+    plan = SyntheticPlan()
+    net = nnUNetTrainer_MLAgg_2D_dt_MS.build_network_architecture(plan, {}, plan, 1, True)
+    n = sum(p.numel() for p in net.parameters())
+    assert abs(n - 27.1e6) < 0.1e6  # ~27.1 M
+    sig = inspect.signature(nnUNetTrainer_MLAgg_2D_dt_MS.build_network_architecture)
+    assert list(sig.parameters) == ["plans_manager", "dataset_json", "configuration_manager", "num_input_channels",
+                                    "enable_deep_supervision"]
+
+
+def test_rope_buffer_matches_reference_layout():
+    from mlagg_unet_b200.mlla import RoPE
+    g = load_golden("mlla_linear_attention.pt")
+    # rotations (H, W, C/2, 2): the rotated tensor of the golden input reproduces the reference's output on CPU
+    r = RoPE((g["H"], g["W"], g["dim"]))
+    assert r.rotations.shape == (g["H"], g["W"], g["dim"] // 2, 2)
+    out = r(g["rope_in"].reshape(2, g["H"], g["W"], g["dim"])).reshape(g["rope_out"].shape)
+    assert (out - g["rope_out"]).abs().max() < 1e-5
+
+
+def test_cosine_scheduler_timm_semantics():
+    from mlagg_unet_b200.thirdparty_shims import CosineLRScheduler
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], 5e-4)
+    s = CosineLRScheduler(opt, t_initial=500, lr_min=1e-6, warmup_t=10, warmup_lr_init=1e-4)
+    assert opt.param_groups[0]["lr"] == pytest.approx(1e-4)
+    s.step(5)
+    assert opt.param_groups[0]["lr"] == pytest.approx(1e-4 + 5 * (5e-4 - 1e-4) / 10)
+    s.step(250)
+    assert opt.param_groups[0]["lr"] == pytest.approx(1e-6 + 0.5 * (5e-4 - 1e-6))
+    s.step(500)
+    assert opt.param_groups[0]["lr"] == pytest.approx(1e-6)
+
+
+def test_droppath_semantics():
+    from mlagg_unet_b200.thirdparty_shims import DropPath
+    d = DropPath(0.5)
+    x = torch.ones(1000, 3, 2)
+    assert torch.equal(d.eval()(x), x)
+    y = d.train()(x)
+    per_sample = y.flatten(1)
+    assert ((per_sample == 0).all(1) | (per_sample == 2).all(1)).all()  # whole sample dropped or scaled by 1/keep
+    assert 0.35 < float((per_sample[:, 0] == 0).float().mean()) < 0.65
+
+
+def test_split_batch_is_the_reference_arithmetic():
+    from mlagg_unet_b200.trainer import split_batch
+    assert split_batch(10, 2) == [5, 5]
+    assert split_batch(10, 4) == [3, 3, 3, 1]
+    assert split_batch(10, 8) == [2, 2, 2, 2, 2, 0, -2, -4]  # invalid in the reference itself
+    with pytest.raises(AssertionError):
+        split_batch(4, 8)
+
+
+def test_product_path_has_no_cpu_fallback():
+    from mlagg_unet_b200._lib import MlaggError
+    from mlagg_unet_b200.attention import local_diff_attention, pooled_diff_attention
+    from mlagg_unet_b200.ops import causal_conv1d_fn, dwconv3x3_tokens
+    from mlagg_unet_b200.selective_scan_interface import selective_scan_fn
+    x = torch.randn(1, 16, 8)
+    with pytest.raises(MlaggError):
+        dwconv3x3_tokens(x, torch.randn(8, 1, 3, 3), None, 4, 4)
+    with pytest.raises(MlaggError):
+        causal_conv1d_fn(torch.randn(1, 4, 8), torch.randn(4, 3))
+    with pytest.raises(MlaggError):
+        selective_scan_fn(torch.randn(1, 4, 8), torch.randn(1, 4, 8), -torch.rand(4, 16), torch.randn(1, 16, 8),
+                          torch.randn(1, 16, 8))
+    with pytest.raises(MlaggError):
+        local_diff_attention(x, torch.randn(1, 16, 16), torch.tensor(0.5), torch.ones(8), 4, 4, 1, 4, 0.5)
+    with pytest.raises(MlaggError):
+        pooled_diff_attention(x, torch.randn(1, 4, 16), torch.tensor(0.5), torch.ones(8), 1, 4, 0.5)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mlagg-unet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "scan_ref" not in src, f
