@@ -96,13 +96,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // softplus(x) = x > 20 ? x : log1p(exp(x))  (torch semantics), plus d softplus/dx = sigmoid(x) (1 above 20).
 // log1p(e) is a 4-term series for e < 1/32 (rel. error < e^4/5 < 2e-7) and ln(1+e) through MUFU.LG2 above.
 __device__ __forceinline__ float softplus_fast(float x, float *dsp = nullptr) {
+    // branch-free: both log1p forms are evaluated and selected, so independent elements interleave freely
     const float e = ex2_approx(fminf(x, 20.f) * kLog2e);
-    float sp;
-    if (e < 0.03125f) {
-        sp = e * (1.f - e * (0.5f - e * (0.33333334f - e * 0.25f)));
-    } else {
-        sp = lg2_approx(1.f + e) * kLn2;
-    }
+    const float series = e * (1.f - e * (0.5f - e * (0.33333334f - e * 0.25f)));
+    const float viaLog = lg2_approx(1.f + e) * kLn2;
+    const float sp = e < 0.03125f ? series : viaLog;
     if (dsp) *dsp = x > 20.f ? 1.f : e * rcp_approx(1.f + e);
     return x > 20.f ? x : sp;
 }

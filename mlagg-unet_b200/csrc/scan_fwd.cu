@@ -1,22 +1,54 @@
 // scan_fwd.cu -- selective scan (S6) forward for sm_100a.
 // Replaces selective_scan_cuda.fwd as called at reference MambaSkip.py:445-451 (math: SURVEY.md App. A.1).
+//
+// CTA = 4 scan warps + 4 helper warps (one of each per SM sub-partition), 32 channels of one (batch, group).
+//   helper warp h : streams its 8 channels' u / delta rows and the B / C rows {h, h+4, h+8, h+12} from HBM with
+//                   coalesced loads that are issued one 64-step tile AHEAD and parked in registers; then runs
+//                   softplus and writes the tile into shared memory in the layout the scan warps consume --
+//                        pk[row][t] = (delta, delta, delta*u, delta*u)      two ready-made f32x2 pairs
+//                        BT[q][t]   = (B[q][t], B[q+4][t], B[q+8][t], B[q+12][t]),   CT likewise
+//                        yt[row][t] = D[row] * u[row][t]
+//                   and, one tile later, writes the finished yt rows back to HBM (coalesced).
+//   scan warp w   : 8 channels x 4 lanes; lane (r, q) owns states q, q+4, q+8, q+12 of channel r and walks time
+//                   in order with the state in registers.  Per step and lane: 3 LDS.128, 4 MUFU.EX2 and 8 packed
+//                   FFMA2/FMUL2 -- the exponential (16/clk/SM) is the designed limiter, not issue slots or HBM.
+//                   The loop is software-pipelined by hand (operands 3 steps ahead, exponentials 2 steps ahead)
+//                   because only one scan warp runs per sub-partition: latency must be hidden by ILP.
+// Hand-off: SP-stage ring in shared memory; mbarriers `ready` (4 helper arrivals) and `sdone` (4 scan arrivals).
+// (Rounds 1's first versions staged raw tiles with 1-D bulk async copies; 96 x 256 B copies per tile serialised in
+//  the issuing warp and bound the kernel at 1.8 ms -- see profiles/README.md.)
 #include <type_traits>
 
 #include "scan_common.cuh"
 
 namespace mlagg {
 
-template <int W, int S, bool kBulk>
-__global__ void __launch_bounds__(2 * W * 32, 1) scan_fwd_kernel(const ScanParams p) {
-    constexpr int R = 8 * W;
+constexpr int kPk = kTT + 5;  // float4 per packed row: 69*16 B = 80 (mod 128) -> 8 rows hit 8 distinct 16 B bank groups; tail reads
+
+struct FwdCfg {
+    static constexpr int W = 4, R = 32, SP = 3;
+    static constexpr size_t bytes = (size_t)SP * R * kPk * 16 + 2 * (size_t)SP * 4 * kPk * 16 +
+                                    (size_t)SP * R * kRowF * 4 + 2 * R * 4 + 64 + 2 * SP * 8 + 16;
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float ldg_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
+    constexpr int W = FwdCfg::W, R = FwdCfg::R, SP = FwdCfg::SP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *u_s = reinterpret_cast<float *>(smem_raw);  // [S][R][kRowF]
-    float *dl_s = u_s + S * R * kRowF;                 // [S][R][kRowF]   delta -> softplus(delta) -> y
-    float *B_s = dl_s + S * R * kRowF;                 // [S][kN][kRowF]
-    float *C_s = B_s + S * kN * kRowF;                 // [S][kN][kRowF]
-    float *bias_s = C_s + S * kN * kRowF;              // [R]
-    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(bias_s + R + 16) + 7) & ~uintptr_t(7));
-    uint64_t *empty = full + S;                                 // [S]
+    float4 *pk = reinterpret_cast<float4 *>(smem_raw);         // [SP][R][kPk]
+    float4 *BT = pk + SP * R * kPk;                            // [SP][4][kPk]
+    float4 *CT = BT + SP * 4 * kPk;                            // [SP][4][kPk]
+    float *yt = reinterpret_cast<float *>(CT + SP * 4 * kPk);  // [SP][R][kRowF]
+    float *bias_s = yt + SP * R * kRowF;                       // [R]
+    float *D_s = bias_s + R;                                   // [R]
+    uint64_t *ready = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(D_s + R + 16) + 7) & ~uintptr_t(7));
+    uint64_t *sdone = ready + SP;                              // [SP]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z, g = blockIdx.y;
@@ -25,140 +57,118 @@ __global__ void __launch_bounds__(2 * W * 32, 1) scan_fwd_kernel(const ScanParam
     const int L = p.L;
     const int ntiles = (L + kTT - 1) / kTT;
 
-    // Zero every tile once: rows past the end of the group and tile tails are never written by the loader.
-    for (int i = threadIdx.x; i < S * (2 * R + 2 * kN) * kRowF; i += blockDim.x) u_s[i] = 0.f;
-    for (int i = threadIdx.x; i < R; i += blockDim.x)
+    for (int i = threadIdx.x; i < (int)((reinterpret_cast<unsigned char *>(bias_s) - smem_raw) / 4); i += blockDim.x)
+        reinterpret_cast<float *>(smem_raw)[i] = 0.f;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
         bias_s[i] = (i < rows_valid && p.bias) ? p.bias[row0 + i] : 0.f;
+        D_s[i] = (i < rows_valid && p.D) ? p.D[row0 + i] : 0.f;
+    }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], W);
-            mbar_init(&empty[s], W);
+        for (int s = 0; s < SP; ++s) {
+            mbar_init(&ready[s], W);
+            mbar_init(&sdone[s], W);
         }
         mbar_fence_init();
     }
-    fence_proxy_async();
     __syncthreads();
 
     if (warp >= W) {
-        const int pw = warp - W;  // W producer warps: each issues (and accounts for) its share of the copies
-        // ------------------------------------------------------------ producer warp
-        const float *ub = p.u + ((size_t)b * p.dim + row0) * L;
-        const float *db = p.delta + ((size_t)b * p.dim + row0) * L;
-        const float *Bb = p.B + ((size_t)b * p.G + g) * kN * (size_t)L;
-        const float *Cb = p.C + ((size_t)b * p.G + g) * kN * (size_t)L;
-        const int ncopies = 2 * rows_valid + 2 * kN;
-        for (int c = 0; c < ntiles; ++c) {
-            const int s = c % S;
-            if (c >= S) mbar_wait(&empty[s], ((c / S) & 1) ^ 1);
+        // =============================================================== helper warp
+        const int h = warp - W;
+        const int myrows = max(0, min(8, rows_valid - 8 * h));
+        const float *ub = p.u + ((size_t)b * p.dim + row0 + 8 * h) * L;
+        const float *db = p.delta + ((size_t)b * p.dim + row0 + 8 * h) * L;
+        const float *Bb = p.B + (((size_t)b * p.G + g) * kN + h) * (size_t)L;   // rows h, h+4, h+8, h+12
+        const float *Cb = p.C + (((size_t)b * p.G + g) * kN + h) * (size_t)L;
+        float *outb = p.out + ((size_t)b * p.dim + row0 + 8 * h) * L;
+        float ur[16], dr[16], Br[8], Cr[8];   // the tile in flight: element e = lane + 32 i  ->  row e >> 6, step e & 63
+
+        auto fetch = [&](int c) {
             const int t0 = c * kTT;
-            const int nvalid = min(kTT, L - t0);
-            float *us = u_s + s * R * kRowF, *ds = dl_s + s * R * kRowF;
-            float *Bs = B_s + s * kN * kRowF, *Cs = C_s + s * kN * kRowF;
-            if (kBulk) {
-                const uint32_t bytes = nvalid * 4;
-                int cnt = 0;
-                for (int i = pw * 32; i < ncopies; i += 32 * W) cnt += min(32, ncopies - i);
-                if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes * cnt);
-                __syncwarp();
-                for (int i = pw * 32 + lane; i < ncopies; i += 32 * W) {
-                    const float *src;
-                    float *dst;
-                    if (i < rows_valid) {
-                        src = ub + (size_t)i * L;
-                        dst = us + i * kRowF;
-                    } else if (i < 2 * rows_valid) {
-                        src = db + (size_t)(i - rows_valid) * L;
-                        dst = ds + (i - rows_valid) * kRowF;
-                    } else if (i < 2 * rows_valid + kN) {
-                        src = Bb + (size_t)(i - 2 * rows_valid) * L;
-                        dst = Bs + (i - 2 * rows_valid) * kRowF;
-                    } else {
-                        src = Cb + (size_t)(i - 2 * rows_valid - kN) * L;
-                        dst = Cs + (i - 2 * rows_valid - kN) * kRowF;
-                    }
-                    bulk_g2s(dst, src + t0, bytes, &full[s]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int rr = i >> 1, t = t0 + lane + 32 * (i & 1);
+                const bool ok = rr < myrows && t < L;
+                ur[i] = ok ? ldg_stream(ub + (size_t)rr * L + t) : 0.f;
+                dr[i] = ok ? ldg_stream(db + (size_t)rr * L + t) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = i >> 1, t = t0 + lane + 32 * (i & 1);
+                Br[i] = t < L ? ldg_stream(Bb + (size_t)(4 * j) * L + t) : 0.f;
+                Cr[i] = t < L ? ldg_stream(Cb + (size_t)(4 * j) * L + t) : 0.f;
+            }
+        };
+        auto write_out = [&](int c) {  // yt rows of tile c -> global, coalesced
+            const int sp = c % SP, t0 = c * kTT;
+            const float *ys = yt + (sp * R + 8 * h) * kRowF;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int rr = i >> 1, tl = lane + 32 * (i & 1);
+                if (rr < myrows && t0 + tl < L) outb[(size_t)rr * L + t0 + tl] = ys[rr * kRowF + tl];
+            }
+        };
+
+        fetch(0);
+        for (int c = 0; c < ntiles; ++c) {
+            const int sp = c % SP;
+            if (c >= SP) mbar_wait(&sdone[sp], ((c / SP) & 1) ^ 1);   // scan warps are done with tile c - SP
+            float4 *pks = pk + (sp * R + 8 * h) * kPk;
+            float *ys = yt + (sp * R + 8 * h) * kRowF;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int rr = i >> 1, tl = lane + 32 * (i & 1);
+                float dl = dr[i] + bias_s[8 * h + rr];
+                if (p.softplus) dl = softplus_fast(dl);
+                const float du = dl * ur[i];
+                pks[rr * kPk + tl] = make_float4(dl, dl, du, du);
+                ys[rr * kRowF + tl] = D_s[8 * h + rr] * ur[i];
+            }
+            {
+                float4 *bt = BT + (sp * 4 + h) * kPk, *ct = CT + (sp * 4 + h) * kPk;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    bt[lane + 32 * k] = make_float4(Br[k], Br[2 + k], Br[4 + k], Br[6 + k]);
+                    ct[lane + 32 * k] = make_float4(Cr[k], Cr[2 + k], Cr[4 + k], Cr[6 + k]);
                 }
-            } else {
-                for (int i = pw; i < ncopies; i += W) {
-                    const float *src;
-                    float *dst;
-                    if (i < rows_valid) {
-                        src = ub + (size_t)i * L;
-                        dst = us + i * kRowF;
-                    } else if (i < 2 * rows_valid) {
-                        src = db + (size_t)(i - rows_valid) * L;
-                        dst = ds + (i - rows_valid) * kRowF;
-                    } else if (i < 2 * rows_valid + kN) {
-                        src = Bb + (size_t)(i - 2 * rows_valid) * L;
-                        dst = Bs + (i - 2 * rows_valid) * kRowF;
-                    } else {
-                        src = Cb + (size_t)(i - 2 * rows_valid - kN) * L;
-                        dst = Cs + (i - 2 * rows_valid - kN) * kRowF;
-                    }
-                    for (int t = lane; t < kTT; t += 32) dst[t] = t < nvalid ? __ldg(src + t0 + t) : 0.f;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[sp]);
+            if (c + 1 < ntiles) fetch(c + 1);   // lands while this warp waits for the scan warps below
+            if (c >= 1) {
+                mbar_wait(&sdone[(c - 1) % SP], ((c - 1) / SP) & 1);
+                write_out(c - 1);
             }
         }
+        mbar_wait(&sdone[(ntiles - 1) % SP], ((ntiles - 1) / SP) & 1);
+        write_out(ntiles - 1);
         return;
     }
 
-    // ---------------------------------------------------------------- consumer warps
+    // =================================================================== scan warp
     const int r = lane >> 2, q = lane & 3;
     const int rl = warp * 8 + r;
     const bool valid = rl < rows_valid;
     const int d = row0 + rl;
-    float A2[4], h[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        A2[j] = valid ? p.A[(size_t)d * kN + q + 4 * j] * kLog2e : 0.f;
-        h[j] = 0.f;
-    }
-    const float Dk = (valid && p.D) ? p.D[d] : 0.f;
+    float2 A01, A23, h01 = f2(0.f, 0.f), h23 = f2(0.f, 0.f);
+    A01.x = valid ? p.A[(size_t)d * kN + q] * kLog2e : 0.f;
+    A01.y = valid ? p.A[(size_t)d * kN + q + 4] * kLog2e : 0.f;
+    A23.x = valid ? p.A[(size_t)d * kN + q + 8] * kLog2e : 0.f;
+    A23.y = valid ? p.A[(size_t)d * kN + q + 12] * kLog2e : 0.f;
     float *ck = p.ckpt ? p.ckpt + ((size_t)b * p.nchunks * p.dim + d) * kN + q * 4 : nullptr;
     const size_t ck_stride = (size_t)p.dim * kN;
-    float *outw = p.out + ((size_t)b * p.dim + row0 + warp * 8) * L;
+    const bool hi = (q & 2) != 0, odd = (q & 1) != 0;
 
     for (int c = 0; c < ntiles; ++c) {
-        const int s = c % S;
-        mbar_wait(&full[s], (c / S) & 1);
+        const int sp = c % SP;
+        mbar_wait(&ready[sp], (c / SP) & 1);
         const int t0 = c * kTT;
         const int nvalid = min(kTT, L - t0);
-        float *us = u_s + (s * R + warp * 8) * kRowF;
-        float *dls = dl_s + (s * R + warp * 8) * kRowF;
-        const float *Bq = B_s + (s * kN + q) * kRowF;
-        const float *Cq = C_s + (s * kN + q) * kRowF;
+        const float4 *pkr = pk + (sp * R + rl) * kPk;
+        const float4 *btq = BT + (sp * 4 + q) * kPk;
+        const float4 *ctq = CT + (sp * 4 + q) * kPk;
+        float *yr = yt + (sp * R + rl) * kRowF;
 
-        // delta <- softplus(delta + bias) for this warp's 8 x kTT tile (one float4 per lane per pass)
-#pragma unroll
-        for (int i = 0; i < (8 * kTT / 4) / 32; ++i) {
-            const int idx = lane + 32 * i;
-            const int rr = idx / (kTT / 4), c4 = idx % (kTT / 4);
-            float4 *ptr = reinterpret_cast<float4 *>(dls + rr * kRowF + c4 * 4);
-            float4 v = *ptr;
-            const float bb = bias_s[warp * 8 + rr];
-            if (p.softplus) {
-                v.x = softplus_fast(v.x + bb);
-                v.y = softplus_fast(v.y + bb);
-                v.z = softplus_fast(v.z + bb);
-                v.w = softplus_fast(v.w + bb);
-            } else {
-                v.x += bb; v.y += bb; v.z += bb; v.w += bb;
-            }
-            *ptr = v;
-        }
-        __syncwarp();
-
-        // Software pipeline, written out by hand because each SM sub-partition runs ONE warp of this kernel
-        // (all latency hiding must come from ILP): while the FMA chain of 4-step group g runs, the B/C tiles
-        // of group g+1 are already in registers, its 16 exponentials are in flight on the MUFU pipe, and the
-        // delta/u of group g+2 are being fetched.  The cross-lane reduction + store of a 16-step block is
-        // issued one block late so its shuffle latency hides behind the next block's MUFU stream.
-        // Reads run up to 2 groups past the tile (row padding / neighbouring rows: finite garbage, never used).
-        const float *dlr = dls + r * kRowF;
-        const float *ur = us + r * kRowF;
-        const bool hi = (q & 2) != 0, odd = (q & 1) != 0;
         auto reduce_store = [&](const float(&y)[16], int tb) {
             // transpose-reduce over the 4 lanes of the channel: lane q ends with steps tb+4q .. tb+4q+3
             float k8[8], z[4];
@@ -168,139 +178,73 @@ __global__ void __launch_bounds__(2 * W * 32, 1) scan_fwd_kernel(const ScanParam
 #pragma unroll
             for (int m = 0; m < 4; ++m)
                 z[m] = (odd ? k8[4 + m] : k8[m]) + __shfl_xor_sync(0xffffffffu, odd ? k8[m] : k8[4 + m], 1);
-            const float4 uq = *reinterpret_cast<const float4 *>(ur + tb + 4 * q);
-            *reinterpret_cast<float4 *>(dls + r * kRowF + tb + 4 * q) =
-                make_float4(fmaf(Dk, uq.x, z[0]), fmaf(Dk, uq.y, z[1]), fmaf(Dk, uq.z, z[2]), fmaf(Dk, uq.w, z[3]));
+            float4 *dst = reinterpret_cast<float4 *>(yr + tb + 4 * q);
+            const float4 du = *dst;  // D * u, written by the helper
+            *dst = make_float4(du.x + z[0], du.y + z[1], du.z + z[2], du.w + z[3]);
         };
-        auto ld4 = [](const float *ptr) { return *reinterpret_cast<const float4 *>(ptr); };
-        // pipeline registers
-        float4 dc = ld4(dlr), uc = ld4(ur);          // delta / u of the group being consumed
-        float4 dn = ld4(dlr + 4), un = ld4(ur + 4);  // ... of the next group
-        float4 Bc[4], Cc[4];
-        float ac[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            Bc[j] = ld4(Bq + j * 4 * kRowF);
-            Cc[j] = ld4(Cq + j * 4 * kRowF);
-        }
+
+        // 3-deep software pipeline over steps: operands of step t+3 loaded, exponentials of step t+2 issued, FMA chain
+        // of step t executed.  Reads run up to 3 steps past the tile (row padding: zeros / stale, never used).
+        float4 P0 = pkr[0], B0 = btq[0], C0 = ctq[0];
+        float4 P1 = pkr[1], B1 = btq[1], C1 = ctq[1];
+        float4 P2 = pkr[2], B2 = btq[2], C2 = ctq[2];
+        float2 ea01, ea23, eb01, eb23;   // exponentials of step t (ea) and t+1 (eb)
         {
-            const float dd[4] = {dc.x, dc.y, dc.z, dc.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) ac[i][j] = ex2_approx(dd[i] * A2[j]);
+            const float2 x01 = __fmul2_rn(f2(P0.x, P0.y), A01), x23 = __fmul2_rn(f2(P0.x, P0.y), A23);
+            ea01 = f2(ex2_approx(x01.x), ex2_approx(x01.y)); ea23 = f2(ex2_approx(x23.x), ex2_approx(x23.y));
+            const float2 y01 = __fmul2_rn(f2(P1.x, P1.y), A01), y23 = __fmul2_rn(f2(P1.x, P1.y), A23);
+            eb01 = f2(ex2_approx(y01.x), ex2_approx(y01.y)); eb23 = f2(ex2_approx(y23.x), ex2_approx(y23.y));
         }
         float yprev[16];
         for (int tb = 0; tb < nvalid; tb += 16) {
-            const int ns = nvalid - tb;  // >= 16 except in the last block of the sequence
+            const int ns = nvalid - tb;
             float y[16];
             auto block = [&](auto full_tag) {
                 constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-                for (int i4 = 0; i4 < 16; i4 += 4) {
-                    const int t = tb + i4;
-                    // stage 1: operands of group g+1 (B, C) and g+2 (delta, u)
-                    float4 Bn[4], Cn[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        Bn[j] = ld4(Bq + j * 4 * kRowF + t + 4);
-                        Cn[j] = ld4(Cq + j * 4 * kRowF + t + 4);
-                    }
-                    const float4 dn2 = ld4(dlr + t + 8), un2 = ld4(ur + t + 8);
-                    // stage 2: exponentials of group g+1
-                    float an[4][4];
-                    {
-                        const float dd[4] = {dn.x, dn.y, dn.z, dn.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) an[i][j] = ex2_approx(dd[i] * A2[j]);
-                    }
-                    // stage 3: recurrence of group g
-                    const float dd[4] = {dc.x, dc.y, dc.z, dc.w};
-                    const float uu[4] = {uc.x, uc.y, uc.z, uc.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const bool on = kFull || (kBulk ? (i4 < ns) : (i4 + i < ns));
-                        const float du = dd[i] * uu[i];
-                        float acc = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float Bji = i == 0 ? Bc[j].x : i == 1 ? Bc[j].y : i == 2 ? Bc[j].z : Bc[j].w;
-                            const float Cji = i == 0 ? Cc[j].x : i == 1 ? Cc[j].y : i == 2 ? Cc[j].z : Cc[j].w;
-                            const float hn = fmaf(ac[i][j], h[j], du * Bji);
-                            h[j] = on ? hn : h[j];
-                            acc = fmaf(Cji, h[j], acc);
-                        }
-                        y[i4 + i] = on ? acc : 0.f;
-                    }
-                    // rotate
-                    dc = dn; uc = un; dn = dn2; un = un2;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        Bc[j] = Bn[j];
-                        Cc[j] = Cn[j];
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) ac[i][j] = an[i][j];
+                for (int i = 0; i < 16; ++i) {
+                    const float4 P3 = pkr[tb + i + 3], B3 = btq[tb + i + 3], C3 = ctq[tb + i + 3];
+                    const float2 x01 = __fmul2_rn(f2(P2.x, P2.y), A01), x23 = __fmul2_rn(f2(P2.x, P2.y), A23);
+                    const float2 ec01 = f2(ex2_approx(x01.x), ex2_approx(x01.y));
+                    const float2 ec23 = f2(ex2_approx(x23.x), ex2_approx(x23.y));
+                    const bool on = kFull || (i < ns);
+                    const float2 bu01 = __fmul2_rn(f2(P0.z, P0.w), f2(B0.x, B0.y));
+                    const float2 bu23 = __fmul2_rn(f2(P0.z, P0.w), f2(B0.z, B0.w));
+                    const float2 n01 = __ffma2_rn(ea01, h01, bu01), n23 = __ffma2_rn(ea23, h23, bu23);
+                    if (on) { h01 = n01; h23 = n23; }
+                    float2 acc = __fmul2_rn(f2(C0.x, C0.y), h01);
+                    acc = __ffma2_rn(f2(C0.z, C0.w), h23, acc);
+                    y[i] = on ? acc.x + acc.y : 0.f;
+                    P0 = P1; B0 = B1; C0 = C1; P1 = P2; B1 = B2; C1 = C2; P2 = P3; B2 = B3; C2 = C3;
+                    ea01 = eb01; ea23 = eb23; eb01 = ec01; eb23 = ec23;
                 }
             };
             if (ns >= 16) block(std::true_type{}); else block(std::false_type{});
             if (ck != nullptr && valid && ns >= 16)
                 *reinterpret_cast<float4 *>(ck + (size_t)((t0 + tb) / kChunk) * ck_stride) =
-                    make_float4(h[0], h[1], h[2], h[3]);
+                    make_float4(h01.x, h01.y, h23.x, h23.y);
             if (tb > 0) reduce_store(yprev, tb - 16);
 #pragma unroll
             for (int i = 0; i < 16; ++i) yprev[i] = y[i];
         }
         reduce_store(yprev, ((nvalid - 1) / 16) * 16);
-
-        if (kBulk) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane < 8 && warp * 8 + lane < rows_valid)
-                bulk_s2g(outw + (size_t)lane * L + t0, dls + lane * kRowF, nvalid * 4);
-            bulk_commit();
-            bulk_wait_read<1>();  // the store issued one tile ago has finished reading its stage
-            __syncwarp();
-            if (lane == 0 && c >= 1) mbar_arrive(&empty[(c - 1) % S]);
-        } else {
-            __syncwarp();
-            for (int rr = 0; rr < 8 && warp * 8 + rr < rows_valid; ++rr)
-                for (int t = lane; t < nvalid; t += 32) outw[(size_t)rr * L + t0 + t] = dls[rr * kRowF + t];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sdone[sp]);
     }
-    if (kBulk) bulk_wait<0>();
     if (p.last_state && valid) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) p.last_state[((size_t)b * p.dim + d) * kN + q + 4 * j] = h[j];
+        float *ls = p.last_state + ((size_t)b * p.dim + d) * kN + q;
+        ls[0] = h01.x; ls[4] = h01.y; ls[8] = h23.x; ls[12] = h23.y;
     }
-}
-
-template <int W, int S>
-static size_t fwd_smem_bytes() {
-    return (size_t)S * (2 * 8 * W + 2 * kN) * kRowF * 4 + 8 * W * 4 + 64 + 8 + 2 * S * 8;
-}
-
-template <int W, int S, bool kBulk>
-static cudaError_t launch_fwd(const ScanParams &p, cudaStream_t st) {
-    const size_t smem = fwd_smem_bytes<W, S>();
-    auto kern = scan_fwd_kernel<W, S, kBulk>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid((p.dpg + 8 * W - 1) / (8 * W), p.G, p.batch);
-    kern<<<grid, 2 * W * 32, smem, st>>>(p);
-    return cudaGetLastError();
 }
 
 cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st) {
-    if (warps >= 4) return bulk ? launch_fwd<4, 4, true>(p, st) : launch_fwd<4, 4, false>(p, st);
-    if (warps >= 2) return bulk ? launch_fwd<2, 4, true>(p, st) : launch_fwd<2, 4, false>(p, st);
-    return bulk ? launch_fwd<1, 4, true>(p, st) : launch_fwd<1, 4, false>(p, st);
+    (void)bulk; (void)warps;
+    const size_t smem = FwdCfg::bytes;
+    cudaError_t e = cudaFuncSetAttribute(scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((p.dpg + 31) / 32, p.G, p.batch);
+    scan_fwd_kernel<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace mlagg
