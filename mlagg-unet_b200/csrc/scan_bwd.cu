@@ -1,367 +1,371 @@
 // scan_bwd.cu -- selective scan (S6) backward for sm_100a.
 // Replaces selective_scan_cuda.bwd (reference FFI shape: vmamba/csms6s.py:235-238); math: SURVEY.md App. A.2.
 //
-// Time tiles are visited in REVERSE order.  Inside a tile, 16-step chunks are visited in reverse; for each
-// chunk the forward states are recomputed from the checkpoint the forward kernel saved (h_t and a_t live in
-// registers: 128 of them), then the adjoint recurrence g_t = C_t dy_t + a_{t+1} g_{t+1} runs backwards.
-// Reductions:
-//   over the 16 states of a channel (du, ddelta)      -> 2-stage butterfly across the 4 lanes of the channel;
-//   over the channels of a group (dB, dC)             -> 3-stage transpose-reduce across the 8 channel lanes of
-//       the warp (state slots are XOR-permuted per lane so no selects are needed in the first two stages),
-//       then across the W warps through per-warp shared-memory tiles, then ONE coalesced fp32 atomic per
-//       (state, step) per CTA into global memory (only when the group spans several CTAs it is contended);
-//   over batch and time (dA, dD, ddelta_bias)          -> registers, then one atomic per thread at the end.
+// Same CTA shape as the forward kernel: 4 scan warps + 4 helper warps, 32 channels of one (batch, group); time tiles of
+// 32 steps are visited in REVERSE order, and inside a tile the two 16-step chunks in reverse.
+//   helper warp h : prefetches (one tile ahead, into registers) its 8 channels' u / delta / dout rows and the B / C rows
+//                   {h, h+4, h+8, h+12}; writes   pkA[row][t] = (delta, delta, delta*u, delta*u)
+//                                                  pkB[row][t] = (dout, dout, u, d softplus)
+//                                                  BT / CT [q][t] = the 4 states of quad q in natural pair order, and
+//                                                  BT2 / CT2 = the same with the two pairs swapped (see below);
+//                   one tile later it writes du / ddelta (left in pkB by the scan warps) to HBM, sums the per-warp
+//                   dB / dC partial tiles over the 4 scan warps and adds them to HBM with coalesced fp32 atomics.
+//   scan warp w   : lane (r, q) = channel r of the warp, states q, q+4, q+8, q+12.  Per chunk: (1) recompute the forward
+//                   states from the checkpoint, keeping a_t and a_t*h_{t-1} in registers (128) and emitting dC;
+//                   (2) run g_t = C_t dy_t + a_{t+1} g_{t+1} backwards emitting dB, du, ddelta, dA, dD, dbias.
+//                   All state math is packed f32x2 (FFMA2 / FMUL2).
+// Reductions: over the 16 states of a channel (du, ddelta): butterfly over the 4 lanes of the channel.  Over the 8
+// channels of a warp (dB, dC): 3-stage transpose-reduce; lanes with channel bit 2 set hold their two state pairs
+// swapped (they read BT2 / CT2), so stage 1 needs no selects.  dA / dD / dbias: registers, one atomic per thread.
+#include <type_traits>
+
 #include "scan_common.cuh"
 
 namespace mlagg {
 
-constexpr int kAccStride = kTT + 1;  // odd: the 32 (array, state) rows a warp writes per step hit 32 banks
+constexpr int kTB = 32;          // steps per tile (backward)
+constexpr int kPB = kTB + 5;     // float4 per packed row: 37*16 B = 80 (mod 128): conflict-free across 8 rows / 4 quads
+constexpr int kAccS = kTB + 1;   // acc row stride (floats), odd
 
-template <int W, int S, bool kBulk>
-__global__ void __launch_bounds__(2 * W * 32, 1) scan_bwd_kernel(const ScanParams p) {
-    constexpr int R = 8 * W;
+struct BwdCfg {
+    static constexpr int W = 4, R = 32, SP = 3;
+    static constexpr size_t f4_stage = (size_t)2 * R * kPB + 4 * 4 * kPB;   // pkA, pkB, BT, BT2, CT, CT2
+    static constexpr size_t bytes = SP * f4_stage * 16 + (size_t)2 * W * 2 * kN * kAccS * 4 + 2 * R * 4 + 64 +
+                                    (2 * SP + 2) * 8 + 16;
+};
+
+__device__ __forceinline__ float2 g2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float ldg_s(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
+    constexpr int W = BwdCfg::W, R = BwdCfg::R, SP = BwdCfg::SP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *u_s = reinterpret_cast<float *>(smem_raw);  // [S][R][kRowF]  u      -> du
-    float *dl_s = u_s + S * R * kRowF;                 // [S][R][kRowF]  delta  -> softplus -> ddelta
-    float *dy_s = dl_s + S * R * kRowF;                // [S][R][kRowF]  dout
-    float *sg_s = dy_s + S * R * kRowF;                // [S][R][kRowF]  d softplus / d x  (computed)
-    float *B_s = sg_s + S * R * kRowF;                 // [S][kN][kRowF]
-    float *C_s = B_s + S * kN * kRowF;                 // [S][kN][kRowF]
-    float *acc_s = C_s + S * kN * kRowF;               // [W][2*kN][kAccStride]  per-warp dB | dC partials
-    float *bias_s = acc_s + W * 2 * kN * kAccStride;   // [R]
-    uint64_t *full = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(bias_s + R) + 7) & ~uintptr_t(7));
-    uint64_t *empty = full + S;
+    float4 *pkA = reinterpret_cast<float4 *>(smem_raw);          // [SP][R][kPB]
+    float4 *pkB = pkA + SP * R * kPB;                            // [SP][R][kPB]
+    float4 *BT = pkB + SP * R * kPB;                             // [SP][4 arrays: B, B2, C, C2][4][kPB]
+    float *acc = reinterpret_cast<float *>(BT + SP * 16 * kPB);  // [2][W][2*kN][kAccS]
+    float *bias_s = acc + 2 * W * 2 * kN * kAccS;                // [R]
+    float *D_s = bias_s + R;                                     // [R]
+    uint64_t *ready = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(D_s + R + 16) + 7) & ~uintptr_t(7));
+    uint64_t *sdone = ready + SP;
+    uint64_t *accfree = sdone + SP;                              // [2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.z, g = blockIdx.y;
     const int row0 = g * p.dpg + blockIdx.x * R;
     const int rows_valid = min(R, (g + 1) * p.dpg - row0);
     const int L = p.L;
-    const int ntiles = (L + kTT - 1) / kTT;
+    const int ntiles = (L + kTB - 1) / kTB;
 
-    for (int i = threadIdx.x; i < S * (4 * R + 2 * kN) * kRowF; i += blockDim.x) u_s[i] = 0.f;
-    for (int i = threadIdx.x; i < R; i += blockDim.x)
+    for (int i = threadIdx.x; i < (int)((reinterpret_cast<unsigned char *>(bias_s) - smem_raw) / 4); i += blockDim.x)
+        reinterpret_cast<float *>(smem_raw)[i] = 0.f;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
         bias_s[i] = (i < rows_valid && p.bias) ? p.bias[row0 + i] : 0.f;
+        D_s[i] = (i < rows_valid && p.D) ? p.D[row0 + i] : 0.f;
+    }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], W);
-            mbar_init(&empty[s], W);
+        for (int s = 0; s < SP; ++s) {
+            mbar_init(&ready[s], W);
+            mbar_init(&sdone[s], W);
         }
+        mbar_init(&accfree[0], W);
+        mbar_init(&accfree[1], W);
         mbar_fence_init();
     }
-    fence_proxy_async();
     __syncthreads();
 
     if (warp >= W) {
-        const int pw = warp - W;  // W producer warps: each issues (and accounts for) its share of the copies
-        // ------------------------------------------------------------ producer warp (tiles in reverse)
-        const size_t rowoff = ((size_t)b * p.dim + row0) * L;
-        const float *srcs[3] = {p.u + rowoff, p.delta + rowoff, p.dout + rowoff};
-        const float *Bb = p.B + ((size_t)b * p.G + g) * kN * (size_t)L;
-        const float *Cb = p.C + ((size_t)b * p.G + g) * kN * (size_t)L;
-        const int ncopies = 3 * rows_valid + 2 * kN;
+        // =============================================================== helper warp
+        const int h = warp - W;
+        const int myrows = max(0, min(8, rows_valid - 8 * h));
+        const size_t rowoff = ((size_t)b * p.dim + row0 + 8 * h) * L;
+        const float *ub = p.u + rowoff, *db = p.delta + rowoff, *gb = p.dout + rowoff;
+        const float *Bb = p.B + (((size_t)b * p.G + g) * kN + h) * (size_t)L;   // rows h, h+4, h+8, h+12
+        const float *Cb = p.C + (((size_t)b * p.G + g) * kN + h) * (size_t)L;
+        float *dub = p.du + rowoff, *ddb = p.ddelta + rowoff;
+        float *dBg = p.dB + ((size_t)b * p.G + g) * kN * (size_t)L;
+        float *dCg = p.dC + ((size_t)b * p.G + g) * kN * (size_t)L;
+        float ur[8], dr[8], yr[8], Br[4], Cr[4];   // tile in flight: row i, step t0 + lane
+
+        auto tile_t0 = [&](int k) { return (ntiles - 1 - k) * kTB; };
+        auto fetch = [&](int k) {
+            const int t = tile_t0(k) + lane;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool ok = i < myrows && t < L;
+                ur[i] = ok ? ldg_s(ub + (size_t)i * L + t) : 0.f;
+                dr[i] = ok ? ldg_s(db + (size_t)i * L + t) : 0.f;
+                yr[i] = ok ? ldg_s(gb + (size_t)i * L + t) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                Br[j] = t < L ? ldg_s(Bb + (size_t)(4 * j) * L + t) : 0.f;
+                Cr[j] = t < L ? ldg_s(Cb + (size_t)(4 * j) * L + t) : 0.f;
+            }
+        };
+        auto finish = [&](int k) {  // outputs of tile k (all scan warps have arrived on sdone)
+            const int sp = k % SP, t = tile_t0(k) + lane;
+            const float4 *pb = pkB + (sp * R + 8 * h) * kPB;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < myrows && t < L) {
+                    const float4 v = pb[i * kPB + lane];
+                    dub[(size_t)i * L + t] = v.x;
+                    ddb[(size_t)i * L + t] = v.y;
+                }
+            }
+            // dB / dC: rows [8h, 8h+8) of the 32 (array, state) rows; sum the 4 scan warps' partial tiles
+            const float *ab = acc + (k & 1) * W * 2 * kN * kAccS;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = 8 * h + i;
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < W; ++w) s += ab[(w * 2 * kN + row) * kAccS + lane];
+                if (t < L) atomicAdd((row < kN ? dBg + (size_t)row * L : dCg + (size_t)(row - kN) * L) + t, s);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&accfree[k & 1]);
+        };
+
+        fetch(0);
         for (int k = 0; k < ntiles; ++k) {
-            const int s = k % S;
-            if (k >= S) mbar_wait(&empty[s], ((k / S) & 1) ^ 1);
-            const int t0 = (ntiles - 1 - k) * kTT;
-            const int nvalid = min(kTT, L - t0);
-            float *own[3] = {u_s + s * R * kRowF, dl_s + s * R * kRowF, dy_s + s * R * kRowF};
-            float *Bs = B_s + s * kN * kRowF, *Cs = C_s + s * kN * kRowF;
-            const uint32_t bytes = nvalid * 4;
-            if (kBulk) {
-                int cnt = 0;
-                for (int i = pw * 32; i < ncopies; i += 32 * W) cnt += min(32, ncopies - i);
-                if (lane == 0) mbar_arrive_expect_tx(&full[s], bytes * cnt);
-                __syncwarp();
+            const int sp = k % SP;
+            if (k >= SP) mbar_wait(&sdone[sp], ((k / SP) & 1) ^ 1);
+            float4 *pa = pkA + (sp * R + 8 * h) * kPB, *pb = pkB + (sp * R + 8 * h) * kPB;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float sg = 1.f;
+                float dl = dr[i] + bias_s[8 * h + i];
+                if (p.softplus) dl = softplus_fast(dl, &sg);
+                const float du = dl * ur[i];
+                pa[i * kPB + lane] = make_float4(dl, dl, du, du);
+                pb[i * kPB + lane] = make_float4(yr[i], yr[i], ur[i], sg);
             }
-            for (int i = kBulk ? pw * 32 + lane : pw; i < ncopies; i += kBulk ? 32 * W : W) {
-                const float *src;
-                float *dst;
-                if (i < 3 * rows_valid) {
-                    const int which = i / rows_valid, rr = i % rows_valid;
-                    src = srcs[which] + (size_t)rr * L;
-                    dst = own[which] + rr * kRowF;
-                } else if (i < 3 * rows_valid + kN) {
-                    src = Bb + (size_t)(i - 3 * rows_valid) * L;
-                    dst = Bs + (i - 3 * rows_valid) * kRowF;
-                } else {
-                    src = Cb + (size_t)(i - 3 * rows_valid - kN) * L;
-                    dst = Cs + (i - 3 * rows_valid - kN) * kRowF;
-                }
-                if (kBulk) {
-                    bulk_g2s(dst, src + t0, bytes, &full[s]);
-                } else {
-                    for (int t = lane; t < kTT; t += 32) dst[t] = t < nvalid ? __ldg(src + t0 + t) : 0.f;
-                }
+            {
+                float4 *bt = BT + (sp * 16 + h) * kPB;   // arrays at +0, +4, +8, +12 quads
+                bt[lane] = make_float4(Br[0], Br[1], Br[2], Br[3]);
+                bt[4 * kPB + lane] = make_float4(Br[2], Br[3], Br[0], Br[1]);
+                bt[8 * kPB + lane] = make_float4(Cr[0], Cr[1], Cr[2], Cr[3]);
+                bt[12 * kPB + lane] = make_float4(Cr[2], Cr[3], Cr[0], Cr[1]);
             }
-            if (!kBulk) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[sp]);
+            if (k + 1 < ntiles) fetch(k + 1);
+            if (k >= 1) {
+                mbar_wait(&sdone[(k - 1) % SP], ((k - 1) / SP) & 1);
+                finish(k - 1);
             }
         }
+        mbar_wait(&sdone[(ntiles - 1) % SP], ((ntiles - 1) / SP) & 1);
+        finish(ntiles - 1);
         return;
     }
 
-    // ---------------------------------------------------------------- consumer warps
+    // =================================================================== scan warp
     const int r = lane >> 2, q = lane & 3;
-    const int x = (r >> 1) & 3;  // slot permutation: slot s holds state n = q + 4 * (s ^ x)
+    const int x1 = (r >> 2) & 1, b1 = (r >> 1) & 1;   // channel-lane bits used by the transpose-reduce
     const int rl = warp * 8 + r;
     const bool valid = rl < rows_valid;
     const int d = row0 + rl;
-    float A2[4], dAacc[4], gst[4], anext[4];
-#pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4) {
-        A2[s4] = valid ? p.A[(size_t)d * kN + q + 4 * (s4 ^ x)] * kLog2e : 0.f;
-        dAacc[s4] = 0.f;
-        gst[s4] = 0.f;
-        anext[s4] = 0.f;
+    // slot s holds state n = q + 4 * (s ^ (2 * x1)): lanes with x1 hold their two pairs swapped
+    float2 A01, A23;
+    {
+        const int c0 = 2 * x1, c2 = 2 - 2 * x1;
+        A01.x = valid ? p.A[(size_t)d * kN + q + 4 * c0] * kLog2e : 0.f;
+        A01.y = valid ? p.A[(size_t)d * kN + q + 4 * (c0 + 1)] * kLog2e : 0.f;
+        A23.x = valid ? p.A[(size_t)d * kN + q + 4 * c2] * kLog2e : 0.f;
+        A23.y = valid ? p.A[(size_t)d * kN + q + 4 * (c2 + 1)] * kLog2e : 0.f;
     }
+    float2 dA01 = g2(0.f, 0.f), dA23 = g2(0.f, 0.f), gs01 = g2(0.f, 0.f), gs23 = g2(0.f, 0.f);
+    float2 an01 = g2(0.f, 0.f), an23 = g2(0.f, 0.f);   // a_{t+1}
     const float Dk = (valid && p.D) ? p.D[d] : 0.f;
     float dDacc = 0.f, dbacc = 0.f;
     const float *ck = p.ckpt_in + ((size_t)b * p.nchunks * p.dim + d) * kN + q * 4;
     const size_t ck_stride = (size_t)p.dim * kN;
-    const size_t rowoff_w = ((size_t)b * p.dim + row0 + warp * 8) * L;
-    float *acc_w = acc_s + warp * 2 * kN * kAccStride;
-    const int acc_row = ((r & 1) * kN + q + 4 * x) * kAccStride;  // where this lane's reduced value goes
-
-    // checkpoint prefetch: state BEFORE chunk gc is ckpt[gc - 1] (zero for gc == 0)
-    auto load_ckpt = [&](int gc) -> float4 {
+    auto load_ckpt = [&](int gc) -> float4 {   // state before chunk gc, in this lane's slot order
         if (gc <= 0 || !valid) return make_float4(0.f, 0.f, 0.f, 0.f);
-        return *reinterpret_cast<const float4 *>(ck + (size_t)(gc - 1) * ck_stride);
+        return *reinterpret_cast<const float4 *>(ck + (size_t)(gc - 1) * ck_stride);   // natural order; swapped at use
     };
     float4 hnext = load_ckpt((L - 1) / kChunk);
+    const int comp = b1 + 2 * x1;                       // state component this lane ends up holding after the reduce
+    const int acc_off = (q + 4 * comp) * kAccS;         // row of dB; dC rows start at kN * kAccS
 
     for (int k = 0; k < ntiles; ++k) {
-        const int s = k % S;
-        mbar_wait(&full[s], (k / S) & 1);
-        const int t0 = (ntiles - 1 - k) * kTT;
-        const int nvalid = min(kTT, L - t0);
-        float *us = u_s + (s * R + warp * 8) * kRowF;
-        float *dls = dl_s + (s * R + warp * 8) * kRowF;
-        const float *dys = dy_s + (s * R + warp * 8) * kRowF;
-        float *sgs = sg_s + (s * R + warp * 8) * kRowF;
-        const float *Bq = B_s + (s * kN + q) * kRowF;
-        const float *Cq = C_s + (s * kN + q) * kRowF;
+        const int sp = k % SP;
+        mbar_wait(&ready[sp], (k / SP) & 1);
+        if (k >= 2) mbar_wait(&accfree[k & 1], ((k >> 1) & 1) ^ 1);
+        const int t0 = (ntiles - 1 - k) * kTB;
+        const int nvalid = min(kTB, L - t0);
+        const float4 *par = pkA + (sp * R + rl) * kPB;
+        float4 *pbr = pkB + (sp * R + rl) * kPB;
+        const float4 *btq = BT + (sp * 16 + 4 * x1 + q) * kPB;        // B (or B2 when x1)
+        const float4 *ctq = BT + (sp * 16 + 8 + 4 * x1 + q) * kPB;    // C (or C2)
+        float *accw = acc + ((k & 1) * W + warp) * 2 * kN * kAccS + acc_off;
 
-        // delta <- softplus(delta + bias), sg <- sigmoid(delta + bias) for the warp's 8 x kTT tile
+        for (int sc = (nvalid - 1) / kChunk; sc >= 0; --sc) {
+            const int tb = sc * kChunk;
+            const int ns = min(kChunk, nvalid - tb);
+            const int gc = (t0 + tb) / kChunk;
+            const float4 h0n = hnext;
+            const float4 h0v = x1 ? make_float4(h0n.z, h0n.w, h0n.x, h0n.y) : h0n;
+            hnext = load_ckpt(gc - 1);
+            float2 aa01[kChunk], aa23[kChunk], ah01[kChunk], ah23[kChunk];
+
+            auto chunk = [&](auto full_tag) {
+                constexpr bool kFull = decltype(full_tag)::value;
+                const int b0 = r & 1;
+                // ---------------- (1) recompute forward states; emit dC.  Steps are handled in groups of 4 so that the
+                // shuffle stages of the cross-channel reduction of 4 steps are in flight together (one scan warp per
+                // sub-partition: shuffle latency must be covered by independent work of the same warp).
+                float2 hp01 = g2(h0v.x, h0v.y), hp23 = g2(h0v.z, h0v.w);
 #pragma unroll
-        for (int i = 0; i < (8 * kTT / 4) / 32; ++i) {
-            const int idx = lane + 32 * i;
-            const int rr = idx / (kTT / 4), c4 = idx % (kTT / 4);
-            float4 *ptr = reinterpret_cast<float4 *>(dls + rr * kRowF + c4 * 4);
-            float4 v = *ptr, sg = make_float4(1.f, 1.f, 1.f, 1.f);
-            const float bb = bias_s[warp * 8 + rr];
-            if (p.softplus) {
-                v.x = softplus_fast(v.x + bb, &sg.x);
-                v.y = softplus_fast(v.y + bb, &sg.y);
-                v.z = softplus_fast(v.z + bb, &sg.z);
-                v.w = softplus_fast(v.w + bb, &sg.w);
-            } else {
-                v.x += bb; v.y += bb; v.z += bb; v.w += bb;
-            }
-            *ptr = v;
-            *reinterpret_cast<float4 *>(sgs + rr * kRowF + c4 * 4) = sg;
+                for (int i0 = 0; i0 < kChunk; i0 += 4) {
+                    float2 q01[4], q23[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i0 + j;
+                        const bool on = kFull || (i < ns);
+                        const float4 P = par[tb + i], Y = pbr[tb + i], Bt = btq[tb + i];
+                        const float2 x01 = __fmul2_rn(g2(P.x, P.y), A01), x23 = __fmul2_rn(g2(P.x, P.y), A23);
+                        const float2 a01 = g2(ex2_approx(x01.x), ex2_approx(x01.y));
+                        const float2 a23 = g2(ex2_approx(x23.x), ex2_approx(x23.y));
+                        const float2 bu01 = __fmul2_rn(g2(P.z, P.w), g2(Bt.x, Bt.y));
+                        const float2 bu23 = __fmul2_rn(g2(P.z, P.w), g2(Bt.z, Bt.w));
+                        aa01[i] = a01; aa23[i] = a23;
+                        ah01[i] = __fmul2_rn(a01, hp01); ah23[i] = __fmul2_rn(a23, hp23);
+                        if (on) { hp01 = __fadd2_rn(ah01[i], bu01); hp23 = __fadd2_rn(ah23[i], bu23); }
+                        q01[j] = __fmul2_rn(g2(Y.x, Y.y), hp01); q23[j] = __fmul2_rn(g2(Y.x, Y.y), hp23);
+                        if (!on) { q01[j] = g2(0.f, 0.f); q23[j] = g2(0.f, 0.f); }
+                    }
+                    float keep[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        q01[j].x += __shfl_xor_sync(0xffffffffu, q23[j].x, 16);
+                        q01[j].y += __shfl_xor_sync(0xffffffffu, q23[j].y, 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        keep[j] = (b1 ? q01[j].y : q01[j].x) + __shfl_xor_sync(0xffffffffu, b1 ? q01[j].x : q01[j].y, 8);
+                    // last stage halves over the step index: even channel lanes end with steps i0, i0+1, odd ones i0+2, i0+3
+                    const float m0 = (b0 ? keep[2] : keep[0]) + __shfl_xor_sync(0xffffffffu, b0 ? keep[0] : keep[2], 4);
+                    const float m1 = (b0 ? keep[3] : keep[1]) + __shfl_xor_sync(0xffffffffu, b0 ? keep[1] : keep[3], 4);
+                    accw[kN * kAccS + tb + i0 + 2 * b0] = m0;
+                    accw[kN * kAccS + tb + i0 + 2 * b0 + 1] = m1;
+                }
+                // ---------------- (2) adjoint recurrence, last step of the chunk first, again in groups of 4
+#pragma unroll
+                for (int i0 = kChunk - 4; i0 >= 0; i0 -= 4) {
+                    float2 p01[4], p23[4];
+                    float s1[4], s2[4];
+#pragma unroll
+                    for (int j = 3; j >= 0; --j) {
+                        const int i = i0 + j;
+                        const bool on = kFull || (i < ns);
+                        const float4 P = par[tb + i], Bt = btq[tb + i], Ct = ctq[tb + i];
+                        const float dyl = pbr[tb + i].x;
+                        const float dy = on ? dyl : 0.f;
+                        const float2 dy2 = g2(dy, dy);
+                        float2 gn01 = __ffma2_rn(an01, gs01, __fmul2_rn(g2(Ct.x, Ct.y), dy2));
+                        float2 gn23 = __ffma2_rn(an23, gs23, __fmul2_rn(g2(Ct.z, Ct.w), dy2));
+                        if (!on) { gn01 = gs01; gn23 = gs23; }
+                        p01[j] = __fmul2_rn(gn01, g2(P.z, P.w)); p23[j] = __fmul2_rn(gn23, g2(P.z, P.w));   // g delta u
+                        float2 s1v = __fmul2_rn(gn01, g2(Bt.x, Bt.y));
+                        s1v = __ffma2_rn(gn23, g2(Bt.z, Bt.w), s1v);
+                        const float2 t01 = __fmul2_rn(gn01, ah01[i]), t23 = __fmul2_rn(gn23, ah23[i]);   // g a_t h_{t-1}
+                        float2 s2v = __fmul2_rn(t01, A01);
+                        s2v = __ffma2_rn(t23, A23, s2v);
+                        if (on) {
+                            dA01 = __ffma2_rn(t01, g2(P.x, P.y), dA01);
+                            dA23 = __ffma2_rn(t23, g2(P.x, P.y), dA23);
+                            an01 = aa01[i]; an23 = aa23[i];
+                        } else {
+                            p01[j] = g2(0.f, 0.f); p23[j] = g2(0.f, 0.f);
+                        }
+                        gs01 = gn01; gs23 = gn23;
+                        s1[j] = on ? s1v.x + s1v.y : 0.f;
+                        s2[j] = on ? s2v.x + s2v.y : 0.f;
+                    }
+                    // sums over the 16 states: butterflies across the 4 lanes of the channel, 8 values in flight
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 1);
+                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 1);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 2);
+                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 2);
+                    }
+                    // dB: sums over the 8 channels of the warp
+                    float keep[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        p01[j].x += __shfl_xor_sync(0xffffffffu, p23[j].x, 16);
+                        p01[j].y += __shfl_xor_sync(0xffffffffu, p23[j].y, 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        keep[j] = (b1 ? p01[j].y : p01[j].x) + __shfl_xor_sync(0xffffffffu, b1 ? p01[j].x : p01[j].y, 8);
+                    const float m0 = (b0 ? keep[2] : keep[0]) + __shfl_xor_sync(0xffffffffu, b0 ? keep[0] : keep[2], 4);
+                    const float m1 = (b0 ? keep[3] : keep[1]) + __shfl_xor_sync(0xffffffffu, b0 ? keep[1] : keep[3], 4);
+                    accw[tb + i0 + 2 * b0] = m0;
+                    accw[tb + i0 + 2 * b0 + 1] = m1;
+                    // du / ddelta of step i0 + q are finalised by lane q of the channel
+                    {
+                        const int i = i0 + q;
+                        const bool on = kFull || (i < ns);
+                        const float s1q = q == 0 ? s1[0] : q == 1 ? s1[1] : q == 2 ? s1[2] : s1[3];
+                        const float s2q = q == 0 ? s2[0] : q == 1 ? s2[1] : q == 2 ? s2[2] : s2[3];
+                        const float delta = par[tb + i].x;
+                        const float4 Y = pbr[tb + i];
+                        const float dy = on ? Y.x : 0.f;
+                        const float ddel = fmaf(s2q, kLn2, Y.z * s1q) * Y.w;     // (sum tmp*A + u*s1) * softplus'
+                        const float duo = fmaf(Dk, dy, delta * s1q);
+                        *reinterpret_cast<float2 *>(pbr + tb + i) = make_float2(duo, ddel);
+                        if (on) {
+                            dDacc = fmaf(dy, Y.z, dDacc);
+                            dbacc += ddel;
+                        }
+                    }
+                }
+            };
+            if (ns >= kChunk) chunk(std::true_type{}); else chunk(std::false_type{});
         }
         __syncwarp();
-
-        const int nsub = (nvalid + kChunk - 1) / kChunk;
-        for (int sc = nsub - 1; sc >= 0; --sc) {
-            const int tb = sc * kChunk;          // first step of the chunk inside the tile
-            const int ns = min(kChunk, nvalid - tb);
-            const int gc = (t0 + tb) / kChunk;   // global chunk index
-            const float4 h0v = hnext;
-            hnext = load_ckpt(gc - 1);
-            float hprev[4], h0[4];
-            {
-                const float hv[4] = {h0v.x, h0v.y, h0v.z, h0v.w};
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {  // checkpoint is stored in natural slot order
-                    const int src = s4 ^ x;
-                    hprev[s4] = src == 0 ? hv[0] : src == 1 ? hv[1] : src == 2 ? hv[2] : hv[3];
-                    h0[s4] = hprev[s4];
-                }
-            }
-            float hh[kChunk][4], aa[kChunk][4];
-            // ---- recompute the forward states of this chunk
-#pragma unroll
-            for (int i4 = 0; i4 < kChunk; i4 += 4) {
-                const float4 d4 = *reinterpret_cast<const float4 *>(dls + r * kRowF + tb + i4);
-                const float4 u4 = *reinterpret_cast<const float4 *>(us + r * kRowF + tb + i4);
-                float4 Bv[4];
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4)
-                    Bv[s4] = *reinterpret_cast<const float4 *>(Bq + (s4 ^ x) * 4 * kRowF + tb + i4);
-                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-                const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const bool on = i4 + i < ns;
-                    const float du = dd[i] * uu[i];
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4) {
-                        const float Bji = i == 0 ? Bv[s4].x : i == 1 ? Bv[s4].y : i == 2 ? Bv[s4].z : Bv[s4].w;
-                        const float a = ex2_approx(dd[i] * A2[s4]);
-                        const float hn = fmaf(a, hprev[s4], du * Bji);
-                        aa[i4 + i][s4] = a;
-                        hh[i4 + i][s4] = on ? hn : hprev[s4];
-                        hprev[s4] = hh[i4 + i][s4];
-                    }
-                }
-            }
-            // ---- adjoint recurrence, last step of the chunk first
-#pragma unroll
-            for (int i4 = kChunk - 4; i4 >= 0; i4 -= 4) {
-                const float4 d4 = *reinterpret_cast<const float4 *>(dls + r * kRowF + tb + i4);
-                const float4 u4 = *reinterpret_cast<const float4 *>(us + r * kRowF + tb + i4);
-                const float4 y4 = *reinterpret_cast<const float4 *>(dys + r * kRowF + tb + i4);
-                const float4 g4 = *reinterpret_cast<const float4 *>(sgs + r * kRowF + tb + i4);
-                float4 Bv[4], Cv[4];
-#pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
-                    Bv[s4] = *reinterpret_cast<const float4 *>(Bq + (s4 ^ x) * 4 * kRowF + tb + i4);
-                    Cv[s4] = *reinterpret_cast<const float4 *>(Cq + (s4 ^ x) * 4 * kRowF + tb + i4);
-                }
-                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-                const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-                const float yy[4] = {y4.x, y4.y, y4.z, y4.w};
-                const float ss[4] = {g4.x, g4.y, g4.z, g4.w};
-                float du_out[4], dd_out[4];
-#pragma unroll
-                for (int i = 3; i >= 0; --i) {
-                    const bool on = i4 + i < ns;  // warp-uniform
-                    const float dy = on ? yy[i] : 0.f;
-                    const float du = dd[i] * uu[i];
-                    float s1 = 0.f, s2 = 0.f, P[4], Q[4];
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4) {
-                        const float Bji = i == 0 ? Bv[s4].x : i == 1 ? Bv[s4].y : i == 2 ? Bv[s4].z : Bv[s4].w;
-                        const float Cji = i == 0 ? Cv[s4].x : i == 1 ? Cv[s4].y : i == 2 ? Cv[s4].z : Cv[s4].w;
-                        const float gn = on ? fmaf(anext[s4], gst[s4], Cji * dy) : gst[s4];
-                        const float ht = hh[i4 + i][s4];
-                        Q[s4] = dy * ht;          // dC contribution
-                        P[s4] = on ? gn * du : 0.f;  // dB contribution
-                        s1 = fmaf(gn, Bji, s1);
-                        const float hm1 = (i4 + i > 0) ? hh[(i4 + i > 0) ? i4 + i - 1 : 0][s4] : h0[s4];
-                        const float tmp = gn * (aa[i4 + i][s4] * hm1);  // g * a_t * h_{t-1}
-                        if (on) {
-                            dAacc[s4] = fmaf(tmp, dd[i], dAacc[s4]);
-                            s2 = fmaf(tmp, A2[s4], s2);
-                            anext[s4] = aa[i4 + i][s4];
-                        }
-                        gst[s4] = gn;
-                    }
-                    if (!on) s1 = 0.f;
-                    // sums over the 16 states: butterfly across the 4 lanes of the channel
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-                    const float ddel = fmaf(s2, kLn2, uu[i] * s1);  // A = A2 * ln2
-                    du_out[i] = fmaf(Dk, dy, dd[i] * s1);
-                    dd_out[i] = ddel * ss[i];
-                    // sums over the 8 channels of the warp (transpose-reduce, see header comment)
-                    P[0] += __shfl_xor_sync(0xffffffffu, P[2], 16);
-                    P[1] += __shfl_xor_sync(0xffffffffu, P[3], 16);
-                    Q[0] += __shfl_xor_sync(0xffffffffu, Q[2], 16);
-                    Q[1] += __shfl_xor_sync(0xffffffffu, Q[3], 16);
-                    P[0] += __shfl_xor_sync(0xffffffffu, P[1], 8);
-                    Q[0] += __shfl_xor_sync(0xffffffffu, Q[1], 8);
-                    const bool oddr = (r & 1) != 0;
-                    const float send = oddr ? P[0] : Q[0];
-                    float keep = oddr ? Q[0] : P[0];
-                    keep += __shfl_xor_sync(0xffffffffu, send, 4);
-                    acc_w[acc_row + tb + i4 + i] = keep;
-                    if (q == 0 && on) {
-                        dDacc = fmaf(dy, uu[i], dDacc);
-                        dbacc += dd_out[i];
-                    }
-                }
-                if (q == 0) {
-                    *reinterpret_cast<float4 *>(us + r * kRowF + tb + i4) =
-                        make_float4(du_out[0], du_out[1], du_out[2], du_out[3]);
-                    *reinterpret_cast<float4 *>(dls + r * kRowF + tb + i4) =
-                        make_float4(dd_out[0], dd_out[1], dd_out[2], dd_out[3]);
-                }
-            }
-        }
-
-        // ---- tile epilogue: du / ddelta out, dB / dC reduced over the W warps and added to global
-        if (kBulk) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane < 8 && warp * 8 + lane < rows_valid) {
-                bulk_s2g(p.du + rowoff_w + (size_t)lane * L + t0, us + lane * kRowF, nvalid * 4);
-                bulk_s2g(p.ddelta + rowoff_w + (size_t)lane * L + t0, dls + lane * kRowF, nvalid * 4);
-            }
-            bulk_commit();
-        } else {
-            __syncwarp();
-            for (int rr = 0; rr < 8 && warp * 8 + rr < rows_valid; ++rr)
-                for (int t = lane; t < nvalid; t += 32) {
-                    p.du[rowoff_w + (size_t)rr * L + t0 + t] = us[rr * kRowF + t];
-                    p.ddelta[rowoff_w + (size_t)rr * L + t0 + t] = dls[rr * kRowF + t];
-                }
-        }
-        named_bar_sync(1, W * 32);
-        {
-            float *dBg = p.dB + ((size_t)b * p.G + g) * kN * (size_t)L + t0;
-            float *dCg = p.dC + ((size_t)b * p.G + g) * kN * (size_t)L + t0;
-            const int tid = warp * 32 + lane;
-            for (int idx = tid; idx < 2 * kN * kTT; idx += W * 32) {
-                const int row = idx / kTT, t = idx % kTT;
-                if (t < nvalid) {
-                    float v = 0.f;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) v += acc_s[(w * 2 * kN + row) * kAccStride + t];
-                    float *dst = (row < kN ? dBg + (size_t)row * L : dCg + (size_t)(row - kN) * L) + t;
-                    atomicAdd(dst, v);
-                }
-            }
-        }
-        named_bar_sync(1, W * 32);
-        if (kBulk) {
-            bulk_wait_read<1>();
-            __syncwarp();
-            if (lane == 0 && k >= 1) mbar_arrive(&empty[(k - 1) % S]);
-        } else {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
+        if (lane == 0) mbar_arrive(&sdone[sp]);
     }
-    if (kBulk) bulk_wait<0>();
 
-    // ---- parameter gradients: one atomic per thread
     if (valid) {
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) atomicAdd(p.dA + (size_t)d * kN + q + 4 * (s4 ^ x), dAacc[s4]);
-        if (q == 0) {
-            if (p.dD) atomicAdd(p.dD + d, dDacc);
-            if (p.dbias) atomicAdd(p.dbias + d, dbacc);
-        }
+        const int c0 = 2 * x1, c2 = 2 - 2 * x1;
+        atomicAdd(p.dA + (size_t)d * kN + q + 4 * c0, dA01.x);
+        atomicAdd(p.dA + (size_t)d * kN + q + 4 * (c0 + 1), dA01.y);
+        atomicAdd(p.dA + (size_t)d * kN + q + 4 * c2, dA23.x);
+        atomicAdd(p.dA + (size_t)d * kN + q + 4 * (c2 + 1), dA23.y);
     }
-}
-
-template <int W, int S>
-static size_t bwd_smem_bytes() {
-    const size_t f = (size_t)S * (4 * 8 * W + 2 * kN) * kRowF + (size_t)W * 2 * kN * kAccStride + 8 * W;
-    return f * 4 + 8 + 2 * S * 8;
-}
-
-template <int W, int S, bool kBulk>
-static cudaError_t launch_bwd(const ScanParams &p, cudaStream_t st) {
-    const size_t smem = bwd_smem_bytes<W, S>();
-    auto kern = scan_bwd_kernel<W, S, kBulk>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid((p.dpg + 8 * W - 1) / (8 * W), p.G, p.batch);
-    kern<<<grid, 2 * W * 32, smem, st>>>(p);
-    return cudaGetLastError();
+    // dD / dbias were accumulated by all 4 lanes of the channel (each finalised every 4th step)
+    dDacc += __shfl_xor_sync(0xffffffffu, dDacc, 1);
+    dbacc += __shfl_xor_sync(0xffffffffu, dbacc, 1);
+    dDacc += __shfl_xor_sync(0xffffffffu, dDacc, 2);
+    dbacc += __shfl_xor_sync(0xffffffffu, dbacc, 2);
+    if (valid && q == 0) {
+        if (p.dD) atomicAdd(p.dD + d, dDacc);
+        if (p.dbias) atomicAdd(p.dbias + d, dbacc);
+    }
 }
 
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st) {
-    if (warps >= 4) return bulk ? launch_bwd<4, 3, true>(p, st) : launch_bwd<4, 3, false>(p, st);
-    if (warps >= 2) return bulk ? launch_bwd<2, 3, true>(p, st) : launch_bwd<2, 3, false>(p, st);
-    return bulk ? launch_bwd<1, 3, true>(p, st) : launch_bwd<1, 3, false>(p, st);
+    (void)bulk; (void)warps;
+    const size_t smem = BwdCfg::bytes;
+    cudaError_t e = cudaFuncSetAttribute(scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((p.dpg + 31) / 32, p.G, p.batch);
+    scan_bwd_kernel<<<grid, 256, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace mlagg
