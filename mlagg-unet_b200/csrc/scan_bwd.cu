@@ -290,16 +290,19 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
                         s1[j] = on ? s1v.x + s1v.y : 0.f;
                         s2[j] = on ? s2v.x + s2v.y : 0.f;
                     }
-                    // sums over the 16 states: butterflies across the 4 lanes of the channel, 8 values in flight
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 1);
-                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 1);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 2);
-                        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 2);
+                    // sums over the 16 states: transpose-reduce across the 4 lanes of the channel -- lane q ends with
+                    // (s1, s2) of step i0 + q, which is the step it finalises below
+                    float s1q, s2q;
+                    {
+                        const bool oddq = (q & 1) != 0, hiq = (q & 2) != 0;
+                        // stage 1 (xor 1): even lanes keep steps {0, 2}, odd lanes steps {1, 3}
+                        const float a0 = (oddq ? s1[1] : s1[0]) + __shfl_xor_sync(0xffffffffu, oddq ? s1[0] : s1[1], 1);
+                        const float a2 = (oddq ? s1[3] : s1[2]) + __shfl_xor_sync(0xffffffffu, oddq ? s1[2] : s1[3], 1);
+                        const float c0 = (oddq ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, oddq ? s2[0] : s2[1], 1);
+                        const float c2 = (oddq ? s2[3] : s2[2]) + __shfl_xor_sync(0xffffffffu, oddq ? s2[2] : s2[3], 1);
+                        // stage 2 (xor 2): lanes with q < 2 keep the lower step of their pair
+                        s1q = (hiq ? a2 : a0) + __shfl_xor_sync(0xffffffffu, hiq ? a0 : a2, 2);
+                        s2q = (hiq ? c2 : c0) + __shfl_xor_sync(0xffffffffu, hiq ? c0 : c2, 2);
                     }
                     // dB: sums over the 8 channels of the warp
                     float keep[4];
@@ -319,8 +322,6 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
                     {
                         const int i = i0 + q;
                         const bool on = kFull || (i < ns);
-                        const float s1q = q == 0 ? s1[0] : q == 1 ? s1[1] : q == 2 ? s1[2] : s1[3];
-                        const float s2q = q == 0 ? s2[0] : q == 1 ? s2[1] : q == 2 ? s2[2] : s2[3];
                         const float delta = par[tb + i].x;
                         const float4 Y = pbr[tb + i];
                         const float dy = on ? Y.x : 0.f;
