@@ -156,6 +156,33 @@ int mlagg_pooled_diffattn_bwd(const void *q, const void *kp, const void *vp, con
                               long long ldd, float scale, const float *lam, float eps, float post_scale,
                               int dtype, mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Fused MSMM scan: SS2D_skip.forward_corev0 (variants/mamba/MambaSkip.py:405-473) without materialising the four
+ * direction-permuted copies of x (:414-422), the dt projection (:434), the fp32 casts (:437-443) or the
+ * un-permutation (:454-471).  Same recurrence and kernels as mlagg_selective_scan_*; only operand addressing differs.
+ *   xrow, xcol         : (batch, d_inner, L) fp32 -- the conv+SiLU output, channels-major, stages concatenated along L,
+ *                        each stage in row-major (xrow) / column-major (xcol: W x H transposed image) order
+ *   xdbl_row, xdbl_col : (batch, 2, dt_rank + 2*dstate, L) fp32 -- x_proj_weight[{0,2}] @ xrow and [{1,3}] @ xcol;
+ *                        per direction: dt_rank rows of dts, dstate rows of B, dstate rows of C
+ *   Wdt (4*d_inner, dt_rank), dt_bias (4*d_inner), A (4*d_inner, dstate) = -exp(A_logs), Ds (4*d_inner): fp32
+ *   stage_lens : HOST array of nstages (<= 8) stage lengths H_s*W_s; L = their sum
+ *   out  : (batch, 4, d_inner, L) fp32; direction k's result in row-major (k even) / column-major (k odd) order
+ *          with the mirroring of directions 2, 3 already undone:  y = out0 + out2 + colmajor_to_rowmajor(out1 + out3)
+ *   ckpt : as in mlagg_selective_scan_fwd (dim = 4*d_inner), nullable
+ * Backward: dout like out; du (batch, 4, d_inner, L) plain stores in the same orders (dxrow = du0 + du2,
+ *   dxcol = du1 + du3); dxdbl_row / dxdbl_col, dWdt, dA, dDs, ddt_bias fp32 ACCUMULATED INTO (zero-fill first).
+ * dt_rank <= 4, dstate == 16.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_msmm_scan_fwd(const float *xrow, const float *xcol, const float *xdbl_row, const float *xdbl_col,
+                        const float *Wdt, const float *dt_bias, const float *A, const float *Ds, float *out,
+                        float *ckpt, int batch, int d_inner, int dstate, int dt_rank, int nstages,
+                        const int *stage_lens, mlagg_stream_t stream);
+int mlagg_msmm_scan_bwd(const float *xrow, const float *xcol, const float *xdbl_row, const float *xdbl_col,
+                        const float *Wdt, const float *dt_bias, const float *A, const float *Ds, const float *dout,
+                        const float *ckpt, float *du, float *dxdbl_row, float *dxdbl_col, float *dWdt,
+                        float *ddt_bias, float *dA, float *dDs, int batch, int d_inner, int dstate, int dt_rank,
+                        int nstages, const int *stage_lens, mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

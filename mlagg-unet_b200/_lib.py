@@ -22,6 +22,8 @@ SIGNATURES = {
     "mlagg_scan_ckpt_bytes": (c_sz, [c_i] * 4),
     "mlagg_selective_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 6 + [c_p]),
     "mlagg_selective_scan_bwd": (c_i, [c_p] * 16 + [c_i] * 6 + [c_p]),
+    "mlagg_msmm_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 5 + [c_p, c_p]),
+    "mlagg_msmm_scan_bwd": (c_i, [c_p] * 17 + [c_i] * 5 + [c_p, c_p]),
     "mlagg_dwconv3x3_fwd": (c_i, [c_p] * 4 + [c_i] * 6 + [c_p]),
     "mlagg_dwconv3x3_bwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
     "mlagg_causal_conv1d_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),

@@ -311,3 +311,60 @@ extern "C" int mlagg_pooled_diffattn_bwd(const void *q, const void *kp, const vo
     if (e == cudaSuccess) e = pooled_attn_dispatch(p, head_dim, dtype, 2, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
+
+static int msmm_fill(ScanParams &p, const float *xrow, const float *xcol, const float *xdbl_row, const float *xdbl_col,
+                     const float *Wdt, const float *dt_bias, const float *A, const float *Ds, int batch, int d_inner,
+                     int dstate, int dt_rank, int nstages, const int *stage_lens) {
+    if (!xrow || !xcol || !xdbl_row || !xdbl_col || !Wdt || !A || !stage_lens) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || d_inner <= 0 || nstages <= 0 || nstages > kMaxStages) return MLAGG_ERR_BAD_SHAPE;
+    if (dstate != kN || dt_rank < 1 || dt_rank > kMaxRk) return MLAGG_ERR_UNSUPPORTED;
+    memset(&p, 0, sizeof(p));
+    long long L = 0;
+    for (int s = 0; s < nstages; ++s) {
+        if (stage_lens[s] <= 0) return MLAGG_ERR_BAD_SHAPE;
+        p.soff[s] = (int)L;
+        L += stage_lens[s];
+    }
+    for (int s = nstages; s <= kMaxStages; ++s) p.soff[s] = (int)L;
+    if (L > 0x7fffffff) return MLAGG_ERR_BAD_SHAPE;
+    p.fused = 1; p.Rk = dt_rank; p.nstage = nstages;
+    p.xrow = xrow; p.xcol = xcol; p.xdbl_row = xdbl_row; p.xdbl_col = xdbl_col; p.Wdt = Wdt;
+    p.A = A; p.D = Ds; p.bias = dt_bias;
+    p.batch = batch; p.dim = 4 * d_inner; p.L = (int)L; p.G = 4; p.dpg = d_inner;
+    p.nchunks = ((int)L + kChunk - 1) / kChunk; p.softplus = 1;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_msmm_scan_fwd(const float *xrow, const float *xcol, const float *xdbl_row, const float *xdbl_col,
+                                   const float *Wdt, const float *dt_bias, const float *A, const float *Ds, float *out,
+                                   float *ckpt, int batch, int d_inner, int dstate, int dt_rank, int nstages,
+                                   const int *stage_lens, mlagg_stream_t stream) {
+    ScanParams p;
+    int rc = msmm_fill(p, xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, batch, d_inner, dstate, dt_rank,
+                       nstages, stage_lens);
+    if (rc) return rc;
+    if (!out) return MLAGG_ERR_NULL;
+    if (ckpt && !aligned(ckpt, 16)) return MLAGG_ERR_ALIGN;
+    p.out = out; p.ckpt = ckpt;
+    cudaError_t e = scan_fwd_dispatch(p, false, 4, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_msmm_scan_bwd(const float *xrow, const float *xcol, const float *xdbl_row, const float *xdbl_col,
+                                   const float *Wdt, const float *dt_bias, const float *A, const float *Ds,
+                                   const float *dout, const float *ckpt, float *du, float *dxdbl_row,
+                                   float *dxdbl_col, float *dWdt, float *ddt_bias, float *dA, float *dDs, int batch,
+                                   int d_inner, int dstate, int dt_rank, int nstages, const int *stage_lens,
+                                   mlagg_stream_t stream) {
+    ScanParams p;
+    int rc = msmm_fill(p, xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, batch, d_inner, dstate, dt_rank,
+                       nstages, stage_lens);
+    if (rc) return rc;
+    if (!dout || !ckpt || !du || !dxdbl_row || !dxdbl_col || !dWdt || !dA) return MLAGG_ERR_NULL;
+    if ((Ds && !dDs) || (dt_bias && !ddt_bias)) return MLAGG_ERR_NULL;
+    if (!aligned(ckpt, 16)) return MLAGG_ERR_ALIGN;
+    p.dout = dout; p.ckpt_in = ckpt; p.du = du; p.dxdbl_row = dxdbl_row; p.dxdbl_col = dxdbl_col; p.dWdt = dWdt;
+    p.dA = dA; p.dD = Ds ? dDs : nullptr; p.dbias = dt_bias ? ddt_bias : nullptr;
+    cudaError_t e = scan_bwd_dispatch(p, false, 4, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}

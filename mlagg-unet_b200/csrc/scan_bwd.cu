@@ -30,8 +30,8 @@ constexpr int kAccS = kTB + 1;   // acc row stride (floats), odd
 struct BwdCfg {
     static constexpr int W = 4, R = 32, SP = 3;
     static constexpr size_t f4_stage = (size_t)2 * R * kPB + 4 * 4 * kPB;   // pkA, pkB, BT, BT2, CT, CT2
-    static constexpr size_t bytes = SP * f4_stage * 16 + (size_t)2 * W * 2 * kN * kAccS * 4 + 2 * R * 4 + 64 +
-                                    (2 * SP + 2) * 8 + 16;
+    static constexpr size_t bytes = SP * f4_stage * 16 + (size_t)2 * W * 2 * kN * kAccS * 4 +
+                                    (size_t)SP * W * kMaxRk * kTB * 4 + 2 * R * 4 + 64 + (2 * SP + 2) * 8 + 16;
 };
 
 __device__ __forceinline__ float2 g2(float a, float b) { return make_float2(a, b); }
@@ -41,6 +41,7 @@ __device__ __forceinline__ float ldg_s(const float *p) {
     return v;
 }
 
+template <bool kFused>
 __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
     constexpr int W = BwdCfg::W, R = BwdCfg::R, SP = BwdCfg::SP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -48,7 +49,8 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
     float4 *pkB = pkA + SP * R * kPB;                            // [SP][R][kPB]
     float4 *BT = pkB + SP * R * kPB;                             // [SP][4 arrays: B, B2, C, C2][4][kPB]
     float *acc = reinterpret_cast<float *>(BT + SP * 16 * kPB);  // [2][W][2*kN][kAccS]
-    float *bias_s = acc + 2 * W * 2 * kN * kAccS;                // [R]
+    float *dts_s = acc + 2 * W * 2 * kN * kAccS;                 // [SP][W][kMaxRk][kTB]  (fused mode)
+    float *bias_s = dts_s + SP * W * kMaxRk * kTB;               // [R]
     float *D_s = bias_s + R;                                     // [R]
     uint64_t *ready = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(D_s + R + 16) + 7) & ~uintptr_t(7));
     uint64_t *sdone = ready + SP;
@@ -83,40 +85,93 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
         const int h = warp - W;
         const int myrows = max(0, min(8, rows_valid - 8 * h));
         const size_t rowoff = ((size_t)b * p.dim + row0 + 8 * h) * L;
-        const float *ub = p.u + rowoff, *db = p.delta + rowoff, *gb = p.dout + rowoff;
-        const float *Bb = p.B + (((size_t)b * p.G + g) * kN + h) * (size_t)L;   // rows h, h+4, h+8, h+12
-        const float *Cb = p.C + (((size_t)b * p.G + g) * kN + h) * (size_t)L;
-        float *dub = p.du + rowoff, *ddb = p.ddelta + rowoff;
-        float *dBg = p.dB + ((size_t)b * p.G + g) * kN * (size_t)L;
-        float *dCg = p.dC + ((size_t)b * p.G + g) * kN * (size_t)L;
-        float ur[8], dr[8], yr[8], Br[4], Cr[4];   // tile in flight: row i, step t0 + lane
+        constexpr bool fused = kFused;
+        const int kdir = g;
+        const int C35 = p.Rk + 2 * kN;
+        const int dloc0 = blockIdx.x * R + 8 * h;
+        const float *ub, *db = nullptr, *Bb, *Cb, *dtb = nullptr;
+        const float *gb = p.dout + rowoff;
+        float *dBg, *dCg, *ddtg = nullptr;
+        if (fused) {
+            ub = ((kdir & 1) ? p.xcol : p.xrow) + ((size_t)b * p.dpg + dloc0) * L;
+            const size_t xo = (((size_t)b * 2 + (kdir >> 1)) * C35) * (size_t)L;
+            const float *xd = ((kdir & 1) ? p.xdbl_col : p.xdbl_row) + xo;
+            float *dxd = ((kdir & 1) ? p.dxdbl_col : p.dxdbl_row) + xo;
+            dtb = xd;
+            Bb = xd + (size_t)(p.Rk + h) * L;
+            Cb = xd + (size_t)(p.Rk + kN + h) * L;
+            ddtg = dxd;
+            dBg = dxd + (size_t)p.Rk * L;
+            dCg = dxd + (size_t)(p.Rk + kN) * L;
+        } else {
+            ub = p.u + rowoff;
+            db = p.delta + rowoff;
+            Bb = p.B + (((size_t)b * p.G + g) * kN + h) * (size_t)L;   // rows h, h+4, h+8, h+12
+            Cb = p.C + (((size_t)b * p.G + g) * kN + h) * (size_t)L;
+            dBg = p.dB + ((size_t)b * p.G + g) * kN * (size_t)L;
+            dCg = p.dC + ((size_t)b * p.G + g) * kN * (size_t)L;
+        }
+        const bool mirrored = fused && kdir >= 2;
+        float *dub = p.du + rowoff, *ddb = fused ? nullptr : p.ddelta + rowoff;
+        float wdt[8][kMaxRk], dwacc[8][kMaxRk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int rr = 0; rr < kMaxRk; ++rr) {
+                wdt[i][rr] = (fused && i < myrows && rr < p.Rk) ? p.Wdt[(size_t)(row0 + 8 * h + i) * p.Rk + rr] : 0.f;
+                dwacc[i][rr] = 0.f;
+            }
+        float ur[8], dr[8], yr[8], Br[4], Cr[4], dtr[kMaxRk];   // tile in flight: row i, step t0 + lane
 
         auto tile_t0 = [&](int k) { return (ntiles - 1 - k) * kTB; };
         auto fetch = [&](int k) {
             const int t = tile_t0(k) + lane;
+            const bool tin = t < L;
+            const int tm = (mirrored && tin) ? mirror_pos(p, t) : t;
+#pragma unroll
+            for (int rr = 0; rr < kMaxRk; ++rr) dtr[rr] = (fused && tin && rr < p.Rk) ? ldg_s(dtb + (size_t)rr * L + tm) : 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const bool ok = i < myrows && t < L;
-                ur[i] = ok ? ldg_s(ub + (size_t)i * L + t) : 0.f;
-                dr[i] = ok ? ldg_s(db + (size_t)i * L + t) : 0.f;
-                yr[i] = ok ? ldg_s(gb + (size_t)i * L + t) : 0.f;
+                const bool ok = i < myrows && tin;
+                ur[i] = ok ? ldg_s(ub + (size_t)i * L + tm) : 0.f;
+                yr[i] = ok ? ldg_s(gb + (size_t)i * L + tm) : 0.f;
+                if constexpr (!fused) dr[i] = ok ? ldg_s(db + (size_t)i * L + tm) : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                Br[j] = t < L ? ldg_s(Bb + (size_t)(4 * j) * L + t) : 0.f;
-                Cr[j] = t < L ? ldg_s(Cb + (size_t)(4 * j) * L + t) : 0.f;
+                Br[j] = tin ? ldg_s(Bb + (size_t)(4 * j) * L + tm) : 0.f;
+                Cr[j] = tin ? ldg_s(Cb + (size_t)(4 * j) * L + tm) : 0.f;
             }
         };
         auto finish = [&](int k) {  // outputs of tile k (all scan warps have arrived on sdone)
             const int sp = k % SP, t = tile_t0(k) + lane;
+            const bool tin = t < L;
+            const int tm = (mirrored && tin) ? mirror_pos(p, t) : t;
             const float4 *pb = pkB + (sp * R + 8 * h) * kPB;
+            const float *dts = dts_s + ((sp * W + h) * kMaxRk) * kTB;
+            float ddt[kMaxRk];
+#pragma unroll
+            for (int rr = 0; rr < kMaxRk; ++rr) ddt[rr] = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (i < myrows && t < L) {
+                if (i < myrows && tin) {
                     const float4 v = pb[i * kPB + lane];
-                    dub[(size_t)i * L + t] = v.x;
-                    ddb[(size_t)i * L + t] = v.y;
+                    dub[(size_t)i * L + tm] = v.x;
+                    if (fused) {
+#pragma unroll
+                        for (int rr = 0; rr < kMaxRk; ++rr) {
+                            ddt[rr] = fmaf(wdt[i][rr], v.y, ddt[rr]);
+                            dwacc[i][rr] = fmaf(v.y, dts[rr * kTB + lane], dwacc[i][rr]);
+                        }
+                    } else {
+                        ddb[(size_t)i * L + tm] = v.y;
+                    }
                 }
+            }
+            if (fused && tin) {
+#pragma unroll
+                for (int rr = 0; rr < kMaxRk; ++rr)
+                    if (rr < p.Rk) atomicAdd(ddtg + (size_t)rr * L + tm, ddt[rr]);
             }
             // dB / dC: rows [8h, 8h+8) of the 32 (array, state) rows; sum the 4 scan warps' partial tiles
             const float *ab = acc + (k & 1) * W * 2 * kN * kAccS;
@@ -126,7 +181,7 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
                 float s = 0.f;
 #pragma unroll
                 for (int w = 0; w < W; ++w) s += ab[(w * 2 * kN + row) * kAccS + lane];
-                if (t < L) atomicAdd((row < kN ? dBg + (size_t)row * L : dCg + (size_t)(row - kN) * L) + t, s);
+                if (tin) atomicAdd((row < kN ? dBg + (size_t)row * L : dCg + (size_t)(row - kN) * L) + tm, s);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&accfree[k & 1]);
@@ -140,11 +195,24 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float sg = 1.f;
-                float dl = dr[i] + bias_s[8 * h + i];
+                float draw;
+                if constexpr (fused) {   // delta = W_dt[row, :] . dts_r, computed when the tile is consumed (not when fetched)
+                    draw = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < kMaxRk; ++rr) draw = fmaf(wdt[i][rr], dtr[rr], draw);
+                } else {
+                    draw = dr[i];
+                }
+                float dl = draw + bias_s[8 * h + i];
                 if (p.softplus) dl = softplus_fast(dl, &sg);
                 const float du = dl * ur[i];
                 pa[i * kPB + lane] = make_float4(dl, dl, du, du);
                 pb[i * kPB + lane] = make_float4(yr[i], yr[i], ur[i], sg);
+            }
+            if (fused) {
+                float *dts = dts_s + ((sp * W + h) * kMaxRk) * kTB;
+#pragma unroll
+                for (int rr = 0; rr < kMaxRk; ++rr) dts[rr * kTB + lane] = dtr[rr];
             }
             {
                 float4 *bt = BT + (sp * 16 + h) * kPB;   // arrays at +0, +4, +8, +12 quads
@@ -163,6 +231,18 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
         }
         mbar_wait(&sdone[(ntiles - 1) % SP], ((ntiles - 1) / SP) & 1);
         finish(ntiles - 1);
+        if (fused) {   // d W_dt[row, :] = sum over time (lanes, then tiles) of d delta * dts_r
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int rr = 0; rr < kMaxRk; ++rr) {
+                    float v = dwacc[i][rr];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && i < myrows && rr < p.Rk)
+                        atomicAdd(p.dWdt + (size_t)(row0 + 8 * h + i) * p.Rk + rr, v);
+                }
+        }
         return;
     }
 
@@ -362,10 +442,11 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st) {
     (void)bulk; (void)warps;
     const size_t smem = BwdCfg::bytes;
-    cudaError_t e = cudaFuncSetAttribute(scan_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = p.fused ? scan_bwd_kernel<true> : scan_bwd_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((p.dpg + 31) / 32, p.G, p.batch);
-    scan_bwd_kernel<<<grid, 256, smem, st>>>(p);
+    kern<<<grid, 256, smem, st>>>(p);
     return cudaGetLastError();
 }
 

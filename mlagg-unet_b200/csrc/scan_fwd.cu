@@ -38,6 +38,7 @@ __device__ __forceinline__ float ldg_stream(const float *p) {
     return v;
 }
 
+template <bool kFused>
 __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
     constexpr int W = FwdCfg::W, R = FwdCfg::R, SP = FwdCfg::SP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -76,36 +77,74 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
         // =============================================================== helper warp
         const int h = warp - W;
         const int myrows = max(0, min(8, rows_valid - 8 * h));
-        const float *ub = p.u + ((size_t)b * p.dim + row0 + 8 * h) * L;
-        const float *db = p.delta + ((size_t)b * p.dim + row0 + 8 * h) * L;
-        const float *Bb = p.B + (((size_t)b * p.G + g) * kN + h) * (size_t)L;   // rows h, h+4, h+8, h+12
-        const float *Cb = p.C + (((size_t)b * p.G + g) * kN + h) * (size_t)L;
+        // operand sources: mamba interface or fused MSMM (see scan_common.cuh)
+        constexpr bool fused = kFused;
+        const int kdir = g;                                   // fused: direction = group
+        const int C35 = p.Rk + 2 * kN;
+        const int dloc0 = blockIdx.x * R + 8 * h;             // first channel of this warp inside the group
+        const float *ub, *db = nullptr, *Bb, *Cb, *dtb = nullptr;
+        if (fused) {
+            ub = ((kdir & 1) ? p.xcol : p.xrow) + ((size_t)b * p.dpg + dloc0) * L;
+            const float *xd = ((kdir & 1) ? p.xdbl_col : p.xdbl_row) + (((size_t)b * 2 + (kdir >> 1)) * C35) * (size_t)L;
+            dtb = xd;
+            Bb = xd + (size_t)(p.Rk + h) * L;
+            Cb = xd + (size_t)(p.Rk + kN + h) * L;
+        } else {
+            ub = p.u + ((size_t)b * p.dim + row0 + 8 * h) * L;
+            db = p.delta + ((size_t)b * p.dim + row0 + 8 * h) * L;
+            Bb = p.B + (((size_t)b * p.G + g) * kN + h) * (size_t)L;   // rows h, h+4, h+8, h+12
+            Cb = p.C + (((size_t)b * p.G + g) * kN + h) * (size_t)L;
+        }
+        const bool mirrored = fused && kdir >= 2;
         float *outb = p.out + ((size_t)b * p.dim + row0 + 8 * h) * L;
-        float ur[16], dr[16], Br[8], Cr[8];   // the tile in flight: element e = lane + 32 i  ->  row e >> 6, step e & 63
+        float wdt[8][kMaxRk];                                 // fused: rows of W_dt for this warp's channels
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int rr = 0; rr < kMaxRk; ++rr)
+                wdt[i][rr] = (fused && i < myrows && rr < p.Rk) ? p.Wdt[(size_t)(row0 + 8 * h + i) * p.Rk + rr] : 0.f;
+        // the tile in flight: element i = 2 * row + half  ->  step lane + 32 * half.  Loaded values are NOT touched until the
+        // next iteration (one tile of scan time later), so the HBM latency is never exposed.
+        float ur[16], dr[16], Br[8], Cr[8], dtr[2][kMaxRk];
 
         auto fetch = [&](int c) {
             const int t0 = c * kTT;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int rr = i >> 1, t = t0 + lane + 32 * (i & 1);
-                const bool ok = rr < myrows && t < L;
-                ur[i] = ok ? ldg_stream(ub + (size_t)rr * L + t) : 0.f;
-                dr[i] = ok ? ldg_stream(db + (size_t)rr * L + t) : 0.f;
-            }
+            for (int hf = 0; hf < 2; ++hf) {
+                const int t = t0 + lane + 32 * hf;
+                const bool tin = t < L;
+                const int tm = (mirrored && tin) ? mirror_pos(p, t) : t;
+                if constexpr (fused) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int j = i >> 1, t = t0 + lane + 32 * (i & 1);
-                Br[i] = t < L ? ldg_stream(Bb + (size_t)(4 * j) * L + t) : 0.f;
-                Cr[i] = t < L ? ldg_stream(Cb + (size_t)(4 * j) * L + t) : 0.f;
+                    for (int rr = 0; rr < kMaxRk; ++rr)
+                        dtr[hf][rr] = (tin && rr < p.Rk) ? ldg_stream(dtb + (size_t)rr * L + tm) : 0.f;
+                }
+#pragma unroll
+                for (int rw = 0; rw < 8; ++rw) {
+                    const int i = 2 * rw + hf;
+                    const bool ok = rw < myrows && tin;
+                    ur[i] = ok ? ldg_stream(ub + (size_t)rw * L + tm) : 0.f;
+                    if constexpr (!fused) dr[i] = ok ? ldg_stream(db + (size_t)rw * L + tm) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Br[2 * j + hf] = tin ? ldg_stream(Bb + (size_t)(4 * j) * L + tm) : 0.f;
+                    Cr[2 * j + hf] = tin ? ldg_stream(Cb + (size_t)(4 * j) * L + tm) : 0.f;
+                }
             }
         };
         auto write_out = [&](int c) {  // yt rows of tile c -> global, coalesced
             const int sp = c % SP, t0 = c * kTT;
             const float *ys = yt + (sp * R + 8 * h) * kRowF;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int rr = i >> 1, tl = lane + 32 * (i & 1);
-                if (rr < myrows && t0 + tl < L) outb[(size_t)rr * L + t0 + tl] = ys[rr * kRowF + tl];
+            for (int hf = 0; hf < 2; ++hf) {
+                const int tl = lane + 32 * hf, t = t0 + tl;
+                if (t < L) {
+                    const int tm = mirrored ? mirror_pos(p, t) : t;
+#pragma unroll
+                    for (int rw = 0; rw < 8; ++rw)
+                        if (rw < myrows) outb[(size_t)rw * L + tm] = ys[rw * kRowF + tl];
+                }
             }
         };
 
@@ -118,7 +157,15 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int rr = i >> 1, tl = lane + 32 * (i & 1);
-                float dl = dr[i] + bias_s[8 * h + rr];
+                float draw;
+                if constexpr (fused) {
+                    draw = 0.f;
+#pragma unroll
+                    for (int k2 = 0; k2 < kMaxRk; ++k2) draw = fmaf(wdt[rr][k2], dtr[i & 1][k2], draw);
+                } else {
+                    draw = dr[i];
+                }
+                float dl = draw + bias_s[8 * h + rr];
                 if (p.softplus) dl = softplus_fast(dl);
                 const float du = dl * ur[i];
                 pks[rr * kPk + tl] = make_float4(dl, dl, du, du);
@@ -240,10 +287,11 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
 cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st) {
     (void)bulk; (void)warps;
     const size_t smem = FwdCfg::bytes;
-    cudaError_t e = cudaFuncSetAttribute(scan_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = p.fused ? scan_fwd_kernel<true> : scan_fwd_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((p.dpg + 31) / 32, p.G, p.batch);
-    scan_fwd_kernel<<<grid, 256, smem, st>>>(p);
+    kern<<<grid, 256, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -26,7 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ops import dwconv3x3_tokens
-from .selective_scan_interface import selective_scan_fn
+from .selective_scan_interface import msmm_scan, selective_scan_fn
 from .thirdparty_shims import DropPath
 
 
@@ -131,7 +131,38 @@ class SS2D_skip(nn.Module):
         return D
 
     # ---- core: tokens (B, L, Di) -> merged scan output (B, L, Di) fp32
+    @staticmethod
+    def _stagewise_transpose(t, hw, to_col):
+        """(B, D, L): per stage, row-major (H, W) order <-> column-major order (the W x H transposed image)."""
+        parts, off = [], 0
+        Bn, Dn, _ = t.shape
+        for (H, W) in hw:
+            a, b_ = (H, W) if to_col else (W, H)
+            parts.append(t[:, :, off:off + H * W].reshape(Bn, Dn, a, b_).transpose(2, 3).reshape(Bn, Dn, H * W))
+            off += H * W
+        return torch.cat(parts, dim=-1)
+
     def forward_core_tokens(self, xc, hw):
+        """Fused path: the cross-scan, dt projection and un-permutation of forward_corev0 (reference :405-473) happen
+        inside the scan kernels' operand addressing; torch only supplies two walk orders of x and the x_proj GEMMs."""
+        Bn, L, Di = xc.shape
+        R, N = self.dt_rank, self.d_state
+        xrow = xc.transpose(1, 2).contiguous()                                  # (B, Di, L) row-major walk
+        xcol = self._stagewise_transpose(xrow, hw, to_col=True)                 # column-major walk
+        Wx = self.x_proj_weight                                                 # (4, R+2N, Di)
+        # W_x[k] @ xs[k] == permute_k(W_x[k] @ x): directions {0,2} on the row walk, {1,3} on the column walk (App. A.3)
+        xdbl_row = torch.matmul(Wx[0::2].reshape(2 * (R + 2 * N), Di), xrow).view(Bn, 2, R + 2 * N, L)
+        xdbl_col = torch.matmul(Wx[1::2].reshape(2 * (R + 2 * N), Di), xcol).view(Bn, 2, R + 2 * N, L)
+        out = msmm_scan(xrow, xcol, xdbl_row, xdbl_col, self.dt_projs_weight.reshape(4 * Di, R),
+                        self.dt_projs_bias.reshape(-1), -torch.exp(self.A_logs.float()), self.Ds,
+                        [h * w for h, w in hw])
+        assert out.dtype == torch.float32
+        y = out[:, 0] + out[:, 2] + self._stagewise_transpose(out[:, 1] + out[:, 3], hw, to_col=False)
+        return y.transpose(1, 2).contiguous()
+
+    def forward_core_tokens_unfused(self, xc, hw):
+        """Mamba-interface path (materialised cross-scan through index maps + selective_scan_fn); kept for parity
+        tests of the fused path and for callers that want the reference's op boundary."""
         Bn, L, Di = xc.shape
         K, R, N = 4, self.dt_rank, self.d_state
         idx, inv = cross_scan_maps(hw, xc.device)

@@ -10,6 +10,8 @@ CUDA only -- there is no CPU path here (the CPU restatement lives in oracle/ and
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 import torch.nn.functional as F
 
@@ -91,3 +93,61 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     if z is not None:
         out = out * F.silu(z)
     return (out, last) if return_last_state else out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Fused MSMM scan (C ABI: mlagg_msmm_scan_fwd / _bwd): SS2D_skip.forward_corev0 without the materialised cross-scan
+# --------------------------------------------------------------------------------------------------------------------
+class MSMMScanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, stage_lens):
+        if not xrow.is_cuda:
+            raise _lib.MlaggError("msmm_scan: CUDA tensors required (no CPU fallback in the product path)")
+        ctx.in_dtypes = tuple(t.dtype for t in (xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds))
+        xrow_, xcol_, xr_, xc_, W_, b_, A_, D_ = map(_f32c, (xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds))
+        Bn, Di, L = xrow_.shape
+        N, R = A_.shape[1], W_.shape[1]
+        assert sum(stage_lens) == L and xr_.shape == (Bn, 2, R + 2 * N, L) and xc_.shape == xr_.shape
+        lens = (ctypes.c_int * len(stage_lens))(*[int(v) for v in stage_lens])
+        need_grad = any(t.requires_grad for t in (xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds))
+        L_ = _lib.lib()
+        out = torch.empty(Bn, 4, Di, L, device=xrow.device, dtype=torch.float32)
+        ckpt = None
+        if need_grad:
+            ckpt = torch.empty(L_.mlagg_scan_ckpt_bytes(Bn, 4 * Di, L, N) // 4, device=xrow.device, dtype=torch.float32)
+        with torch.cuda.device(xrow.device), _lib.timed("scan_fwd"):
+            rc = L_.mlagg_msmm_scan_fwd(_lib.ptr(xrow_), _lib.ptr(xcol_), _lib.ptr(xr_), _lib.ptr(xc_), _lib.ptr(W_),
+                                        _lib.ptr(b_), _lib.ptr(A_), _lib.ptr(D_), _lib.ptr(out), _lib.ptr(ckpt),
+                                        Bn, Di, N, R, len(stage_lens), lens, _lib.stream_ptr())
+        _lib.check(rc, "mlagg_msmm_scan_fwd")
+        ctx.stage_lens = tuple(int(v) for v in stage_lens)
+        ctx.save_for_backward(xrow_, xcol_, xr_, xc_, W_, b_, A_, D_, ckpt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xrow, xcol, xr, xc, W, b, A, D, ckpt = ctx.saved_tensors
+        Bn, Di, L = xrow.shape
+        N, R = A.shape[1], W.shape[1]
+        dout = dout.float().contiguous()
+        du = torch.empty(Bn, 4, Di, L, device=xrow.device, dtype=torch.float32)
+        dxr, dxc = torch.zeros_like(xr), torch.zeros_like(xc)
+        dW, db, dA, dD = torch.zeros_like(W), torch.zeros_like(b), torch.zeros_like(A), torch.zeros_like(D)
+        lens = (ctypes.c_int * len(ctx.stage_lens))(*ctx.stage_lens)
+        L_ = _lib.lib()
+        with torch.cuda.device(xrow.device), _lib.timed("scan_bwd"):
+            rc = L_.mlagg_msmm_scan_bwd(_lib.ptr(xrow), _lib.ptr(xcol), _lib.ptr(xr), _lib.ptr(xc), _lib.ptr(W),
+                                        _lib.ptr(b), _lib.ptr(A), _lib.ptr(D), _lib.ptr(dout), _lib.ptr(ckpt),
+                                        _lib.ptr(du), _lib.ptr(dxr), _lib.ptr(dxc), _lib.ptr(dW), _lib.ptr(db),
+                                        _lib.ptr(dA), _lib.ptr(dD), Bn, Di, N, R, len(ctx.stage_lens), lens,
+                                        _lib.stream_ptr())
+        _lib.check(rc, "mlagg_msmm_scan_bwd")
+        dt = ctx.in_dtypes
+        return ((du[:, 0] + du[:, 2]).to(dt[0]), (du[:, 1] + du[:, 3]).to(dt[1]), dxr.to(dt[2]), dxc.to(dt[3]),
+                dW.to(dt[4]), db.to(dt[5]), dA.to(dt[6]), dD.to(dt[7]), None)
+
+
+def msmm_scan(xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, stage_lens):
+    """4-direction multi-scale selective scan on un-permuted operands; see include/mlagg_b200.h (mlagg_msmm_scan_fwd).
+    Returns out (B, 4, Di, L): direction k in row-major (k even) / column-major (k odd) order, mirroring undone."""
+    return MSMMScanFn.apply(xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, tuple(stage_lens))

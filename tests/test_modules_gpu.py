@@ -60,6 +60,33 @@ def test_ss2d_skip_matches_reference():
     assert rel_err(x.grad.cpu(), g["grad_input"]) < TOL32
 
 
+def test_fused_msmm_scan_equals_materialised_cross_scan():
+    """The fused operand addressing (mlagg_msmm_scan_*) against the mamba-interface path on the same weights:
+    forward, input gradient and every parameter gradient, at a multi-tile non-square multi-stage size."""
+    from mlagg_unet_b200.mamba_skip import SS2D_skip
+    torch.manual_seed(5)
+    hw = [(12, 10), (6, 5), (3, 4), (2, 2)]
+    L = sum(h * w for h, w in hw)
+    m = SS2D_skip(len(hw), 24).cuda()
+    with torch.no_grad():
+        m.A_logs.add_(0.2 * torch.randn_like(m.A_logs))
+        m.Ds.add_(0.3 * torch.randn_like(m.Ds))
+    xc = torch.randn(2, L, m.d_inner, device="cuda")
+    res = {}
+    for name, fn in (("fused", m.forward_core_tokens), ("plain", m.forward_core_tokens_unfused)):
+        x = xc.clone().requires_grad_()
+        m.zero_grad()
+        y = fn(x, hw)
+        torch.manual_seed(1)
+        (y * torch.randn_like(y)).sum().backward()
+        res[name] = (y.detach(), x.grad, {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    assert rel_err(res["fused"][0], res["plain"][0]) < TOL32
+    assert rel_err(res["fused"][1], res["plain"][1]) < TOL32
+    assert set(res["fused"][2]) == set(res["plain"][2])
+    for n in res["plain"][2]:
+        assert rel_err(res["fused"][2][n], res["plain"][2][n]) < TOL32, n
+
+
 def test_vss_conv_layer_matches_reference():
     from mlagg_unet_b200.mamba_skip import VSS_Conv_Layer
     g = load_golden("msmm_vss_conv_layer.pt")
