@@ -259,7 +259,8 @@ class VSS_Conv_Block(nn.Module):
         W = [t.shape[3] for t in inputs]
         L_split = [h * w for h, w in zip(H, W)]
         hd = self.hidden_dim
-        m = torch.cat([t[:, :hd].flatten(2) for t in inputs], dim=-1).transpose(1, 2).contiguous()  # (B, L, hd)
+        # tokens-major (B, L, hd): NHWC views of the inputs (free when they are channels_last), first hd channels
+        m = torch.cat([t.permute(0, 2, 3, 1)[..., :hd].reshape(Bn, L_split[s], hd) for s, t in enumerate(inputs)], dim=1)
         m = m + self.drop_path(self.self_attention(self.ln_1(m), Bn, H, W, L_split))
         m = self.norm2(m)
         outs, off = [], 0
@@ -267,8 +268,8 @@ class VSS_Conv_Block(nn.Module):
             ms = m[:, off:off + L_split[s]]
             off += L_split[s]
             ms = ms + self.drop_path(self.mlps[s](ms, H[s], W[s]))
-            ms = ms.transpose(1, 2).reshape(Bn, hd, H[s], W[s])
-            outs.append(torch.cat([ms, self.conv_branches[s](t[:, hd:])], dim=1))
+            cb = self.conv_branches[s](t[:, hd:]).permute(0, 2, 3, 1)                  # NHWC view
+            outs.append(torch.cat([ms.reshape(Bn, H[s], W[s], hd), cb], dim=-1).permute(0, 3, 1, 2))  # channels_last
         return outs
 
 

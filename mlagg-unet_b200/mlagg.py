@@ -182,7 +182,7 @@ class MLLABlock(nn.Module):
         H, W = self.input_resolution
         Bn, C, h_, w_ = x.shape
         assert (H == h_) and (W == w_), "input feature has wrong size"
-        t = self.forward_tokens(x.reshape(Bn, C, H * W).transpose(1, 2), H, W)
+        t = self.forward_tokens(x.permute(0, 2, 3, 1).reshape(Bn, H * W, C), H, W)   # a view when x is channels_last
         return t.reshape(Bn, H, W, C).permute(0, 3, 1, 2)
 
     def extra_repr(self):
@@ -209,7 +209,7 @@ class BasicLayer(nn.Module):
         H, W = self.input_resolution
         Bn, C, h_, w_ = x.shape
         assert (H == h_) and (W == w_), "input feature has wrong size"
-        t = x.reshape(Bn, C, H * W).transpose(1, 2)
+        t = x.permute(0, 2, 3, 1).reshape(Bn, H * W, C)   # tokens-major == NHWC: a view when x is channels_last
         for blk in self.blocks:
             if self.use_checkpoint:
                 t = torch.utils.checkpoint.checkpoint(blk.forward_tokens, t, H, W, use_reentrant=False)
@@ -241,10 +241,10 @@ class project(nn.Module):
             self.norm2 = norm(out_dim)
 
     def forward(self, x):
-        x = _TokensLN.apply(self.norm1, self.activate(self.conv1(x))).contiguous()
+        x = _TokensLN.apply(self.norm1, self.activate(self.conv1(x)))
         x = self.conv2(x)
         if not self.last:
-            x = _TokensLN.apply(self.norm2, self.activate(x)).contiguous()
+            x = _TokensLN.apply(self.norm2, self.activate(x))
         return x
 
 
@@ -265,7 +265,7 @@ class PatchEmbed(nn.Module):
             x = F.pad(x, (0, 0, 0, self.patch_size[0] - H % self.patch_size[0]))
         x = self.proj2(self.proj1(x))
         if self.norm is not None:
-            x = _TokensLN.apply(self.norm, x).contiguous()
+            x = _TokensLN.apply(self.norm, x)
         return x
 
 
@@ -408,6 +408,9 @@ class MLLA_Uper(nn.Module):
             self.out_4 = OutBlock(in_channels=E * 8, n_classes=out_channels, dim=spatial_dims)
 
     def forward(self, x_in):
+        # the whole network runs channels_last (NHWC): the conv stages get cuDNN's native layout and the token blocks
+        # read the same memory as (B, N, C) without a copy
+        x_in = x_in.contiguous(memory_format=torch.channels_last)
         hs = self.mlla(x_in, self.normalize)
         hs[1:] = self.mambaskip(hs[1:])
         ds = self.deep_supervision

@@ -161,6 +161,8 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         self.network = self.build_network_architecture(self.plans_manager, self.dataset_json,
                                                        self.configuration_manager, self.plans.num_input_channels,
                                                        True).to(self.device)
+        if self.device.type == "cuda":
+            self.network = self.network.to(memory_format=torch.channels_last)
         self.optimizer, self.lr_scheduler = self.configure_optimizers()
         if self.is_ddp:
             from torch.nn.parallel import DistributedDataParallel as DDP
