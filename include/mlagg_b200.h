@@ -183,6 +183,21 @@ int mlagg_msmm_scan_bwd(const float *xrow, const float *xcol, const float *xdbl_
                         float *ddt_bias, float *dA, float *dDs, int batch, int d_inner, int dstate, int dt_rank,
                         int nstages, const int *stage_lens, mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension of tokens-major activations, fp32 math, fp32 or bf16 input and output.
+ * Replaces nn.LayerNorm (+ the fp32 up-cast and the consumers' down-cast copies autocast inserts) at
+ *   nnUNetTrainer_MLAgg_2D_dt_MS.py:848,871 (norm1, norm2), :670 (pooled-token norm);
+ *   variants/mamba/MambaSkip.py:344 (out_norm), :686,690 (ln_1, norm2 of VSS_Conv_Block).
+ *   x (M, C) of dt_in, y (M, C) of dt_out, weight / bias (C) fp32 (bias nullable), mean / rstd (M) fp32 saved for backward;
+ *   C % 4 == 0, C <= 1024.
+ * Backward: dy (M, C) of dt_out -> dx (M, C) of dt_in; dweight / dbias (C) fp32 ACCUMULATED INTO (zero-fill first).
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_layernorm_fwd(const void *x, const float *weight, const float *bias, void *y, float *mean, float *rstd,
+                        long long M, int C, float eps, int dt_in, int dt_out, mlagg_stream_t stream);
+int mlagg_layernorm_bwd(const void *x, const float *weight, const float *mean, const float *rstd, const void *dy,
+                        void *dx, float *dweight, float *dbias, long long M, int C, int dt_in, int dt_out,
+                        mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

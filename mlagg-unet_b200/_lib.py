@@ -24,6 +24,8 @@ SIGNATURES = {
     "mlagg_selective_scan_bwd": (c_i, [c_p] * 16 + [c_i] * 6 + [c_p]),
     "mlagg_msmm_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 5 + [c_p, c_p]),
     "mlagg_msmm_scan_bwd": (c_i, [c_p] * 17 + [c_i] * 5 + [c_p, c_p]),
+    "mlagg_layernorm_fwd": (c_i, [c_p] * 6 + [c_ll, c_i, c_f, c_i, c_i, c_p]),
+    "mlagg_layernorm_bwd": (c_i, [c_p] * 8 + [c_ll, c_i, c_i, c_i, c_p]),
     "mlagg_dwconv3x3_fwd": (c_i, [c_p] * 4 + [c_i] * 6 + [c_p]),
     "mlagg_dwconv3x3_bwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
     "mlagg_causal_conv1d_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),

@@ -48,6 +48,10 @@ struct PooledAttnParams {
 };
 cudaError_t pooled_attn_dispatch(const PooledAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
 
+cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
+                               const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
+                               int dt_in, int dt_out, bool bwd, cudaStream_t st);
+
 static thread_local char g_last_err[256] = "";
 
 static int fail_cuda(cudaError_t e) {
@@ -366,5 +370,37 @@ extern "C" int mlagg_msmm_scan_bwd(const float *xrow, const float *xcol, const f
     p.dout = dout; p.ckpt_in = ckpt; p.du = du; p.dxdbl_row = dxdbl_row; p.dxdbl_col = dxdbl_col; p.dWdt = dWdt;
     p.dA = dA; p.dD = Ds ? dDs : nullptr; p.dbias = dt_bias ? ddt_bias : nullptr;
     cudaError_t e = scan_bwd_dispatch(p, false, 4, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+static int ln_check(const void *x, const float *w, long long M, int C, int dt_in, int dt_out) {
+    if (!x || !w) return MLAGG_ERR_NULL;
+    if (M <= 0 || C <= 0 || C % 4 != 0 || C > 1024) return MLAGG_ERR_BAD_SHAPE;
+    if ((dt_in != MLAGG_F32 && dt_in != MLAGG_BF16) || (dt_out != MLAGG_F32 && dt_out != MLAGG_BF16)) return MLAGG_ERR_UNSUPPORTED;
+    if (!aligned(x, dt_in == MLAGG_F32 ? 16 : 8) || !aligned(w, 16)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_layernorm_fwd(const void *x, const float *weight, const float *bias, void *y, float *mean,
+                                   float *rstd, long long M, int C, float eps, int dt_in, int dt_out,
+                                   mlagg_stream_t stream) {
+    int rc = ln_check(x, weight, M, C, dt_in, dt_out);
+    if (rc) return rc;
+    if (!y || !mean || !rstd) return MLAGG_ERR_NULL;
+    if (!aligned(y, dt_out == MLAGG_F32 ? 16 : 8) || (bias && !aligned(bias, 16))) return MLAGG_ERR_ALIGN;
+    cudaError_t e = layernorm_dispatch(x, weight, bias, y, mean, rstd, nullptr, nullptr, nullptr, nullptr, M, C, eps,
+                                       dt_in, dt_out, false, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_layernorm_bwd(const void *x, const float *weight, const float *mean, const float *rstd,
+                                   const void *dy, void *dx, float *dweight, float *dbias, long long M, int C,
+                                   int dt_in, int dt_out, mlagg_stream_t stream) {
+    int rc = ln_check(x, weight, M, C, dt_in, dt_out);
+    if (rc) return rc;
+    if (!mean || !rstd || !dy || !dx || !dweight) return MLAGG_ERR_NULL;
+    if (!aligned(dy, dt_out == MLAGG_F32 ? 16 : 8) || !aligned(dx, dt_in == MLAGG_F32 ? 16 : 8)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = layernorm_dispatch(x, weight, nullptr, nullptr, const_cast<float *>(mean), const_cast<float *>(rstd),
+                                       dy, dx, dweight, dbias, M, C, 0.f, dt_in, dt_out, true, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

@@ -1,0 +1,212 @@
+// layernorm.cu -- LayerNorm over the channel dimension of tokens-major activations (rows = tokens), fp32 math with
+// fp32 or bf16 input AND output.  Replaces nn.LayerNorm at reference nnUNetTrainer_MLAgg_2D_dt_MS.py:848,871,887,907
+// (norm1 / norm2 of MLLABlock), :670,723 (pooled-token norm), MambaSkip.py:344,536 (out_norm), :686,690,741,742 (ln_1 /
+// norm2 of VSS_Conv_Block).  Under the reference's autocast, layer_norm runs in fp32: the input is up-cast by a copy
+// kernel, the fp32 result is written, and every consuming Linear down-casts it again with another copy.  Here one
+// kernel reads the activation once in its storage type and writes the consumer's type.  HBM-bound:
+// algorithmic bytes = M*C*(e_in + e_out) + 8*M (mean, rstd saved for the backward pass).
+// One warp per row; a lane owns NV groups of 4 consecutive channels (128-bit fp32 / 64-bit bf16 accesses).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mlagg {
+
+template <typename T>
+__device__ __forceinline__ float4 ln_ld4(const T *p);
+template <>
+__device__ __forceinline__ float4 ln_ld4<float>(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+template <>
+__device__ __forceinline__ float4 ln_ld4<__nv_bfloat16>(const __nv_bfloat16 *p) {
+    const uint2 raw = *reinterpret_cast<const uint2 *>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T>
+__device__ __forceinline__ void ln_st4(T *p, float4 v);
+template <>
+__device__ __forceinline__ void ln_st4<float>(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+template <>
+__device__ __forceinline__ void ln_st4<__nv_bfloat16>(__nv_bfloat16 *p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t *>(&a);
+    raw.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = raw;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename TI, typename TO, int NV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const TI *__restrict__ x, const float *__restrict__ w,
+                                                            const float *__restrict__ b, TO *__restrict__ y,
+                                                            float *__restrict__ mean, float *__restrict__ rstd,
+                                                            long long M, int C, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    float4 wv[NV], bv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        wv[i] = c < C ? __ldg(reinterpret_cast<const float4 *>(w + c)) : make_float4(0, 0, 0, 0);
+        bv[i] = (c < C && b) ? __ldg(reinterpret_cast<const float4 *>(b + c)) : make_float4(0, 0, 0, 0);
+    }
+    const float invC = 1.f / C;
+    for (long long row = warp0; row < M; row += nwarps) {
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            v[i] = c < C ? ln_ld4<TI>(x + row * C + c) : make_float4(0, 0, 0, 0);
+            s += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+        const float mu = warp_sum(s) * invC;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            if (c < C) {
+                const float a0 = v[i].x - mu, a1 = v[i].y - mu, a2 = v[i].z - mu, a3 = v[i].w - mu;
+                q += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+            }
+        }
+        const float rs = rsqrtf(warp_sum(q) * invC + eps);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            if (c < C) {
+                float4 o;
+                o.x = (v[i].x - mu) * rs * wv[i].x + bv[i].x;
+                o.y = (v[i].y - mu) * rs * wv[i].y + bv[i].y;
+                o.z = (v[i].z - mu) * rs * wv[i].z + bv[i].z;
+                o.w = (v[i].w - mu) * rs * wv[i].w + bv[i].w;
+                ln_st4<TO>(y + row * C + c, o);
+            }
+        }
+        if (lane == 0) {
+            mean[row] = mu;
+            rstd[row] = rs;
+        }
+    }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * w;  dw += dy * xhat, db += dy (per-lane partials over the
+// rows this warp visits -> shared memory -> one atomic per channel per block)
+template <typename TI, typename TO, int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI *__restrict__ x, const float *__restrict__ w,
+                                                            const float *__restrict__ mean,
+                                                            const float *__restrict__ rstd, const TO *__restrict__ dy,
+                                                            TI *__restrict__ dx, float *__restrict__ dw,
+                                                            float *__restrict__ db, long long M, int C) {
+    extern __shared__ float red[];  // [2][C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    float4 wv[NV], aw[NV], ab[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        wv[i] = c < C ? __ldg(reinterpret_cast<const float4 *>(w + c)) : make_float4(0, 0, 0, 0);
+        aw[i] = ab[i] = make_float4(0, 0, 0, 0);
+    }
+    const float invC = 1.f / C;
+    for (long long row = warp0; row < M; row += nwarps) {
+        const float mu = mean[row], rs = rstd[row];
+        float4 xh[NV], g[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            if (c < C) {
+                const float4 xv = ln_ld4<TI>(x + row * C + c), gv = ln_ld4<TO>(dy + row * C + c);
+                xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+                aw[i].x += gv.x * xh[i].x; aw[i].y += gv.y * xh[i].y; aw[i].z += gv.z * xh[i].z; aw[i].w += gv.w * xh[i].w;
+                ab[i].x += gv.x; ab[i].y += gv.y; ab[i].z += gv.z; ab[i].w += gv.w;
+                g[i] = make_float4(gv.x * wv[i].x, gv.y * wv[i].y, gv.z * wv[i].z, gv.w * wv[i].w);
+                s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+                s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+            } else {
+                xh[i] = g[i] = make_float4(0, 0, 0, 0);
+            }
+        }
+        const float c1 = warp_sum(s1) * invC, c2 = warp_sum(s2) * invC;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            if (c < C) {
+                float4 o;
+                o.x = rs * (g[i].x - c1 - xh[i].x * c2);
+                o.y = rs * (g[i].y - c1 - xh[i].y * c2);
+                o.z = rs * (g[i].z - c1 - xh[i].z * c2);
+                o.w = rs * (g[i].w - c1 - xh[i].w * c2);
+                ln_st4<TI>(dx + row * C + c, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < C) {
+            atomicAdd(&red[c], aw[i].x); atomicAdd(&red[c + 1], aw[i].y); atomicAdd(&red[c + 2], aw[i].z); atomicAdd(&red[c + 3], aw[i].w);
+            atomicAdd(&red[C + c], ab[i].x); atomicAdd(&red[C + c + 1], ab[i].y); atomicAdd(&red[C + c + 2], ab[i].z); atomicAdd(&red[C + c + 3], ab[i].w);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        atomicAdd(dw + i, red[i]);
+        if (db) atomicAdd(db + i, red[C + i]);
+    }
+}
+
+template <typename TI, typename TO, int NV>
+static cudaError_t ln_launch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
+                             const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps, bool bwd,
+                             cudaStream_t st) {
+    long long blocks = (M + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (!bwd) {
+        layernorm_fwd_kernel<TI, TO, NV><<<(int)blocks, 256, 0, st>>>(static_cast<const TI *>(x), w, b,
+                                                                      static_cast<TO *>(y), mean, rstd, M, C, eps);
+    } else {
+        layernorm_bwd_kernel<TI, TO, NV><<<(int)blocks, 256, 2 * C * sizeof(float), st>>>(
+            static_cast<const TI *>(x), w, mean, rstd, static_cast<const TO *>(dy), static_cast<TI *>(dx), dw, db, M, C);
+    }
+    return cudaGetLastError();
+}
+
+template <typename TI, typename TO>
+static cudaError_t ln_nv(int nv, const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
+                         const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps, bool bwd,
+                         cudaStream_t st) {
+    switch (nv) {
+        case 1: return ln_launch<TI, TO, 1>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+        case 2: return ln_launch<TI, TO, 2>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+        case 3: return ln_launch<TI, TO, 3>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+        case 4: return ln_launch<TI, TO, 4>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+        case 5: case 6: return ln_launch<TI, TO, 6>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+        case 7: case 8: return ln_launch<TI, TO, 8>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// dt_in / dt_out: 0 = fp32, 1 = bf16
+cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
+                               const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
+                               int dt_in, int dt_out, bool bwd, cudaStream_t st) {
+    const int nv = (C / 4 + 31) / 32;
+    using bf = __nv_bfloat16;
+    if (dt_in == 0 && dt_out == 0) return ln_nv<float, float>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+    if (dt_in == 0 && dt_out == 1) return ln_nv<float, bf>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+    if (dt_in == 1 && dt_out == 0) return ln_nv<bf, float>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+    return ln_nv<bf, bf>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+}
+
+}  // namespace mlagg

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import dwconv3x3_tokens
+from .ops import dwconv3x3_tokens, layer_norm_tokens
 from .selective_scan_interface import msmm_scan, selective_scan_fn
 from .thirdparty_shims import DropPath
 
@@ -201,7 +201,7 @@ class SS2D_skip(nn.Module):
             off += h * w
         y = self.forward_core_tokens(torch.cat(parts, dim=1), hw)
         assert y.dtype == torch.float32
-        out = self.out_proj(self.out_norm(y))
+        out = self.out_proj(layer_norm_tokens(y, self.out_norm))
         return self.dropout(out) if self.dropout is not None else out
 
 
@@ -261,8 +261,8 @@ class VSS_Conv_Block(nn.Module):
         hd = self.hidden_dim
         # tokens-major (B, L, hd): NHWC views of the inputs (free when they are channels_last), first hd channels
         m = torch.cat([t.permute(0, 2, 3, 1)[..., :hd].reshape(Bn, L_split[s], hd) for s, t in enumerate(inputs)], dim=1)
-        m = m + self.drop_path(self.self_attention(self.ln_1(m), Bn, H, W, L_split))
-        m = self.norm2(m)
+        m = m + self.drop_path(self.self_attention(layer_norm_tokens(m, self.ln_1), Bn, H, W, L_split))
+        m = layer_norm_tokens(m, self.norm2)
         outs, off = [], 0
         for s, t in enumerate(inputs):
             ms = m[:, off:off + L_split[s]]

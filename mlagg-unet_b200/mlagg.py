@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import dwconv3x3_tokens
+from .ops import dwconv3x3_tokens, layer_norm_tokens
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock
 
 
@@ -115,7 +115,8 @@ class AggregatedAttention(nn.Module):
             # pooled tokens: 1x1 conv == per-token Linear; pooling on the tokens-major image view
             t = F.gelu(F.linear(x, self.sr.weight.view(C, C), self.sr.bias))
             t = self.pool(t.transpose(1, 2).reshape(Bn, C, H, W)).flatten(2).transpose(1, 2)
-            o = att.pooled_diff_attention(q, self.kv(self.norm(t)), lam, self.subln.weight, h, hd, self.scale)
+            o = att.pooled_diff_attention(q, self.kv(layer_norm_tokens(t, self.norm)), lam, self.subln.weight, h, hd,
+                                          self.scale)
         return o + dwconv3x3_tokens(v_local.contiguous(), self.lepe.weight, self.lepe.bias, H, W)
 
 
@@ -167,7 +168,7 @@ class MLLABlock(nn.Module):
     def forward_tokens(self, t, H, W):
         """tokens-major (B, N, C) -> (B, N, C)"""
         shortcut = t
-        t = self.norm1(t)
+        t = layer_norm_tokens(t, self.norm1)
         gate = self.act(self.act_proj(t))
         t = dwconv3x3_tokens(self.in_proj(t), self.dwc.weight, self.dwc.bias, H, W, silu=True)
         if self.sr_ratio == 1:
@@ -176,7 +177,7 @@ class MLLABlock(nn.Module):
             a, b = torch.chunk(t, 2, dim=-1)
             t = torch.cat([self.attn[0](a, H, W), self.attn[1](b, H, W)], dim=-1)
         t = shortcut + self.drop_path(self.out_proj(t * gate))
-        return t + self.drop_path(self.mlp(self.norm2(t)))
+        return t + self.drop_path(self.mlp(layer_norm_tokens(t, self.norm2)))
 
     def forward(self, x):
         H, W = self.input_resolution

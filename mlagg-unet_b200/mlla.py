@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import attention as att
 from .mlagg import Mlp
-from .ops import dwconv3x3_tokens
+from .ops import dwconv3x3_tokens, layer_norm_tokens
 from .thirdparty_shims import DropPath
 
 
@@ -77,13 +77,13 @@ class MLLABlock(nn.Module):
         assert L == H * W, "input feature has wrong size"
         x = x + dwconv3x3_tokens(x.contiguous(), self.cpe1.weight, self.cpe1.bias, H, W)
         shortcut = x
-        t = self.norm1(x)
+        t = layer_norm_tokens(x, self.norm1)
         gate = self.act(self.act_proj(t))
         t = dwconv3x3_tokens(self.in_proj(t), self.dwc.weight, self.dwc.bias, H, W, silu=True)
         t = self.attn(t)
         x = shortcut + self.drop_path(self.out_proj(t.to(gate.dtype) * gate))
         x = x + dwconv3x3_tokens(x.contiguous(), self.cpe2.weight, self.cpe2.bias, H, W)
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        return x + self.drop_path(self.mlp(layer_norm_tokens(x, self.norm2)))
 
     def extra_repr(self):
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "

@@ -101,3 +101,56 @@ def causal_conv1d_fn(x, weight, bias=None, activation=None):
     if activation not in (None, "silu", "swish"):
         raise NotImplementedError("activation must be None, silu, or swish")
     return _CausalConv1d.apply(x, weight, bias, activation is not None)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        if not x.is_cuda:
+            raise _lib.MlaggError("layer_norm_tokens: CUDA tensor required (no CPU fallback in the product path)")
+        C = x.shape[-1]
+        xin = _io(x).contiguous()
+        odt = out_dtype if out_dtype in _DT else torch.float32
+        w32 = weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        M = xin.numel() // C
+        y = torch.empty(xin.shape, device=x.device, dtype=odt)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _lib.timed("layernorm_fwd"):
+            rc = _lib.lib().mlagg_layernorm_fwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), _lib.ptr(mean),
+                                                _lib.ptr(rstd), M, C, float(eps), _DT[xin.dtype], _DT[odt],
+                                                _lib.stream_ptr())
+        _lib.check(rc, "mlagg_layernorm_fwd")
+        ctx.save_for_backward(xin, w32, mean, rstd)
+        ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype, odt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xin, w32, mean, rstd = ctx.saved_tensors
+        xdt, wdt, bdt, odt = ctx.meta
+        C = xin.shape[-1]
+        M = xin.numel() // C
+        dy = dy.to(odt).contiguous()
+        dx = torch.empty_like(xin)
+        dw = torch.zeros(C, device=xin.device, dtype=torch.float32)
+        db = torch.zeros(C, device=xin.device, dtype=torch.float32) if bdt is not None else None
+        with torch.cuda.device(xin.device), _lib.timed("layernorm_bwd"):
+            rc = _lib.lib().mlagg_layernorm_bwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dy),
+                                                _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), M, C, _DT[xin.dtype], _DT[odt],
+                                                _lib.stream_ptr())
+        _lib.check(rc, "mlagg_layernorm_bwd")
+        return dx.to(xdt), dw.to(wdt), None if db is None else db.to(bdt), None, None
+
+
+def layer_norm_tokens(x, norm: torch.nn.LayerNorm, out_dtype=None):
+    """LayerNorm over the last dim with `norm`'s parameters.  out_dtype None -> the dtype the consumer wants: the
+    autocast dtype when autocast is on (the reference's fp32 result is down-cast by every consuming Linear anyway),
+    else x.dtype."""
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    C = x.shape[-1]
+    if C % 4 != 0 or C > 1024 or norm.weight is None:
+        return norm(x)
+    return _LayerNorm.apply(x, norm.weight, norm.bias, norm.eps, out_dtype)

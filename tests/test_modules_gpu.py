@@ -216,3 +216,32 @@ def test_causal_conv1d_matches_oracle(K, silu, L):
     y.backward(dy.cuda())
     for a, r_ in ((xc, xr), (wc, wr), (bc, br)):
         assert rel_err(a.grad.cpu(), r_.grad) < 1e-5
+
+
+@pytest.mark.parametrize("C", [48, 96, 192, 768])
+@pytest.mark.parametrize("din,dout,tol", [(torch.float32, torch.float32, 1e-5), (torch.bfloat16, torch.bfloat16, TOL16),
+                                          (torch.float32, torch.bfloat16, TOL16)])
+def test_layer_norm_tokens_matches_torch(C, din, dout, tol):
+    from mlagg_unet_b200.ops import layer_norm_tokens
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(3, 37, C, generator=g) * 2 + 0.5
+    ln = torch.nn.LayerNorm(C)
+    with torch.no_grad():
+        ln.weight.copy_(torch.randn(C, generator=g))
+        ln.bias.copy_(torch.randn(C, generator=g))
+    xr = x.to(din).double().requires_grad_()
+    ref = torch.nn.functional.layer_norm(xr, (C,), ln.weight.detach().double(), ln.bias.detach().double(), ln.eps)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.to(dout).double())
+    lnc = ln.cuda()
+    xc = x.cuda().to(din).requires_grad_()
+    y = layer_norm_tokens(xc, lnc, out_dtype=dout)
+    assert y.dtype == dout
+    assert rel_err(y.float().cpu(), ref) < tol
+    y.backward(dy.cuda().to(dout))
+    assert rel_err(xc.grad.float().cpu(), xr.grad) < tol
+    wg, bg = torch.autograd.grad(torch.nn.functional.layer_norm(xr.detach(), (C,), w := ln.weight.detach().cpu().double().requires_grad_(),
+                                                                b := ln.bias.detach().cpu().double().requires_grad_(), ln.eps),
+                                 [w, b], dy.to(dout).double())
+    assert rel_err(lnc.weight.grad.cpu(), wg) < 10 * tol
+    assert rel_err(lnc.bias.grad.cpu(), bg) < 10 * tol
