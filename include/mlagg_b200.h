@@ -198,6 +198,30 @@ int mlagg_layernorm_bwd(const void *x, const float *weight, const float *mean, c
                         void *dx, float *dweight, float *dbias, long long M, int C, int dt_in, int dt_out,
                         mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * elu+1 linear attention core of MLLA (the ops BASELINE.json:north_star names).
+ * Replaces the op sequence at nnUNetTrainer_MLLA_UNet.py:234-246 (LinearAttention.forward: elu+1 on q and k,
+ * RoPE.forward :190-195 on both, z = 1/(q . mean_n k + 1e-6), kv = (k_rope^T n^-1/2)(v n^-1/2), q_rope kv z);
+ * the qk projection (:229) and the LePE conv (:250) stay outside (cuBLAS / mlagg_dwconv3x3_*).
+ *   q, k, v, out : tokens-major (batch, N = H*W, heads, head_dim) of `dtype`, row strides ldq, ldk, ldv, ldo in
+ *                  ELEMENTS (q and k are the halves of the qk projection, consumed in place); 16-byte aligned rows
+ *   rope_cs      : (H + W, C/4, 2) fp32, C = heads*head_dim: [cos, sin] of row*theta_i for the H rows, then of
+ *                  col*theta_i for the W columns, theta_i = base^(-i/(C/4)) (the reference's table, :181-187, separable)
+ *   state        : mlagg_linattn_state_bytes(...) bytes; receives S (batch, heads, hd, hd) then kmean (batch, heads, hd),
+ *                  fp32; saved for the backward pass
+ *   head_dim in {8, 16, 32} (MLLA-UNet ships 32, :53-56)
+ * Backward: dout like out (row stride lddo); dq, dk, dv plain stores with row strides lddq, lddk, lddv;
+ *   ws: scratch of mlagg_linattn_state_bytes(...) bytes (dS, dkmean).
+ * ------------------------------------------------------------------------------------------ */
+size_t mlagg_linattn_state_bytes(int batch, int heads, int head_dim);
+int mlagg_linattn_fwd(const void *q, const void *k, const void *v, const float *rope_cs, void *out, float *state,
+                      int batch, int H, int W, int heads, int head_dim, long long ldq, long long ldk, long long ldv,
+                      long long ldo, float eps, int dtype, mlagg_stream_t stream);
+int mlagg_linattn_bwd(const void *q, const void *k, const void *v, const float *rope_cs, const float *state,
+                      const void *dout, void *dq, void *dk, void *dv, float *ws, int batch, int H, int W, int heads,
+                      int head_dim, long long ldq, long long ldk, long long ldv, long long lddo, long long lddq,
+                      long long lddk, long long lddv, float eps, int dtype, mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,10 +7,8 @@
                          INCLUDING flash-attn's second head_dim**-0.5 scale
   linear_attention_core  elu+1 / RoPE / per-head K^T V state / normaliser (nnUNetTrainer_MLLA_UNet.py:234-246)
 
-STATUS (round 1): `local_diff_attention` and `pooled_diff_attention` are fused sm_100a kernels
-(csrc/local_attn.cu, csrc/pooled_attn.cu).  `linear_attention_core` is still a composition of torch CUDA ops
-(cuBLAS batched GEMM + elementwise) written from the math in App. A.5; it is the slot `linattn_state/apply`
- plugs into and DESIGN.md lists it as "not yet native".
+All three are sm_100a kernels behind the C ABI (csrc/local_attn.cu, csrc/pooled_attn.cu, csrc/linattn.cu); the
+torch ops left here are the RoPE module's standalone forward (API compatibility) and the scalar lambda.
 """
 from __future__ import annotations
 
@@ -165,15 +163,83 @@ def rope_apply(x, H, W):
     return torch.stack([re, im], dim=-1).reshape(Bn, N, C)
 
 
+_ROPE_SEP = {}
+
+
+def rope_table_separable(H, W, C, device, base=10000.0):
+    """(H + W, C/4, 2) fp32 [cos, sin]: rows 0..H-1 hold row*theta_i, rows H..H+W-1 hold col*theta_i -- the reference's
+    `rotations` buffer (MLLA_UNet.py:181-187) is exactly the outer arrangement of these two; built on the CPU with the
+    same expressions so the values are bit-identical to that buffer."""
+    key = (H, W, C, str(device), float(base))
+    if key not in _ROPE_SEP:
+        k = C // 4
+        theta = 1 / (base ** (torch.arange(k) / k))
+        ang = torch.cat([torch.arange(H).unsqueeze(-1) * theta, torch.arange(W).unsqueeze(-1) * theta], dim=0)
+        _ROPE_SEP[key] = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(device)
+    return _ROPE_SEP[key]
+
+
+def _rows(t):
+    """tokens-major (B, N, C) view usable by the C ABI: unit channel stride, one uniform row stride over B*N."""
+    if t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1) or (t.stride(1) * t.element_size()) % 16 \
+            or t.data_ptr() % 16:
+        t = t.contiguous()
+    return t
+
+
+class _LinAttn(torch.autograd.Function):
+    """C ABI: mlagg_linattn_fwd / _bwd (csrc/linattn.cu)."""
+
+    @staticmethod
+    def forward(ctx, qk, v, H, W, num_heads):
+        if not qk.is_cuda:
+            raise _lib.MlaggError("linear_attention: CUDA tensors required (no CPU fallback in the product path)")
+        Bn, N, C2 = qk.shape
+        C = C2 // 2
+        hd = C // num_heads
+        assert N == H * W and v.shape == (Bn, N, C) and C % num_heads == 0 and C % 4 == 0
+        dt = qk.dtype if qk.dtype in _DT else torch.float32
+        qk_, v_ = _rows(qk.detach().to(dt)), _rows(v.detach().to(dt))
+        rope = rope_table_separable(H, W, C, qk.device)
+        L = _lib.lib()
+        out = torch.empty(Bn, N, C, device=qk.device, dtype=dt)
+        state = torch.empty(L.mlagg_linattn_state_bytes(Bn, num_heads, hd) // 4, device=qk.device, dtype=torch.float32)
+        es = qk_.element_size()
+        with torch.cuda.device(qk.device), _lib.timed("linattn_fwd", 2):
+            rc = L.mlagg_linattn_fwd(qk_.data_ptr(), qk_.data_ptr() + C * es, v_.data_ptr(), rope.data_ptr(),
+                                     out.data_ptr(), state.data_ptr(), Bn, H, W, num_heads, hd, qk_.stride(1),
+                                     qk_.stride(1), v_.stride(1), C, 1e-6, _DT[dt], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_linattn_fwd")
+        ctx.save_for_backward(qk_, v_, rope, state)
+        ctx.meta = (H, W, num_heads, hd, qk.dtype, v.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qk_, v_, rope, state = ctx.saved_tensors
+        H, W, h, hd, qkdt, vdt = ctx.meta
+        Bn, N, C = v_.shape
+        dt, es = qk_.dtype, qk_.element_size()
+        dout = _rows(dout.to(dt))
+        dqk = torch.empty(Bn, N, 2 * C, device=qk_.device, dtype=dt)
+        dv = torch.empty(Bn, N, C, device=qk_.device, dtype=dt)
+        L = _lib.lib()
+        ws = torch.empty(state.numel(), device=qk_.device, dtype=torch.float32)
+        with torch.cuda.device(qk_.device), _lib.timed("linattn_bwd", 2):
+            rc = L.mlagg_linattn_bwd(qk_.data_ptr(), qk_.data_ptr() + C * es, v_.data_ptr(), rope.data_ptr(),
+                                     state.data_ptr(), dout.data_ptr(), dqk.data_ptr(), dqk.data_ptr() + C * es,
+                                     dv.data_ptr(), ws.data_ptr(), Bn, H, W, h, hd, qk_.stride(1), qk_.stride(1),
+                                     v_.stride(1), dout.stride(1), 2 * C, 2 * C, C, 1e-6, _DT[dt], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_linattn_bwd")
+        return dqk.to(qkdt), dv.to(vdt), None, None, None
+
+
+def linear_attention_qk(qk, v, H, W, num_heads):
+    """qk (B,N,2C) = the raw [q | k] projection, consumed in place; v (B,N,C) -> (B,N,C) in qk's dtype (fp32 math):
+    phi = elu+1, RoPE, per-head state (1/N) sum rope(phi k) (x) v, normaliser 1/(phi q . mean phi k + 1e-6)."""
+    return _LinAttn.apply(qk, v, H, W, num_heads)
+
+
 def linear_attention_core(q, k, v, H, W, num_heads):
-    """q, k (B,N,C) raw projections; v (B,N,C) -> (B,N,C) fp32: phi = elu+1, RoPE, state, normaliser."""
-    Bn, N, C = q.shape
-    hd = C // num_heads
-    q, k = F.elu(q) + 1.0, F.elu(k) + 1.0
-    heads = lambda t: t.reshape(Bn, N, num_heads, hd).transpose(1, 2)
-    qr, kr = heads(rope_apply(q, H, W)), heads(rope_apply(k, H, W))
-    qh, kh, vh = heads(q), heads(k), heads(v)
-    z = 1.0 / (torch.einsum("bhnd,bhd->bhn", qh, kh.mean(dim=2)) + 1e-6)
-    state = torch.einsum("bhnd,bhne->bhde", kr * N ** -0.5, (vh * N ** -0.5).to(kr.dtype))
-    o = torch.einsum("bhnd,bhde->bhne", qr, state) * z[..., None]
-    return o.transpose(1, 2).reshape(Bn, N, C)
+    """Same op with q and k given separately (B,N,C each)."""
+    return _LinAttn.apply(torch.cat([q, k], dim=-1), v, H, W, num_heads)

@@ -48,6 +48,18 @@ struct PooledAttnParams {
 };
 cudaError_t pooled_attn_dispatch(const PooledAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
 
+struct LinAttnParams {
+    const void *q, *k, *v, *dout;
+    void *out, *dq, *dk, *dv;
+    float *S, *kmean, *dS, *dkm;
+    const float *rope;
+    long long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+    int Bn, H, W, h, chunk;
+    float eps;
+};
+bool linattn_hd_supported(int hd);
+cudaError_t linattn_dispatch(const LinAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
+
 cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                                const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
                                int dt_in, int dt_out, bool bwd, cudaStream_t st);
@@ -402,5 +414,66 @@ extern "C" int mlagg_layernorm_bwd(const void *x, const float *weight, const flo
     if (!aligned(dy, dt_out == MLAGG_F32 ? 16 : 8) || !aligned(dx, dt_in == MLAGG_F32 ? 16 : 8)) return MLAGG_ERR_ALIGN;
     cudaError_t e = layernorm_dispatch(x, weight, nullptr, nullptr, const_cast<float *>(mean), const_cast<float *>(rstd),
                                        dy, dx, dweight, dbias, M, C, 0.f, dt_in, dt_out, true, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+// ------------------------------------------------------------------------------------------------ linear attention
+extern "C" size_t mlagg_linattn_state_bytes(int batch, int heads, int head_dim) {
+    if (batch <= 0 || heads <= 0 || head_dim <= 0) return 0;
+    return (size_t)batch * heads * (head_dim * head_dim + head_dim) * sizeof(float);
+}
+
+static int linattn_check(int batch, int H, int W, int heads, int head_dim, int dtype, const long long *lds, int nld,
+                         const void *const *ptrs, int nptr) {
+    for (int i = 0; i < nptr; ++i)
+        if (!ptrs[i]) return MLAGG_ERR_NULL;
+    if (batch <= 0 || H <= 0 || W <= 0 || heads <= 0 || batch > 65535 || heads > 65535) return MLAGG_ERR_BAD_SHAPE;
+    if (!linattn_hd_supported(head_dim) || (dtype != MLAGG_F32 && dtype != MLAGG_BF16)) return MLAGG_ERR_UNSUPPORTED;
+    if ((heads * head_dim) % 4 != 0) return MLAGG_ERR_BAD_SHAPE;
+    const size_t es = dtype == MLAGG_F32 ? 4 : 2;
+    for (int i = 0; i < nld; ++i)
+        if (lds[i] < (long long)heads * head_dim || (lds[i] * es) % 16 != 0) return MLAGG_ERR_ALIGN;
+    for (int i = 0; i < nptr; ++i)
+        if (!aligned(ptrs[i], 16)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_linattn_fwd(const void *q, const void *k, const void *v, const float *rope_cs, void *out,
+                                 float *state, int batch, int H, int W, int heads, int head_dim, long long ldq,
+                                 long long ldk, long long ldv, long long ldo, float eps, int dtype,
+                                 mlagg_stream_t stream) {
+    const long long lds[] = {ldq, ldk, ldv, ldo};
+    const void *ptrs[] = {q, k, v, rope_cs, out, state};
+    int rc = linattn_check(batch, H, W, heads, head_dim, dtype, lds, 4, ptrs, 6);
+    if (rc) return rc;
+    LinAttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = q; p.k = k; p.v = v; p.rope = rope_cs; p.out = out;
+    p.S = state; p.kmean = state + (size_t)batch * heads * head_dim * head_dim;
+    p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+    p.Bn = batch; p.H = H; p.W = W; p.h = heads; p.eps = eps;
+    cudaError_t e = cudaMemsetAsync(state, 0, mlagg_linattn_state_bytes(batch, heads, head_dim), (cudaStream_t)stream);
+    if (e == cudaSuccess) e = linattn_dispatch(p, head_dim, dtype, 0, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_linattn_bwd(const void *q, const void *k, const void *v, const float *rope_cs, const float *state,
+                                 const void *dout, void *dq, void *dk, void *dv, float *ws, int batch, int H, int W,
+                                 int heads, int head_dim, long long ldq, long long ldk, long long ldv, long long lddo,
+                                 long long lddq, long long lddk, long long lddv, float eps, int dtype,
+                                 mlagg_stream_t stream) {
+    const long long lds[] = {ldq, ldk, ldv, lddo, lddq, lddk, lddv};
+    const void *ptrs[] = {q, k, v, rope_cs, state, dout, dq, dk, dv, ws};
+    int rc = linattn_check(batch, H, W, heads, head_dim, dtype, lds, 7, ptrs, 10);
+    if (rc) return rc;
+    LinAttnParams p;
+    memset(&p, 0, sizeof(p));
+    p.q = q; p.k = k; p.v = v; p.rope = rope_cs; p.dout = dout; p.dq = dq; p.dk = dk; p.dv = dv;
+    p.S = const_cast<float *>(state); p.kmean = p.S + (size_t)batch * heads * head_dim * head_dim;
+    p.dS = ws; p.dkm = ws + (size_t)batch * heads * head_dim * head_dim;
+    p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.lddo = lddo; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+    p.Bn = batch; p.H = H; p.W = W; p.h = heads; p.eps = eps;
+    cudaError_t e = cudaMemsetAsync(ws, 0, mlagg_linattn_state_bytes(batch, heads, head_dim), (cudaStream_t)stream);
+    if (e == cudaSuccess) e = linattn_dispatch(p, head_dim, dtype, 1, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

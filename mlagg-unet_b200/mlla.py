@@ -45,8 +45,7 @@ class LinearAttention(nn.Module):
     def forward(self, x):
         """x (B, N, C) -> (B, N, C)"""
         H, W = self.input_resolution
-        q, k = self.qk(x).chunk(2, dim=-1)
-        o = att.linear_attention_core(q, k, x, H, W, self.num_heads)
+        o = att.linear_attention_qk(self.qk(x), x, H, W, self.num_heads)
         return o + dwconv3x3_tokens(x.contiguous(), self.lepe.weight, self.lepe.bias, H, W)
 
     def extra_repr(self):

@@ -42,20 +42,27 @@ def rope(x, H, W):
     return torch.stack([re, im], dim=-1).reshape(Bn, Ntok, C)
 
 
-def linear_attention_forward(p, x, H, W, num_heads, prefix=""):
-    """x (B,N,C) -> (B,N,C): q,k = W_qk x; v = x; elu+1; RoPE; per-head state; normaliser; + LePE(v)."""
-    g = lambda k: p[prefix + k]
-    Bn, Ntok, C = x.shape
+def linear_attention_core(q, k, v, H, W, num_heads):
+    """q, k raw projections, v: (B,N,C) -> (B,N,C).  nnUNetTrainer_MLLA_UNet.py:234-246: elu+1, RoPE on q and k,
+    z = 1/(q . mean_n k + 1e-6), kv = (k_rope^T n^-1/2)(v n^-1/2), out = q_rope kv z.  Runs in the input dtype
+    (fp64 inputs give the arbiter used by the GPU parity tests)."""
+    Bn, Ntok, C = q.shape
     hd = C // num_heads
-    q, k = F.linear(x, g("qk.weight"), g("qk.bias")).chunk(2, dim=-1)
     q, k = F.elu(q) + 1.0, F.elu(k) + 1.0
     heads = lambda t: t.reshape(Bn, Ntok, num_heads, hd).transpose(1, 2)  # (B,h,N,hd)
     qr, kr = heads(rope(q, H, W)), heads(rope(k, H, W))
-    qh, kh, vh = heads(q), heads(k), heads(x)
+    qh, kh, vh = heads(q), heads(k), heads(v)
     z = 1.0 / (torch.einsum("bhnd,bhd->bhn", qh, kh.mean(dim=2)) + 1e-6)
     state = torch.einsum("bhnd,bhne->bhde", kr * Ntok ** -0.5, vh * Ntok ** -0.5)
     o = torch.einsum("bhnd,bhde->bhne", qr, state) * z[..., None]
-    o = o.transpose(1, 2).reshape(Bn, Ntok, C)
+    return o.transpose(1, 2).reshape(Bn, Ntok, C)
+
+
+def linear_attention_forward(p, x, H, W, num_heads, prefix=""):
+    """x (B,N,C) -> (B,N,C): q,k = W_qk x; v = x; elu+1; RoPE; per-head state; normaliser; + LePE(v)."""
+    g = lambda k: p[prefix + k]
+    q, k = F.linear(x, g("qk.weight"), g("qk.bias")).chunk(2, dim=-1)
+    o = linear_attention_core(q, k, x, H, W, num_heads)
     return o + dwconv3x3_tokens(x, g("lepe.weight"), g("lepe.bias"), H, W)
 
 
