@@ -5,9 +5,9 @@
 //   helper warp h : streams its 8 channels' u / delta rows and the B / C rows {h, h+4, h+8, h+12} from HBM with
 //                   coalesced loads that are issued one 64-step tile AHEAD and parked in registers; then runs
 //                   softplus and writes the tile into shared memory in the layout the scan warps consume --
-//                        pk[row][t] = (delta, delta, delta*u, delta*u)      two ready-made f32x2 pairs
-//                        BT[q][t]   = (B[q][t], B[q+4][t], B[q+8][t], B[q+12][t]),   CT likewise
-//                        yt[row][t] = D[row] * u[row][t]
+//                        pk[t][row]  = (delta, delta, delta*u, delta*u)      two ready-made f32x2 pairs
+//                        bc[t][q]    = (B[q][t], B[q+4][t], B[q+8][t], B[q+12][t]),   bc[t][4+q] likewise for C
+//                        yt[row][t]  = D[row] * u[row][t]
 //                   and, one tile later, writes the finished yt rows back to HBM (coalesced).
 //   scan warp w   : 8 channels x 4 lanes; lane (r, q) owns states q, q+4, q+8, q+12 of channel r and walks time
 //                   in order with the state in registers.  Per step and lane: 3 LDS.128, 4 MUFU.EX2 and 8 packed
@@ -23,11 +23,17 @@
 
 namespace mlagg {
 
-constexpr int kPk = kTT + 5;  // float4 per packed row: 69*16 B = 80 (mod 128) -> 8 rows hit 8 distinct 16 B bank groups; tail reads
+// Operand tiles are TIME-major: one 128-byte line per step holds the eight 16-byte chunks a scan warp reads in that
+// step (pk: one chunk per channel; bc: B chunks q = 0..3 then C chunks q = 0..3).  Measured on B200
+// (tools/micro/smem_bench.cu): an LDS.128 whose 32 lanes fall into ONE line costs ~3.3 cycles of the shared-memory
+// pipe however the lanes share chunks, while 8 (4) chunks in 8 (4) different lines cost 8 (5.1) -- the [row][t] layout
+// of the previous version spent 73 of its ~80 cycles per step there.  Chunk c of step t sits at c ^ (t & 7), so the
+// helper warps' stores (lane = step, fixed chunk) are conflict-free as well.
+constexpr int kTS = kTT + 4;  // lines per tile: 64 steps + read-ahead padding of the 3-deep software pipeline
 
 struct FwdCfg {
     static constexpr int W = 4, R = 32, SP = 3;
-    static constexpr size_t bytes = (size_t)SP * R * kPk * 16 + 2 * (size_t)SP * 4 * kPk * 16 +
+    static constexpr size_t bytes = (size_t)SP * W * kTS * 128 + (size_t)SP * kTS * 128 +
                                     (size_t)SP * R * kRowF * 4 + 2 * R * 4 + 64 + 2 * SP * 8 + 16;
 };
 
@@ -42,10 +48,9 @@ template <bool kFused>
 __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
     constexpr int W = FwdCfg::W, R = FwdCfg::R, SP = FwdCfg::SP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4 *pk = reinterpret_cast<float4 *>(smem_raw);         // [SP][R][kPk]
-    float4 *BT = pk + SP * R * kPk;                            // [SP][4][kPk]
-    float4 *CT = BT + SP * 4 * kPk;                            // [SP][4][kPk]
-    float *yt = reinterpret_cast<float *>(CT + SP * 4 * kPk);  // [SP][R][kRowF]
+    float4 *pk = reinterpret_cast<float4 *>(smem_raw);         // [SP][W][kTS][8 chunks]
+    float4 *bc = pk + SP * W * kTS * 8;                        // [SP][kTS][8 chunks]
+    float *yt = reinterpret_cast<float *>(bc + SP * kTS * 8);  // [SP][R][kRowF]
     float *bias_s = yt + SP * R * kRowF;                       // [R]
     float *D_s = bias_s + R;                                   // [R]
     uint64_t *ready = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(D_s + R + 16) + 7) & ~uintptr_t(7));
@@ -133,26 +138,41 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
                 }
             }
         };
-        auto write_out = [&](int c) {  // yt rows of tile c -> global, coalesced
+        // per-row constants in registers (shared-memory reads here were dependent-load stalls on the helper's path)
+        float bias_r[8], D_r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            bias_r[i] = (i < myrows && p.bias) ? p.bias[row0 + 8 * h + i] : 0.f;
+            D_r[i] = (i < myrows && p.D) ? p.D[row0 + 8 * h + i] : 0.f;
+        }
+        auto write_out = [&](int c) {  // yt rows of tile c -> global, coalesced; all loads first, then all stores
             const int sp = c % SP, t0 = c * kTT;
             const float *ys = yt + (sp * R + 8 * h) * kRowF;
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = ys[(i >> 1) * kRowF + lane + 32 * (i & 1)];
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                const int tl = lane + 32 * hf, t = t0 + tl;
+                const int t = t0 + lane + 32 * hf;
                 if (t < L) {
                     const int tm = mirrored ? mirror_pos(p, t) : t;
 #pragma unroll
                     for (int rw = 0; rw < 8; ++rw)
-                        if (rw < myrows) outb[(size_t)rw * L + tm] = ys[rw * kRowF + tl];
+                        if (rw < myrows) outb[(size_t)rw * L + tm] = v[2 * rw + hf];
                 }
             }
         };
 
+        // The helper runs up to SP - 1 tiles ahead of the scan warps: tile c is produced as soon as the scan warps
+        // have released its ring slot (tile c - SP), whose finished y rows are written out first.
         fetch(0);
         for (int c = 0; c < ntiles; ++c) {
             const int sp = c % SP;
-            if (c >= SP) mbar_wait(&sdone[sp], ((c / SP) & 1) ^ 1);   // scan warps are done with tile c - SP
-            float4 *pks = pk + (sp * R + 8 * h) * kPk;
+            if (c >= SP) {
+                mbar_wait(&sdone[sp], ((c / SP) & 1) ^ 1);   // scan warps are done with tile c - SP
+                write_out(c - SP);
+            }
+            float4 *pks = pk + (sp * W + h) * kTS * 8;             // feeds scan warp h (same 8 channels)
             float *ys = yt + (sp * R + 8 * h) * kRowF;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -165,30 +185,29 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
                 } else {
                     draw = dr[i];
                 }
-                float dl = draw + bias_s[8 * h + rr];
+                float dl = draw + bias_r[rr];
                 if (p.softplus) dl = softplus_fast(dl);
                 const float du = dl * ur[i];
-                pks[rr * kPk + tl] = make_float4(dl, dl, du, du);
-                ys[rr * kRowF + tl] = D_s[8 * h + rr] * ur[i];
+                pks[tl * 8 + (rr ^ (tl & 7))] = make_float4(dl, dl, du, du);
+                ys[rr * kRowF + tl] = D_r[rr] * ur[i];
             }
             {
-                float4 *bt = BT + (sp * 4 + h) * kPk, *ct = CT + (sp * 4 + h) * kPk;
+                float4 *bcs = bc + sp * kTS * 8;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    bt[lane + 32 * k] = make_float4(Br[k], Br[2 + k], Br[4 + k], Br[6 + k]);
-                    ct[lane + 32 * k] = make_float4(Cr[k], Cr[2 + k], Cr[4 + k], Cr[6 + k]);
+                    const int tl = lane + 32 * k;
+                    bcs[tl * 8 + (h ^ (tl & 7))] = make_float4(Br[k], Br[2 + k], Br[4 + k], Br[6 + k]);
+                    bcs[tl * 8 + ((4 + h) ^ (tl & 7))] = make_float4(Cr[k], Cr[2 + k], Cr[4 + k], Cr[6 + k]);
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[sp]);
-            if (c + 1 < ntiles) fetch(c + 1);   // lands while this warp waits for the scan warps below
-            if (c >= 1) {
-                mbar_wait(&sdone[(c - 1) % SP], ((c - 1) / SP) & 1);
-                write_out(c - 1);
-            }
+            if (c + 1 < ntiles) fetch(c + 1);   // in flight while this warp waits for a free slot / writes y out
         }
-        mbar_wait(&sdone[(ntiles - 1) % SP], ((ntiles - 1) / SP) & 1);
-        write_out(ntiles - 1);
+        for (int c = max(0, ntiles - SP); c < ntiles; ++c) {
+            mbar_wait(&sdone[c % SP], (c / SP) & 1);
+            write_out(c);
+        }
         return;
     }
 
@@ -211,9 +230,12 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
         mbar_wait(&ready[sp], (c / SP) & 1);
         const int t0 = c * kTT;
         const int nvalid = min(kTT, L - t0);
-        const float4 *pkr = pk + (sp * R + rl) * kPk;
-        const float4 *btq = BT + (sp * 4 + q) * kPk;
-        const float4 *ctq = CT + (sp * 4 + q) * kPk;
+        const float4 *pkw = pk + (sp * W + warp) * kTS * 8;
+        const float4 *bcw = bc + sp * kTS * 8;
+        // operands of tile step t (t & 7 is a compile-time constant wherever this is used)
+        auto ldP = [&](int t) { return pkw[t * 8 + (r ^ (t & 7))]; };
+        auto ldB = [&](int t) { return bcw[t * 8 + (q ^ (t & 7))]; };
+        auto ldC = [&](int t) { return bcw[t * 8 + ((4 + q) ^ (t & 7))]; };
         float *yr = yt + (sp * R + rl) * kRowF;
 
         auto reduce_store = [&](const float(&y)[16], int tb) {
@@ -232,9 +254,9 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
 
         // 3-deep software pipeline over steps: operands of step t+3 loaded, exponentials of step t+2 issued, FMA chain
         // of step t executed.  Reads run up to 3 steps past the tile (row padding: zeros / stale, never used).
-        float4 P0 = pkr[0], B0 = btq[0], C0 = ctq[0];
-        float4 P1 = pkr[1], B1 = btq[1], C1 = ctq[1];
-        float4 P2 = pkr[2], B2 = btq[2], C2 = ctq[2];
+        float4 P0 = ldP(0), B0 = ldB(0), C0 = ldC(0);
+        float4 P1 = ldP(1), B1 = ldB(1), C1 = ldC(1);
+        float4 P2 = ldP(2), B2 = ldB(2), C2 = ldC(2);
         float2 ea01, ea23, eb01, eb23;   // exponentials of step t (ea) and t+1 (eb)
         {
             const float2 x01 = __fmul2_rn(f2(P0.x, P0.y), A01), x23 = __fmul2_rn(f2(P0.x, P0.y), A23);
@@ -250,7 +272,7 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
                 constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float4 P3 = pkr[tb + i + 3], B3 = btq[tb + i + 3], C3 = ctq[tb + i + 3];
+                    const float4 P3 = ldP(tb + i + 3), B3 = ldB(tb + i + 3), C3 = ldC(tb + i + 3);
                     const float2 x01 = __fmul2_rn(f2(P2.x, P2.y), A01), x23 = __fmul2_rn(f2(P2.x, P2.y), A23);
                     const float2 ec01 = f2(ex2_approx(x01.x), ex2_approx(x01.y));
                     const float2 ec23 = f2(ex2_approx(x23.x), ex2_approx(x23.y));

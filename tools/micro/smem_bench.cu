@@ -13,7 +13,14 @@ __global__ void k(float *out, long long *cyc, int iters) {
     else if (PAT == 2) idx = q * 68 * 4;         // by q: 4 distinct, interleaved lanes (BT pattern)
     else if (PAT == 3) idx = lane * VEC;         // all distinct, contiguous
     else if (PAT == 4) idx = r * 68;             // by row, 4B-row-stride layout (v1 delta pattern)
-    else idx = (lane >> 3) * 68 * 4;             // by quarter-warp: 4 distinct, 8 contiguous lanes share
+    else if (PAT == 5) idx = (lane >> 3) * 68 * 4;  // by quarter-warp: 4 distinct, 8 contiguous lanes share
+    else if (PAT == 6) idx = (lane >> 1) * VEC;  // 16 distinct contiguous, lane pairs share
+    else if (PAT == 7) idx = (lane & 3) * VEC;   // 4 distinct contiguous, interleaved share
+    else if (PAT == 8) idx = (lane >> 2) * VEC;  // 8 distinct contiguous, 4 contiguous lanes share
+    else if (PAT == 9) idx = (lane & 7) * VEC;   // 8 distinct contiguous; every quarter-warp reads the same 8
+    else if (PAT == 10) idx = (lane >> 3) * VEC; // 4 distinct contiguous, 8 contiguous lanes share
+    else if (PAT == 11) idx = (lane >> 4) * VEC; // 2 distinct, half-warps share
+    else idx = (lane & 15) * VEC;                // 16 distinct contiguous; both half-warps read the same 16
     float acc = 0.f;
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
@@ -48,6 +55,13 @@ int main() {
     run<4, 0>("uniform", out, cyc); run<4, 1>("by row (4 contiguous lanes share)", out, cyc);
     run<4, 2>("by q (interleaved share)", out, cyc); run<4, 3>("all distinct contiguous", out, cyc);
     run<4, 5>("by quarter-warp", out, cyc);
+    run<4, 6>("16 distinct contig, pairs share", out, cyc); run<4, 7>("4 distinct contig, interleaved", out, cyc);
+    run<4, 8>("8 distinct contig, 4 lanes share", out, cyc); run<4, 9>("8 distinct contig, per quarter", out, cyc);
+    run<4, 10>("4 distinct contig, 8 lanes share", out, cyc); run<4, 11>("2 distinct, half-warps", out, cyc);
+    run<4, 12>("16 distinct contig, per half", out, cyc);
+    run<2, 6>("16 distinct contig, pairs share", out, cyc); run<2, 9>("8 distinct contig, per quarter", out, cyc);
+    run<2, 10>("4 distinct contig, 8 lanes share", out, cyc); run<2, 12>("16 distinct contig, per half", out, cyc);
+    run<2, 8>("8 distinct contig, 4 lanes share", out, cyc);
     run<2, 0>("uniform", out, cyc); run<2, 1>("by row", out, cyc); run<2, 2>("by q", out, cyc); run<2, 3>("all distinct", out, cyc);
     run<1, 0>("uniform", out, cyc); run<1, 4>("by row", out, cyc); run<1, 2>("by q", out, cyc); run<1, 3>("all distinct", out, cyc);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
