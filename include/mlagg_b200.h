@@ -222,6 +222,14 @@ int mlagg_linattn_bwd(const void *q, const void *k, const void *v, const float *
                       int head_dim, long long ldq, long long ldk, long long ldv, long long lddo, long long lddq,
                       long long lddk, long long lddv, float eps, int dtype, mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Column sums of a tokens-major matrix: out[c] += sum_m x[m * ld + c]  (out fp32, ACCUMULATED INTO: zero-fill first).
+ * Replaces autograd's `grad_output.sum(0)` for the bias gradient of the nn.Linear layers of the hot path
+ *   (nnUNetTrainer_MLAgg_2D_dt_MS.py:849-850, :868, :180-186, :673-674; variants/mamba/MambaSkip.py:567,570).
+ *   x (M, C) of `dtype`, row stride ld >= C in ELEMENTS.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_colsum(const void *x, float *out, long long M, int C, long long ld, int dtype, mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

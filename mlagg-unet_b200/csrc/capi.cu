@@ -60,6 +60,8 @@ struct LinAttnParams {
 bool linattn_hd_supported(int hd);
 cudaError_t linattn_dispatch(const LinAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
 
+cudaError_t colsum_dispatch(const void *x, float *out, long long M, int C, long long ld, int dtype, cudaStream_t st);
+
 cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                                const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
                                int dt_in, int dt_out, bool bwd, cudaStream_t st);
@@ -475,5 +477,16 @@ extern "C" int mlagg_linattn_bwd(const void *q, const void *k, const void *v, co
     p.Bn = batch; p.H = H; p.W = W; p.h = heads; p.eps = eps;
     cudaError_t e = cudaMemsetAsync(ws, 0, mlagg_linattn_state_bytes(batch, heads, head_dim), (cudaStream_t)stream);
     if (e == cudaSuccess) e = linattn_dispatch(p, head_dim, dtype, 1, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+extern "C" int mlagg_colsum(const void *x, float *out, long long M, int C, long long ld, int dtype,
+                            mlagg_stream_t stream) {
+    if (!x || !out) return MLAGG_ERR_NULL;
+    if (M <= 0 || C <= 0 || ld < C) return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    if (!aligned(x, dtype == MLAGG_F32 ? 4 : 2) || !aligned(out, 4)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = colsum_dispatch(x, out, M, C, ld, dtype, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import dwconv3x3_tokens, layer_norm_tokens
+from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
 from .selective_scan_interface import msmm_scan, selective_scan_fn
 from .thirdparty_shims import DropPath
 
@@ -226,12 +226,12 @@ class ConvolutionalGLU(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, H, W):
-        a, v = self.fc1(x).chunk(2, dim=-1)
+        a, v = linear_tokens(x, self.fc1).chunk(2, dim=-1)
         if isinstance(self.act, nn.SiLU):
             a = self.dwconv(a, H, W, silu=True)  # SiLU fused into the stencil
         else:
             a = self.act(self.dwconv(a, H, W))
-        return self.drop(self.fc2(self.drop(a * v)))
+        return self.drop(linear_tokens(self.drop(a * v), self.fc2))
 
 
 class VSS_Conv_Block(nn.Module):

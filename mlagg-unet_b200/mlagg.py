@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import dwconv3x3_tokens, layer_norm_tokens
+from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock
 
 
@@ -35,7 +35,7 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        return self.drop(linear_tokens(self.drop(self.act(linear_tokens(x, self.fc1))), self.fc2))
 
 
 class RMSNorm(nn.Module):
@@ -105,8 +105,8 @@ class AggregatedAttention(nn.Module):
         Bn, N, C = x.shape
         assert N == H * W
         h, hd = self.num_heads, self.head_dim
-        q = self.q(x)
-        kv = self.kv(x)
+        q = linear_tokens(x, self.q)
+        kv = linear_tokens(x, self.kv)
         v_local = kv[..., C:]
         lam = att.diff_lambda(self.lambda_q1, self.lambda_k1, self.lambda_q2, self.lambda_k2)
         if self.local:
@@ -115,8 +115,8 @@ class AggregatedAttention(nn.Module):
             # pooled tokens: 1x1 conv == per-token Linear; pooling on the tokens-major image view
             t = F.gelu(F.linear(x, self.sr.weight.view(C, C), self.sr.bias))
             t = self.pool(t.transpose(1, 2).reshape(Bn, C, H, W)).flatten(2).transpose(1, 2)
-            o = att.pooled_diff_attention(q, self.kv(layer_norm_tokens(t, self.norm)), lam, self.subln.weight, h, hd,
-                                          self.scale)
+            o = att.pooled_diff_attention(q, linear_tokens(layer_norm_tokens(t, self.norm), self.kv), lam,
+                                          self.subln.weight, h, hd, self.scale)
         return o + dwconv3x3_tokens(v_local.contiguous(), self.lepe.weight, self.lepe.bias, H, W)
 
 
@@ -169,14 +169,14 @@ class MLLABlock(nn.Module):
         """tokens-major (B, N, C) -> (B, N, C)"""
         shortcut = t
         t = layer_norm_tokens(t, self.norm1)
-        gate = self.act(self.act_proj(t))
-        t = dwconv3x3_tokens(self.in_proj(t), self.dwc.weight, self.dwc.bias, H, W, silu=True)
+        gate = self.act(linear_tokens(t, self.act_proj))
+        t = dwconv3x3_tokens(linear_tokens(t, self.in_proj), self.dwc.weight, self.dwc.bias, H, W, silu=True)
         if self.sr_ratio == 1:
             t = self.attn(t, H, W)
         else:
             a, b = torch.chunk(t, 2, dim=-1)
             t = torch.cat([self.attn[0](a, H, W), self.attn[1](b, H, W)], dim=-1)
-        t = shortcut + self.drop_path(self.out_proj(t * gate))
+        t = shortcut + self.drop_path(linear_tokens(t * gate, self.out_proj))
         return t + self.drop_path(self.mlp(layer_norm_tokens(t, self.norm2)))
 
     def forward(self, x):

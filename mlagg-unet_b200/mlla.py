@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import attention as att
 from .mlagg import Mlp
-from .ops import dwconv3x3_tokens, layer_norm_tokens
+from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
 from .thirdparty_shims import DropPath
 
 
@@ -45,7 +45,7 @@ class LinearAttention(nn.Module):
     def forward(self, x):
         """x (B, N, C) -> (B, N, C)"""
         H, W = self.input_resolution
-        o = att.linear_attention_qk(self.qk(x), x, H, W, self.num_heads)
+        o = att.linear_attention_qk(linear_tokens(x, self.qk), x, H, W, self.num_heads)
         return o + dwconv3x3_tokens(x.contiguous(), self.lepe.weight, self.lepe.bias, H, W)
 
     def extra_repr(self):
@@ -77,10 +77,10 @@ class MLLABlock(nn.Module):
         x = x + dwconv3x3_tokens(x.contiguous(), self.cpe1.weight, self.cpe1.bias, H, W)
         shortcut = x
         t = layer_norm_tokens(x, self.norm1)
-        gate = self.act(self.act_proj(t))
-        t = dwconv3x3_tokens(self.in_proj(t), self.dwc.weight, self.dwc.bias, H, W, silu=True)
+        gate = self.act(linear_tokens(t, self.act_proj))
+        t = dwconv3x3_tokens(linear_tokens(t, self.in_proj), self.dwc.weight, self.dwc.bias, H, W, silu=True)
         t = self.attn(t)
-        x = shortcut + self.drop_path(self.out_proj(t.to(gate.dtype) * gate))
+        x = shortcut + self.drop_path(linear_tokens(t.to(gate.dtype) * gate, self.out_proj))
         x = x + dwconv3x3_tokens(x.contiguous(), self.cpe2.weight, self.cpe2.bias, H, W)
         return x + self.drop_path(self.mlp(layer_norm_tokens(x, self.norm2)))
 

@@ -154,3 +154,52 @@ def layer_norm_tokens(x, norm: torch.nn.LayerNorm, out_dtype=None):
     if C % 4 != 0 or C > 1024 or norm.weight is None:
         return norm(x)
     return _LayerNorm.apply(x, norm.weight, norm.bias, norm.eps, out_dtype)
+
+
+def colsum(x2d):
+    """fp32 column sums of a (M, C) fp32 / bf16 matrix with unit column stride (C ABI: mlagg_colsum)."""
+    if not x2d.is_cuda:
+        raise _lib.MlaggError("colsum: CUDA tensor required (no CPU fallback in the product path)")
+    if x2d.dtype not in _DT or x2d.stride(1) != 1:
+        x2d = _io(x2d).contiguous()
+    M, C = x2d.shape
+    out = torch.zeros(C, device=x2d.device, dtype=torch.float32)
+    with torch.cuda.device(x2d.device), _lib.timed("colsum"):
+        rc = _lib.lib().mlagg_colsum(_lib.ptr(x2d), _lib.ptr(out), M, C, x2d.stride(0), _DT[x2d.dtype], _lib.stream_ptr())
+    _lib.check(rc, "mlagg_colsum")
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b with the GEMMs on cuBLAS (library GEMMs) in the autocast dtype and the bias
+    gradient as ONE HBM-bound column-sum pass (csrc/reduce.cu) instead of autograd's generic reduction."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        xc, wc = x.to(cdt), weight.to(cdt)
+        with torch.autocast("cuda", enabled=False):
+            y = torch.nn.functional.linear(xc, wc, None if bias is None else bias.to(cdt))
+        ctx.save_for_backward(xc, wc)
+        ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc = ctx.saved_tensors
+        xdt, wdt, bdt = ctx.meta
+        Cout, Cin = wc.shape
+        dy2 = dy.to(wc.dtype).reshape(-1, Cout)
+        x2 = xc.reshape(-1, Cin)
+        with torch.autocast("cuda", enabled=False):
+            dx = torch.mm(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
+            dw = torch.mm(dy2.t(), x2).to(wdt) if ctx.needs_input_grad[1] else None
+        db = colsum(dy2).to(bdt) if (bdt is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
+def linear_tokens(x, lin: torch.nn.Linear):
+    """`lin(x)` for tokens-major activations; same numbers as nn.Linear under the surrounding autocast state."""
+    if not x.is_cuda:
+        raise _lib.MlaggError("linear_tokens: CUDA tensor required (no CPU fallback in the product path)")
+    return _Linear.apply(x, lin.weight, lin.bias)

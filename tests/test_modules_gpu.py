@@ -306,3 +306,37 @@ def test_linear_attention_rejects_unsupported():
         att.linear_attention_qk(torch.randn(1, 4, 2 * 24, device="cuda"), torch.randn(1, 4, 24, device="cuda"), 2, 2, 2)  # hd 12
     with pytest.raises(_lib.MlaggError):
         att.linear_attention_qk(torch.randn(1, 4, 64), torch.randn(1, 4, 32), 2, 2, 2)  # CPU tensors
+
+
+def test_colsum_and_linear_tokens_match_torch():
+    """mlagg_colsum against a float64 column sum (ragged M, strided rows, C % 4 != 0 scalar path, bf16); linear_tokens
+    against nn.Linear forward/backward in fp32 and under bf16 autocast."""
+    from mlagg_unet_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for M, C, dt in [(1000, 96, torch.float32), (33, 768, torch.float32), (4097, 50, torch.float32),
+                     (2500, 192, torch.bfloat16), (7, 4, torch.bfloat16)]:
+        x = torch.randn(M, C, generator=g).to(dt)
+        ref = x.double().sum(0)
+        assert rel_err(ops.colsum(x.cuda()).cpu().double(), ref) < (TOL32 if dt == torch.float32 else 1e-3)
+    wide = torch.randn(300, 128, generator=g).cuda()
+    assert rel_err(ops.colsum(wide[:, 32:96]).cpu(), wide[:, 32:96].sum(0).cpu()) < TOL32   # row stride 128, offset 32
+    lin = torch.nn.Linear(64, 48).cuda()
+    x = torch.randn(3, 50, 128, generator=g).cuda()
+    xa, xb = x[..., :64].detach().requires_grad_(), x[..., :64].detach().requires_grad_()   # strided view, like chunk()
+    w = torch.randn(3, 50, 48, generator=g).cuda()
+    ya = ops.linear_tokens(xa, lin)
+    (ya * w).sum().backward()
+    ga = (xa.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    lin.zero_grad()
+    yb = lin(xb)
+    (yb * w).sum().backward()
+    assert rel_err(ya.detach().cpu(), yb.detach().cpu()) < TOL32
+    for a, b in zip(ga, (xb.grad, lin.weight.grad, lin.bias.grad)):
+        assert rel_err(a.cpu(), b.cpu()) < TOL32
+    lin.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = ops.linear_tokens(xa, lin)
+        assert y16.dtype == torch.bfloat16
+        (y16.float() * w).sum().backward()
+    assert lin.bias.grad.dtype == torch.float32 and rel_err(lin.bias.grad.cpu(), ga[2].cpu()) < TOL16
+    assert rel_err(lin.weight.grad.cpu(), ga[1].cpu()) < TOL16
