@@ -230,6 +230,21 @@ int mlagg_linattn_bwd(const void *q, const void *k, const void *v, const float *
  * ------------------------------------------------------------------------------------------ */
 int mlagg_colsum(const void *x, float *out, long long M, int C, long long ld, int dtype, mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Per-(image, channel) normalisation over the pixels of a channels-last / tokens-major (batch, N, C) map, fp32 math:
+ *   y = act(w[c] * (x - mean[b,c]) * rstd[b,c] + b[c]),   act: 0 = identity, 1 = LeakyReLU(slope), 2 = SiLU.
+ * Replaces nn.InstanceNorm2d (variants/mamba/MambaSkip.py:714-716; monai UnetResBlock norms of encoder0 / decoder0,
+ *   nnUNetTrainer_MLAgg_2D_dt_MS.py:1339-1357) and nn.GroupNorm(num_groups=C) (:262, :497) without torch's NCHW copies.
+ *   x, y (batch, N, C) of `dtype`; w, b (C) fp32, nullable (no affine); stats (batch, C, 2) fp32 receives (mean, rstd);
+ *   C % 4 == 0, 16-byte aligned rows.
+ * Backward: dy like y -> dx like x; sums (batch, C, 2) fp32 scratch; dw, db (C) fp32 nullable, ACCUMULATED INTO.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_instnorm_fwd(const void *x, const float *w, const float *b, void *y, float *stats, int batch, int N, int C,
+                       float eps, int act, float slope, int dtype, mlagg_stream_t stream);
+int mlagg_instnorm_bwd(const void *x, const float *w, const float *b, const float *stats, const void *dy, void *dx,
+                       float *sums, float *dw, float *db, int batch, int N, int C, int act, float slope, int dtype,
+                       mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,10 @@ cudaError_t linattn_dispatch(const LinAttnParams &p, int hd, int dtype, int whic
 
 cudaError_t colsum_dispatch(const void *x, float *out, long long M, int C, long long ld, int dtype, cudaStream_t st);
 
+cudaError_t instnorm_dispatch(const void *x, const void *dy, const float *w, const float *b, void *out, float *stats,
+                              float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
+                              int dtype, bool bwd, cudaStream_t st);
+
 cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                                const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
                                int dt_in, int dt_out, bool bwd, cudaStream_t st);
@@ -488,5 +492,41 @@ extern "C" int mlagg_colsum(const void *x, float *out, long long M, int C, long 
     if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
     if (!aligned(x, dtype == MLAGG_F32 ? 4 : 2) || !aligned(out, 4)) return MLAGG_ERR_ALIGN;
     cudaError_t e = colsum_dispatch(x, out, M, C, ld, dtype, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+// ------------------------------------------------------------------------------------------------ instance norm
+static int instnorm_check(const void *x, const void *y, const float *stats, int batch, int N, int C, int dtype) {
+    if (!x || !y || !stats) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || N <= 0 || C <= 0 || C % 4 != 0) return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    const size_t a = dtype == MLAGG_F32 ? 16 : 8;
+    if (!aligned(x, a) || !aligned(y, a) || !aligned(stats, 8)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_instnorm_fwd(const void *x, const float *w, const float *b, void *y, float *stats, int batch,
+                                  int N, int C, float eps, int act, float slope, int dtype, mlagg_stream_t stream) {
+    int rc = instnorm_check(x, y, stats, batch, N, C, dtype);
+    if (rc) return rc;
+    if (act < 0 || act > 2) return MLAGG_ERR_UNSUPPORTED;
+    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)batch * C * 2 * sizeof(float), (cudaStream_t)stream);
+    if (e == cudaSuccess)
+        e = instnorm_dispatch(x, nullptr, w, b, y, stats, nullptr, nullptr, nullptr, batch, N, C, eps, act, slope, dtype, false,
+                              (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_instnorm_bwd(const void *x, const float *w, const float *b, const float *stats, const void *dy,
+                                  void *dx, float *sums, float *dw, float *db, int batch, int N, int C, int act,
+                                  float slope, int dtype, mlagg_stream_t stream) {
+    int rc = instnorm_check(x, dx, stats, batch, N, C, dtype);
+    if (rc) return rc;
+    if (!dy || !sums) return MLAGG_ERR_NULL;
+    if (act < 0 || act > 2) return MLAGG_ERR_UNSUPPORTED;
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)batch * C * 2 * sizeof(float), (cudaStream_t)stream);
+    if (e == cudaSuccess)
+        e = instnorm_dispatch(x, dy, w, b, dx, const_cast<float *>(stats), sums, dw, db, batch, N, C, 0.f, act, slope,
+                              dtype, true, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

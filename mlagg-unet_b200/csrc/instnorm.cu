@@ -1,0 +1,219 @@
+// instnorm.cu -- per-(image, channel) normalisation over the pixels of a CHANNELS-LAST / tokens-major (B, N, C) map,
+// optional affine, optional fused LeakyReLU.  One implementation serves nn.InstanceNorm2d (reference
+// MambaSkip.py:714-716 conv branches of VSS_Conv_Block; monai UnetResBlock norm1..3 of encoder0 / decoder0,
+// nnUNetTrainer_MLAgg_2D_dt_MS.py:1339-1357) and nn.GroupNorm(num_groups=C) (MedNeXtBlock / PatchExpand, :262,:497).
+// These sit next to the hot path, not on it; they are here because torch's instance_norm / group_norm force an NCHW
+// copy of every channels_last activation (and an fp32 round trip under autocast), which made them -- not the convs --
+// the largest non-GEMM cost of the decoder.  Three HBM-bound passes forward (sums, finalise, apply), three backward.
+//   stats (B, C, 2) fp32: (sum, sum of squares) -> finalised in place to (mean, rstd).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace mlagg {
+
+__device__ __forceinline__ void in_ld4(const float *p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+__device__ __forceinline__ void in_ld4(const __nv_bfloat16 *p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    v[0] = __uint_as_float(t.x << 16), v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16), v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+__device__ __forceinline__ void in_st4(float *p, const float (&v)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void in_st4(__nv_bfloat16 *p, const float (&v)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 raw;
+    raw.x = *reinterpret_cast<const uint32_t *>(&a);
+    raw.y = *reinterpret_cast<const uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = raw;
+}
+
+constexpr int kInWarps = 8;
+
+// activation fused behind the affine: 0 none, 1 LeakyReLU(slope), 2 SiLU
+__device__ __forceinline__ float in_act(float z, int act, float slope) {
+    if (act == 1) return z < 0.f ? z * slope : z;
+    if (act == 2) return silu_f(z);
+    return z;
+}
+__device__ __forceinline__ float in_dact(float z, int act, float slope) {
+    if (act == 1) return z < 0.f ? slope : 1.f;
+    if (act == 2) {
+        const float sg = rcp_approx(1.f + ex2_approx(-z * kLog2e));
+        return sg * (1.f + z * (1.f - sg));
+    }
+    return 1.f;
+}
+
+// kBwd == false: acc0 = sum x, acc1 = sum x^2.
+// kBwd == true : acc0 = sum dz, acc1 = sum dz * xhat, dz = dy * act'(xhat * w + b).
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(32 * kInWarps) in_sums_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+                                                                const float *__restrict__ stats_in,
+                                                                const float *__restrict__ w, const float *__restrict__ b,
+                                                                float *__restrict__ out, int N, int C, int rows_per_block,
+                                                                int act, float slope) {
+    __shared__ float red[kInWarps][2][32 * 4 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * 32 + lane) * 4;
+    const int bi = blockIdx.z;
+    const int n0 = blockIdx.y * rows_per_block, n1 = min(N, n0 + rows_per_block);
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c0 < C) {
+        float mean[4], rstd[4], wv[4], bv[4];
+        if (kBwd) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                mean[i] = stats_in[((size_t)bi * C + c0 + i) * 2];
+                rstd[i] = stats_in[((size_t)bi * C + c0 + i) * 2 + 1];
+                wv[i] = w ? w[c0 + i] : 1.f;
+                bv[i] = b ? b[c0 + i] : 0.f;
+            }
+        }
+        const T *xb = x + (size_t)bi * N * C + c0;
+        const T *db = kBwd ? dy + (size_t)bi * N * C + c0 : nullptr;
+        for (int n = n0 + warp; n < n1; n += kInWarps) {
+            float v[4];
+            in_ld4(xb + (size_t)n * C, v);
+            if (!kBwd) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    a0[i] += v[i];
+                    a1[i] = fmaf(v[i], v[i], a1[i]);
+                }
+            } else {
+                float g[4];
+                in_ld4(db + (size_t)n * C, g);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xh = (v[i] - mean[i]) * rstd[i];
+                    const float dz = g[i] * in_dact(fmaf(xh, wv[i], bv[i]), act, slope);
+                    a0[i] += dz;
+                    a1[i] = fmaf(dz, xh, a1[i]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        red[warp][0][lane * 4 + i] = a0[i];
+        red[warp][1][lane * 4 + i] = a1[i];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * 128; j += blockDim.x) {
+        const int k = j >> 7, cc = j & 127;
+        float s = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kInWarps; ++ww) s += red[ww][k][cc];
+        const int c = blockIdx.x * 128 + cc;
+        if (c < C) atomicAdd(out + ((size_t)bi * C + c) * 2 + k, s);
+    }
+}
+
+// (sum, sumsq) -> (mean, rstd)
+__global__ void in_finalize_kernel(float *stats, int BC, float invN, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BC) return;
+    const float m = stats[2 * i] * invN;
+    const float var = fmaxf(stats[2 * i + 1] * invN - m * m, 0.f);
+    stats[2 * i] = m;
+    stats[2 * i + 1] = rsqrtf(var + eps);
+}
+// per-channel parameter gradients: dw[c] += sum_b S2[b][c], db[c] += sum_b S1[b][c]
+__global__ void in_param_grad_kernel(const float *sums, float *dw, float *db, int Bn, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s1 = 0.f, s2 = 0.f;
+    for (int bi = 0; bi < Bn; ++bi) {
+        s1 += sums[((size_t)bi * C + c) * 2];
+        s2 += sums[((size_t)bi * C + c) * 2 + 1];
+    }
+    if (dw) atomicAdd(dw + c, s2);
+    if (db) atomicAdd(db + c, s1);
+}
+
+// forward: y = lrelu(xhat * w + b).  backward: dx = rstd * w * (dz - S1/N - xhat * S2/N).
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(256) in_apply_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+                                                       const float *__restrict__ stats, const float *__restrict__ sums,
+                                                       const float *__restrict__ w, const float *__restrict__ b,
+                                                       T *__restrict__ out, int N, int C, int act, float slope,
+                                                       float invN) {
+    const int cv = C >> 2;
+    const size_t total = (size_t)gridDim.y * N * cv;   // gridDim.y = batch
+    (void)total;
+    const int bi = blockIdx.y;
+    const size_t per = (size_t)N * cv;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < per; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(idx % cv) * 4;
+        const size_t off = (size_t)bi * N * C + (idx / cv) * C + c0;
+        float v[4], o[4];
+        in_ld4(x + off, v);
+        float g[4];
+        if (kBwd) in_ld4(dy + off, g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 st = __ldg(reinterpret_cast<const float2 *>(stats) + (size_t)bi * C + c0 + i);
+            const float wv = w ? __ldg(w + c0 + i) : 1.f, bv = b ? __ldg(b + c0 + i) : 0.f;
+            const float xh = (v[i] - st.x) * st.y;
+            const float z = fmaf(xh, wv, bv);
+            if (!kBwd) {
+                o[i] = in_act(z, act, slope);
+            } else {
+                const float2 sm = __ldg(reinterpret_cast<const float2 *>(sums) + (size_t)bi * C + c0 + i);
+                const float dz = g[i] * in_dact(z, act, slope);
+                o[i] = st.y * wv * (dz - sm.x * invN - xh * sm.y * invN);
+            }
+        }
+        in_st4(out + off, o);
+    }
+}
+
+static void in_grid(int N, int C, int Bn, dim3 &gs, int &rpb) {
+    const int gx = (C + 127) / 128;
+    int by = (148 * 8 + gx * Bn - 1) / (gx * Bn);
+    rpb = (N + by - 1) / by;
+    if (rpb < 64) rpb = 64;
+    by = (N + rpb - 1) / rpb;
+    gs = dim3(gx, by, Bn);
+}
+
+template <typename T>
+static cudaError_t instnorm_run(const T *x, const T *dy, const float *w, const float *b, T *out, float *stats,
+                                float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
+                                bool bwd, cudaStream_t st) {
+    dim3 gs;
+    int rpb;
+    in_grid(N, C, Bn, gs, rpb);
+    const size_t per = (size_t)N * (C / 4);
+    const dim3 ga((unsigned)std::min<size_t>((per + 255) / 256, 148 * 16), Bn);
+    const float invN = 1.f / (float)N;
+    if (!bwd) {
+        in_sums_kernel<T, false><<<gs, 32 * kInWarps, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, N, C, rpb, act, slope);
+        in_finalize_kernel<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, Bn * C, invN, eps);
+        in_apply_kernel<T, false><<<ga, 256, 0, st>>>(x, nullptr, stats, nullptr, w, b, out, N, C, act, slope, invN);
+    } else {
+        in_sums_kernel<T, true><<<gs, 32 * kInWarps, 0, st>>>(x, dy, stats, w, b, sums, N, C, rpb, act, slope);
+        if (dw || db) in_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dw, db, Bn, C);
+        in_apply_kernel<T, true><<<ga, 256, 0, st>>>(x, dy, stats, sums, w, b, out, N, C, act, slope, invN);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t instnorm_dispatch(const void *x, const void *dy, const float *w, const float *b, void *out, float *stats,
+                              float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
+                              int dtype, bool bwd, cudaStream_t st) {
+    if (dtype == 0)
+        return instnorm_run<float>(static_cast<const float *>(x), static_cast<const float *>(dy), w, b,
+                                   static_cast<float *>(out), stats, sums, dw, db, Bn, N, C, eps, act, slope, bwd, st);
+    return instnorm_run<__nv_bfloat16>(static_cast<const __nv_bfloat16 *>(x), static_cast<const __nv_bfloat16 *>(dy), w, b,
+                                       static_cast<__nv_bfloat16 *>(out), stats, sums, dw, db, Bn, N, C, eps, act, slope, bwd, st);
+}
+
+}  // namespace mlagg

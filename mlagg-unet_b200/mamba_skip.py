@@ -27,7 +27,7 @@ import torch.nn.functional as F
 
 from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
 from .selective_scan_interface import msmm_scan, selective_scan_fn
-from .thirdparty_shims import DropPath
+from .thirdparty_shims import DropPath, _inst_norm
 
 
 @lru_cache(maxsize=64)
@@ -268,7 +268,8 @@ class VSS_Conv_Block(nn.Module):
             ms = m[:, off:off + L_split[s]]
             off += L_split[s]
             ms = ms + self.drop_path(self.mlps[s](ms, H[s], W[s]))
-            cb = self.conv_branches[s](t[:, hd:]).permute(0, 2, 3, 1)                  # NHWC view
+            br = self.conv_branches[s]                                                 # Conv2d, InstanceNorm2d, SiLU
+            cb = _inst_norm(br[1], br[0](t[:, hd:]), "silu").permute(0, 2, 3, 1)       # NHWC view
             outs.append(torch.cat([ms.reshape(Bn, H[s], W[s], hd), cb], dim=-1).permute(0, 3, 1, 2))  # channels_last
         return outs
 

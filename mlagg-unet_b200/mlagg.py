@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
 from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
-from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock
+from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
 
 class Mlp(nn.Module):
@@ -284,7 +284,7 @@ class MedNeXtBlock(nn.Module):
         self.conv3 = nn.Conv2d(exp_r * in_channels, out_channels, kernel_size=1)
 
     def forward(self, x, dummy_tensor=None):
-        y = self.conv3(self.act(self.conv2(self.norm(self.conv1(x)))))
+        y = self.conv3(self.act(self.conv2(_inst_norm(self.norm, self.conv1(x)))))
         return x + y if self.do_res else y
 
 
@@ -316,7 +316,7 @@ class PatchExpand(nn.Module):
         self.norm = nn.GroupNorm(num_groups=in_channels, num_channels=in_channels)
 
     def forward(self, x, dummy_tensor=None):
-        y = F.pad(self.conv1(self.norm(x)), (1, 0, 1, 0))
+        y = F.pad(self.conv1(_inst_norm(self.norm, x)), (1, 0, 1, 0))
         if self.resample_do_res:
             y = y + F.pad(self.res_conv(x), (1, 0, 1, 0))
         return y

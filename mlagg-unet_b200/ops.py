@@ -203,3 +203,60 @@ def linear_tokens(x, lin: torch.nn.Linear):
     if not x.is_cuda:
         raise _lib.MlaggError("linear_tokens: CUDA tensor required (no CPU fallback in the product path)")
     return _Linear.apply(x, lin.weight, lin.bias)
+
+
+_ACT = {None: 0, "none": 0, "leaky_relu": 1, "silu": 2}
+
+
+class _InstNorm(torch.autograd.Function):
+    """C ABI: mlagg_instnorm_fwd / _bwd (csrc/instnorm.cu) on a channels_last (B, C, H, W) map."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, act, slope):
+        Bn, C, H, W = x.shape
+        xt = x.permute(0, 2, 3, 1)                                 # (B, H, W, C): contiguous when x is channels_last
+        if not xt.is_contiguous():
+            xt = xt.contiguous()
+        w32 = None if weight is None else weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty_like(xt)
+        stats = torch.empty(Bn, C, 2, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _lib.timed("instnorm_fwd", 3):
+            rc = _lib.lib().mlagg_instnorm_fwd(_lib.ptr(xt), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), _lib.ptr(stats),
+                                               Bn, H * W, C, float(eps), act, float(slope), _DT[xt.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_instnorm_fwd")
+        ctx.save_for_backward(xt, w32, b32, stats)
+        ctx.meta = (act, float(slope), None if weight is None else weight.dtype, None if bias is None else bias.dtype)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xt, w32, b32, stats = ctx.saved_tensors
+        act, slope, wdt, bdt = ctx.meta
+        Bn, H, W, C = xt.shape
+        dyt = dy.to(xt.dtype).permute(0, 2, 3, 1)
+        if not dyt.is_contiguous():
+            dyt = dyt.contiguous()
+        dx = torch.empty_like(xt)
+        sums = torch.empty(Bn, C, 2, device=xt.device, dtype=torch.float32)
+        dw = torch.zeros(C, device=xt.device, dtype=torch.float32) if w32 is not None else None
+        db = torch.zeros(C, device=xt.device, dtype=torch.float32) if b32 is not None else None
+        with torch.cuda.device(xt.device), _lib.timed("instnorm_bwd", 3):
+            rc = _lib.lib().mlagg_instnorm_bwd(_lib.ptr(xt), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(stats), _lib.ptr(dyt),
+                                               _lib.ptr(dx), _lib.ptr(sums), _lib.ptr(dw), _lib.ptr(db), Bn, H * W, C, act,
+                                               slope, _DT[xt.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_instnorm_bwd")
+        return (dx.permute(0, 3, 1, 2), None if dw is None else dw.to(wdt), None if db is None else db.to(bdt),
+                None, None, None)
+
+
+def instance_norm_cl(x, weight=None, bias=None, eps=1e-5, act=None, slope=0.01):
+    """Per-(image, channel) normalisation of a (B, C, H, W) map kept in channels_last memory, optional affine and a
+    fused activation (None | 'leaky_relu' | 'silu').  Equals nn.InstanceNorm2d (training statistics) and
+    nn.GroupNorm(num_groups=C).  Shapes / dtypes the kernel does not take (C % 4 != 0, fp16, CPU) are the caller's
+    business -- see `supports_instance_norm_cl`."""
+    return _InstNorm.apply(x, weight, bias, eps, _ACT[act], slope)
+
+
+def supports_instance_norm_cl(x):
+    return x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.dtype in _DT

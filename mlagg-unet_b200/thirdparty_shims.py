@@ -16,6 +16,21 @@ import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _inst_norm(norm, x, act=None):
+    """nn.InstanceNorm2d / nn.GroupNorm(num_groups=C) [+ LeakyReLU(0.01) | SiLU] of a channels_last map: the sm_100a
+    kernel when it applies (CUDA, C % 4 == 0, fp32 / bf16), the torch module otherwise (CPU oracle runs, odd widths).
+    torch's own kernels force an NCHW copy of every channels_last activation."""
+    from .ops import instance_norm_cl, supports_instance_norm_cl
+    ok = supports_instance_norm_cl(x) and not getattr(norm, "track_running_stats", False)
+    if isinstance(norm, nn.GroupNorm):
+        ok = ok and norm.num_groups == norm.num_channels
+    if ok:
+        return instance_norm_cl(x, norm.weight, norm.bias, norm.eps, act, 0.01)
+    y = norm(x)
+    return F.leaky_relu(y, 0.01) if act == "leaky_relu" else F.silu(y) if act == "silu" else y
 
 
 def to_2tuple(x):
@@ -114,10 +129,10 @@ class UnetResBlock2d(nn.Module):
 
     def forward(self, x):
         res = x
-        y = self.lrelu(self.norm1(self.conv1(x)))
-        y = self.norm2(self.conv2(y))
+        y = _inst_norm(self.norm1, self.conv1(x), "leaky_relu")
+        y = _inst_norm(self.norm2, self.conv2(y))
         if self.downsample:
-            res = self.norm3(self.conv3(res))
+            res = _inst_norm(self.norm3, self.conv3(res))
         return self.lrelu(y + res)
 
 

@@ -340,3 +340,39 @@ def test_colsum_and_linear_tokens_match_torch():
         (y16.float() * w).sum().backward()
     assert lin.bias.grad.dtype == torch.float32 and rel_err(lin.bias.grad.cpu(), ga[2].cpu()) < TOL16
     assert rel_err(lin.weight.grad.cpu(), ga[1].cpu()) < TOL16
+
+
+@pytest.mark.parametrize("act", [None, "leaky_relu", "silu"])
+@pytest.mark.parametrize("affine", [False, True])
+def test_instance_norm_channels_last_matches_torch(act, affine):
+    """mlagg_instnorm_* against nn.InstanceNorm2d (+ activation) in float64, forward and backward, on a channels_last
+    map with a ragged pixel count; the same kernel against nn.GroupNorm(num_groups=C); bf16 I/O at 2e-2."""
+    from mlagg_unet_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    Bn, C, H, W = 3, 20, 37, 23
+    x = (torch.randn(Bn, C, H, W, generator=g) * 2 + 0.5)
+    wgt = torch.randn(Bn, C, H, W, generator=g)
+    ref_m = torch.nn.InstanceNorm2d(C, affine=affine).double()
+    if affine:
+        with torch.no_grad():
+            ref_m.weight.copy_(torch.randn(C, generator=g)); ref_m.bias.copy_(torch.randn(C, generator=g))
+    f = {None: lambda t: t, "leaky_relu": lambda t: torch.nn.functional.leaky_relu(t, 0.01), "silu": torch.nn.functional.silu}[act]
+    x64 = x.double().requires_grad_()
+    ref = f(ref_m(x64))
+    (ref * wgt.double()).sum().backward()
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_()
+    w = ref_m.weight.detach().float().cuda().requires_grad_() if affine else None
+    b = ref_m.bias.detach().float().cuda().requires_grad_() if affine else None
+    y = ops.instance_norm_cl(xc, w, b, 1e-5, act, 0.01)
+    assert y.shape == x.shape and y.is_contiguous(memory_format=torch.channels_last)
+    assert rel_err(y.detach().cpu(), ref.detach()) < TOL32
+    (y * wgt.cuda()).sum().backward()
+    assert rel_err(xc.grad.cpu(), x64.grad) < TOL32
+    if affine:
+        assert rel_err(w.grad.cpu(), ref_m.weight.grad) < TOL32 and rel_err(b.grad.cpu(), ref_m.bias.grad) < TOL32
+        gn = torch.nn.GroupNorm(C, C).cuda()
+        with torch.no_grad():
+            gn.weight.copy_(w); gn.bias.copy_(b)
+        assert rel_err(ops.instance_norm_cl(xc.detach(), gn.weight, gn.bias, gn.eps).cpu(), gn(xc.detach()).cpu()) < TOL32
+    y16 = ops.instance_norm_cl(xc.detach().bfloat16(), w, b, 1e-5, act, 0.01)
+    assert y16.dtype == torch.bfloat16 and rel_err(y16.float().cpu(), ref.detach()) < TOL16
