@@ -245,6 +245,19 @@ int mlagg_instnorm_bwd(const void *x, const float *w, const float *b, const floa
                        float *sums, float *dw, float *db, int batch, int N, int C, int act, float slope, int dtype,
                        mlagg_stream_t stream);
 
+/* --------------------------------------------------------------------------------------------
+ * Adaptive average pooling of a tokens-major map, optional exact GELU applied to x on the fly:
+ *   y[b, (i, j), c] = mean over rows floor(i*H/pH) .. ceil((i+1)*H/pH) - 1 and the matching columns of act(x[b, (r, s), c]).
+ * Replaces  self.pool(self.act(...))  of the pooled-token branch, nnUNetTrainer_MLAgg_2D_dt_MS.py:720-723
+ *   (nn.AdaptiveAvgPool2d :668, nn.GELU :671) without the NCHW view or the materialised GELU output.
+ *   x (batch, H*W, C), y (batch, pH*pW, C) of `dtype`; C % 4 == 0, C <= 4096.
+ * Backward: dy like y -> dx like x (x is the forward input; only read when act_gelu != 0).
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_avgpool_tokens_fwd(const void *x, void *y, int batch, int H, int W, int C, int pH, int pW, int act_gelu,
+                             int dtype, mlagg_stream_t stream);
+int mlagg_avgpool_tokens_bwd(const void *x, const void *dy, void *dx, int batch, int H, int W, int C, int pH, int pW,
+                             int act_gelu, int dtype, mlagg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

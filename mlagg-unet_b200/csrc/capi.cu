@@ -66,6 +66,9 @@ cudaError_t instnorm_dispatch(const void *x, const void *dy, const float *w, con
                               float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
                               int dtype, bool bwd, cudaStream_t st);
 
+cudaError_t avgpool_dispatch(const void *x, const void *dy, void *out, int Bn, int H, int W, int C, int pH, int pW,
+                             int gelu, int dtype, bool bwd, cudaStream_t st);
+
 cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                                const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
                                int dt_in, int dt_out, bool bwd, cudaStream_t st);
@@ -528,5 +531,31 @@ extern "C" int mlagg_instnorm_bwd(const void *x, const float *w, const float *b,
     if (e == cudaSuccess)
         e = instnorm_dispatch(x, dy, w, b, dx, const_cast<float *>(stats), sums, dw, db, batch, N, C, 0.f, act, slope,
                               dtype, true, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+// ------------------------------------------------------------------------------------------------ adaptive avg pool
+static int avgpool_check(const void *x, const void *y, int batch, int H, int W, int C, int pH, int pW, int dtype) {
+    if (!x || !y) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || H <= 0 || W <= 0 || pH <= 0 || pW <= 0 || pH > H || pW > W || C <= 0 || C % 4)
+        return MLAGG_ERR_BAD_SHAPE;
+    if (C > 4096 || (dtype != MLAGG_F32 && dtype != MLAGG_BF16)) return MLAGG_ERR_UNSUPPORTED;
+    const size_t a = dtype == MLAGG_F32 ? 16 : 8;
+    if (!aligned(x, a) || !aligned(y, a)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+extern "C" int mlagg_avgpool_tokens_fwd(const void *x, void *y, int batch, int H, int W, int C, int pH, int pW,
+                                        int act_gelu, int dtype, mlagg_stream_t stream) {
+    int rc = avgpool_check(x, y, batch, H, W, C, pH, pW, dtype);
+    if (rc) return rc;
+    cudaError_t e = avgpool_dispatch(x, nullptr, y, batch, H, W, C, pH, pW, act_gelu, dtype, false, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+extern "C" int mlagg_avgpool_tokens_bwd(const void *x, const void *dy, void *dx, int batch, int H, int W, int C, int pH,
+                                        int pW, int act_gelu, int dtype, mlagg_stream_t stream) {
+    int rc = avgpool_check(x, dx, batch, H, W, C, pH, pW, dtype);
+    if (rc) return rc;
+    if (!dy) return MLAGG_ERR_NULL;
+    cudaError_t e = avgpool_dispatch(x, dy, dx, batch, H, W, C, pH, pW, act_gelu, dtype, true, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }

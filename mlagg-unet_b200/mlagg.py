@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
+from .ops import avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
 
@@ -65,6 +65,15 @@ def get_seqlen_and_mask(input_resolution, window_size):
     c = torch.arange(W).view(1, W, 1, 1) + torch.arange(-h, h + 1).view(1, 1, 1, -1)
     outside = ~((r >= 0) & (r < H) & (c >= 0) & (c < W)).reshape(H * W, window_size ** 2)
     return (~outside).sum(-1, keepdim=True).float(), outside
+
+
+class _Linear1x1:
+    """nn.Conv2d(C, C, 1) on a tokens-major map == per-token Linear with the conv's (C, C, 1, 1) weight viewed (C, C)."""
+
+    @staticmethod
+    def apply_conv(x, conv):
+        from .ops import _Linear
+        return _Linear.apply(x, conv.weight.view(conv.out_channels, conv.in_channels), conv.bias)
 
 
 class AggregatedAttention(nn.Module):
@@ -113,8 +122,11 @@ class AggregatedAttention(nn.Module):
             o = att.local_diff_attention(q, kv, lam, self.subln.weight, H, W, h, hd, self.scale)
         else:
             # pooled tokens: 1x1 conv == per-token Linear; pooling on the tokens-major image view
-            t = F.gelu(F.linear(x, self.sr.weight.view(C, C), self.sr.bias))
-            t = self.pool(t.transpose(1, 2).reshape(Bn, C, H, W)).flatten(2).transpose(1, 2)
+            t = _Linear1x1.apply_conv(x, self.sr)
+            if C % 4 == 0 and isinstance(self.act, nn.GELU):
+                t = avgpool_tokens(t, H, W, self.pool_H, self.pool_W, gelu=True)     # GELU folded into the pooling read
+            else:
+                t = self.pool(self.act(t).transpose(1, 2).reshape(Bn, C, H, W)).flatten(2).transpose(1, 2)
             o = att.pooled_diff_attention(q, linear_tokens(layer_norm_tokens(t, self.norm), self.kv), lam,
                                           self.subln.weight, h, hd, self.scale)
         return o + dwconv3x3_tokens(v_local.contiguous(), self.lepe.weight, self.lepe.bias, H, W)

@@ -260,3 +260,41 @@ def instance_norm_cl(x, weight=None, bias=None, eps=1e-5, act=None, slope=0.01):
 
 def supports_instance_norm_cl(x):
     return x.is_cuda and x.dim() == 4 and x.shape[1] % 4 == 0 and x.dtype in _DT
+
+
+class _AvgPoolTokens(torch.autograd.Function):
+    """C ABI: mlagg_avgpool_tokens_fwd / _bwd (csrc/pool.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, pH, pW, gelu):
+        if not x.is_cuda:
+            raise _lib.MlaggError("avgpool_tokens: CUDA tensor required (no CPU fallback in the product path)")
+        Bn, N, C = x.shape
+        assert N == H * W
+        xin = _io(x).contiguous()
+        y = torch.empty(Bn, pH * pW, C, device=x.device, dtype=xin.dtype)
+        with torch.cuda.device(x.device), _lib.timed("avgpool_fwd"):
+            rc = _lib.lib().mlagg_avgpool_tokens_fwd(_lib.ptr(xin), _lib.ptr(y), Bn, H, W, C, pH, pW, int(gelu),
+                                                     _DT[xin.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_avgpool_tokens_fwd")
+        ctx.save_for_backward(xin)
+        ctx.meta = (H, W, pH, pW, bool(gelu), x.dtype)
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xin,) = ctx.saved_tensors
+        H, W, pH, pW, gelu, xdt = ctx.meta
+        Bn, N, C = xin.shape
+        dy = dy.to(xin.dtype).contiguous()
+        dx = torch.empty_like(xin)
+        with torch.cuda.device(xin.device), _lib.timed("avgpool_bwd"):
+            rc = _lib.lib().mlagg_avgpool_tokens_bwd(_lib.ptr(xin), _lib.ptr(dy), _lib.ptr(dx), Bn, H, W, C, pH, pW,
+                                                     int(gelu), _DT[xin.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_avgpool_tokens_bwd")
+        return dx.to(xdt), None, None, None, None, None
+
+
+def avgpool_tokens(x, H, W, pH, pW, gelu=False):
+    """x (B, H*W, C) -> adaptive average pool to (B, pH*pW, C) of gelu(x) (gelu=True) or x, torch bin semantics."""
+    return _AvgPoolTokens.apply(x, H, W, pH, pW, gelu)

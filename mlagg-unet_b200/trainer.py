@@ -152,7 +152,8 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
 
     def configure_optimizers(self):
         params = [p for p in self.network.parameters() if p.requires_grad]
-        opt = torch.optim.AdamW(params, self.initial_lr, weight_decay=self.weight_decay, eps=1e-4)
+        opt = torch.optim.AdamW(params, self.initial_lr, weight_decay=self.weight_decay, eps=1e-4,
+                                fused=self.device.type == "cuda")
         sched = CosineLRScheduler(opt, t_initial=self.num_epochs, lr_min=1e-6, warmup_t=10, warmup_lr_init=1e-4)
         return opt, sched
 

@@ -376,3 +376,25 @@ def test_instance_norm_channels_last_matches_torch(act, affine):
         assert rel_err(ops.instance_norm_cl(xc.detach(), gn.weight, gn.bias, gn.eps).cpu(), gn(xc.detach()).cpu()) < TOL32
     y16 = ops.instance_norm_cl(xc.detach().bfloat16(), w, b, 1e-5, act, 0.01)
     assert y16.dtype == torch.bfloat16 and rel_err(y16.float().cpu(), ref.detach()) < TOL16
+
+
+@pytest.mark.parametrize("H,W,pH,pW,C,gelu", [(32, 48, 4, 6, 48, True), (37, 23, 5, 4, 20, True), (20, 20, 10, 10, 384, False),
+                                              (9, 7, 9, 7, 8, True)])
+def test_avgpool_tokens_matches_torch(H, W, pH, pW, C, gelu):
+    """mlagg_avgpool_tokens_* against nn.AdaptiveAvgPool2d(nn.GELU(x)) in float64 (overlapping bins when H % pH != 0)."""
+    from mlagg_unet_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    Bn = 2
+    x = torch.randn(Bn, H * W, C, generator=g)
+    wgt = torch.randn(Bn, pH * pW, C, generator=g)
+    x64 = x.double().requires_grad_()
+    t = torch.nn.functional.gelu(x64) if gelu else x64
+    ref = torch.nn.functional.adaptive_avg_pool2d(t.transpose(1, 2).reshape(Bn, C, H, W), (pH, pW)).flatten(2).transpose(1, 2)
+    (ref * wgt.double()).sum().backward()
+    xc = x.cuda().requires_grad_()
+    y = ops.avgpool_tokens(xc, H, W, pH, pW, gelu=gelu)
+    assert rel_err(y.detach().cpu(), ref.detach()) < TOL32
+    (y * wgt.cuda()).sum().backward()
+    assert rel_err(xc.grad.cpu(), x64.grad) < TOL32
+    y16 = ops.avgpool_tokens(x.cuda().bfloat16(), H, W, pH, pW, gelu=gelu)
+    assert rel_err(y16.float().cpu(), ref.detach()) < TOL16
