@@ -49,45 +49,84 @@ __device__ __forceinline__ float silu_grad(float z) {  // d/dz [z * sigmoid(z)]
 // weights as (C, 9) fp32 (the nn.Conv2d (C,1,3,3) tensor, contiguous); tap p = 3*(dr+1) + (dc+1).
 // FLIP=false: y[pix] = b + sum_p w[p] x[pix + off_p]           (forward)
 // FLIP=true : y[pix] =     sum_p w[p] x[pix - off_p]           (input gradient)
+// A thread owns 4 consecutive channels and walks a strip of kStrip pixels along a row with the 3x3 window in
+// registers: 3 new 64/128-bit loads, 36 FMAs and one store per pixel; the 36 weights are loaded once per strip (the first
+// version re-read 9 neighbours and 36 weights for every pixel and ran at ~1/12 of the HBM roofline).
+constexpr int kStrip = 16;
+
+struct Row3 {
+    const void *p[3];
+};
+
+template <typename T>
+__device__ __forceinline__ void dw_col(const Row3 &rows, int wc, int W, int C, float4 (&o)[3]) {
+    const bool in = wc >= 0 && wc < W;
+#pragma unroll
+    for (int dr = 0; dr < 3; ++dr)
+        o[dr] = (in && rows.p[dr]) ? ld4<T>(static_cast<const T *>(rows.p[dr]) + (long long)wc * C) : make_float4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void dw_fma(float4 &acc, const float (&wr)[4][9], int p, const float4 &v) {
+    acc.x = fmaf(wr[0][p], v.x, acc.x);
+    acc.y = fmaf(wr[1][p], v.y, acc.y);
+    acc.z = fmaf(wr[2][p], v.z, acc.z);
+    acc.w = fmaf(wr[3][p], v.w, acc.w);
+}
+__device__ __forceinline__ float4 dw_window(const float4 &b, const float (&wr)[4][9], const float4 (&L)[3],
+                                            const float4 (&M)[3], const float4 (&R)[3]) {
+    float4 acc = b;
+#pragma unroll
+    for (int dr = 0; dr < 3; ++dr) {
+        dw_fma(acc, wr, 3 * dr, L[dr]);
+        dw_fma(acc, wr, 3 * dr + 1, M[dr]);
+        dw_fma(acc, wr, 3 * dr + 2, R[dr]);
+    }
+    return acc;
+}
+
 template <typename T, bool FLIP, int ACT>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, T *__restrict__ y, int Bn,
                                                         int H, int W, int C) {
     const int cv = C >> 2;
-    const long long total = (long long)Bn * H * W * cv;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % cv) << 2;
-        const long long pix = idx / cv;
-        const int wc = (int)(pix % W);
-        const int hr = (int)((pix / W) % H);
-        const T *xb = x + (pix - (long long)hr * W - wc) * C + c;  // image base + channel
-        float4 acc = (!FLIP && bias) ? __ldg(reinterpret_cast<const float4 *>(bias + c)) : make_float4(0, 0, 0, 0);
-        float wr[4][9];
+    const int SW = (W + kStrip - 1) / kStrip;
+    const long long total = (long long)Bn * H * SW * cv;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % cv) << 2;
+    long long s = idx / cv;
+    const int w0 = (int)(s % SW) * kStrip;
+    s /= SW;
+    const int hr = (int)(s % H);
+    const long long img = (s / H) * H;   // first row of this image, in rows
+    float wr[4][9];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int p = 0; p < 9; ++p) wr[k][p] = __ldg(w + (c + k) * 9 + p);
+        for (int p = 0; p < 9; ++p) wr[k][p] = __ldg(w + (c + k) * 9 + (FLIP ? 8 - p : p));
+    const float4 bv = (!FLIP && bias) ? __ldg(reinterpret_cast<const float4 *>(bias + c)) : make_float4(0, 0, 0, 0);
+    Row3 rows;
 #pragma unroll
-        for (int dr = -1; dr <= 1; ++dr) {
-            const int rr = hr + dr;
-            if (rr < 0 || rr >= H) continue;
-#pragma unroll
-            for (int dc = -1; dc <= 1; ++dc) {
-                const int cc = wc + dc;
-                if (cc < 0 || cc >= W) continue;
-                const float4 v = ld4<T>(xb + ((long long)rr * W + cc) * C);
-                const int p = FLIP ? (3 * (1 - dr) + (1 - dc)) : (3 * (dr + 1) + (dc + 1));
-                acc.x = fmaf(wr[0][p], v.x, acc.x);
-                acc.y = fmaf(wr[1][p], v.y, acc.y);
-                acc.z = fmaf(wr[2][p], v.z, acc.z);
-                acc.w = fmaf(wr[3][p], v.w, acc.w);
-            }
-        }
+    for (int dr = 0; dr < 3; ++dr) {
+        const int rr = hr + dr - 1;
+        rows.p[dr] = (rr >= 0 && rr < H) ? static_cast<const void *>(x + ((img + rr) * W) * C + c) : nullptr;
+    }
+    T *yr = y + ((img + hr) * W) * C + c;
+    const int w1 = min(W, w0 + kStrip);
+    float4 A[3], Bc[3], Cc[3];
+    dw_col<T>(rows, w0 - 1, W, C, A);
+    dw_col<T>(rows, w0, W, C, Bc);
+    auto step = [&](int wc, const float4 (&L)[3], const float4 (&M)[3], float4 (&R)[3]) {
+        dw_col<T>(rows, wc + 1, W, C, R);
+        float4 acc = dw_window(bv, wr, L, M, R);
         if (ACT == 1) {
             acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
         }
-        st4<T>(y + pix * C + c, acc);
+        st4<T>(yr + (long long)wc * C, acc);
+    };
+    for (int wc = w0; wc < w1; wc += 3) {
+        step(wc, A, Bc, Cc);
+        if (wc + 1 < w1) step(wc + 1, Bc, Cc, A);
+        if (wc + 2 < w1) step(wc + 2, Cc, A, Bc);
     }
 }
 
@@ -147,19 +186,23 @@ __global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restri
 
 // Backward, pass 1: recompute z = conv(x) + b, dz = dy * act'(z); store dz; accumulate
 // dw[c, p] += sum_pix dz[pix] x[pix + off_p] and db[c] += sum_pix dz[pix] (registers -> smem -> atomics).
-// Block = (C/4 channel vectors) x PP pixel lanes; each block walks `pix_per_block` pixels.
+// Block = (C/4 channel vectors) x PP strip lanes; lane pl walks `strips_per_lane` row strips of kStripW pixels with the
+// 3x3 window of x in registers (same walk as the forward kernel).
+constexpr int kStripW = 32;
+
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                               const float *__restrict__ bias,
                                                               const T *__restrict__ dy, T *__restrict__ dz,
                                                               float *__restrict__ dw, float *__restrict__ db,
-                                                              int Bn, int H, int W, int C, int pix_per_block) {
+                                                              int Bn, int H, int W, int C, int strips_per_lane) {
     extern __shared__ float red[];  // [PP][cv][40]
     const int cv = C >> 2;
     const int PP = blockDim.x / cv;
     const int cvi = threadIdx.x % cv, pl = threadIdx.x / cv;
     const int c = cvi << 2;
-    const long long npix = (long long)Bn * H * W;
+    const int SW = (W + kStripW - 1) / kStripW;
+    const long long nstrips = (long long)Bn * H * SW;
     float aw[4][9], ab[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -174,39 +217,53 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restric
 #pragma unroll
             for (int p = 0; p < 9; ++p) wr[k][p] = __ldg(w + (c + k) * 9 + p);
         const float4 bv = bias ? __ldg(reinterpret_cast<const float4 *>(bias + c)) : make_float4(0, 0, 0, 0);
-        const long long p0 = (long long)blockIdx.x * pix_per_block;
-        const long long p1 = min(npix, p0 + pix_per_block);
-        for (long long pix = p0 + pl; pix < p1; pix += PP) {
-            const int wc = (int)(pix % W);
-            const int hr = (int)((pix / W) % H);
-            const T *xb = x + (pix - (long long)hr * W - wc) * C + c;
-            float4 xn[9];
-            float4 z = bv;
+        for (int j = 0; j < strips_per_lane; ++j) {
+            long long s = ((long long)blockIdx.x * strips_per_lane + j) * PP + pl;
+            if (s >= nstrips) break;
+            const int w0 = (int)(s % SW) * kStripW;
+            s /= SW;
+            const int hr = (int)(s % H);
+            const long long img = (s / H) * H;
+            Row3 rows;
 #pragma unroll
-            for (int dr = -1; dr <= 1; ++dr)
-#pragma unroll
-                for (int dc = -1; dc <= 1; ++dc) {
-                    const int p = 3 * (dr + 1) + (dc + 1);
-                    const int rr = hr + dr, cc = wc + dc;
-                    const bool ok = rr >= 0 && rr < H && cc >= 0 && cc < W;
-                    xn[p] = ok ? ld4<T>(xb + ((long long)rr * W + cc) * C) : make_float4(0, 0, 0, 0);
-                    z.x = fmaf(wr[0][p], xn[p].x, z.x);
-                    z.y = fmaf(wr[1][p], xn[p].y, z.y);
-                    z.z = fmaf(wr[2][p], xn[p].z, z.z);
-                    z.w = fmaf(wr[3][p], xn[p].w, z.w);
-                }
-            float4 g = ld4<T>(dy + pix * C + c);
-            if (ACT == 1) {
-                g.x *= silu_grad(z.x); g.y *= silu_grad(z.y); g.z *= silu_grad(z.z); g.w *= silu_grad(z.w);
+            for (int dr = 0; dr < 3; ++dr) {
+                const int rr = hr + dr - 1;
+                rows.p[dr] = (rr >= 0 && rr < H) ? static_cast<const void *>(x + ((img + rr) * W) * C + c) : nullptr;
             }
-            st4<T>(dz + pix * C + c, g);
-            ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w;
+            const long long rowoff = ((img + hr) * W) * C + c;
+            const int w1 = min(W, w0 + kStripW);
+            float4 A[3], Bc[3], Cc[3];
+            dw_col<T>(rows, w0 - 1, W, C, A);
+            dw_col<T>(rows, w0, W, C, Bc);
+            auto step = [&](int wc, const float4 (&L)[3], const float4 (&M)[3], float4 (&R)[3]) {
+                dw_col<T>(rows, wc + 1, W, C, R);
+                float4 g = ld4<T>(dy + rowoff + (long long)wc * C);
+                if (ACT == 1) {
+                    const float4 z = dw_window(bv, wr, L, M, R);
+                    g.x *= silu_grad(z.x); g.y *= silu_grad(z.y); g.z *= silu_grad(z.z); g.w *= silu_grad(z.w);
+                }
+                st4<T>(dz + rowoff + (long long)wc * C, g);
+                ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w;
 #pragma unroll
-            for (int p = 0; p < 9; ++p) {
-                aw[0][p] = fmaf(g.x, xn[p].x, aw[0][p]);
-                aw[1][p] = fmaf(g.y, xn[p].y, aw[1][p]);
-                aw[2][p] = fmaf(g.z, xn[p].z, aw[2][p]);
-                aw[3][p] = fmaf(g.w, xn[p].w, aw[3][p]);
+                for (int dr = 0; dr < 3; ++dr) {
+                    aw[0][3 * dr] = fmaf(g.x, L[dr].x, aw[0][3 * dr]);
+                    aw[1][3 * dr] = fmaf(g.y, L[dr].y, aw[1][3 * dr]);
+                    aw[2][3 * dr] = fmaf(g.z, L[dr].z, aw[2][3 * dr]);
+                    aw[3][3 * dr] = fmaf(g.w, L[dr].w, aw[3][3 * dr]);
+                    aw[0][3 * dr + 1] = fmaf(g.x, M[dr].x, aw[0][3 * dr + 1]);
+                    aw[1][3 * dr + 1] = fmaf(g.y, M[dr].y, aw[1][3 * dr + 1]);
+                    aw[2][3 * dr + 1] = fmaf(g.z, M[dr].z, aw[2][3 * dr + 1]);
+                    aw[3][3 * dr + 1] = fmaf(g.w, M[dr].w, aw[3][3 * dr + 1]);
+                    aw[0][3 * dr + 2] = fmaf(g.x, R[dr].x, aw[0][3 * dr + 2]);
+                    aw[1][3 * dr + 2] = fmaf(g.y, R[dr].y, aw[1][3 * dr + 2]);
+                    aw[2][3 * dr + 2] = fmaf(g.z, R[dr].z, aw[2][3 * dr + 2]);
+                    aw[3][3 * dr + 2] = fmaf(g.w, R[dr].w, aw[3][3 * dr + 2]);
+                }
+            };
+            for (int wc = w0; wc < w1; wc += 3) {
+                step(wc, A, Bc, Cc);
+                if (wc + 1 < w1) step(wc + 1, Bc, Cc, A);
+                if (wc + 2 < w1) step(wc + 2, Cc, A, Bc);
             }
         }
         float *mine = red + ((size_t)pl * cv + cvi) * 40;
@@ -333,10 +390,8 @@ static cudaError_t dwconv_fwd_t(const void *x, const float *w, const float *b, v
         else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xp0, w, b, nullptr, yp0, nullptr, nullptr, Bn, H, W, C, flip ? 1 : 0);
         return cudaGetLastError();
     }
-    const long long total = (long long)Bn * H * W * (C / 4);
-    long long nb = (total + 255) / 256;
-    if (nb > 148LL * 32) nb = 148LL * 32;
-    const int blocks = (int)nb;
+    const long long total = (long long)Bn * H * ((W + kStrip - 1) / kStrip) * (C / 4);   // one thread per strip
+    const int blocks = (int)((total + 255) / 256);
     const T *xp = static_cast<const T *>(x);
     T *yp = static_cast<T *>(y);
     if (flip) dwconv3x3_kernel<T, true, 0><<<blocks, 256, 0, st>>>(xp, w, nullptr, yp, Bn, H, W, C);
@@ -368,9 +423,10 @@ static cudaError_t dwconv_bwd_t(const void *x, const float *w, const float *b, c
     const int cv = C / 4;
     const int PP = max(1, 256 / cv);
     const int threads = cv * PP;  // <= 256 when cv <= 256
-    const long long npix = (long long)Bn * H * W;
-    const int ppb = PP * 32;  // pixels per block
-    const int blocks = (int)((npix + ppb - 1) / ppb);
+    const long long nstrips = (long long)Bn * H * ((W + kStripW - 1) / kStripW);
+    int ppb = 1;   // strips per lane: keep >= ~2 blocks per SM, otherwise fewer atomics
+    while (ppb < 4 && nstrips / ((long long)PP * ppb * 2) >= 148 * 2) ppb *= 2;
+    const int blocks = (int)((nstrips + (long long)PP * ppb - 1) / ((long long)PP * ppb));
     const size_t smem = (size_t)PP * cv * 40 * sizeof(float);
     const T *xp = static_cast<const T *>(x), *gp = static_cast<const T *>(dy);
     T *zp = static_cast<T *>(dz);
