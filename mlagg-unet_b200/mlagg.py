@@ -282,6 +282,22 @@ class PatchEmbed(nn.Module):
         return x
 
 
+def _conv1x1_cl(conv, x):
+    """1x1 (transposed) convolution of a channels_last map == per-token Linear: cuBLAS GEMM on the (B*H*W, C) view and
+    the bias gradient through mlagg_colsum (torch's conv backward reduces the bias with its generic reduce kernel)."""
+    from .ops import _Linear
+    Bn, C, H, W = x.shape
+    t = x.permute(0, 2, 3, 1)
+    if not (x.is_cuda and t.is_contiguous() and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
+            and conv.padding == (0, 0) and conv.groups == 1):
+        return conv(x)
+    wgt = conv.weight.view(conv.weight.shape[0], conv.weight.shape[1])
+    if isinstance(conv, nn.ConvTranspose2d):
+        wgt = wgt.t()                                        # (in, out, 1, 1) -> (out, in)
+    y = _Linear.apply(t.reshape(Bn, H * W, C), wgt, conv.bias)
+    return y.reshape(Bn, H, W, -1).permute(0, 3, 1, 2)
+
+
 class MedNeXtBlock(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, exp_r: int = 4, kernel_size: int = 7, do_res: int = True,
                  norm_type: str = "group", n_groups=None, dim="3d", grn=False):
@@ -296,7 +312,7 @@ class MedNeXtBlock(nn.Module):
         self.conv3 = nn.Conv2d(exp_r * in_channels, out_channels, kernel_size=1)
 
     def forward(self, x, dummy_tensor=None):
-        y = self.conv3(self.act(self.conv2(_inst_norm(self.norm, self.conv1(x)))))
+        y = _conv1x1_cl(self.conv3, self.act(_conv1x1_cl(self.conv2, _inst_norm(self.norm, self.conv1(x)))))
         return x + y if self.do_res else y
 
 
@@ -341,7 +357,7 @@ class OutBlock(nn.Module):
         self.conv_out = nn.ConvTranspose2d(in_channels, n_classes, kernel_size=1)
 
     def forward(self, x, dummy_tensor=None):
-        return self.conv_out(x)
+        return _conv1x1_cl(self.conv_out, x)
 
 
 class MLLA_Enc(nn.Module):
