@@ -9,6 +9,8 @@ hot path plus the cuDNN conv stages and the optimizer; nothing is skipped.  `val
 the batch resident in HBM; `e2e` repeats the measurement through trainer.train_step with a PINNED HOST batch
 (H2D copy of data + 5 targets and a D2H read of the loss every step).  `roofline` is the dominant kernel of the
 named hot path (selective-scan backward): algorithmic bytes / CUDA-event time measured live in the timed region.
+The timed steps replay the whole-step CUDA graph the trainer captures after three eager steps; the per-kernel events
+(roofline, gpu_launches) come from one more pass over the same K steps run eagerly.
 `cpu_baseline` / `--impl reference` time the reference's CPU path (oracle/: the reference module math restated and
 pinned to the reference's own source via tests/golden; scan_ref.c with OpenMP) on the host cores.
 """
@@ -175,14 +177,19 @@ def main():
         ev, _lib.STATS["events"] = _lib.STATS["events"], None
         return float(ms.item()), _lib.STATS["launches"], ev, out
 
-    for _ in range(a.warmup):
+    # warm-up: >= 3 eager steps, then train_step captures the whole step in a CUDA graph (trainer._capture) and replays it
+    for _ in range(a.warmup + 2):
         tr.train_step(resident, sync=False)
+    graphed = tr._graph is not None
     sampler = ClockSampler(local).start() if rank == 0 else None
-    ms, launches, ev, _ = timed(resident, False, a.steps, events=True)
+    ms, _, _, _ = timed(resident, False, a.steps)
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         tr.train_step(host, sync=True)
     ms_e2e, _, _, out = timed(host, True, a.steps)
+    # per-kernel CUDA events need Python between the launches: the same K steps once more, eagerly (not part of `value`);
+    # the graph replays exactly this launch sequence, so the launch count is taken here too
+    ms_eager, launches, ev, _ = timed(resident, False, a.steps, events=True)
 
     if rank != 0:
         if world > 1:
@@ -224,6 +231,7 @@ def main():
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": a.batch_per_gpu * world, "per_gpu_batch": a.batch_per_gpu,
                    "parallelism": f"dp{world}" if world > 1 else "single", "scan_state_dtype": "f32",
+                   "cuda_graph": graphed, "eager_ms_per_step_with_kernel_events": ms_eager / a.steps,
                    "l2": "per-step working set (~14 GB of activations) >> 126 MB L2, no flush needed"},
         "clocks": clocks,
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

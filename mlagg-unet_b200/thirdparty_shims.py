@@ -69,7 +69,7 @@ class CosineLRScheduler:
         self.optimizer = optimizer
         self.t_initial, self.lr_min = t_initial, lr_min
         self.warmup_t, self.warmup_lr_init = warmup_t, warmup_lr_init
-        self.base_values = [g["lr"] for g in optimizer.param_groups]
+        self.base_values = [float(g["lr"]) for g in optimizer.param_groups]
         for g in optimizer.param_groups:
             g.setdefault("initial_lr", g["lr"])
         if warmup_t:
@@ -85,7 +85,10 @@ class CosineLRScheduler:
 
     def _apply(self, values):
         for g, v in zip(self.optimizer.param_groups, values):
-            g["lr"] = v
+            if isinstance(g["lr"], torch.Tensor):
+                g["lr"].fill_(v)     # capturable optimizers keep lr on the device (CUDA-graph safe)
+            else:
+                g["lr"] = v
 
     def step(self, epoch, metric=None):
         self._apply(self._values(epoch))

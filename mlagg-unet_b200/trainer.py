@@ -19,6 +19,8 @@ import math
 from dataclasses import dataclass, field
 
 import numpy as np
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -130,6 +132,9 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         self.amp_dtype = amp_dtype
         self.grad_scaler = torch.amp.GradScaler("cuda") if (amp_dtype == torch.float16 and self.device.type == "cuda") else None
         self.network = self.optimizer = self.lr_scheduler = self.loss = None
+        self.use_cuda_graph = os.environ.get("MLAGG_CUDA_GRAPH", "1") != "0"
+        self._graph = self._graph_key = self._static = self._flat_grad = None
+        self._eager_steps = 0
 
     # ---- reference static API
     @staticmethod
@@ -154,8 +159,10 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
 
     def configure_optimizers(self):
         params = [p for p in self.network.parameters() if p.requires_grad]
-        opt = torch.optim.AdamW(params, self.initial_lr, weight_decay=self.weight_decay, eps=1e-4,
-                                fused=self.device.type == "cuda")
+        cuda = self.device.type == "cuda"
+        # fused + capturable: the step (and the learning rate, kept as a device scalar) can live inside a CUDA graph
+        lr = torch.tensor(self.initial_lr, device=self.device, dtype=torch.float32) if cuda else self.initial_lr
+        opt = torch.optim.AdamW(params, lr, weight_decay=self.weight_decay, eps=1e-4, fused=cuda, capturable=cuda)
         sched = CosineLRScheduler(opt, t_initial=self.num_epochs, lr_min=1e-6, warmup_t=10, warmup_lr_init=1e-4)
         return opt, sched
 
@@ -166,11 +173,14 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
                                                        True).to(self.device)
         if self.device.type == "cuda":
             self.network = self.network.to(memory_format=torch.channels_last)
-        self.optimizer, self.lr_scheduler = self.configure_optimizers()
         if self.is_ddp:
-            from torch.nn.parallel import DistributedDataParallel as DDP
-            ids = [self.device.index] if self.device.type == "cuda" else None
-            self.network = DDP(self.network, device_ids=ids, gradient_as_bucket_view=True, bucket_cap_mb=64)
+            # data parallel without the DDP wrapper: identical start (rank 0's weights), one flat gradient all-reduce per
+            # step (see _step_math).  The reference wraps in DDP (nnUNetTrainer.py:205-207), which cannot survive its own
+            # unused `dummy_tensor` parameter; the arithmetic -- averaged gradients -- is the same.
+            for t in list(self.network.parameters()) + list(self.network.buffers()):
+                dist.broadcast(t.data, 0)
+        self.optimizer, self.lr_scheduler = self.configure_optimizers()
+        self._bind_flat_grads()
         self.loss = self._build_loss()
         return self
 
@@ -189,22 +199,149 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             data, target = data.to(device), [t.to(device) for t in target]
         return {"data": data, "target": target}
 
-    def train_step(self, batch: dict, sync: bool = True) -> dict:
-        data = batch["data"].to(self.device, non_blocking=True)
-        target = [t.to(self.device, non_blocking=True) for t in batch["target"]]
-        self.optimizer.zero_grad(set_to_none=True)
+    # ---- one training step (nnUNetTrainer.train_step, :833-863)
+    def _step_math(self, data, target):
+        """zero grads -> forward -> DiceCE-DS loss -> backward -> gradient all-reduce -> clip(12) -> AdamW.
+        Gradients live in ONE flat fp32 buffer (parameter .grad tensors are views into it), so the data-parallel
+        exchange is a single NCCL all-reduce over NVSwitch (108 MB: well under a millisecond, cheaper than DDP's
+        per-bucket hooks and copies) and clipping is two kernels.  Everything here is capturable in a CUDA graph."""
+        self._flat_grad.zero_()
         with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
             output = self.network(data)
             l = self.loss(output, target)
+        l.backward()
+        if self.is_ddp:
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+            self._flat_grad.div_(dist.get_world_size())
+        # torch.nn.utils.clip_grad_norm_(params, 12): total 2-norm over all gradients == norm of the flat buffer
+        coef = torch.clamp(12.0 / (torch.linalg.vector_norm(self._flat_grad) + 1e-6), max=1.0)
+        self._flat_grad.mul_(coef)
+        self.optimizer.step()
+        return l.detach()
+
+    def _bind_flat_grads(self):
         params = [p for p in self.network.parameters() if p.requires_grad]
-        if self.grad_scaler is not None:
-            self.grad_scaler.scale(l).backward()
-            self.grad_scaler.unscale_(self.optimizer)
-            torch.nn.utils.clip_grad_norm_(params, 12)
-            self.grad_scaler.step(self.optimizer)
-            self.grad_scaler.update()
+        self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=self.device, dtype=torch.float32)
+        off = 0
+        for p in params:
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            assert p.dtype == torch.float32 and dense, "flat gradient views need dense fp32 parameters"
+            # same strides as the parameter (channels_last conv weights): fused AdamW pairs elements by memory order
+            p.grad = self._flat_grad[off:off + p.numel()].as_strided(p.size(), p.stride())
+            off += p.numel()
+
+    def _alloc_static(self, batch):
+        self._static = {"data": torch.empty_like(batch["data"], device=self.device),
+                        "target": [torch.empty_like(t, device=self.device) for t in batch["target"]]}
+        self._static["data"].copy_(batch["data"])
+        for d, t in zip(self._static["target"], batch["target"]):
+            d.copy_(t)
+
+    def _side_stream_warmup(self, fn, n=2):
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                       # warm-up on a side stream, as graph capture requires
+            for _ in range(n):
+                fn()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+
+    def _capture(self, batch):
+        """CUDA graphs over static input buffers.
+        One process: ONE graph holds the whole step (forward, loss, backward, clip, AdamW).
+        Data parallel: collectives stay outside the graphs -- graph A = zero grads + network forward, eager = loss (its
+        batch-dice all-gathers) and d loss / d logits, graph B = network backward, eager = flat gradient all-reduce,
+        clip, AdamW."""
+        self._alloc_static(batch)
+        st = self._static
+        # the side-stream warm-up runs real steps: snapshot weights + optimizer state and put them back afterwards, so
+        # that capturing never changes the training trajectory
+        params = [p for p in self.network.parameters()]
+        snap_p = [p.detach().clone() for p in params]
+        snap_o = [(v, v.clone()) for stt in self.optimizer.state.values() for v in stt.values() if torch.is_tensor(v)]
+        if not self.is_ddp:
+            self._side_stream_warmup(lambda: self._step_math(st["data"], st["target"]))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["loss"] = self._step_math(st["data"], st["target"])
+            self._graph = (graph,)
         else:
-            l.backward()
-            torch.nn.utils.clip_grad_norm_(params, 12)
-            self.optimizer.step()
+            self._side_stream_warmup(lambda: self._step_math(st["data"], st["target"]))
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                self._flat_grad.zero_()
+                with torch.autocast("cuda", dtype=self.amp_dtype):
+                    outs = self.network(st["data"])
+            outs = list(outs) if isinstance(outs, (list, tuple)) else [outs]
+            st["outs"] = outs
+            st["douts"] = [torch.zeros_like(o) for o in outs]
+            with torch.cuda.graph(gb, pool=ga.pool()):
+                torch.autograd.backward(outs, grad_tensors=st["douts"])
+            self._graph = (ga, gb)
+        with torch.no_grad():
+            for p, c in zip(params, snap_p):
+                p.copy_(c)
+            for v, c in snap_o:
+                v.copy_(c)
+        self._graph_key = self._batch_key(batch)
+
+    def _replay(self):
+        st = self._static
+        if len(self._graph) == 1:
+            self._graph[0].replay()
+            return st["loss"]
+        ga, gb = self._graph
+        ga.replay()
+        heads = [o.detach().requires_grad_() for o in st["outs"]]
+        with torch.autocast("cuda", dtype=self.amp_dtype):
+            l = self.loss(heads if len(heads) > 1 else heads[0], st["target"])
+        for d, g in zip(st["douts"], torch.autograd.grad(l, heads)):
+            d.copy_(g)
+        gb.replay()
+        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+        self._flat_grad.div_(dist.get_world_size())
+        coef = torch.clamp(12.0 / (torch.linalg.vector_norm(self._flat_grad) + 1e-6), max=1.0)
+        self._flat_grad.mul_(coef)
+        self.optimizer.step()
+        return l.detach()
+
+    @staticmethod
+    def _batch_key(batch):
+        return (tuple(batch["data"].shape), batch["data"].dtype, tuple(tuple(t.shape) for t in batch["target"]))
+
+    def train_step(self, batch: dict, sync: bool = True) -> dict:
+        from . import _lib
+        if self.grad_scaler is not None:                    # fp16 + GradScaler (the reference's recipe): plain eager step
+            return self._train_step_scaled(batch, sync)
+        graphable = (self.use_cuda_graph and self.device.type == "cuda" and _lib.STATS["events"] is None
+                     and self.network.training)
+        if graphable and self._graph is None and self._eager_steps >= 3:
+            self._capture(batch)
+        if graphable and self._graph is not None and self._graph_key == self._batch_key(batch):
+            self._static["data"].copy_(batch["data"], non_blocking=True)
+            for d, t in zip(self._static["target"], batch["target"]):
+                d.copy_(t, non_blocking=True)
+            l = self._replay()
+        else:
+            data = batch["data"].to(self.device, non_blocking=True)
+            target = [t.to(self.device, non_blocking=True) for t in batch["target"]]
+            l = self._step_math(data, target)
+            self._eager_steps += 1
+        return {"loss": l.cpu().numpy() if sync else l}
+
+    def _train_step_scaled(self, batch: dict, sync: bool = True) -> dict:
+        data = batch["data"].to(self.device, non_blocking=True)
+        target = [t.to(self.device, non_blocking=True) for t in batch["target"]]
+        self._flat_grad.zero_()
+        with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
+            l = self.loss(self.network(data), target)
+        params = [p for p in self.network.parameters() if p.requires_grad]
+        self.grad_scaler.scale(l).backward()
+        if self.is_ddp:
+            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
+            self._flat_grad.div_(dist.get_world_size())
+        self.grad_scaler.unscale_(self.optimizer)
+        torch.nn.utils.clip_grad_norm_(params, 12)
+        self.grad_scaler.step(self.optimizer)
+        self.grad_scaler.update()
         return {"loss": l.detach().cpu().numpy() if sync else l.detach()}

@@ -398,3 +398,25 @@ def test_avgpool_tokens_matches_torch(H, W, pH, pW, C, gelu):
     assert rel_err(xc.grad.cpu(), x64.grad) < TOL32
     y16 = ops.avgpool_tokens(x.cuda().bfloat16(), H, W, pH, pW, gelu=gelu)
     assert rel_err(y16.float().cpu(), ref.detach()) < TOL16
+
+
+def test_cuda_graph_train_step_matches_eager():
+    """The whole-step CUDA graph (trainer._capture) replays the same arithmetic as the eager step: same losses over
+    6 steps on a fixed batch with stochastic depth switched off (its RNG stream differs between the two modes)."""
+    from mlagg_unet_b200.thirdparty_shims import DropPath
+    from mlagg_unet_b200.trainer import SyntheticPlan, nnUNetTrainer_MLAgg_2D_dt_MS
+    losses = {}
+    for graph in (False, True):
+        torch.manual_seed(0)
+        tr = nnUNetTrainer_MLAgg_2D_dt_MS(SyntheticPlan(patch_size=(64, 64), batch_size=2, num_classes=5))
+        tr.use_cuda_graph = graph
+        tr.initialize()
+        for m in tr.network.modules():
+            if isinstance(m, DropPath):
+                m.drop_prob = 0.0
+        batch = tr.synthetic_batch(seed=3, device="cuda")
+        losses[graph] = [float(tr.train_step(batch)["loss"]) for _ in range(6)]
+        assert (tr._graph is not None) == graph
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 2e-2 * abs(a), (losses[False], losses[True])
+    assert losses[True][-1] < losses[True][0]          # and it trains
