@@ -115,6 +115,9 @@ def main():
     ap.add_argument("--size", type=int, default=320)
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="one extra (eagerly launched) step between cudaProfilerStart/Stop, for "
+                         "`ncu --profile-from-start off` launch lists (profiles/README.md)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -187,6 +190,14 @@ def main():
     for _ in range(2):
         tr.train_step(host, sync=True)
     ms_e2e, _, _, out = timed(host, True, a.steps)
+    if a.profile_step:
+        barrier()
+        _lib.STATS["events"] = {}          # eager launches (ncu cannot replay some graph kernel nodes); same kernels
+        torch.cuda.profiler.start()
+        tr.train_step(resident, sync=False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        _lib.STATS["events"] = None
     # per-kernel CUDA events need Python between the launches: the same K steps once more, eagerly (not part of `value`);
     # the graph replays exactly this launch sequence, so the launch count is taken here too
     ms_eager, launches, ev, _ = timed(resident, False, a.steps, events=True)

@@ -133,7 +133,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         self.grad_scaler = torch.amp.GradScaler("cuda") if (amp_dtype == torch.float16 and self.device.type == "cuda") else None
         self.network = self.optimizer = self.lr_scheduler = self.loss = None
         self.use_cuda_graph = os.environ.get("MLAGG_CUDA_GRAPH", "1") != "0"
-        self._graph = self._graph_key = self._static = self._flat_grad = None
+        self._graph = self._graph_key = self._static = self._flat_grad = self._params = self._flat_views = None
         self._eager_steps = 0
 
     # ---- reference static API
@@ -200,34 +200,50 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         return {"data": data, "target": target}
 
     # ---- one training step (nnUNetTrainer.train_step, :833-863)
-    def _step_math(self, data, target):
-        """zero grads -> forward -> DiceCE-DS loss -> backward -> gradient all-reduce -> clip(12) -> AdamW.
-        Gradients live in ONE flat fp32 buffer (parameter .grad tensors are views into it), so the data-parallel
-        exchange is a single NCCL all-reduce over NVSwitch (108 MB: well under a millisecond, cheaper than DDP's
-        per-bucket hooks and copies) and clipping is two kernels.  Everything here is capturable in a CUDA graph."""
-        self._flat_grad.zero_()
+    def _forward_loss(self, data, target):
         with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
-            output = self.network(data)
-            l = self.loss(output, target)
-        l.backward()
+            return self.loss(self.network(data), target)
+
+    def _drop_grads(self):
+        for p in self._params:        # undefined .grad: autograd hands its gradient tensors over instead of adding
+            p.grad = None
+
+    def _reduce_clip_step(self, grads=None):
+        """Gather the per-parameter gradients into ONE flat fp32 buffer (a handful of batched-copy launches), all-reduce
+        it once over NCCL / NVSwitch (108 MB: well under a millisecond, no DDP hooks or buckets), clip the global norm to
+        12 with two kernels on the flat buffer, and let AdamW read its gradients as views of that buffer."""
+        grads = [p.grad for p in self._params] if grads is None else grads
+        parts = [(g if g.stride() == p.stride() else torch.empty_like(p).copy_(g)).as_strided((g.numel(),), (1,))
+                 for g, p in zip(grads, self._params)]
+        torch.cat(parts, out=self._flat_grad)
         if self.is_ddp:
             dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
             self._flat_grad.div_(dist.get_world_size())
         # torch.nn.utils.clip_grad_norm_(params, 12): total 2-norm over all gradients == norm of the flat buffer
         coef = torch.clamp(12.0 / (torch.linalg.vector_norm(self._flat_grad) + 1e-6), max=1.0)
         self._flat_grad.mul_(coef)
+        for p, v in zip(self._params, self._flat_views):
+            p.grad = v
         self.optimizer.step()
+
+    def _step_math(self, data, target):
+        """forward -> DiceCE-DS loss -> backward -> gradient all-reduce -> clip(12) -> AdamW; capturable in a CUDA graph."""
+        self._drop_grads()
+        l = self._forward_loss(data, target)
+        l.backward()
+        self._reduce_clip_step()
         return l.detach()
 
     def _bind_flat_grads(self):
-        params = [p for p in self.network.parameters() if p.requires_grad]
-        self._flat_grad = torch.zeros(sum(p.numel() for p in params), device=self.device, dtype=torch.float32)
-        off = 0
-        for p in params:
+        self._params = [p for p in self.network.parameters() if p.requires_grad]
+        self._flat_grad = torch.zeros(sum(p.numel() for p in self._params), device=self.device, dtype=torch.float32)
+        self._flat_views, off = [], 0
+        for p in self._params:
             dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
             assert p.dtype == torch.float32 and dense, "flat gradient views need dense fp32 parameters"
-            # same strides as the parameter (channels_last conv weights): fused AdamW pairs elements by memory order
-            p.grad = self._flat_grad[off:off + p.numel()].as_strided(p.size(), p.stride())
+            # same strides as the parameter (channels_last conv weights): autograd's gradient layout contract gives
+            # .grad the parameter's strides, and fused AdamW pairs elements by memory order
+            self._flat_views.append(self._flat_grad[off:off + p.numel()].as_strided(p.size(), p.stride()))
             off += p.numel()
 
     def _alloc_static(self, batch):
@@ -269,14 +285,15 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             self._side_stream_warmup(lambda: self._step_math(st["data"], st["target"]))
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(ga):
-                self._flat_grad.zero_()
                 with torch.autocast("cuda", dtype=self.amp_dtype):
                     outs = self.network(st["data"])
             outs = list(outs) if isinstance(outs, (list, tuple)) else [outs]
             st["outs"] = outs
             st["douts"] = [torch.zeros_like(o) for o in outs]
+            self._drop_grads()
             with torch.cuda.graph(gb, pool=ga.pool()):
                 torch.autograd.backward(outs, grad_tensors=st["douts"])
+            st["grads"] = [p.grad for p in self._params]     # written in place by every replay of graph B
             self._graph = (ga, gb)
         with torch.no_grad():
             for p, c in zip(params, snap_p):
@@ -298,11 +315,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         for d, g in zip(st["douts"], torch.autograd.grad(l, heads)):
             d.copy_(g)
         gb.replay()
-        dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
-        self._flat_grad.div_(dist.get_world_size())
-        coef = torch.clamp(12.0 / (torch.linalg.vector_norm(self._flat_grad) + 1e-6), max=1.0)
-        self._flat_grad.mul_(coef)
-        self.optimizer.step()
+        self._reduce_clip_step(st["grads"])
         return l.detach()
 
     @staticmethod
@@ -332,14 +345,13 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
     def _train_step_scaled(self, batch: dict, sync: bool = True) -> dict:
         data = batch["data"].to(self.device, non_blocking=True)
         target = [t.to(self.device, non_blocking=True) for t in batch["target"]]
-        self._flat_grad.zero_()
-        with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
-            l = self.loss(self.network(data), target)
-        params = [p for p in self.network.parameters() if p.requires_grad]
+        self._drop_grads()
+        l = self._forward_loss(data, target)
+        params = self._params
         self.grad_scaler.scale(l).backward()
         if self.is_ddp:
-            dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
-            self._flat_grad.div_(dist.get_world_size())
+            for p in params:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
         self.grad_scaler.unscale_(self.optimizer)
         torch.nn.utils.clip_grad_norm_(params, 12)
         self.grad_scaler.step(self.optimizer)
