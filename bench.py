@@ -226,13 +226,20 @@ def main():
         kern[name] = {"launches": len(ts), "ms_avg": sum(ts) / len(ts), "ms_total": sum(ts)}
     dom = "scan_bwd"
     roof = None
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "scan_bwd_r01_ncu.json")))
+        if prof["shape"] == {"batch": a.batch_per_gpu, "dim": D, "groups": G, "dstate": N, "L": Lcat}:
+            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+    except Exception:
+        pass
     if dom in kern:
         ach = alg[dom] / (kern[dom]["ms_avg"] * 1e-3) / 1e9
         roof = {"kernel": "mlagg::scan_bwd_kernel (selective-scan backward, mamba interface, fp32 I/O)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": kern[dom]["ms_avg"],
-                "traffic": None,
+                "traffic": traffic,
                 "also": {k: {"ms_avg": v["ms_avg"], "launches_per_step": v["launches"] / a.steps,
                              **({"achieved_GBps": alg[k] / (v["ms_avg"] * 1e-3) / 1e9} if k in alg else {})}
                          for k, v in kern.items()}}
