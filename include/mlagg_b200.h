@@ -140,11 +140,14 @@ int mlagg_local_diffattn_bwd(const void *q, const void *k, const void *v, const 
  * `scale` = hd**-0.5 (once at :688, once more as flash-attn's default softmax_scale).
  *   q   : (batch, N, h, 2, hd) RAW projection, row stride ldq
  *   kp  : (batch, P, h, 2, hd), vp : (batch, P, h, 2hd); common row stride ldkv; P <= 256, P*hd*16 B of shared memory
- *   out : (batch, N, h, 2hd) row stride ldo;   lse : (batch, N, h, 2) fp32, nullable (needed by the backward)
+ *   out : (batch, N, h, 2hd) row stride ldo;
+ *   lse : nullable; mlagg_pooled_diffattn_saved_bytes(...) bytes, 16-byte aligned, saved for the backward pass:
+ *         (batch, N, h, 2) log-sum-exps followed by the normalised per-map outputs O0 | O1 (batch, N, h, 2, 2hd) fp32
  * Backward: dkp / dvp are fp32 (batch, P, h, 2hd) with common row stride ldd, ACCUMULATED INTO (zero-fill);
  *   d_subln_w (2hd), d_lambda (1) ACCUMULATED INTO; ws: mlagg_pooled_diffattn_ws_bytes(...) bytes of scratch.
  * ------------------------------------------------------------------------------------------ */
 size_t mlagg_pooled_diffattn_ws_bytes(int batch, int N, int heads, int head_dim);
+size_t mlagg_pooled_diffattn_saved_bytes(int batch, int N, int heads, int head_dim);
 int mlagg_pooled_diffattn_fwd(const void *q, const void *kp, const void *vp, const float *subln_w, void *out,
                               float *lse, int batch, int N, int P, int heads, int head_dim, long long ldq,
                               long long ldkv, long long ldo, float scale, const float *lam, float eps,

@@ -39,6 +39,7 @@ SIGNATURES = {
     "mlagg_causal_conv1d_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),
     "mlagg_causal_conv1d_bwd": (c_i, [c_p] * 7 + [c_i] * 5 + [c_p]),
     "mlagg_pooled_diffattn_ws_bytes": (c_sz, [c_i] * 4),
+    "mlagg_pooled_diffattn_saved_bytes": (c_sz, [c_i] * 4),
     "mlagg_pooled_diffattn_fwd": (c_i, [c_p] * 6 + [c_i] * 5 + [c_ll] * 3 + [c_f, c_p, c_f, c_f] + [c_i, c_p]),
     "mlagg_pooled_diffattn_bwd": (c_i, [c_p] * 12 + [c_i] * 5 + [c_ll] * 5 + [c_f, c_p, c_f, c_f] + [c_i, c_p]),
     "mlagg_local_diffattn_ws_bytes": (c_sz, [c_i] * 5),

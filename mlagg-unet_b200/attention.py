@@ -95,7 +95,8 @@ class _PooledDiffAttn(torch.autograd.Function):
         lam_ = lam.detach().float().reshape(1).contiguous()
         w_ = subln_w.detach().float().contiguous()
         out = torch.empty_like(q_)
-        lse = torch.empty(Bn, N, h, 2, device=q.device, dtype=torch.float32)
+        lse = torch.empty(_lib.lib().mlagg_pooled_diffattn_saved_bytes(Bn, N, h, hd) // 4, device=q.device,
+                          dtype=torch.float32)      # log-sum-exps + the per-map outputs O0 | O1 (for the backward pass)
         es = q_.element_size()
         with torch.cuda.device(q.device), _lib.timed("pooled_diffattn_fwd"):
             rc = _lib.lib().mlagg_pooled_diffattn_fwd(q_.data_ptr(), kv_.data_ptr(), kv_.data_ptr() + C * es,

@@ -288,6 +288,12 @@ extern "C" size_t mlagg_pooled_diffattn_ws_bytes(int batch, int N, int heads, in
     return (size_t)batch * N * heads * (2 * head_dim + 2) * sizeof(float);
 }
 
+extern "C" size_t mlagg_pooled_diffattn_saved_bytes(int batch, int N, int heads, int head_dim) {
+    if (batch <= 0 || N <= 0 || heads <= 0 || head_dim <= 0) return 0;
+    const size_t lse = (((size_t)batch * N * heads * 2) + 3) & ~(size_t)3;       // floats, O rows stay 16 B aligned
+    return (lse + (size_t)batch * N * heads * 4 * head_dim) * sizeof(float);
+}
+
 static int pooled_check(const void *q, const void *kp, const void *vp, const float *w, const float *lam, int batch,
                         int N, int P, int heads, int head_dim, int dtype) {
     if (!q || !kp || !vp || !w || !lam) return MLAGG_ERR_NULL;
@@ -323,6 +329,7 @@ extern "C" int mlagg_pooled_diffattn_bwd(const void *q, const void *kp, const vo
     int rc = pooled_check(q, kp, vp, subln_w, lam, batch, N, P, heads, head_dim, dtype);
     if (rc) return rc;
     if (!lse || !dout || !dq || !dkp || !dvp || !d_subln_w || !d_lambda || !ws) return MLAGG_ERR_NULL;
+    if (!aligned(lse, 16) || !aligned(ws, 16)) return MLAGG_ERR_ALIGN;
     PooledAttnParams p;
     memset(&p, 0, sizeof(p));
     p.q = q; p.kp = kp; p.vp = vp; p.dout = dout; p.dq = dq; p.lse = const_cast<float *>(lse);

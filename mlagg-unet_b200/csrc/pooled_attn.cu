@@ -33,7 +33,7 @@ __device__ __forceinline__ void pl_st<__nv_bfloat16>(__nv_bfloat16 *p, float v) 
 struct PooledAttnParams {
     const void *q, *kp, *vp, *dout;
     void *out, *dq;
-    float *lse;                  // (B,N,h,2)
+    float *lse;                  // saved: (B,N,h,2) log-sum-exps, then (16 B aligned) (B,N,h,2,2hd) normalised O0 | O1
     float *dkp, *dvp;            // (B,P,h,2hd) fp32 each, row stride ldd (accumulated)
     const float *subln_w;
     float *d_subln_w, *d_lambda;
@@ -46,96 +46,121 @@ struct PooledAttnParams {
 
 constexpr int kPTok = 128;       // query tokens per block (fwd / token-parallel bwd)
 
+// All inner products are PACKED f32x2 (FFMA2: two fp32 FMAs per issue slot; exact fp32 arithmetic):
+//   logits (d0, d1) += (q0[c], q1[c]) * (k0[c], k1[c])        K staged interleaved:  kI[p][c] = (K[p][c], K[p][hd + c])
+//   (o0[c], o1[c])  += (w0, w1) * (v[c], v[c])
+// and every shared-memory read is a warp-wide broadcast LDS.128.  ncu (profiles/pooled_fwd_r01_ncu_raw.txt): these
+// kernels are bound by the shared-memory return path -- a broadcast LDS.128 still delivers 512 B of lane data, i.e. 4
+// cycles of the 128 B/clk pipe, for 8..16 FMAs per lane -- at ~19 % of the FP32 peak; the way out is operand reuse in
+// registers across tokens, i.e. tensor-core fragments.
+__device__ __forceinline__ float2 p2(float a, float b) { return make_float2(a, b); }
+
+__device__ __forceinline__ size_t pooled_osave_offset(const PooledAttnParams &p) {
+    return (((size_t)p.Bn * p.N * p.h * 2) + 3) & ~(size_t)3;   // floats; keeps the O rows 16-byte aligned
+}
+
 template <typename T, int HD>
-__device__ __forceinline__ void stage_kv(const PooledAttnParams &p, int b, int m, float *ks, float *vs) {
+__device__ __forceinline__ void stage_k_interleaved(const PooledAttnParams &p, int b, int m, float2 *kI) {
     const T *kb = static_cast<const T *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
+    for (int i = threadIdx.x; i < p.P * HD; i += blockDim.x) {
+        const int pp = i / HD, c = i % HD;
+        kI[i] = p2(pl_ld<T>(kb + (long long)pp * p.ldkv + c), pl_ld<T>(kb + (long long)pp * p.ldkv + HD + c));
+    }
+}
+template <typename T, int HD, bool DUP>
+__device__ __forceinline__ void stage_v(const PooledAttnParams &p, int b, int m, float *vs) {
     const T *vb = static_cast<const T *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
     for (int i = threadIdx.x; i < p.P * 2 * HD; i += blockDim.x) {
         const int pp = i / (2 * HD), c = i % (2 * HD);
-        ks[i] = pl_ld<T>(kb + (long long)pp * p.ldkv + c);
-        vs[i] = pl_ld<T>(vb + (long long)pp * p.ldkv + c);
+        const float v = pl_ld<T>(vb + (long long)pp * p.ldkv + c);
+        if (DUP) reinterpret_cast<float2 *>(vs)[i] = p2(v, v);
+        else vs[i] = v;
     }
+}
+// (d0, d1) = sum_c q2[c] * kI[pp][c]
+template <int HD>
+__device__ __forceinline__ float2 logits2(const float2 (&q2)[HD], const float2 *krow) {
+    float2 acc[4] = {p2(0.f, 0.f), p2(0.f, 0.f), p2(0.f, 0.f), p2(0.f, 0.f)};   // 4 independent chains
+#pragma unroll
+    for (int c = 0; c < HD; c += 2) {
+        const float4 kk = *reinterpret_cast<const float4 *>(krow + c);
+        acc[c & 3] = __ffma2_rn(q2[c], p2(kk.x, kk.y), acc[c & 3]);
+        acc[(c & 3) + 1] = __ffma2_rn(q2[c + 1], p2(kk.z, kk.w), acc[(c & 3) + 1]);
+    }
+    return __fadd2_rn(__fadd2_rn(acc[0], acc[1]), __fadd2_rn(acc[2], acc[3]));
 }
 
 template <typename T, int HD>
 __global__ void __launch_bounds__(kPTok) pooled_attn_fwd_kernel(const PooledAttnParams p) {
     extern __shared__ __align__(16) float smem[];
-    float *ks = smem, *vs = smem + p.P * 2 * HD;
+    float2 *kI = reinterpret_cast<float2 *>(smem);                 // [P][HD]
+    float *vP = reinterpret_cast<float *>(kI + p.P * HD);          // [P][2HD]
     const int b = blockIdx.z, m = blockIdx.y;
-    stage_kv<T, HD>(p, b, m, ks, vs);
+    stage_k_interleaved<T, HD>(p, b, m, kI);
+    stage_v<T, HD, false>(p, b, m, vP);
     __syncthreads();
     const int n = blockIdx.x * kPTok + threadIdx.x;
     if (n >= p.N) return;
     const long long tok = (long long)b * p.N + n;
-    float q[2 * HD];
+    float2 q2[HD];
     const T *qp = static_cast<const T *>(p.q) + tok * p.ldq + (long long)m * 2 * HD;
     const float qs = p.scale2 * kLog2e;  // work in the exp2 domain
 #pragma unroll
-    for (int c = 0; c < 2 * HD; ++c) q[c] = pl_ld<T>(qp + c) * qs;
-    float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-    float o0[2 * HD], o1[2 * HD];
+    for (int c = 0; c < HD; ++c) q2[c] = p2(pl_ld<T>(qp + c) * qs, pl_ld<T>(qp + HD + c) * qs);
+    float2 mx = p2(-INFINITY, -INFINITY), l = p2(0.f, 0.f);
+    float2 o[2 * HD];                                              // (o0[c], o1[c])
 #pragma unroll
-    for (int c = 0; c < 2 * HD; ++c) o0[c] = o1[c] = 0.f;
+    for (int c = 0; c < 2 * HD; ++c) o[c] = p2(0.f, 0.f);
+    float2 dnext = logits2<HD>(q2, kI);
     for (int pp = 0; pp < p.P; ++pp) {
-        const float4 *k4 = reinterpret_cast<const float4 *>(ks + pp * 2 * HD);
-        float d0 = 0.f, d1 = 0.f;
-        if constexpr (HD % 4 == 0) {
+        const float2 d = dnext;
+        if (pp + 1 < p.P) dnext = logits2<HD>(q2, kI + (pp + 1) * HD);   // independent of the softmax / AV work below
+        if (d.x > mx.x || d.y > mx.y) {
+            const float2 nm = p2(fmaxf(mx.x, d.x), fmaxf(mx.y, d.y));
+            const float2 f = p2(ex2_approx(mx.x - nm.x), ex2_approx(mx.y - nm.y));
+            l = __fmul2_rn(l, f);
 #pragma unroll
-            for (int c = 0; c < HD / 4; ++c) {
-                const float4 a = k4[c], bb = k4[HD / 4 + c];
-                d0 = fmaf(q[4 * c], a.x, fmaf(q[4 * c + 1], a.y, fmaf(q[4 * c + 2], a.z, fmaf(q[4 * c + 3], a.w, d0))));
-                d1 = fmaf(q[HD + 4 * c], bb.x, fmaf(q[HD + 4 * c + 1], bb.y, fmaf(q[HD + 4 * c + 2], bb.z, fmaf(q[HD + 4 * c + 3], bb.w, d1))));
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < HD; ++c) {
-                d0 = fmaf(q[c], ks[pp * 2 * HD + c], d0);
-                d1 = fmaf(q[HD + c], ks[pp * 2 * HD + HD + c], d1);
-            }
+            for (int c = 0; c < 2 * HD; ++c) o[c] = __fmul2_rn(o[c], f);
+            mx = nm;
         }
-        float w0, w1;
-        if (d0 > mx[0]) {
-            const float f = ex2_approx(mx[0] - d0);
-            l[0] *= f;
+        const float2 w = p2(ex2_approx(d.x - mx.x), ex2_approx(d.y - mx.y));
+        l = __fadd2_rn(l, w);
+        // the shared-memory return path (128 B of lane data per cycle and SM), not the FMA pipe, bounds this loop: a
+        // duplicated-pair layout of V would save the four register moves below but double the LDS traffic
+        const float *vrow = vP + pp * 2 * HD;
 #pragma unroll
-            for (int c = 0; c < 2 * HD; ++c) o0[c] *= f;
-            mx[0] = d0;
-        }
-        if (d1 > mx[1]) {
-            const float f = ex2_approx(mx[1] - d1);
-            l[1] *= f;
-#pragma unroll
-            for (int c = 0; c < 2 * HD; ++c) o1[c] *= f;
-            mx[1] = d1;
-        }
-        w0 = ex2_approx(d0 - mx[0]);
-        w1 = ex2_approx(d1 - mx[1]);
-        l[0] += w0;
-        l[1] += w1;
-        const float *vrow = vs + pp * 2 * HD;
-#pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) {
-            const float vv = vrow[c];
-            o0[c] = fmaf(w0, vv, o0[c]);
-            o1[c] = fmaf(w1, vv, o1[c]);
+        for (int c = 0; c < 2 * HD; c += 4) {
+            const float4 vv = *reinterpret_cast<const float4 *>(vrow + c);
+            o[c] = __ffma2_rn(w, p2(vv.x, vv.x), o[c]);
+            o[c + 1] = __ffma2_rn(w, p2(vv.y, vv.y), o[c + 1]);
+            o[c + 2] = __ffma2_rn(w, p2(vv.z, vv.z), o[c + 2]);
+            o[c + 3] = __ffma2_rn(w, p2(vv.w, vv.w), o[c + 3]);
         }
     }
     const float lam = __ldg(p.lamp);
-    const float i0 = 1.f / l[0], i1 = lam / l[1];
+    const float2 inv = p2(1.f / l.x, 1.f / l.y);
     float ss = 0.f;
+    float oc[2 * HD];
 #pragma unroll
     for (int c = 0; c < 2 * HD; ++c) {
-        o0[c] = o0[c] * i0 - o1[c] * i1;
-        ss = fmaf(o0[c], o0[c], ss);
+        o[c] = __fmul2_rn(o[c], inv);                              // normalised O0, O1
+        oc[c] = o[c].x - lam * o[c].y;
+        ss = fmaf(oc[c], oc[c], ss);
     }
     const float r = 1.f / sqrtf(ss * (1.f / (2 * HD)) + p.eps);
     T *op = static_cast<T *>(p.out) + tok * p.ldo + (long long)m * 2 * HD;
 #pragma unroll
-    for (int c = 0; c < 2 * HD; ++c) pl_st<T>(op + c, o0[c] * r * __ldg(p.subln_w + c) * p.post);
+    for (int c = 0; c < 2 * HD; ++c) pl_st<T>(op + c, oc[c] * r * __ldg(p.subln_w + c) * p.post);
     if (p.lse) {
-        // natural-log-domain log-sum-exp of the scaled logits, kept in the exp2 domain: lse2 = mx + log2(l)
-        p.lse[(tok * p.h + m) * 2 + 0] = mx[0] + lg2_approx(l[0]);
-        p.lse[(tok * p.h + m) * 2 + 1] = mx[1] + lg2_approx(l[1]);
+        // log-sum-exp of the scaled logits in the exp2 domain (lse2 = mx + log2 l), then O0 | O1 for the backward pass
+        p.lse[(tok * p.h + m) * 2 + 0] = mx.x + lg2_approx(l.x);
+        p.lse[(tok * p.h + m) * 2 + 1] = mx.y + lg2_approx(l.y);
+        float4 *os = reinterpret_cast<float4 *>(p.lse + pooled_osave_offset(p) + (tok * p.h + m) * 4 * HD);
+#pragma unroll
+        for (int c = 0; c < 2 * HD; c += 4) {
+            os[c / 4] = make_float4(o[c].x, o[c + 1].x, o[c + 2].x, o[c + 3].x);
+            os[(2 * HD + c) / 4] = make_float4(o[c].y, o[c + 1].y, o[c + 2].y, o[c + 3].y);
+        }
     }
 }
 
@@ -143,9 +168,11 @@ template <typename T, int HD>
 __global__ void __launch_bounds__(kPTok) pooled_attn_bwd_q_kernel(const PooledAttnParams p) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float red[2 * HD + 1];
-    float *ks = smem, *vs = smem + p.P * 2 * HD;
+    float2 *kI = reinterpret_cast<float2 *>(smem);                 // [P][HD]
+    float *vP = reinterpret_cast<float *>(kI + p.P * HD);          // [P][2HD]
     const int b = blockIdx.z, m = blockIdx.y;
-    stage_kv<T, HD>(p, b, m, ks, vs);
+    stage_k_interleaved<T, HD>(p, b, m, kI);
+    stage_v<T, HD, false>(p, b, m, vP);
     for (int i = threadIdx.x; i < 2 * HD + 1; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
     const int n = blockIdx.x * kPTok + threadIdx.x;
@@ -154,86 +181,97 @@ __global__ void __launch_bounds__(kPTok) pooled_attn_bwd_q_kernel(const PooledAt
     for (int c = 0; c < 2 * HD; ++c) dw[c] = 0.f;
     if (n < p.N) {
         const long long tok = (long long)b * p.N + n;
-        float q[2 * HD];
+        const float lam = __ldg(p.lamp);
+        // ---- RMSNorm backward from the saved O0, O1:  o = O0 - lam O1
+        float g[2 * HD];
+        float D0 = 0.f, D1 = 0.f;
+        {
+            float o0[2 * HD], o1[2 * HD];
+            const float4 *os = reinterpret_cast<const float4 *>(p.lse + pooled_osave_offset(p) + (tok * p.h + m) * 4 * HD);
+#pragma unroll
+            for (int c = 0; c < 2 * HD; c += 4) {
+                const float4 a = os[c / 4], bb = os[(2 * HD + c) / 4];
+                o0[c] = a.x, o0[c + 1] = a.y, o0[c + 2] = a.z, o0[c + 3] = a.w;
+                o1[c] = bb.x, o1[c + 1] = bb.y, o1[c + 2] = bb.z, o1[c + 3] = bb.w;
+            }
+            float ss = 0.f;
+            const T *gp = static_cast<const T *>(p.dout) + tok * p.lddo + (long long)m * 2 * HD;
+#pragma unroll
+            for (int c = 0; c < 2 * HD; ++c) {
+                const float oc = o0[c] - lam * o1[c];
+                ss = fmaf(oc, oc, ss);
+                g[c] = pl_ld<T>(gp + c);
+            }
+            const float r = 1.f / sqrtf(ss * (1.f / (2 * HD)) + p.eps);
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2 * HD; ++c) {
+                const float oc = o0[c] - lam * o1[c];
+                dw[c] = g[c] * p.post * oc * r;
+                g[c] *= p.post * __ldg(p.subln_w + c);
+                dot = fmaf(g[c], oc, dot);
+            }
+            const float k3 = r * r * r * dot * (1.f / (2 * HD));
+            float *wdO = p.ws_dO + (tok * p.h + m) * 2 * HD;
+#pragma unroll
+            for (int c = 0; c < 2 * HD; ++c) {
+                const float oc = o0[c] - lam * o1[c];
+                g[c] = r * g[c] - oc * k3;  // g now holds dO
+                D0 = fmaf(g[c], o0[c], D0);
+                D1 = fmaf(g[c], o1[c], D1);
+            }
+#pragma unroll
+            for (int c = 0; c < 2 * HD; c += 4)
+                *reinterpret_cast<float4 *>(wdO + c) = make_float4(g[c], g[c + 1], g[c + 2], g[c + 3]);
+            p.ws_D[(tok * p.h + m) * 2 + 0] = D0;
+            p.ws_D[(tok * p.h + m) * 2 + 1] = D1;
+            dlam = -D1;
+        }
+        // ---- dq_j = scale2 * sum_p dlogit_jp k_jp
+        float2 q2[HD], dq2[HD];
         const T *qp = static_cast<const T *>(p.q) + tok * p.ldq + (long long)m * 2 * HD;
         const float qs = p.scale2 * kLog2e;
 #pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) q[c] = pl_ld<T>(qp + c) * qs;
+        for (int c = 0; c < HD; ++c) {
+            q2[c] = p2(pl_ld<T>(qp + c) * qs, pl_ld<T>(qp + HD + c) * qs);
+            dq2[c] = p2(0.f, 0.f);
+        }
         const float lse0 = p.lse[(tok * p.h + m) * 2 + 0], lse1 = p.lse[(tok * p.h + m) * 2 + 1];
-        const float lam = __ldg(p.lamp);
-        float o0[2 * HD], o1[2 * HD];
+        auto dot_v = [&](int pp) {   // dO . v_p
+            float2 da = p2(0.f, 0.f), db = p2(0.f, 0.f);
+            const float *vrow = vP + pp * 2 * HD;
 #pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) o0[c] = o1[c] = 0.f;
+            for (int c = 0; c < 2 * HD; c += 4) {
+                const float4 vv = *reinterpret_cast<const float4 *>(vrow + c);
+                da = __ffma2_rn(p2(g[c], g[c + 1]), p2(vv.x, vv.y), da);
+                db = __ffma2_rn(p2(g[c + 2], g[c + 3]), p2(vv.z, vv.w), db);
+            }
+            return (da.x + da.y) + (db.x + db.y);
+        };
+        float2 dnext = logits2<HD>(q2, kI);
+        float dabnext = dot_v(0);
         for (int pp = 0; pp < p.P; ++pp) {
-            float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < HD; ++c) {
-                d0 = fmaf(q[c], ks[pp * 2 * HD + c], d0);
-                d1 = fmaf(q[HD + c], ks[pp * 2 * HD + HD + c], d1);
+            const float2 d = dnext;
+            const float dab = dabnext;
+            if (pp + 1 < p.P) {          // next pooled token's reductions overlap this one's dq update
+                dnext = logits2<HD>(q2, kI + (pp + 1) * HD);
+                dabnext = dot_v(pp + 1);
             }
-            const float w0 = ex2_approx(d0 - lse0), w1 = ex2_approx(d1 - lse1);
+            const float2 dl = p2(ex2_approx(d.x - lse0) * (dab - D0), -lam * ex2_approx(d.y - lse1) * (dab - D1));
+            const float2 *krow = kI + pp * HD;
 #pragma unroll
-            for (int c = 0; c < 2 * HD; ++c) {
-                const float vv = vs[pp * 2 * HD + c];
-                o0[c] = fmaf(w0, vv, o0[c]);
-                o1[c] = fmaf(w1, vv, o1[c]);
-            }
-        }
-        // o = o0 - lam o1; RMSNorm backward
-        float g[2 * HD], ss = 0.f;
-        const T *gp = static_cast<const T *>(p.dout) + tok * p.lddo + (long long)m * 2 * HD;
-#pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) {
-            const float oc = o0[c] - lam * o1[c];
-            ss = fmaf(oc, oc, ss);
-            g[c] = pl_ld<T>(gp + c);
-        }
-        const float r = 1.f / sqrtf(ss * (1.f / (2 * HD)) + p.eps);
-        float dot = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) {
-            const float oc = o0[c] - lam * o1[c];
-            dw[c] = g[c] * p.post * oc * r;
-            g[c] *= p.post * __ldg(p.subln_w + c);
-            dot = fmaf(g[c], oc, dot);
-        }
-        const float k3 = r * r * r * dot * (1.f / (2 * HD));
-        float D0 = 0.f, D1 = 0.f;
-        float *wdO = p.ws_dO + (tok * p.h + m) * 2 * HD;
-#pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) {
-            const float oc = o0[c] - lam * o1[c];
-            g[c] = r * g[c] - oc * k3;  // g now holds dO
-            D0 = fmaf(g[c], o0[c], D0);
-            D1 = fmaf(g[c], o1[c], D1);
-            wdO[c] = g[c];
-        }
-        p.ws_D[(tok * p.h + m) * 2 + 0] = D0;
-        p.ws_D[(tok * p.h + m) * 2 + 1] = D1;
-        dlam = -D1;
-        // second pass: dq_j = scale2 * sum_p dlogit_jp k_jp   (o0 / o1 registers are reused as the accumulator)
-#pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) o0[c] = 0.f;
-        for (int pp = 0; pp < p.P; ++pp) {
-            float d0 = 0.f, d1 = 0.f, dab = 0.f;
-#pragma unroll
-            for (int c = 0; c < HD; ++c) {
-                d0 = fmaf(q[c], ks[pp * 2 * HD + c], d0);
-                d1 = fmaf(q[HD + c], ks[pp * 2 * HD + HD + c], d1);
-            }
-#pragma unroll
-            for (int c = 0; c < 2 * HD; ++c) dab = fmaf(g[c], vs[pp * 2 * HD + c], dab);
-            const float dl0 = ex2_approx(d0 - lse0) * (dab - D0);
-            const float dl1 = -lam * ex2_approx(d1 - lse1) * (dab - D1);
-#pragma unroll
-            for (int c = 0; c < HD; ++c) {
-                o0[c] = fmaf(dl0, ks[pp * 2 * HD + c], o0[c]);
-                o0[HD + c] = fmaf(dl1, ks[pp * 2 * HD + HD + c], o0[HD + c]);
+            for (int c = 0; c < HD; c += 2) {
+                const float4 kk = *reinterpret_cast<const float4 *>(krow + c);
+                dq2[c] = __ffma2_rn(dl, p2(kk.x, kk.y), dq2[c]);
+                dq2[c + 1] = __ffma2_rn(dl, p2(kk.z, kk.w), dq2[c + 1]);
             }
         }
         T *dqp = static_cast<T *>(p.dq) + tok * p.lddq + (long long)m * 2 * HD;
 #pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) pl_st<T>(dqp + c, o0[c] * p.scale2);
+        for (int c = 0; c < HD; ++c) {
+            pl_st<T>(dqp + c, dq2[c].x * p.scale2);
+            pl_st<T>(dqp + HD + c, dq2[c].y * p.scale2);
+        }
     }
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) dlam += __shfl_xor_sync(0xffffffffu, dlam, o2);
@@ -259,34 +297,42 @@ constexpr int kSlab = 512, kSub = 32;
 
 template <typename T, int HD>
 __global__ void __launch_bounds__(256) pooled_attn_bwd_kv_kernel(const PooledAttnParams p) {
-    __shared__ __align__(16) float sq[kSub][2 * HD];
+    __shared__ __align__(16) float2 sq[kSub][HD];       // (q0[c], q1[c]), already in the exp2 domain
     __shared__ __align__(16) float sdo[kSub][2 * HD];
-    __shared__ float sl[kSub][4];  // lse0, lse1, D0, D1
+    __shared__ float sl[kSub][4];                       // lse0, lse1, D0, D1
     const int b = blockIdx.z, m = blockIdx.y;
     const int pp = threadIdx.x;
     const bool active = pp < p.P;
-    float k[2 * HD], v[2 * HD], dk[2 * HD], dv[2 * HD];
+    float2 k2[HD], v2[HD], dk2[HD], dv2[HD];            // k2 interleaved (k0[c], k1[c]); v2, dv2 = consecutive pairs
     if (active) {
         const T *kb = static_cast<const T *>(p.kp) + ((long long)b * p.P + pp) * p.ldkv + (long long)m * 2 * HD;
         const T *vb = static_cast<const T *>(p.vp) + ((long long)b * p.P + pp) * p.ldkv + (long long)m * 2 * HD;
 #pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) {
-            k[c] = pl_ld<T>(kb + c);
-            v[c] = pl_ld<T>(vb + c);
+        for (int c = 0; c < HD; ++c) {
+            k2[c] = p2(pl_ld<T>(kb + c), pl_ld<T>(kb + HD + c));
+            v2[c] = p2(pl_ld<T>(vb + 2 * c), pl_ld<T>(vb + 2 * c + 1));
         }
+    } else {
+#pragma unroll
+        for (int c = 0; c < HD; ++c) k2[c] = v2[c] = p2(0.f, 0.f);
     }
 #pragma unroll
-    for (int c = 0; c < 2 * HD; ++c) dk[c] = dv[c] = 0.f;
+    for (int c = 0; c < HD; ++c) dk2[c] = dv2[c] = p2(0.f, 0.f);
     const float lam = __ldg(p.lamp);
     const float qs = p.scale2 * kLog2e;
     const int n0 = blockIdx.x * kSlab, n1 = min(p.N, n0 + kSlab);
     for (int base = n0; base < n1; base += kSub) {
         const int cnt = min(kSub, n1 - base);
         __syncthreads();
+        for (int i = threadIdx.x; i < cnt * HD; i += blockDim.x) {
+            const int t = i / HD, c = i % HD;
+            const long long tok = (long long)b * p.N + base + t;
+            const T *qp = static_cast<const T *>(p.q) + tok * p.ldq + (long long)m * 2 * HD;
+            sq[t][c] = p2(pl_ld<T>(qp + c) * qs, pl_ld<T>(qp + HD + c) * qs);
+        }
         for (int i = threadIdx.x; i < cnt * 2 * HD; i += blockDim.x) {
             const int t = i / (2 * HD), c = i % (2 * HD);
             const long long tok = (long long)b * p.N + base + t;
-            sq[t][c] = pl_ld<T>(static_cast<const T *>(p.q) + tok * p.ldq + (long long)m * 2 * HD + c);
             sdo[t][c] = p.ws_dO[(tok * p.h + m) * 2 * HD + c];
         }
         for (int i = threadIdx.x; i < cnt * 4; i += blockDim.x) {
@@ -297,24 +343,27 @@ __global__ void __launch_bounds__(256) pooled_attn_bwd_kv_kernel(const PooledAtt
         __syncthreads();
         if (active) {
             for (int t = 0; t < cnt; ++t) {
-                float d0 = 0.f, d1 = 0.f, dab = 0.f;
+                const float2 d = logits2<HD>(k2, &sq[t][0]);
+                float2 da = p2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < HD; ++c) {
-                    d0 = fmaf(sq[t][c], k[c], d0);
-                    d1 = fmaf(sq[t][HD + c], k[HD + c], d1);
+                for (int c = 0; c < HD; c += 2) {
+                    const float4 gg = *reinterpret_cast<const float4 *>(&sdo[t][2 * c]);
+                    da = __ffma2_rn(p2(gg.x, gg.y), v2[c], da);
+                    da = __ffma2_rn(p2(gg.z, gg.w), v2[c + 1], da);
                 }
-#pragma unroll
-                for (int c = 0; c < 2 * HD; ++c) dab = fmaf(sdo[t][c], v[c], dab);
-                const float a0 = ex2_approx(d0 * qs - sl[t][0]), a1 = ex2_approx(d1 * qs - sl[t][1]);
+                const float dab = da.x + da.y;
+                const float a0 = ex2_approx(d.x - sl[t][0]), a1 = ex2_approx(d.y - sl[t][1]);
                 const float ab = a0 - lam * a1;
-                const float dl0 = a0 * (dab - sl[t][2]);
-                const float dl1 = -lam * a1 * (dab - sl[t][3]);
+                const float2 ab2 = p2(ab, ab);
+                const float2 dl = p2(a0 * (dab - sl[t][2]), -lam * a1 * (dab - sl[t][3]));
 #pragma unroll
-                for (int c = 0; c < 2 * HD; ++c) dv[c] = fmaf(ab, sdo[t][c], dv[c]);
-#pragma unroll
-                for (int c = 0; c < HD; ++c) {
-                    dk[c] = fmaf(dl0, sq[t][c], dk[c]);
-                    dk[HD + c] = fmaf(dl1, sq[t][HD + c], dk[HD + c]);
+                for (int c = 0; c < HD; c += 2) {
+                    const float4 gg = *reinterpret_cast<const float4 *>(&sdo[t][2 * c]);
+                    dv2[c] = __ffma2_rn(ab2, p2(gg.x, gg.y), dv2[c]);
+                    dv2[c + 1] = __ffma2_rn(ab2, p2(gg.z, gg.w), dv2[c + 1]);
+                    const float4 qq = *reinterpret_cast<const float4 *>(&sq[t][c]);
+                    dk2[c] = __ffma2_rn(dl, p2(qq.x, qq.y), dk2[c]);
+                    dk2[c + 1] = __ffma2_rn(dl, p2(qq.z, qq.w), dk2[c + 1]);
                 }
             }
         }
@@ -322,17 +371,20 @@ __global__ void __launch_bounds__(256) pooled_attn_bwd_kv_kernel(const PooledAtt
     if (active) {
         float *dkb = p.dkp + ((long long)b * p.P + pp) * p.ldd + (long long)m * 2 * HD;
         float *dvb = p.dvp + ((long long)b * p.P + pp) * p.ldd + (long long)m * 2 * HD;
+        // sq carried scale2 * log2e: d logit / d k = q * scale2, and the exp2-domain factor cancels against ln 2
 #pragma unroll
-        for (int c = 0; c < 2 * HD; ++c) {
-            atomicAdd(dkb + c, dk[c] * p.scale2);
-            atomicAdd(dvb + c, dv[c]);
+        for (int c = 0; c < HD; ++c) {
+            atomicAdd(dkb + c, dk2[c].x * (1.f / kLog2e));
+            atomicAdd(dkb + HD + c, dk2[c].y * (1.f / kLog2e));
+            atomicAdd(dvb + 2 * c, dv2[c].x);
+            atomicAdd(dvb + 2 * c + 1, dv2[c].y);
         }
     }
 }
 
 template <typename T, int HD>
 static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStream_t st) {
-    const size_t smem = (size_t)p.P * 4 * HD * sizeof(float);
+    const size_t smem = (size_t)p.P * HD * 16;   // kI (P x hd float2) + V (P x 2hd float)
     cudaError_t e;
     if (which == 0) {
         auto k = pooled_attn_fwd_kernel<T, HD>;
