@@ -199,6 +199,36 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             data, target = data.to(device), [t.to(device) for t in target]
         return {"data": data, "target": target}
 
+    # ---- checkpoints (nnUNetTrainer.save_checkpoint / load_checkpoint, nnUNetTrainer.py:1007-1054): same dict keys, so a
+    # reference `checkpoint_final.pth` loads here and one written here loads in the reference
+    def save_checkpoint(self, filename: str) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
+            return
+        net = self.network.module if hasattr(self.network, "module") else self.network
+        torch.save({"network_weights": net.state_dict(), "optimizer_state": self.optimizer.state_dict(),
+                    "grad_scaler_state": self.grad_scaler.state_dict() if self.grad_scaler is not None else None,
+                    "logging": {}, "_best_ema": None, "current_epoch": self.current_epoch + 1,
+                    "init_args": {"configuration": "2d_bs10", "fold": 0}, "trainer_name": self.__class__.__name__,
+                    "inference_allowed_mirroring_axes": (0, 1)}, filename)
+
+    def load_checkpoint(self, filename_or_checkpoint, load_optimizer: bool = True) -> None:
+        if self.network is None:
+            self.initialize()
+        ck = filename_or_checkpoint
+        if isinstance(ck, str):
+            ck = torch.load(ck, map_location=self.device, weights_only=False)
+        net = self.network.module if hasattr(self.network, "module") else self.network
+        own = net.state_dict().keys()
+        state = {(k[7:] if k not in own and k.startswith("module.") else k): v for k, v in ck["network_weights"].items()}
+        net.load_state_dict(state)            # strict: names and shapes are the reference's
+        self.current_epoch = ck.get("current_epoch", 0)
+        if load_optimizer and ck.get("optimizer_state") is not None:
+            self.optimizer.load_state_dict(ck["optimizer_state"])
+        if self.grad_scaler is not None and ck.get("grad_scaler_state") is not None:
+            self.grad_scaler.load_state_dict(ck["grad_scaler_state"])
+        self._graph = None                    # captured graphs hold the old optimizer state tensors
+        self._eager_steps = 0
+
     # ---- one training step (nnUNetTrainer.train_step, :833-863)
     def _forward_loss(self, data, target):
         with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):

@@ -2,6 +2,8 @@
 compatibility with the reference, scheduler + DropPath semantics, batch split, and that the product path refuses to
 run on CPU tensors (there is no fallback)."""
 import inspect
+
+import numpy as np
 import os
 import re
 
@@ -148,3 +150,15 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "scan_ref" not in src, f
+
+
+def test_sliding_window_steps_and_gaussian_follow_the_reference():
+    """compute_steps_for_sliding_window / compute_gaussian (reference sliding_window_prediction.py:13-58): the worked
+    example from the reference's own comment (image 110, tile 64, step 0.5 -> 0, 23, 46) and map properties."""
+    from mlagg_unet_b200 import inference as inf
+    assert inf.compute_steps_for_sliding_window((110,), (64,), 0.5) == [[0, 23, 46]]
+    assert inf.compute_steps_for_sliding_window((64, 64), (64, 64), 0.5) == [[0], [0]]
+    assert inf.compute_steps_for_sliding_window((320, 400), (320, 320), 0.5) == [[0], [0, 80]]
+    g = inf.compute_gaussian((32, 48))
+    assert g.shape == (32, 48) and g.max() == 1.0 and g[16, 24] == 1.0 and g.min() > 0
+    assert inf._mirror_sets(None) == [()] and inf._mirror_sets((0, 1)) == [(), (2,), (3,), (2, 3)]

@@ -99,3 +99,27 @@ def test_scan_cpu_tensor_fails_loudly():
     t = _inputs(1, 8, 16, 1)
     with pytest.raises(MlaggError):
         selective_scan_fn(t["u"], t["delta"], t["A"], t["B"], t["C"])
+
+
+def test_scan_config5_length_properties():
+    """BASELINE config 5 (Endovis17-shaped 3x512x512): L_cat = 256^2 + 128^2 + 64^2 + 32^2 = 87040 per image.  Too long
+    for the CPU oracle in test time, so size-independent properties: linearity in u, and agreement of the first 4096
+    steps with the fp64 oracle run on that prefix (the scan is causal)."""
+    import torch
+    from mlagg_unet_b200.selective_scan_interface import selective_scan_fn
+    from oracle.scan import scan_fwd_c
+    Bn, D, G, N, L = 2, 64, 4, 16, 87040
+    g = torch.Generator().manual_seed(5)
+    u1, u2 = torch.randn(Bn, D, L, generator=g), torch.randn(Bn, D, L, generator=g)
+    dl = torch.randn(Bn, D, L, generator=g)
+    A = -torch.arange(1, N + 1, dtype=torch.float32).repeat(D, 1)
+    Bm, Cm = torch.randn(Bn, G, N, L, generator=g), torch.randn(Bn, G, N, L, generator=g)
+    Dk, bias = torch.ones(D), torch.randn(D, generator=g) - 3.0
+    run = lambda u: selective_scan_fn(u.cuda(), dl.cuda(), A.cuda(), Bm.cuda(), Cm.cuda(), Dk.cuda(), None, bias.cuda(), True)
+    y1, y2, y12 = run(u1), run(u2), run(1.5 * u1 - 0.25 * u2)
+    assert torch.isfinite(y12).all()
+    assert float((y12 - (1.5 * y1 - 0.25 * y2)).abs().max() / y12.abs().max()) < 1e-4
+    P = 4096
+    ref = scan_fwd_c(u1[..., :P].contiguous(), dl[..., :P].contiguous(), A, Bm[..., :P].contiguous(),
+                     Cm[..., :P].contiguous(), Dk, bias, True, fp64=True)
+    assert float((y1[..., :P].cpu().double() - ref.double()).abs().max() / ref.abs().max()) < 1e-4
