@@ -235,11 +235,15 @@ class BasicLayer(nn.Module):
 # Conv stages: PyTorch / cuDNN, not the named hot path.  Parameter names follow the reference.
 # ----------------------------------------------------------------------------------------------------------
 class _TokensLN(nn.Module):
-    """LayerNorm over channels of an NCHW map (the reference flattens, norms, and reshapes back)."""
+    """LayerNorm over channels of an NCHW map (the reference flattens, norms, and reshapes back).  On a channels_last
+    CUDA map this is the tokens-major LayerNorm kernel on the same memory (no fp32 round trip under autocast)."""
 
     @staticmethod
     def apply(norm, x):
-        return norm(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        t = x.permute(0, 2, 3, 1)
+        if x.is_cuda and t.is_contiguous() and x.shape[1] % 4 == 0:
+            return layer_norm_tokens(t, norm).permute(0, 3, 1, 2)
+        return norm(t).permute(0, 3, 1, 2)
 
 
 class project(nn.Module):
