@@ -170,6 +170,42 @@ def colsum(x2d):
     return out
 
 
+# ---- per-step cache of parameters already cast to the autocast dtype.  Autocast (and a plain `.to(bf16)` here) launches
+# one cast kernel per weight and bias per forward -- ~330 tiny launches per train step.  The trainer instead refreshes
+# ONE list of bf16 copies with a multi-tensor copy at the start of its step (`refresh_cast_cache`), and `_Linear` picks its
+# operands from it while the step is running.  Outside a trainer step the cache is inactive and the cast happens inline.
+_CAST = {"active": False, "dtype": None, "src": [], "dst": [], "map": {}}
+
+
+def build_cast_cache(params, dtype):
+    _CAST["src"] = [p for p in params if p.is_cuda and p.dtype == torch.float32]
+    _CAST["dst"] = [torch.empty_like(p, dtype=dtype) for p in _CAST["src"]]
+    _CAST["map"] = {id(p): d for p, d in zip(_CAST["src"], _CAST["dst"])}
+    _CAST["dtype"] = dtype
+
+
+def refresh_cast_cache():
+    if _CAST["src"]:
+        with torch.no_grad():
+            torch._foreach_copy_(_CAST["dst"], _CAST["src"])
+        _CAST["active"] = True
+
+
+def release_cast_cache():
+    _CAST["active"] = False
+
+
+def _cast_param(t, dtype):
+    if t is None:
+        return None
+    if _CAST["active"] and dtype == _CAST["dtype"]:
+        base = t._base if t._base is not None else t           # views of a parameter (conv weight .view(C, C), .t())
+        hit = _CAST["map"].get(id(base))
+        if hit is not None:
+            return hit if base is t else hit.as_strided(t.size(), t.stride(), t.storage_offset())
+    return t.to(dtype)
+
+
 class _Linear(torch.autograd.Function):
     """y = x W^T + b with the GEMMs on cuBLAS (library GEMMs) in the autocast dtype and the bias
     gradient as ONE HBM-bound column-sum pass (csrc/reduce.cu) instead of autograd's generic reduction."""
@@ -177,9 +213,9 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-        xc, wc = x.to(cdt), weight.to(cdt)
+        xc, wc = x.to(cdt), _cast_param(weight, cdt)
         with torch.autocast("cuda", enabled=False):
-            y = torch.nn.functional.linear(xc, wc, None if bias is None else bias.to(cdt))
+            y = torch.nn.functional.linear(xc, wc, _cast_param(bias, cdt))
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
         return y

@@ -181,6 +181,9 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
                 dist.broadcast(t.data, 0)
         self.optimizer, self.lr_scheduler = self.configure_optimizers()
         self._bind_flat_grads()
+        if self.device.type == "cuda" and self.grad_scaler is None:
+            from . import ops
+            ops.build_cast_cache(self._params, self.amp_dtype)
         self.loss = self._build_loss()
         return self
 
@@ -231,6 +234,8 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
 
     # ---- one training step (nnUNetTrainer.train_step, :833-863)
     def _forward_loss(self, data, target):
+        from . import ops
+        ops.refresh_cast_cache()      # one multi-tensor fp32 -> bf16 copy of the parameters instead of a cast per layer
         with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
             return self.loss(self.network(data), target)
 
@@ -259,8 +264,10 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
     def _step_math(self, data, target):
         """forward -> DiceCE-DS loss -> backward -> gradient all-reduce -> clip(12) -> AdamW; capturable in a CUDA graph."""
         self._drop_grads()
+        from . import ops
         l = self._forward_loss(data, target)
         l.backward()
+        ops.release_cast_cache()
         self._reduce_clip_step()
         return l.detach()
 
@@ -314,7 +321,9 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         else:
             self._side_stream_warmup(lambda: self._step_math(st["data"], st["target"]))
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            from . import ops
             with torch.cuda.graph(ga):
+                ops.refresh_cast_cache()
                 with torch.autocast("cuda", dtype=self.amp_dtype):
                     outs = self.network(st["data"])
             outs = list(outs) if isinstance(outs, (list, tuple)) else [outs]
@@ -323,6 +332,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             self._drop_grads()
             with torch.cuda.graph(gb, pool=ga.pool()):
                 torch.autograd.backward(outs, grad_tensors=st["douts"])
+            ops.release_cast_cache()
             st["grads"] = [p.grad for p in self._params]     # written in place by every replay of graph B
             self._graph = (ga, gb)
         with torch.no_grad():
