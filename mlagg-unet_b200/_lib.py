@@ -54,7 +54,7 @@ class MlaggError(RuntimeError):
 
 def build(verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> mlagg-unet_b200/libmlagg_b200.so"""
-    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    r = subprocess.run(["make", f"-j{os.cpu_count() or 4}", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode != 0:
