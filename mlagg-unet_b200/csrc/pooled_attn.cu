@@ -13,6 +13,9 @@
 // atomic per element per slab).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mlagg {
@@ -481,11 +484,186 @@ __global__ void __launch_bounds__(256) pooled_attn_bwd_kv2_kernel(const PooledAt
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core forward (bf16 I/O, hd = 24, P <= 112): the two contractions of each map -- S_j = Q_j K_j^T (k = hd padded
+// to 32) and O_j = softmax(S_j) V (k = P padded to 112) -- run as mma.sync.m16n8k16 bf16 with fp32 accumulators; the
+// probabilities go from the accumulator layout straight into the A-operand layout (two adjacent n8 tiles = one k16
+// step), so nothing but K and V^T ever sits in shared memory.  A warp owns 16 query tokens at a time; softmax, the
+// lambda-combine and the RMSNorm reduce over the 4 lanes of a row with two shuffles.  Same saved tensors (log-sum-exps,
+// normalised O0 | O1) as the FMA kernel, so the backward kernels are shared.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+
+constexpr int kMmaHD = 24, kMmaNT = 14, kMmaPmax = 8 * kMmaNT;   // 112 pooled tokens at most
+constexpr int kMmaKS = 40;                                       // K row stride (bf16): 24 channels + zero pad, conflict-free
+constexpr int kMmaVS = kMmaPmax + 8;                             // V^T row stride (bf16)
+constexpr int kMmaTok = 256;                                     // query tokens per block (4 warps x 4 tiles of 16)
+
+__global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAttnParams p) {
+    constexpr int HD = kMmaHD;
+    __shared__ __align__(16) __nv_bfloat16 sK[2][kMmaPmax][kMmaKS];
+    __shared__ __align__(16) __nv_bfloat16 sVt[2 * HD][kMmaVS];
+    const int b = blockIdx.z, m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    {   // stage K (both maps, zero-padded to 32 channels / 112 rows) and V^T
+        const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
+        const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+        for (int i = threadIdx.x; i < 2 * kMmaPmax * kMmaKS; i += blockDim.x) {
+            const int j = i / (kMmaPmax * kMmaKS), pp = (i / kMmaKS) % kMmaPmax, d = i % kMmaKS;
+            sK[j][pp][d] = (pp < p.P && d < HD) ? kb[(long long)pp * p.ldkv + j * HD + d] : z;
+        }
+        for (int i = threadIdx.x; i < 2 * HD * kMmaVS; i += blockDim.x) {
+            const int pp = i / (2 * HD), c = i % (2 * HD);         // coalesced read of a V row, transposed store
+            if (pp < kMmaVS) sVt[c][pp] = pp < p.P ? vb[(long long)pp * p.ldkv + c] : z;
+        }
+    }
+    __syncthreads();
+    const float qs = p.scale2 * kLog2e;
+    const float lam = __ldg(p.lamp);
+    float wv[6][2];
+#pragma unroll
+    for (int nc = 0; nc < 6; ++nc) {
+        wv[nc][0] = __ldg(p.subln_w + nc * 8 + 2 * t) * p.post;
+        wv[nc][1] = __ldg(p.subln_w + nc * 8 + 2 * t + 1) * p.post;
+    }
+    for (int tile = warp; tile < kMmaTok / 16; tile += 4) {
+        const int n0 = blockIdx.x * kMmaTok + tile * 16;
+        if (n0 >= p.N) break;
+        const int nr[2] = {n0 + g, n0 + g + 8};
+        const bool ok[2] = {nr[0] < p.N, nr[1] < p.N};
+        float O[2][6][4];
+        float lsev[2][2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            // ---- Q_j fragments (k = 32: channels 24..31 are zero)
+            uint32_t qa[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const __nv_bfloat16 *qp = static_cast<const __nv_bfloat16 *>(p.q) + ((long long)b * p.N + nr[r]) * p.ldq +
+                                          (long long)m * 2 * HD + j * HD;
+                qa[0][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 2 * t) : 0u;
+                qa[0][2 + r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 8 + 2 * t) : 0u;
+                qa[1][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 16 + 2 * t) : 0u;
+                qa[1][2 + r] = 0u;
+            }
+            // ---- S_j = Q_j K_j^T
+            float S[kMmaNT][4];
+#pragma unroll
+            for (int nt = 0; nt < kMmaNT; ++nt) {
+                S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+                const __nv_bfloat16 *kr = &sK[j][nt * 8 + g][2 * t];
+                mma_bf16_16816(S[nt], qa[0], *reinterpret_cast<const uint32_t *>(kr), *reinterpret_cast<const uint32_t *>(kr + 8));
+                mma_bf16_16816(S[nt], qa[1], *reinterpret_cast<const uint32_t *>(kr + 16), *reinterpret_cast<const uint32_t *>(kr + 24));
+            }
+            // ---- softmax over the P valid columns (exp2 domain)
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < kMmaNT; ++nt) {
+                const int c0 = nt * 8 + 2 * t;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    S[nt][e] = (c0 + (e & 1) < p.P) ? S[nt][e] * qs : -INFINITY;
+                }
+                mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
+                mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
+            }
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < kMmaNT; ++nt) {
+                S[nt][0] = ex2_approx(S[nt][0] - mx0); S[nt][1] = ex2_approx(S[nt][1] - mx0);
+                S[nt][2] = ex2_approx(S[nt][2] - mx1); S[nt][3] = ex2_approx(S[nt][3] - mx1);
+                l0 += S[nt][0] + S[nt][1];
+                l1 += S[nt][2] + S[nt][3];
+            }
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            lsev[j][0] = mx0 + lg2_approx(l0);
+            lsev[j][1] = mx1 + lg2_approx(l1);
+            // ---- O_j = P V  (probabilities: accumulator layout -> A operand)
+#pragma unroll
+            for (int nc = 0; nc < 6; ++nc) O[j][nc][0] = O[j][nc][1] = O[j][nc][2] = O[j][nc][3] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < kMmaNT / 2; ++kk) {
+                uint32_t pa[4];
+                pa[0] = pack_bf16(S[2 * kk][0], S[2 * kk][1]);
+                pa[1] = pack_bf16(S[2 * kk][2], S[2 * kk][3]);
+                pa[2] = pack_bf16(S[2 * kk + 1][0], S[2 * kk + 1][1]);
+                pa[3] = pack_bf16(S[2 * kk + 1][2], S[2 * kk + 1][3]);
+#pragma unroll
+                for (int nc = 0; nc < 6; ++nc) {
+                    const __nv_bfloat16 *vr = &sVt[nc * 8 + g][kk * 16 + 2 * t];
+                    mma_bf16_16816(O[j][nc], pa, *reinterpret_cast<const uint32_t *>(vr), *reinterpret_cast<const uint32_t *>(vr + 8));
+                }
+            }
+            const float i0 = 1.f / l0, i1 = 1.f / l1;
+#pragma unroll
+            for (int nc = 0; nc < 6; ++nc) {
+                O[j][nc][0] *= i0; O[j][nc][1] *= i0;
+                O[j][nc][2] *= i1; O[j][nc][3] *= i1;
+            }
+        }
+        // ---- o = O0 - lam O1, RMSNorm over the 48 channels of the row, scale, store
+        float ss0 = 0.f, ss1 = 0.f;
+        float oc[6][4];
+#pragma unroll
+        for (int nc = 0; nc < 6; ++nc)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                oc[nc][e] = O[0][nc][e] - lam * O[1][nc][e];
+                if (e < 2) ss0 = fmaf(oc[nc][e], oc[nc][e], ss0); else ss1 = fmaf(oc[nc][e], oc[nc][e], ss1);
+            }
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, 1); ss0 += __shfl_xor_sync(0xffffffffu, ss0, 2);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, 1); ss1 += __shfl_xor_sync(0xffffffffu, ss1, 2);
+        const float rr[2] = {1.f / sqrtf(ss0 * (1.f / (2 * HD)) + p.eps), 1.f / sqrtf(ss1 * (1.f / (2 * HD)) + p.eps)};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!ok[r]) continue;
+            const long long tok = (long long)b * p.N + nr[r];
+            __nv_bfloat16 *op = static_cast<__nv_bfloat16 *>(p.out) + tok * p.ldo + (long long)m * 2 * HD;
+#pragma unroll
+            for (int nc = 0; nc < 6; ++nc)
+                *reinterpret_cast<uint32_t *>(op + nc * 8 + 2 * t) =
+                    pack_bf16(oc[nc][2 * r] * rr[r] * wv[nc][0], oc[nc][2 * r + 1] * rr[r] * wv[nc][1]);
+            if (p.lse) {
+                if (t == 0) {
+                    p.lse[(tok * p.h + m) * 2 + 0] = lsev[0][r];
+                    p.lse[(tok * p.h + m) * 2 + 1] = lsev[1][r];
+                }
+                float *os = p.lse + pooled_osave_offset(p) + (tok * p.h + m) * 4 * HD;
+#pragma unroll
+                for (int nc = 0; nc < 6; ++nc) {
+                    *reinterpret_cast<float2 *>(os + nc * 8 + 2 * t) = make_float2(O[0][nc][2 * r], O[0][nc][2 * r + 1]);
+                    *reinterpret_cast<float2 *>(os + 2 * HD + nc * 8 + 2 * t) = make_float2(O[1][nc][2 * r], O[1][nc][2 * r + 1]);
+                }
+            }
+        }
+    }
+}
+
+static bool pooled_use_mma() {
+    const char *e = getenv("MLAGG_POOLED_MMA");
+    return !(e && e[0] == '0');
+}
+
 template <typename T, int HD>
 static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStream_t st) {
     const size_t smem = (size_t)p.P * HD * 16;   // kI (P x hd float2) + V (P x 2hd float)
     cudaError_t e;
-    if (which == 0) {
+    if (which == 0 && std::is_same<T, __nv_bfloat16>::value && HD == kMmaHD && p.P <= kMmaPmax && pooled_use_mma() &&
+        p.ldq % 2 == 0 && p.ldkv % 2 == 0 && p.ldo % 2 == 0) {
+        pooled_attn_fwd_mma_kernel<<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, 0, st>>>(p);
+    } else if (which == 0) {
         auto k = pooled_attn_fwd_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);

@@ -420,3 +420,28 @@ def test_cuda_graph_train_step_matches_eager():
     for a, b in zip(losses[False], losses[True]):
         assert abs(a - b) <= 2e-2 * abs(a), (losses[False], losses[True])
     assert losses[True][-1] < losses[True][0]          # and it trains
+
+
+def test_pooled_attention_tensor_core_forward_matches_fp32_path():
+    """bf16 / hd 24 / P <= 112 takes the mma.sync forward kernel: output and (through the shared saved tensors) all
+    gradients agree with the fp32 FMA kernels at the bf16 tolerance; ragged token count, P = 100 (not a multiple of 16),
+    and P = 7 (a single, mostly masked k-step)."""
+    from mlagg_unet_b200 import attention as att
+    g = torch.Generator().manual_seed(23)
+    for Bn, N, h, P in [(2, 700, 2, 100), (1, 37, 1, 7), (1, 256, 3, 112)]:
+        hd = 24
+        C = 2 * h * hd
+        q0 = torch.randn(Bn, N, C, generator=g).cuda()
+        kv0 = torch.randn(Bn, P, 2 * C, generator=g).cuda()
+        do = torch.randn(Bn, N, C, generator=g).cuda()
+        w0 = (torch.rand(2 * hd, generator=g) + 0.5).cuda()
+        outs = {}
+        for dt in (torch.float32, torch.bfloat16):
+            q, kv = q0.to(dt).requires_grad_(), kv0.to(dt).requires_grad_()
+            lam = torch.tensor(0.7, device="cuda", requires_grad=True)
+            w = w0.clone().requires_grad_()
+            o = att.pooled_diff_attention(q, kv, lam, w, h, hd, hd ** -0.5)
+            outs[dt] = (o.detach().float(),) + tuple(t.float() for t in torch.autograd.grad(o, [q, kv, lam, w], do.to(dt)))
+        for a, b in zip(outs[torch.float32], outs[torch.bfloat16]):
+            assert torch.isfinite(b).all()
+            assert rel_err(b.cpu(), a.cpu()) < TOL16, (N, P)
