@@ -651,6 +651,215 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
     }
 }
 
+// Tensor-core backward, token-owner half: a warp owns 16 query tokens; RMSNorm backward on the saved O0 | O1 gives dO
+// (accumulator layout), dab = dO V^T, S_j is recomputed, dS_j = A_j o (dab - D_j) and dq_j = dS_j K_j are mma products
+// (B operands: V row-major, K_j row-major for S, K_j^T for dq).  Also writes dO / D_j for the dK, dV kernel and
+// accumulates d lambda and d subln_w.
+constexpr int kMmaVR = 2 * kMmaHD + 8;                           // V row stride (bf16), conflict-free
+
+__global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const PooledAttnParams p) {
+    constexpr int HD = kMmaHD;
+    __shared__ __align__(16) __nv_bfloat16 sK[2][kMmaPmax][kMmaKS];     // K_j[p][d]
+    __shared__ __align__(16) __nv_bfloat16 sKt[2][HD][kMmaVS];          // K_j^T[d][p]
+    __shared__ __align__(16) __nv_bfloat16 sV[kMmaPmax][kMmaVR];        // V[p][c]
+    __shared__ float red[2 * HD + 1];
+    const int b = blockIdx.z, m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    {
+        const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
+        const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
+        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+        for (int i = threadIdx.x; i < 2 * kMmaPmax * kMmaKS; i += blockDim.x) {
+            const int j = i / (kMmaPmax * kMmaKS), pp = (i / kMmaKS) % kMmaPmax, d = i % kMmaKS;
+            sK[j][pp][d] = (pp < p.P && d < HD) ? kb[(long long)pp * p.ldkv + j * HD + d] : z;
+        }
+        for (int i = threadIdx.x; i < kMmaVS * 2 * HD; i += blockDim.x) {
+            const int pp = i / (2 * HD), c = i % (2 * HD);                // c = j * HD + d
+            sKt[c / HD][c % HD][pp] = pp < p.P ? kb[(long long)pp * p.ldkv + c] : z;
+        }
+        for (int i = threadIdx.x; i < kMmaPmax * kMmaVR; i += blockDim.x) {
+            const int pp = i / kMmaVR, c = i % kMmaVR;
+            sV[pp][c] = (pp < p.P && c < 2 * HD) ? vb[(long long)pp * p.ldkv + c] : z;
+        }
+        for (int i = threadIdx.x; i < 2 * HD + 1; i += blockDim.x) red[i] = 0.f;
+    }
+    __syncthreads();
+    const float qs = p.scale2 * kLog2e;
+    const float lam = __ldg(p.lamp);
+    float wv[6][2], dwacc[6][2];
+#pragma unroll
+    for (int nc = 0; nc < 6; ++nc) {
+        wv[nc][0] = __ldg(p.subln_w + nc * 8 + 2 * t);
+        wv[nc][1] = __ldg(p.subln_w + nc * 8 + 2 * t + 1);
+        dwacc[nc][0] = dwacc[nc][1] = 0.f;
+    }
+    float dlam = 0.f;
+    for (int tile = warp; tile < kMmaTok / 16; tile += 4) {
+        const int n0 = blockIdx.x * kMmaTok + tile * 16;
+        if (n0 >= p.N) break;
+        const int nr[2] = {n0 + g, n0 + g + 8};
+        const bool ok[2] = {nr[0] < p.N, nr[1] < p.N};
+        // ---- RMSNorm backward on the saved O0 | O1 (accumulator layout: row r, columns nc*8 + 2t, +1)
+        float dO[6][4];
+        float D0[2], D1[2], lse0[2], lse1[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const long long tok = (long long)b * p.N + (ok[r] ? nr[r] : 0);
+            const float *os = p.lse + pooled_osave_offset(p) + (tok * p.h + m) * 4 * HD;
+            const __nv_bfloat16 *gp = static_cast<const __nv_bfloat16 *>(p.dout) + tok * p.lddo + (long long)m * 2 * HD;
+            float o0[6][2], o1[6][2], oc[6][2], gs[6][2];
+            float ss = 0.f;
+#pragma unroll
+            for (int nc = 0; nc < 6; ++nc) {
+                const float2 a = ok[r] ? *reinterpret_cast<const float2 *>(os + nc * 8 + 2 * t) : make_float2(0.f, 0.f);
+                const float2 c = ok[r] ? *reinterpret_cast<const float2 *>(os + 2 * HD + nc * 8 + 2 * t) : make_float2(0.f, 0.f);
+                o0[nc][0] = a.x, o0[nc][1] = a.y, o1[nc][0] = c.x, o1[nc][1] = c.y;
+                oc[nc][0] = a.x - lam * c.x, oc[nc][1] = a.y - lam * c.y;
+                ss = fmaf(oc[nc][0], oc[nc][0], fmaf(oc[nc][1], oc[nc][1], ss));
+                const uint32_t gg = ok[r] ? *reinterpret_cast<const uint32_t *>(gp + nc * 8 + 2 * t) : 0u;
+                gs[nc][0] = __uint_as_float(gg << 16), gs[nc][1] = __uint_as_float(gg & 0xffff0000u);
+            }
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            const float rn = 1.f / sqrtf(ss * (1.f / (2 * HD)) + p.eps);
+            float dot = 0.f;
+#pragma unroll
+            for (int nc = 0; nc < 6; ++nc)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    dwacc[nc][e] = fmaf(gs[nc][e] * p.post, oc[nc][e] * rn, dwacc[nc][e]);
+                    gs[nc][e] *= p.post * wv[nc][e];
+                    dot = fmaf(gs[nc][e], oc[nc][e], dot);
+                }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1); dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            const float k3 = rn * rn * rn * dot * (1.f / (2 * HD));
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int nc = 0; nc < 6; ++nc)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float v = rn * gs[nc][e] - oc[nc][e] * k3;
+                    dO[nc][2 * r + e] = v;
+                    d0 = fmaf(v, o0[nc][e], d0);
+                    d1 = fmaf(v, o1[nc][e], d1);
+                }
+            d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+            D0[r] = d0, D1[r] = d1;
+            lse0[r] = ok[r] ? p.lse[(tok * p.h + m) * 2 + 0] : 0.f;
+            lse1[r] = ok[r] ? p.lse[(tok * p.h + m) * 2 + 1] : 0.f;
+            if (ok[r]) {
+                if (t == 0) dlam -= d1;
+                if (p.ws_dO) {
+                    float *wdO = p.ws_dO + (tok * p.h + m) * 2 * HD;
+#pragma unroll
+                    for (int nc = 0; nc < 6; ++nc)
+                        *reinterpret_cast<float2 *>(wdO + nc * 8 + 2 * t) = make_float2(dO[nc][2 * r], dO[nc][2 * r + 1]);
+                    if (t == 0) {
+                        p.ws_D[(tok * p.h + m) * 2 + 0] = d0;
+                        p.ws_D[(tok * p.h + m) * 2 + 1] = d1;
+                    }
+                }
+            }
+        }
+        // ---- dab = dO V^T  (k = 48 channels = 3 steps; dO: accumulator layout -> A operand)
+        float dab[kMmaNT][4];
+        {
+            uint32_t da[3][4];
+#pragma unroll
+            for (int kc = 0; kc < 3; ++kc) {
+                da[kc][0] = pack_bf16(dO[2 * kc][0], dO[2 * kc][1]);
+                da[kc][1] = pack_bf16(dO[2 * kc][2], dO[2 * kc][3]);
+                da[kc][2] = pack_bf16(dO[2 * kc + 1][0], dO[2 * kc + 1][1]);
+                da[kc][3] = pack_bf16(dO[2 * kc + 1][2], dO[2 * kc + 1][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < kMmaNT; ++nt) {
+                dab[nt][0] = dab[nt][1] = dab[nt][2] = dab[nt][3] = 0.f;
+#pragma unroll
+                for (int kc = 0; kc < 3; ++kc) {
+                    const __nv_bfloat16 *vr = &sV[nt * 8 + g][kc * 16 + 2 * t];
+                    mma_bf16_16816(dab[nt], da[kc], *reinterpret_cast<const uint32_t *>(vr), *reinterpret_cast<const uint32_t *>(vr + 8));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint32_t qa[2][4];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const __nv_bfloat16 *qp = static_cast<const __nv_bfloat16 *>(p.q) + ((long long)b * p.N + (ok[r] ? nr[r] : 0)) * p.ldq +
+                                          (long long)m * 2 * HD + j * HD;
+                qa[0][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 2 * t) : 0u;
+                qa[0][2 + r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 8 + 2 * t) : 0u;
+                qa[1][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 16 + 2 * t) : 0u;
+                qa[1][2 + r] = 0u;
+            }
+            const float ls[2] = {j == 0 ? lse0[0] : lse1[0], j == 0 ? lse0[1] : lse1[1]};
+            const float Dj[2] = {j == 0 ? D0[0] : D1[0], j == 0 ? D0[1] : D1[1]};
+            const float sgn = j == 0 ? 1.f : -lam;
+            float dq[3][4];
+#pragma unroll
+            for (int nd = 0; nd < 3; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < kMmaNT / 2; ++kk) {
+                uint32_t sa[4];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int nt = 2 * kk + hf;
+                    float S[4] = {0.f, 0.f, 0.f, 0.f};
+                    const __nv_bfloat16 *kr = &sK[j][nt * 8 + g][2 * t];
+                    mma_bf16_16816(S, qa[0], *reinterpret_cast<const uint32_t *>(kr), *reinterpret_cast<const uint32_t *>(kr + 8));
+                    mma_bf16_16816(S, qa[1], *reinterpret_cast<const uint32_t *>(kr + 16), *reinterpret_cast<const uint32_t *>(kr + 24));
+                    float ds[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int r = e >> 1;
+                        const bool in = nt * 8 + 2 * t + (e & 1) < p.P;
+                        const float a = in ? ex2_approx(S[e] * qs - ls[r]) : 0.f;
+                        ds[e] = sgn * a * (dab[nt][e] - Dj[r]);
+                    }
+                    sa[2 * hf] = pack_bf16(ds[0], ds[1]);
+                    sa[2 * hf + 1] = pack_bf16(ds[2], ds[3]);
+                }
+#pragma unroll
+                for (int nd = 0; nd < 3; ++nd) {
+                    const __nv_bfloat16 *kt = &sKt[j][nd * 8 + g][kk * 16 + 2 * t];
+                    mma_bf16_16816(dq[nd], sa, *reinterpret_cast<const uint32_t *>(kt), *reinterpret_cast<const uint32_t *>(kt + 8));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (!ok[r]) continue;
+                __nv_bfloat16 *dqp = static_cast<__nv_bfloat16 *>(p.dq) + ((long long)b * p.N + nr[r]) * p.lddq +
+                                     (long long)m * 2 * HD + j * HD;
+#pragma unroll
+                for (int nd = 0; nd < 3; ++nd)
+                    *reinterpret_cast<uint32_t *>(dqp + nd * 8 + 2 * t) =
+                        pack_bf16(dq[nd][2 * r] * p.scale2, dq[nd][2 * r + 1] * p.scale2);
+            }
+        }
+    }
+    // ---- d subln_w (column sums over the block's tokens) and d lambda
+#pragma unroll
+    for (int nc = 0; nc < 6; ++nc)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            float v = dwacc[nc][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) atomicAdd(&red[nc * 8 + 2 * t + e], v);
+        }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) dlam += __shfl_xor_sync(0xffffffffu, dlam, o2);
+    if (lane == 0) atomicAdd(&red[2 * HD], dlam);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * HD + 1; i += blockDim.x) {
+        if (i < 2 * HD) atomicAdd(p.d_subln_w + i, red[i]);
+        else atomicAdd(p.d_lambda, red[i]);
+    }
+}
+
 static bool pooled_use_mma() {
     const char *e = getenv("MLAGG_POOLED_MMA");
     return !(e && e[0] == '0');
@@ -667,6 +876,9 @@ static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStrea
         auto k = pooled_attn_fwd_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);
+    } else if (which == 1 && std::is_same<T, __nv_bfloat16>::value && HD == kMmaHD && p.P <= kMmaPmax && pooled_use_mma() &&
+               p.ldq % 2 == 0 && p.ldkv % 2 == 0 && p.lddo % 2 == 0 && p.lddq % 2 == 0) {
+        pooled_attn_bwd_q_mma_kernel<<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, 0, st>>>(p);
     } else if (which == 1) {
         auto k = pooled_attn_bwd_q_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
