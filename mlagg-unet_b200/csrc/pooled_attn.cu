@@ -860,6 +860,174 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
     }
 }
 
+// Tensor-core backward, pooled-token-owner half (dK, dV): warp w owns the 16 pooled tokens [16w, 16w+16) with their K / V
+// rows as A-operand registers and walks the block's query tokens 16 at a time: S_j^T = K_j Q_j^T and dab^T = V dO^T
+// (B operands: Q, dO row-major in shared memory), probabilities and dS_j^T in the accumulator layout, then
+// dV += Abar^T dO and dK_j += dS_j^T Q_j with the accumulator tiles reused as A operands (B operands: dO^T, Q_j^T,
+// staged transposed).  One fp32 atomic per element and block at the end.
+constexpr int kKvChunk = 64;                  // query tokens staged per iteration
+constexpr int kKvSlab = 1024;                 // query tokens per block
+constexpr int kKvTS = kKvChunk + 8;           // row stride of the transposed tiles (bf16), conflict-free
+
+__global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const PooledAttnParams p) {
+    constexpr int HD = kMmaHD;
+    __shared__ __align__(16) __nv_bfloat16 sQ[2][kKvChunk][kMmaKS];      // Q_j[tok][d] (zero-padded to 32 channels)
+    __shared__ __align__(16) __nv_bfloat16 sQt[2][HD][kKvTS];            // Q_j^T[d][tok]
+    __shared__ __align__(16) __nv_bfloat16 sG[kKvChunk][kMmaVR];         // dO[tok][c]
+    __shared__ __align__(16) __nv_bfloat16 sGt[2 * HD][kKvTS];           // dO^T[c][tok]
+    __shared__ float sl[kKvChunk][4];                                    // lse0, lse1, D0, D1
+    const int b = blockIdx.z, m = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int prow[2] = {warp * 16 + g, warp * 16 + g + 8};
+    const bool pok[2] = {prow[0] < p.P, prow[1] < p.P};
+    const bool warp_on = warp * 16 < p.P;
+    // ---- A operands: K_j rows (k = 32 channels, 24..31 zero) and V rows (k = 48 channels) of this warp's pooled tokens
+    uint32_t ka[2][2][4], va[3][4];
+    {
+        const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
+        const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const __nv_bfloat16 *kr = kb + (long long)(pok[r] ? prow[r] : 0) * p.ldkv;
+            const __nv_bfloat16 *vr = vb + (long long)(pok[r] ? prow[r] : 0) * p.ldkv;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                ka[j][0][r] = pok[r] ? *reinterpret_cast<const uint32_t *>(kr + j * HD + 2 * t) : 0u;
+                ka[j][0][2 + r] = pok[r] ? *reinterpret_cast<const uint32_t *>(kr + j * HD + 8 + 2 * t) : 0u;
+                ka[j][1][r] = pok[r] ? *reinterpret_cast<const uint32_t *>(kr + j * HD + 16 + 2 * t) : 0u;
+                ka[j][1][2 + r] = 0u;
+            }
+#pragma unroll
+            for (int kc = 0; kc < 3; ++kc) {
+                va[kc][r] = pok[r] ? *reinterpret_cast<const uint32_t *>(vr + kc * 16 + 2 * t) : 0u;
+                va[kc][2 + r] = pok[r] ? *reinterpret_cast<const uint32_t *>(vr + kc * 16 + 8 + 2 * t) : 0u;
+            }
+        }
+    }
+    float dV[6][4], dK[2][3][4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dV[i][0] = dV[i][1] = dV[i][2] = dV[i][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dK[j][i][0] = dK[j][i][1] = dK[j][i][2] = dK[j][i][3] = 0.f;
+    const float qs = p.scale2 * kLog2e;
+    const float lam = __ldg(p.lamp);
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    const int n0 = blockIdx.x * kKvSlab, n1 = min(p.N, n0 + kKvSlab);
+    for (int base = n0; base < n1; base += kKvChunk) {
+        __syncthreads();
+        // ---- stage Q (both maps), dO, lse / D of the chunk; rows past the end are zero
+        for (int i = threadIdx.x; i < kKvChunk * HD; i += blockDim.x) {         // pairs of channels
+            const int tk = i / HD, c2 = (i % HD) * 2;                            // c2 in 0..46 over the 48 q channels
+            const int n = base + tk;
+            uint32_t v = 0u;
+            if (n < n1) v = *reinterpret_cast<const uint32_t *>(static_cast<const __nv_bfloat16 *>(p.q) +
+                                                              ((long long)b * p.N + n) * p.ldq + (long long)m * 2 * HD + c2);
+            const int j = c2 / HD, d = c2 % HD;
+            *reinterpret_cast<uint32_t *>(&sQ[j][tk][d]) = v;
+            const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&v);
+            sQt[j][d][tk] = h2.x;
+            sQt[j][d + 1][tk] = h2.y;
+        }
+        for (int i = threadIdx.x; i < 2 * kKvChunk * (kMmaKS - HD); i += blockDim.x) {   // zero pad channels 24..39
+            const int j = i / (kKvChunk * (kMmaKS - HD)), tk = (i / (kMmaKS - HD)) % kKvChunk, d = HD + i % (kMmaKS - HD);
+            sQ[j][tk][d] = z;
+        }
+        for (int i = threadIdx.x; i < kKvChunk * HD; i += blockDim.x) {         // pairs of dO channels (fp32 -> bf16)
+            const int tk = i / HD, c2 = (i % HD) * 2;
+            const int n = base + tk;
+            float2 v = make_float2(0.f, 0.f);
+            if (n < n1) v = *reinterpret_cast<const float2 *>(p.ws_dO + (((long long)b * p.N + n) * p.h + m) * 2 * HD + c2);
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y);
+            *reinterpret_cast<__nv_bfloat162 *>(&sG[tk][c2]) = h2;
+            sGt[c2][tk] = h2.x;
+            sGt[c2 + 1][tk] = h2.y;
+        }
+        for (int i = threadIdx.x; i < kKvChunk * 4; i += blockDim.x) {
+            const int tk = i / 4, w = i % 4;
+            const int n = base + tk;
+            const long long tm = ((long long)b * p.N + n) * p.h + m;
+            sl[tk][w] = n < n1 ? (w < 2 ? p.lse[tm * 2 + w] : p.ws_D[tm * 2 + (w - 2)]) : (w < 2 ? INFINITY : 0.f);
+        }
+        __syncthreads();
+        if (!warp_on) continue;
+#pragma unroll 1
+        for (int tk0 = 0; tk0 < kKvChunk; tk0 += 16) {
+            if (base + tk0 >= n1) break;
+            // ---- dab^T = V dO^T : rows = pooled tokens, columns = the 16 query tokens (two n8 tiles)
+            float dab[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                dab[nt][0] = dab[nt][1] = dab[nt][2] = dab[nt][3] = 0.f;
+#pragma unroll
+                for (int kc = 0; kc < 3; ++kc) {
+                    const __nv_bfloat16 *gr = &sG[tk0 + nt * 8 + g][kc * 16 + 2 * t];
+                    mma_bf16_16816(dab[nt], va[kc], *reinterpret_cast<const uint32_t *>(gr), *reinterpret_cast<const uint32_t *>(gr + 8));
+                }
+            }
+            uint32_t abar[4] = {0u, 0u, 0u, 0u};
+            float ab[2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t dsa[4];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    float S[4] = {0.f, 0.f, 0.f, 0.f};
+                    const __nv_bfloat16 *qr = &sQ[j][tk0 + nt * 8 + g][2 * t];
+                    mma_bf16_16816(S, ka[j][0], *reinterpret_cast<const uint32_t *>(qr), *reinterpret_cast<const uint32_t *>(qr + 8));
+                    mma_bf16_16816(S, ka[j][1], *reinterpret_cast<const uint32_t *>(qr + 16), *reinterpret_cast<const uint32_t *>(qr + 24));
+                    float ds[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int tk = tk0 + nt * 8 + 2 * t + (e & 1);       // column = query token
+                        const float a = pok[e >> 1] ? ex2_approx(S[e] * qs - sl[tk][j]) : 0.f;   // lse = +inf past the end -> 0
+                        ds[e] = (j == 0 ? a : -lam * a) * (dab[nt][e] - sl[tk][2 + j]);
+                        ab[nt][e] = j == 0 ? a : ab[nt][e] - lam * a;
+                    }
+                    dsa[2 * nt] = pack_bf16(ds[0], ds[1]);
+                    dsa[2 * nt + 1] = pack_bf16(ds[2], ds[3]);
+                }
+                // dK_j += dS_j^T Q_j   (A = accumulator tiles of the two n8 token tiles, k = 16 tokens)
+                const uint32_t a4[4] = {dsa[0], dsa[1], dsa[2], dsa[3]};
+#pragma unroll
+                for (int nd = 0; nd < 3; ++nd) {
+                    const __nv_bfloat16 *qt = &sQt[j][nd * 8 + g][tk0 + 2 * t];
+                    mma_bf16_16816(dK[j][nd], a4, *reinterpret_cast<const uint32_t *>(qt), *reinterpret_cast<const uint32_t *>(qt + 8));
+                }
+            }
+            abar[0] = pack_bf16(ab[0][0], ab[0][1]);
+            abar[1] = pack_bf16(ab[0][2], ab[0][3]);
+            abar[2] = pack_bf16(ab[1][0], ab[1][1]);
+            abar[3] = pack_bf16(ab[1][2], ab[1][3]);
+#pragma unroll
+            for (int nc = 0; nc < 6; ++nc) {
+                const __nv_bfloat16 *gt = &sGt[nc * 8 + g][tk0 + 2 * t];
+                mma_bf16_16816(dV[nc], abar, *reinterpret_cast<const uint32_t *>(gt), *reinterpret_cast<const uint32_t *>(gt + 8));
+            }
+        }
+    }
+    if (!warp_on) return;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (!pok[r]) continue;
+        float *dkb = p.dkp + ((long long)b * p.P + prow[r]) * p.ldd + (long long)m * 2 * HD;
+        float *dvb = p.dvp + ((long long)b * p.P + prow[r]) * p.ldd + (long long)m * 2 * HD;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int nd = 0; nd < 3; ++nd) {
+                atomicAdd(dkb + j * HD + nd * 8 + 2 * t, dK[j][nd][2 * r] * p.scale2);
+                atomicAdd(dkb + j * HD + nd * 8 + 2 * t + 1, dK[j][nd][2 * r + 1] * p.scale2);
+            }
+#pragma unroll
+        for (int nc = 0; nc < 6; ++nc) {
+            atomicAdd(dvb + nc * 8 + 2 * t, dV[nc][2 * r]);
+            atomicAdd(dvb + nc * 8 + 2 * t + 1, dV[nc][2 * r + 1]);
+        }
+    }
+}
+
 static bool pooled_use_mma() {
     const char *e = getenv("MLAGG_POOLED_MMA");
     return !(e && e[0] == '0');
@@ -883,6 +1051,9 @@ static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStrea
         auto k = pooled_attn_bwd_q_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);
+    } else if (std::is_same<T, __nv_bfloat16>::value && HD == kMmaHD && p.P <= kMmaPmax && pooled_use_mma() &&
+               p.ldq % 2 == 0 && p.ldkv % 2 == 0) {
+        pooled_attn_bwd_kv_mma_kernel<<<dim3((p.N + kKvSlab - 1) / kKvSlab, p.h, p.Bn), 224, 0, st>>>(p);
     } else {
         if (HD % 4 == 0 && 2 * p.P <= 256) {
             const int threads = ((2 * p.P + 31) / 32) * 32;
