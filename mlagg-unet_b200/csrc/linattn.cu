@@ -18,6 +18,8 @@
 //   rope_cs (H + W, C/4, 2) = [cos, sin] of row * theta_i (first H rows) and col * theta_i (next W rows).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mlagg {
@@ -394,6 +396,437 @@ __global__ void __launch_bounds__(kLTok) linattn_bwd_kv_kernel(const LinAttnPara
     la_store<HD>(static_cast<T *>(p.dk) + tok * p.lddk + hh * HD, vv);
 }
 
+int linattn_chunk(int Bn, int N, int h);
+
+// ================================================================= tensor-core variants (bf16 I/O, hd 16 / 32)
+// The phi(K)^T V state contraction (k = tokens), the apply product (k = hd) and their backward counterparts as
+// mma.sync.m16n8k16 bf16 with fp32 accumulators.  elu+1, RoPE, the normaliser and every reduction stay fp32; only the
+// MMA operands are rounded to bf16 (the I/O type of this path).  RoPE rotates channel pairs (2i, 2i+1) -- exactly the
+// register pairs of the A-operand / accumulator layouts -- so q, k rows are loaded, mapped and rotated directly in
+// fragment layout without shared memory; contractions over tokens stage their operands transposed ([channel][token]).
+__device__ __forceinline__ void la_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t la_pack(float lo, float hi) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&t);
+}
+__device__ __forceinline__ float2 la_unpack(uint32_t v) {
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t la_lds32(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint32_t *>(p); }
+
+constexpr int kLmTok = 256;      // tokens per block of the token-parallel mma kernels (4 warps x 4 tiles of 16)
+
+// One token row pair set of a warp tile in fragment layout: rows (g, g+8), pairs pi = 0 .. HD/8-1 at columns 8*pi + 2t.
+template <int HD>
+struct LaFrag {
+    float2 phi[2][HD / 8];   // elu+1 values
+    float2 cs[2][HD / 8];    // (cos, sin) of the pair
+};
+template <int HD>
+__device__ __forceinline__ void la_frag_load(const LinAttnParams &p, const __nv_bfloat16 *base, long long ld, int hh, int b,
+                                             const int (&nr)[2], const bool (&ok)[2], int t, LaFrag<HD> &f) {
+    const int N = p.H * p.W, quarter = p.h * HD / 4;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int n = ok[r] ? nr[r] : 0;
+        const __nv_bfloat16 *row = base + ((long long)b * N + n) * ld + hh * HD;
+        const int rr = n / p.W, cc = n - rr * p.W;
+        const float2 *tr = reinterpret_cast<const float2 *>(p.rope) + (long long)rr * quarter;
+        const float2 *tc = reinterpret_cast<const float2 *>(p.rope) + (long long)(p.H + cc) * quarter - quarter;
+#pragma unroll
+        for (int pi = 0; pi < HD / 8; ++pi) {
+            const float2 x = ok[r] ? la_unpack(la_lds32(row + 8 * pi + 2 * t)) : make_float2(0.f, 0.f);
+            f.phi[r][pi] = ok[r] ? make_float2(la_phi(x.x), la_phi(x.y)) : make_float2(0.f, 0.f);
+            const int i = hh * (HD / 2) + 4 * pi + t;
+            f.cs[r][pi] = __ldg(i < quarter ? tr + i : tc + i);
+        }
+    }
+}
+// rope(phi) packed as the A operands of the HD/16 k-steps
+template <int HD>
+__device__ __forceinline__ void la_frag_rope_a(const LaFrag<HD> &f, uint32_t (&a)[HD / 16][4]) {
+#pragma unroll
+    for (int ks = 0; ks < HD / 16; ++ks)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float2 x = f.phi[r][2 * ks + hf], c = f.cs[r][2 * ks + hf];
+                a[ks][2 * hf + r] = la_pack(c.x * x.x - c.y * x.y, c.y * x.x + c.x * x.y);
+            }
+}
+
+// ---- forward 1: S = (1/N) sum rope(phi k) (x) v, kmean = (1/N) sum phi k        (k = tokens)
+template <int HD>
+__global__ void __launch_bounds__(kLTok) linattn_state_mma_kernel(const LinAttnParams p) {
+    constexpr int TS = kLTok + 8;                               // row stride of the transposed tiles (bf16)
+    __shared__ __align__(16) __nv_bfloat16 sKt[HD][TS], sPt[HD][TS], sVt[HD][TS];
+    const int b = blockIdx.z, hh = blockIdx.y, N = p.H * p.W;
+    const int n0 = blockIdx.x * p.chunk, n1 = min(N, n0 + p.chunk);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float S[HD / 16][HD / 8][4], KM[HD / 16][4];
+#pragma unroll
+    for (int mt = 0; mt < HD / 16; ++mt) {
+        KM[mt][0] = KM[mt][1] = KM[mt][2] = KM[mt][3] = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.f;
+    }
+    const uint32_t ones = (g == 0) ? la_pack(1.f, 1.f) : 0u;     // B operand whose column 0 is all ones
+    for (int t0 = n0; t0 < n1; t0 += kLTok) {
+        const int n = t0 + threadIdx.x;
+        {   // thread = token: phi, RoPE in fp32, transposed bf16 tiles
+            float x[HD], y[HD];
+            const bool in = n < n1;
+            const long long tok = (long long)b * N + (in ? n : 0);
+            la_load<HD>(static_cast<const __nv_bfloat16 *>(p.k) + tok * p.ldk + hh * HD, x);
+#pragma unroll
+            for (int c = 0; c < HD; ++c) x[c] = in ? la_phi(x[c]) : 0.f;
+            float cs[HD];
+            la_angles<HD>(p, hh, in ? n : 0, cs);
+            la_rope<HD>(x, cs, y);
+#pragma unroll
+            for (int c = 0; c < HD; ++c) {
+                sPt[c][threadIdx.x] = __float2bfloat16_rn(x[c]);
+                sKt[c][threadIdx.x] = __float2bfloat16_rn(y[c]);
+            }
+            la_load<HD>(static_cast<const __nv_bfloat16 *>(p.v) + tok * p.ldv + hh * HD, x);
+#pragma unroll
+            for (int c = 0; c < HD; ++c) sVt[c][threadIdx.x] = __float2bfloat16_rn(in ? x[c] : 0.f);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            const int tk = 16 * (warp + 4 * kk);
+#pragma unroll
+            for (int mt = 0; mt < HD / 16; ++mt) {
+                const int d0 = mt * 16 + g;
+                const uint32_t a[4] = {la_lds32(&sKt[d0][tk + 2 * t]), la_lds32(&sKt[d0 + 8][tk + 2 * t]),
+                                       la_lds32(&sKt[d0][tk + 8 + 2 * t]), la_lds32(&sKt[d0 + 8][tk + 8 + 2 * t])};
+#pragma unroll
+                for (int nt = 0; nt < HD / 8; ++nt)
+                    la_mma(S[mt][nt], a, la_lds32(&sVt[nt * 8 + g][tk + 2 * t]), la_lds32(&sVt[nt * 8 + g][tk + 8 + 2 * t]));
+                const uint32_t ap[4] = {la_lds32(&sPt[d0][tk + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 2 * t]),
+                                        la_lds32(&sPt[d0][tk + 8 + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 8 + 2 * t])};
+                la_mma(KM[mt], ap, ones, ones);
+            }
+        }
+        __syncthreads();
+    }
+    // fold the four warps' partial sums through shared memory, then one scaled atomic per element
+    float *red = reinterpret_cast<float *>(&sKt[0][0]);
+    for (int i = threadIdx.x; i < HD * HD + HD; i += kLTok) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < HD / 16; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                atomicAdd(red + (mt * 16 + g + 8 * (e >> 1)) * HD + nt * 8 + 2 * t + (e & 1), S[mt][nt][e]);
+        if (t == 0) {
+            atomicAdd(red + HD * HD + mt * 16 + g, KM[mt][0]);
+            atomicAdd(red + HD * HD + mt * 16 + g + 8, KM[mt][2]);
+        }
+    }
+    __syncthreads();
+    const long long bh = (long long)b * p.h + hh;
+    const float scale = 1.f / (float)N;
+    for (int i = threadIdx.x; i < HD * HD; i += kLTok) atomicAdd(p.S + bh * HD * HD + i, red[i] * scale);
+    if (threadIdx.x < HD) atomicAdd(p.kmean + bh * HD + threadIdx.x, red[HD * HD + threadIdx.x] * scale);
+}
+
+// stage an HD x HD fp32 matrix as bf16, row-major (sM[d][e]) and / or transposed (sMt[e][d])
+template <int HD>
+__device__ __forceinline__ void la_stage_bf16(const float *gM, __nv_bfloat16 (*sM)[HD + 8], __nv_bfloat16 (*sMt)[HD + 8]) {
+    for (int i = threadIdx.x; i < HD * HD; i += blockDim.x) {
+        const __nv_bfloat16 v = __float2bfloat16_rn(gM[i]);
+        if (sM) sM[i / HD][i % HD] = v;
+        if (sMt) sMt[i % HD][i / HD] = v;
+    }
+}
+
+// ---- forward 2: out = z * rope(phi q) S                                           (k = hd)
+template <int HD>
+__global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const LinAttnParams p) {
+    __shared__ __align__(16) __nv_bfloat16 sSt[HD][HD + 8];
+    __shared__ float sKm[HD];
+    const int b = blockIdx.z, hh = blockIdx.y, N = p.H * p.W;
+    const long long bh = (long long)b * p.h + hh;
+    la_stage_bf16<HD>(p.S + bh * HD * HD, nullptr, sSt);
+    if (threadIdx.x < HD) sKm[threadIdx.x] = p.kmean[bh * HD + threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int tile = warp; tile < kLmTok / 16; tile += 4) {
+        const int nb = blockIdx.x * kLmTok + tile * 16;
+        if (nb >= N) break;
+        const int nr[2] = {nb + g, nb + g + 8};
+        const bool ok[2] = {nr[0] < N, nr[1] < N};
+        LaFrag<HD> f;
+        la_frag_load<HD>(p, static_cast<const __nv_bfloat16 *>(p.q), p.ldq, hh, b, nr, ok, t, f);
+        float z[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float den = 0.f;
+#pragma unroll
+            for (int pi = 0; pi < HD / 8; ++pi)
+                den = fmaf(f.phi[r][pi].x, sKm[8 * pi + 2 * t], fmaf(f.phi[r][pi].y, sKm[8 * pi + 2 * t + 1], den));
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            z[r] = 1.f / (den + p.eps);
+        }
+        uint32_t a[HD / 16][4];
+        la_frag_rope_a<HD>(f, a);
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks)
+                la_mma(o, a[ks], la_lds32(&sSt[nt * 8 + g][16 * ks + 2 * t]), la_lds32(&sSt[nt * 8 + g][16 * ks + 8 + 2 * t]));
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                if (ok[r])
+                    *reinterpret_cast<uint32_t *>(static_cast<__nv_bfloat16 *>(p.out) + ((long long)b * N + nr[r]) * p.ldo +
+                                                  hh * HD + nt * 8 + 2 * t) = la_pack(o[2 * r] * z[r], o[2 * r + 1] * z[r]);
+        }
+    }
+}
+
+// ---- backward 1: dq; dS = (1/N) sum rope(phi q) (x) z dO, dkmean = (1/N) sum c phi q     (k = hd, then k = tokens)
+template <int HD>
+__global__ void __launch_bounds__(128) linattn_bwd_q_mma_kernel(const LinAttnParams p) {
+    constexpr int GT = 64, TS = GT + 8;                         // tokens per group (4 warps x 16), transposed row stride
+    __shared__ __align__(16) __nv_bfloat16 sS[HD][HD + 8], sSt[HD][HD + 8];
+    __shared__ __align__(16) __nv_bfloat16 sQt[HD][TS], sPt[HD][TS], sDt[HD][TS];
+    __shared__ float sKm[HD], sc[GT];
+    const int b = blockIdx.z, hh = blockIdx.y, N = p.H * p.W;
+    const long long bh = (long long)b * p.h + hh;
+    const int n0 = blockIdx.x * p.chunk, n1 = min(N, n0 + p.chunk);
+    la_stage_bf16<HD>(p.S + bh * HD * HD, sS, sSt);
+    if (threadIdx.x < HD) sKm[threadIdx.x] = p.kmean[bh * HD + threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float dS[HD / 16][HD / 8][4], dKM[HD / 16][4];
+#pragma unroll
+    for (int mt = 0; mt < HD / 16; ++mt) {
+        dKM[mt][0] = dKM[mt][1] = dKM[mt][2] = dKM[mt][3] = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) dS[mt][nt][0] = dS[mt][nt][1] = dS[mt][nt][2] = dS[mt][nt][3] = 0.f;
+    }
+    for (int t0 = n0; t0 < n1; t0 += GT) {
+        const int nb = t0 + warp * 16;
+        const int nr[2] = {nb + g, nb + g + 8};
+        const bool ok[2] = {nr[0] < n1, nr[1] < n1};
+        LaFrag<HD> f;
+        la_frag_load<HD>(p, static_cast<const __nv_bfloat16 *>(p.q), p.ldq, hh, b, nr, ok, t, f);
+        float z[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float den = 0.f;
+#pragma unroll
+            for (int pi = 0; pi < HD / 8; ++pi)
+                den = fmaf(f.phi[r][pi].x, sKm[8 * pi + 2 * t], fmaf(f.phi[r][pi].y, sKm[8 * pi + 2 * t + 1], den));
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            z[r] = 1.f / (den + p.eps);
+        }
+        uint32_t a[HD / 16][4];
+        la_frag_rope_a<HD>(f, a);
+        // t = q_rope S (out / z);  dz = dO . t;  dt = z dO
+        float dt[HD / 8][4];
+        float dz[2] = {0.f, 0.f};
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks)
+                la_mma(o, a[ks], la_lds32(&sSt[nt * 8 + g][16 * ks + 2 * t]), la_lds32(&sSt[nt * 8 + g][16 * ks + 8 + 2 * t]));
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const float2 go = ok[r] ? la_unpack(la_lds32(static_cast<const __nv_bfloat16 *>(p.dout) +
+                                                            ((long long)b * N + nr[r]) * p.lddo + hh * HD + nt * 8 + 2 * t))
+                                        : make_float2(0.f, 0.f);
+                dz[r] = fmaf(go.x, o[2 * r], fmaf(go.y, o[2 * r + 1], dz[r]));
+                dt[nt][2 * r] = go.x * z[r];
+                dt[nt][2 * r + 1] = go.y * z[r];
+            }
+        }
+        float cden[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            dz[r] += __shfl_xor_sync(0xffffffffu, dz[r], 1);
+            dz[r] += __shfl_xor_sync(0xffffffffu, dz[r], 2);
+            cden[r] = -z[r] * z[r] * dz[r];
+        }
+        // transposed operands of the token contraction: q_rope, phi q, dt as [channel][token of the group]; c per token
+        {
+            const int tl[2] = {warp * 16 + g, warp * 16 + g + 8};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int pi = 0; pi < HD / 8; ++pi) {
+                    const float2 qr = la_unpack(a[pi >> 1][2 * (pi & 1) + r]);
+                    sQt[8 * pi + 2 * t][tl[r]] = __float2bfloat16_rn(qr.x);
+                    sQt[8 * pi + 2 * t + 1][tl[r]] = __float2bfloat16_rn(qr.y);
+                    sPt[8 * pi + 2 * t][tl[r]] = __float2bfloat16_rn(f.phi[r][pi].x);
+                    sPt[8 * pi + 2 * t + 1][tl[r]] = __float2bfloat16_rn(f.phi[r][pi].y);
+                    sDt[8 * pi + 2 * t][tl[r]] = __float2bfloat16_rn(dt[pi][2 * r]);
+                    sDt[8 * pi + 2 * t + 1][tl[r]] = __float2bfloat16_rn(dt[pi][2 * r + 1]);
+                }
+                if (t == 0) sc[tl[r]] = cden[r];
+            }
+        }
+        // d q_rope = dt S^T  (k = hd over e), rotate back, normaliser term, elu'
+        {
+            uint32_t da[HD / 16][4];
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) {
+                da[kk][0] = la_pack(dt[2 * kk][0], dt[2 * kk][1]);
+                da[kk][1] = la_pack(dt[2 * kk][2], dt[2 * kk][3]);
+                da[kk][2] = la_pack(dt[2 * kk + 1][0], dt[2 * kk + 1][1]);
+                da[kk][3] = la_pack(dt[2 * kk + 1][2], dt[2 * kk + 1][3]);
+            }
+#pragma unroll
+            for (int nd = 0; nd < HD / 8; ++nd) {
+                float dq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk)
+                    la_mma(dq, da[kk], la_lds32(&sS[nd * 8 + g][16 * kk + 2 * t]), la_lds32(&sS[nd * 8 + g][16 * kk + 8 + 2 * t]));
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (!ok[r]) continue;
+                    const float2 c = f.cs[r][nd], ph = f.phi[r][nd];
+                    const float g0 = dq[2 * r], g1 = dq[2 * r + 1];
+                    float e0 = c.x * g0 + c.y * g1 + cden[r] * sKm[nd * 8 + 2 * t];
+                    float e1 = c.x * g1 - c.y * g0 + cden[r] * sKm[nd * 8 + 2 * t + 1];
+                    e0 *= ph.x > 1.f ? 1.f : ph.x;
+                    e1 *= ph.y > 1.f ? 1.f : ph.y;
+                    *reinterpret_cast<uint32_t *>(static_cast<__nv_bfloat16 *>(p.dq) + ((long long)b * N + nr[r]) * p.lddq +
+                                                  hh * HD + nd * 8 + 2 * t) = la_pack(e0, e1);
+                }
+            }
+        }
+        __syncthreads();
+        {   // dS += q_rope^T dt, dkmean += (phi q)^T c over this warp's 16 tokens of the group
+            const int tk = warp * 16;
+            const uint32_t cb0 = (g == 0) ? la_pack(sc[tk + 2 * t], sc[tk + 2 * t + 1]) : 0u;
+            const uint32_t cb1 = (g == 0) ? la_pack(sc[tk + 8 + 2 * t], sc[tk + 8 + 2 * t + 1]) : 0u;
+#pragma unroll
+            for (int mt = 0; mt < HD / 16; ++mt) {
+                const int d0 = mt * 16 + g;
+                const uint32_t aq[4] = {la_lds32(&sQt[d0][tk + 2 * t]), la_lds32(&sQt[d0 + 8][tk + 2 * t]),
+                                        la_lds32(&sQt[d0][tk + 8 + 2 * t]), la_lds32(&sQt[d0 + 8][tk + 8 + 2 * t])};
+#pragma unroll
+                for (int nt = 0; nt < HD / 8; ++nt)
+                    la_mma(dS[mt][nt], aq, la_lds32(&sDt[nt * 8 + g][tk + 2 * t]), la_lds32(&sDt[nt * 8 + g][tk + 8 + 2 * t]));
+                const uint32_t ap[4] = {la_lds32(&sPt[d0][tk + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 2 * t]),
+                                        la_lds32(&sPt[d0][tk + 8 + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 8 + 2 * t])};
+                la_mma(dKM[mt], ap, cb0, cb1);
+            }
+        }
+        __syncthreads();
+    }
+    float *red = reinterpret_cast<float *>(&sQt[0][0]);   // HD * HD + HD floats fit in the three transposed tiles
+    for (int i = threadIdx.x; i < HD * HD + HD; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < HD / 16; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                atomicAdd(red + (mt * 16 + g + 8 * (e >> 1)) * HD + nt * 8 + 2 * t + (e & 1), dS[mt][nt][e]);
+        if (t == 0) {
+            atomicAdd(red + HD * HD + mt * 16 + g, dKM[mt][0]);
+            atomicAdd(red + HD * HD + mt * 16 + g + 8, dKM[mt][2]);
+        }
+    }
+    __syncthreads();
+    const float scale = 1.f / (float)N;
+    for (int i = threadIdx.x; i < HD * HD; i += blockDim.x) atomicAdd(p.dS + bh * HD * HD + i, red[i] * scale);
+    if (threadIdx.x < HD) atomicAdd(p.dkm + bh * HD + threadIdx.x, red[HD * HD + threadIdx.x] * scale);
+}
+
+// ---- backward 2: dv = rope(phi k) dS, dk from dS v                                (k = hd)
+template <int HD>
+__global__ void __launch_bounds__(128) linattn_bwd_kv_mma_kernel(const LinAttnParams p) {
+    __shared__ __align__(16) __nv_bfloat16 sdS[HD][HD + 8], sdSt[HD][HD + 8];
+    __shared__ float sdkm[HD];
+    const int b = blockIdx.z, hh = blockIdx.y, N = p.H * p.W;
+    const long long bh = (long long)b * p.h + hh;
+    la_stage_bf16<HD>(p.dS + bh * HD * HD, sdS, sdSt);          // already scaled by 1/N
+    if (threadIdx.x < HD) sdkm[threadIdx.x] = p.dkm[bh * HD + threadIdx.x];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int tile = warp; tile < kLmTok / 16; tile += 4) {
+        const int nb = blockIdx.x * kLmTok + tile * 16;
+        if (nb >= N) break;
+        const int nr[2] = {nb + g, nb + g + 8};
+        const bool ok[2] = {nr[0] < N, nr[1] < N};
+        LaFrag<HD> f;
+        la_frag_load<HD>(p, static_cast<const __nv_bfloat16 *>(p.k), p.ldk, hh, b, nr, ok, t, f);
+        uint32_t ak[HD / 16][4], av[HD / 16][4];
+        la_frag_rope_a<HD>(f, ak);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+                    av[ks][2 * hf + r] = ok[r] ? la_lds32(static_cast<const __nv_bfloat16 *>(p.v) + ((long long)b * N + nr[r]) * p.ldv +
+                                                         hh * HD + 16 * ks + 8 * hf + 2 * t)
+                                               : 0u;
+#pragma unroll
+        for (int nt = 0; nt < HD / 8; ++nt) {
+            float dv[4] = {0.f, 0.f, 0.f, 0.f}, dk[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks) {
+                la_mma(dv, ak[ks], la_lds32(&sdSt[nt * 8 + g][16 * ks + 2 * t]), la_lds32(&sdSt[nt * 8 + g][16 * ks + 8 + 2 * t]));
+                la_mma(dk, av[ks], la_lds32(&sdS[nt * 8 + g][16 * ks + 2 * t]), la_lds32(&sdS[nt * 8 + g][16 * ks + 8 + 2 * t]));
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                if (!ok[r]) continue;
+                const long long tok = (long long)b * N + nr[r];
+                *reinterpret_cast<uint32_t *>(static_cast<__nv_bfloat16 *>(p.dv) + tok * p.lddv + hh * HD + nt * 8 + 2 * t) =
+                    la_pack(dv[2 * r], dv[2 * r + 1]);
+                const float2 c = f.cs[r][nt], ph = f.phi[r][nt];
+                const float g0 = dk[2 * r], g1 = dk[2 * r + 1];
+                float e0 = c.x * g0 + c.y * g1 + sdkm[nt * 8 + 2 * t];
+                float e1 = c.x * g1 - c.y * g0 + sdkm[nt * 8 + 2 * t + 1];
+                e0 *= ph.x > 1.f ? 1.f : ph.x;
+                e1 *= ph.y > 1.f ? 1.f : ph.y;
+                *reinterpret_cast<uint32_t *>(static_cast<__nv_bfloat16 *>(p.dk) + tok * p.lddk + hh * HD + nt * 8 + 2 * t) =
+                    la_pack(e0, e1);
+            }
+        }
+    }
+}
+
+template <int HD>
+static cudaError_t linattn_launch_mma(LinAttnParams p, int which, cudaStream_t st) {
+    const int N = p.H * p.W;
+    p.chunk = linattn_chunk(p.Bn, N, p.h);
+    const dim3 gtok((N + kLmTok - 1) / kLmTok, p.h, p.Bn), gred((N + p.chunk - 1) / p.chunk, p.h, p.Bn);
+    if (which == 0) {
+        linattn_state_mma_kernel<HD><<<gred, kLTok, 0, st>>>(p);
+        linattn_apply_mma_kernel<HD><<<gtok, 128, 0, st>>>(p);
+    } else {
+        linattn_bwd_q_mma_kernel<HD><<<gred, 128, 0, st>>>(p);
+        linattn_bwd_kv_mma_kernel<HD><<<gtok, 128, 0, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+static bool linattn_use_mma(const LinAttnParams &p, int which) {
+    const char *e = getenv("MLAGG_LINATTN_MMA");
+    if (e && e[0] == '0') return false;
+    const bool ev = p.ldq % 2 == 0 && p.ldk % 2 == 0 && p.ldv % 2 == 0;
+    return which == 0 ? (ev && p.ldo % 2 == 0) : (ev && p.lddo % 2 == 0 && p.lddq % 2 == 0 && p.lddk % 2 == 0 && p.lddv % 2 == 0);
+}
+
 // ---------------------------------------------------------------- dispatch
 bool linattn_hd_supported(int hd) { return hd == 8 || hd == 16 || hd == 32; }
 
@@ -440,6 +873,8 @@ static cudaError_t linattn_by_hd(const LinAttnParams &p, int hd, int which, cuda
 }
 
 cudaError_t linattn_dispatch(const LinAttnParams &p, int hd, int dtype, int which, cudaStream_t st) {
+    if (dtype == 1 && (hd == 16 || hd == 32) && linattn_use_mma(p, which))
+        return hd == 16 ? linattn_launch_mma<16>(p, which, st) : linattn_launch_mma<32>(p, which, st);
     return dtype == 0 ? linattn_by_hd<float>(p, hd, which, st) : linattn_by_hd<__nv_bfloat16>(p, hd, which, st);
 }
 

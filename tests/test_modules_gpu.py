@@ -278,6 +278,10 @@ def test_linear_attention_core_matches_fp64_oracle(Bn, H, W, heads, hd):
     out16 = att.linear_attention_qk(qk.cuda().bfloat16(), v.cuda().bfloat16(), H, W, heads)
     assert out16.dtype == torch.bfloat16
     assert rel_err(out16.float().cpu(), ref.detach()) < TOL16
+    # bf16 backward (tensor-core kernels for hd 16 / 32) against the same fp64 gradients
+    qk16, v16 = qk.cuda().bfloat16().requires_grad_(), v.cuda().bfloat16().requires_grad_()
+    gq16, gv16 = torch.autograd.grad(att.linear_attention_qk(qk16, v16, H, W, heads), [qk16, v16], w.cuda().bfloat16())
+    assert rel_err(gq16.float().cpu(), gq_ref) < TOL16 and rel_err(gv16.float().cpu(), gv_ref) < TOL16
     # separate q / k entry point and a strided v (a channel slice of a wider tensor) give the same numbers
     wide = torch.randn(Bn, N, C + 8, generator=g).cuda()
     wide[..., :C] = v.cuda()
