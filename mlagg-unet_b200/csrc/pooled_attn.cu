@@ -502,13 +502,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t *>(&t);
 }
 
-constexpr int kMmaHD = 24, kMmaNT = 14, kMmaPmax = 8 * kMmaNT;   // 112 pooled tokens at most
-constexpr int kMmaKS = 40;                                       // K row stride (bf16): 24 channels + zero pad, conflict-free
+constexpr int kMmaNT = 14, kMmaPmax = 8 * kMmaNT;                // 112 pooled tokens at most; hd = 24 (shipped) or 32
+constexpr int kMmaKS = 40;                                       // K row stride (bf16): <= 32 channels + zero pad, conflict-free
 constexpr int kMmaVS = kMmaPmax + 8;                             // V^T row stride (bf16)
 constexpr int kMmaTok = 256;                                     // query tokens per block (4 warps x 4 tiles of 16)
 
+template <int HD>
 __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAttnParams p) {
-    constexpr int HD = kMmaHD;
+    constexpr int NC = 2 * HD / 8;      // n8 tiles over the 2hd output channels
     __shared__ __align__(16) __nv_bfloat16 sK[2][kMmaPmax][kMmaKS];
     __shared__ __align__(16) __nv_bfloat16 sVt[2 * HD][kMmaVS];
     const int b = blockIdx.z, m = blockIdx.y;
@@ -529,9 +530,9 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
     __syncthreads();
     const float qs = p.scale2 * kLog2e;
     const float lam = __ldg(p.lamp);
-    float wv[6][2];
+    float wv[NC][2];
 #pragma unroll
-    for (int nc = 0; nc < 6; ++nc) {
+    for (int nc = 0; nc < NC; ++nc) {
         wv[nc][0] = __ldg(p.subln_w + nc * 8 + 2 * t) * p.post;
         wv[nc][1] = __ldg(p.subln_w + nc * 8 + 2 * t + 1) * p.post;
     }
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
         if (n0 >= p.N) break;
         const int nr[2] = {n0 + g, n0 + g + 8};
         const bool ok[2] = {nr[0] < p.N, nr[1] < p.N};
-        float O[2][6][4];
+        float O[2][NC][4];
         float lsev[2][2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
                 qa[0][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 2 * t) : 0u;
                 qa[0][2 + r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 8 + 2 * t) : 0u;
                 qa[1][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 16 + 2 * t) : 0u;
-                qa[1][2 + r] = 0u;
+                qa[1][2 + r] = (HD > 24 && ok[r]) ? *reinterpret_cast<const uint32_t *>(qp + 24 + 2 * t) : 0u;
             }
             // ---- S_j = Q_j K_j^T
             float S[kMmaNT][4];
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
             lsev[j][1] = mx1 + lg2_approx(l1);
             // ---- O_j = P V  (probabilities: accumulator layout -> A operand)
 #pragma unroll
-            for (int nc = 0; nc < 6; ++nc) O[j][nc][0] = O[j][nc][1] = O[j][nc][2] = O[j][nc][3] = 0.f;
+            for (int nc = 0; nc < NC; ++nc) O[j][nc][0] = O[j][nc][1] = O[j][nc][2] = O[j][nc][3] = 0.f;
 #pragma unroll
             for (int kk = 0; kk < kMmaNT / 2; ++kk) {
                 uint32_t pa[4];
@@ -601,23 +602,23 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
                 pa[2] = pack_bf16(S[2 * kk + 1][0], S[2 * kk + 1][1]);
                 pa[3] = pack_bf16(S[2 * kk + 1][2], S[2 * kk + 1][3]);
 #pragma unroll
-                for (int nc = 0; nc < 6; ++nc) {
+                for (int nc = 0; nc < NC; ++nc) {
                     const __nv_bfloat16 *vr = &sVt[nc * 8 + g][kk * 16 + 2 * t];
                     mma_bf16_16816(O[j][nc], pa, *reinterpret_cast<const uint32_t *>(vr), *reinterpret_cast<const uint32_t *>(vr + 8));
                 }
             }
             const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
-            for (int nc = 0; nc < 6; ++nc) {
+            for (int nc = 0; nc < NC; ++nc) {
                 O[j][nc][0] *= i0; O[j][nc][1] *= i0;
                 O[j][nc][2] *= i1; O[j][nc][3] *= i1;
             }
         }
         // ---- o = O0 - lam O1, RMSNorm over the 48 channels of the row, scale, store
         float ss0 = 0.f, ss1 = 0.f;
-        float oc[6][4];
+        float oc[NC][4];
 #pragma unroll
-        for (int nc = 0; nc < 6; ++nc)
+        for (int nc = 0; nc < NC; ++nc)
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 oc[nc][e] = O[0][nc][e] - lam * O[1][nc][e];
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
             const long long tok = (long long)b * p.N + nr[r];
             __nv_bfloat16 *op = static_cast<__nv_bfloat16 *>(p.out) + tok * p.ldo + (long long)m * 2 * HD;
 #pragma unroll
-            for (int nc = 0; nc < 6; ++nc)
+            for (int nc = 0; nc < NC; ++nc)
                 *reinterpret_cast<uint32_t *>(op + nc * 8 + 2 * t) =
                     pack_bf16(oc[nc][2 * r] * rr[r] * wv[nc][0], oc[nc][2 * r + 1] * rr[r] * wv[nc][1]);
             if (p.lse) {
@@ -642,7 +643,7 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
                 }
                 float *os = p.lse + pooled_osave_offset(p) + (tok * p.h + m) * 4 * HD;
 #pragma unroll
-                for (int nc = 0; nc < 6; ++nc) {
+                for (int nc = 0; nc < NC; ++nc) {
                     *reinterpret_cast<float2 *>(os + nc * 8 + 2 * t) = make_float2(O[0][nc][2 * r], O[0][nc][2 * r + 1]);
                     *reinterpret_cast<float2 *>(os + 2 * HD + nc * 8 + 2 * t) = make_float2(O[1][nc][2 * r], O[1][nc][2 * r + 1]);
                 }
@@ -655,13 +656,14 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
 // (accumulator layout), dab = dO V^T, S_j is recomputed, dS_j = A_j o (dab - D_j) and dq_j = dS_j K_j are mma products
 // (B operands: V row-major, K_j row-major for S, K_j^T for dq).  Also writes dO / D_j for the dK, dV kernel and
 // accumulates d lambda and d subln_w.
-constexpr int kMmaVR = 2 * kMmaHD + 8;                           // V row stride (bf16), conflict-free
 
+template <int HD>
 __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const PooledAttnParams p) {
-    constexpr int HD = kMmaHD;
-    __shared__ __align__(16) __nv_bfloat16 sK[2][kMmaPmax][kMmaKS];     // K_j[p][d]
-    __shared__ __align__(16) __nv_bfloat16 sKt[2][HD][kMmaVS];          // K_j^T[d][p]
-    __shared__ __align__(16) __nv_bfloat16 sV[kMmaPmax][kMmaVR];        // V[p][c]
+    constexpr int NC = 2 * HD / 8, KC = 2 * HD / 16, ND = HD / 8, kMmaVR = 2 * HD + 8;
+    extern __shared__ __align__(16) unsigned char bq_smem[];
+    auto sK = reinterpret_cast<__nv_bfloat16 (*)[kMmaPmax][kMmaKS]>(bq_smem);                                  // K_j[p][d]
+    auto sKt = reinterpret_cast<__nv_bfloat16 (*)[HD][kMmaVS]>(bq_smem + sizeof(__nv_bfloat16) * 2 * kMmaPmax * kMmaKS);   // K_j^T[d][p]
+    auto sV = reinterpret_cast<__nv_bfloat16 (*)[kMmaVR]>(bq_smem + sizeof(__nv_bfloat16) * (2 * kMmaPmax * kMmaKS + 2 * HD * kMmaVS));   // V[p][c]
     __shared__ float red[2 * HD + 1];
     const int b = blockIdx.z, m = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -686,9 +688,9 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
     __syncthreads();
     const float qs = p.scale2 * kLog2e;
     const float lam = __ldg(p.lamp);
-    float wv[6][2], dwacc[6][2];
+    float wv[NC][2], dwacc[NC][2];
 #pragma unroll
-    for (int nc = 0; nc < 6; ++nc) {
+    for (int nc = 0; nc < NC; ++nc) {
         wv[nc][0] = __ldg(p.subln_w + nc * 8 + 2 * t);
         wv[nc][1] = __ldg(p.subln_w + nc * 8 + 2 * t + 1);
         dwacc[nc][0] = dwacc[nc][1] = 0.f;
@@ -700,17 +702,17 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
         const int nr[2] = {n0 + g, n0 + g + 8};
         const bool ok[2] = {nr[0] < p.N, nr[1] < p.N};
         // ---- RMSNorm backward on the saved O0 | O1 (accumulator layout: row r, columns nc*8 + 2t, +1)
-        float dO[6][4];
+        float dO[NC][4];
         float D0[2], D1[2], lse0[2], lse1[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const long long tok = (long long)b * p.N + (ok[r] ? nr[r] : 0);
             const float *os = p.lse + pooled_osave_offset(p) + (tok * p.h + m) * 4 * HD;
             const __nv_bfloat16 *gp = static_cast<const __nv_bfloat16 *>(p.dout) + tok * p.lddo + (long long)m * 2 * HD;
-            float o0[6][2], o1[6][2], oc[6][2], gs[6][2];
+            float o0[NC][2], o1[NC][2], oc[NC][2], gs[NC][2];
             float ss = 0.f;
 #pragma unroll
-            for (int nc = 0; nc < 6; ++nc) {
+            for (int nc = 0; nc < NC; ++nc) {
                 const float2 a = ok[r] ? *reinterpret_cast<const float2 *>(os + nc * 8 + 2 * t) : make_float2(0.f, 0.f);
                 const float2 c = ok[r] ? *reinterpret_cast<const float2 *>(os + 2 * HD + nc * 8 + 2 * t) : make_float2(0.f, 0.f);
                 o0[nc][0] = a.x, o0[nc][1] = a.y, o1[nc][0] = c.x, o1[nc][1] = c.y;
@@ -723,7 +725,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
             const float rn = 1.f / sqrtf(ss * (1.f / (2 * HD)) + p.eps);
             float dot = 0.f;
 #pragma unroll
-            for (int nc = 0; nc < 6; ++nc)
+            for (int nc = 0; nc < NC; ++nc)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     dwacc[nc][e] = fmaf(gs[nc][e] * p.post, oc[nc][e] * rn, dwacc[nc][e]);
@@ -734,7 +736,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
             const float k3 = rn * rn * rn * dot * (1.f / (2 * HD));
             float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-            for (int nc = 0; nc < 6; ++nc)
+            for (int nc = 0; nc < NC; ++nc)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const float v = rn * gs[nc][e] - oc[nc][e] * k3;
@@ -752,7 +754,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                 if (p.ws_dO) {
                     float *wdO = p.ws_dO + (tok * p.h + m) * 2 * HD;
 #pragma unroll
-                    for (int nc = 0; nc < 6; ++nc)
+                    for (int nc = 0; nc < NC; ++nc)
                         *reinterpret_cast<float2 *>(wdO + nc * 8 + 2 * t) = make_float2(dO[nc][2 * r], dO[nc][2 * r + 1]);
                     if (t == 0) {
                         p.ws_D[(tok * p.h + m) * 2 + 0] = d0;
@@ -764,9 +766,9 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
         // ---- dab = dO V^T  (k = 48 channels = 3 steps; dO: accumulator layout -> A operand)
         float dab[kMmaNT][4];
         {
-            uint32_t da[3][4];
+            uint32_t da[KC][4];
 #pragma unroll
-            for (int kc = 0; kc < 3; ++kc) {
+            for (int kc = 0; kc < KC; ++kc) {
                 da[kc][0] = pack_bf16(dO[2 * kc][0], dO[2 * kc][1]);
                 da[kc][1] = pack_bf16(dO[2 * kc][2], dO[2 * kc][3]);
                 da[kc][2] = pack_bf16(dO[2 * kc + 1][0], dO[2 * kc + 1][1]);
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
             for (int nt = 0; nt < kMmaNT; ++nt) {
                 dab[nt][0] = dab[nt][1] = dab[nt][2] = dab[nt][3] = 0.f;
 #pragma unroll
-                for (int kc = 0; kc < 3; ++kc) {
+                for (int kc = 0; kc < KC; ++kc) {
                     const __nv_bfloat16 *vr = &sV[nt * 8 + g][kc * 16 + 2 * t];
                     mma_bf16_16816(dab[nt], da[kc], *reinterpret_cast<const uint32_t *>(vr), *reinterpret_cast<const uint32_t *>(vr + 8));
                 }
@@ -792,14 +794,14 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                 qa[0][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 2 * t) : 0u;
                 qa[0][2 + r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 8 + 2 * t) : 0u;
                 qa[1][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 16 + 2 * t) : 0u;
-                qa[1][2 + r] = 0u;
+                qa[1][2 + r] = (HD > 24 && ok[r]) ? *reinterpret_cast<const uint32_t *>(qp + 24 + 2 * t) : 0u;
             }
             const float ls[2] = {j == 0 ? lse0[0] : lse1[0], j == 0 ? lse0[1] : lse1[1]};
             const float Dj[2] = {j == 0 ? D0[0] : D1[0], j == 0 ? D0[1] : D1[1]};
             const float sgn = j == 0 ? 1.f : -lam;
-            float dq[3][4];
+            float dq[ND][4];
 #pragma unroll
-            for (int nd = 0; nd < 3; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
+            for (int nd = 0; nd < ND; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
 #pragma unroll
             for (int kk = 0; kk < kMmaNT / 2; ++kk) {
                 uint32_t sa[4];
@@ -822,7 +824,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                     sa[2 * hf + 1] = pack_bf16(ds[2], ds[3]);
                 }
 #pragma unroll
-                for (int nd = 0; nd < 3; ++nd) {
+                for (int nd = 0; nd < ND; ++nd) {
                     const __nv_bfloat16 *kt = &sKt[j][nd * 8 + g][kk * 16 + 2 * t];
                     mma_bf16_16816(dq[nd], sa, *reinterpret_cast<const uint32_t *>(kt), *reinterpret_cast<const uint32_t *>(kt + 8));
                 }
@@ -833,7 +835,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                 __nv_bfloat16 *dqp = static_cast<__nv_bfloat16 *>(p.dq) + ((long long)b * p.N + nr[r]) * p.lddq +
                                      (long long)m * 2 * HD + j * HD;
 #pragma unroll
-                for (int nd = 0; nd < 3; ++nd)
+                for (int nd = 0; nd < ND; ++nd)
                     *reinterpret_cast<uint32_t *>(dqp + nd * 8 + 2 * t) =
                         pack_bf16(dq[nd][2 * r] * p.scale2, dq[nd][2 * r + 1] * p.scale2);
             }
@@ -841,7 +843,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
     }
     // ---- d subln_w (column sums over the block's tokens) and d lambda
 #pragma unroll
-    for (int nc = 0; nc < 6; ++nc)
+    for (int nc = 0; nc < NC; ++nc)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             float v = dwacc[nc][e];
@@ -869,8 +871,9 @@ constexpr int kKvChunk = 64;                  // query tokens staged per iterati
 constexpr int kKvSlab = 1024;                 // query tokens per block
 constexpr int kKvTS = kKvChunk + 8;           // row stride of the transposed tiles (bf16), conflict-free
 
+template <int HD>
 __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const PooledAttnParams p) {
-    constexpr int HD = kMmaHD;
+    constexpr int NC = 2 * HD / 8, KC = 2 * HD / 16, ND = HD / 8, kMmaVR = 2 * HD + 8;
     __shared__ __align__(16) __nv_bfloat16 sQ[2][kKvChunk][kMmaKS];      // Q_j[tok][d] (zero-padded to 32 channels)
     __shared__ __align__(16) __nv_bfloat16 sQt[2][HD][kKvTS];            // Q_j^T[d][tok]
     __shared__ __align__(16) __nv_bfloat16 sG[kKvChunk][kMmaVR];         // dO[tok][c]
@@ -882,7 +885,7 @@ __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const Poole
     const bool pok[2] = {prow[0] < p.P, prow[1] < p.P};
     const bool warp_on = warp * 16 < p.P;
     // ---- A operands: K_j rows (k = 32 channels, 24..31 zero) and V rows (k = 48 channels) of this warp's pooled tokens
-    uint32_t ka[2][2][4], va[3][4];
+    uint32_t ka[2][2][4], va[KC][4];
     {
         const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
         const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
@@ -895,22 +898,22 @@ __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const Poole
                 ka[j][0][r] = pok[r] ? *reinterpret_cast<const uint32_t *>(kr + j * HD + 2 * t) : 0u;
                 ka[j][0][2 + r] = pok[r] ? *reinterpret_cast<const uint32_t *>(kr + j * HD + 8 + 2 * t) : 0u;
                 ka[j][1][r] = pok[r] ? *reinterpret_cast<const uint32_t *>(kr + j * HD + 16 + 2 * t) : 0u;
-                ka[j][1][2 + r] = 0u;
+                ka[j][1][2 + r] = (HD > 24 && pok[r]) ? *reinterpret_cast<const uint32_t *>(kr + j * HD + 24 + 2 * t) : 0u;
             }
 #pragma unroll
-            for (int kc = 0; kc < 3; ++kc) {
+            for (int kc = 0; kc < KC; ++kc) {
                 va[kc][r] = pok[r] ? *reinterpret_cast<const uint32_t *>(vr + kc * 16 + 2 * t) : 0u;
                 va[kc][2 + r] = pok[r] ? *reinterpret_cast<const uint32_t *>(vr + kc * 16 + 8 + 2 * t) : 0u;
             }
         }
     }
-    float dV[6][4], dK[2][3][4];
+    float dV[NC][4], dK[2][ND][4];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) dV[i][0] = dV[i][1] = dV[i][2] = dV[i][3] = 0.f;
+    for (int i = 0; i < NC; ++i) dV[i][0] = dV[i][1] = dV[i][2] = dV[i][3] = 0.f;
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int i = 0; i < 3; ++i) dK[j][i][0] = dK[j][i][1] = dK[j][i][2] = dK[j][i][3] = 0.f;
+        for (int i = 0; i < ND; ++i) dK[j][i][0] = dK[j][i][1] = dK[j][i][2] = dK[j][i][3] = 0.f;
     const float qs = p.scale2 * kLog2e;
     const float lam = __ldg(p.lamp);
     const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
@@ -961,7 +964,7 @@ __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const Poole
             for (int nt = 0; nt < 2; ++nt) {
                 dab[nt][0] = dab[nt][1] = dab[nt][2] = dab[nt][3] = 0.f;
 #pragma unroll
-                for (int kc = 0; kc < 3; ++kc) {
+                for (int kc = 0; kc < KC; ++kc) {
                     const __nv_bfloat16 *gr = &sG[tk0 + nt * 8 + g][kc * 16 + 2 * t];
                     mma_bf16_16816(dab[nt], va[kc], *reinterpret_cast<const uint32_t *>(gr), *reinterpret_cast<const uint32_t *>(gr + 8));
                 }
@@ -991,7 +994,7 @@ __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const Poole
                 // dK_j += dS_j^T Q_j   (A = accumulator tiles of the two n8 token tiles, k = 16 tokens)
                 const uint32_t a4[4] = {dsa[0], dsa[1], dsa[2], dsa[3]};
 #pragma unroll
-                for (int nd = 0; nd < 3; ++nd) {
+                for (int nd = 0; nd < ND; ++nd) {
                     const __nv_bfloat16 *qt = &sQt[j][nd * 8 + g][tk0 + 2 * t];
                     mma_bf16_16816(dK[j][nd], a4, *reinterpret_cast<const uint32_t *>(qt), *reinterpret_cast<const uint32_t *>(qt + 8));
                 }
@@ -1001,7 +1004,7 @@ __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const Poole
             abar[2] = pack_bf16(ab[1][0], ab[1][1]);
             abar[3] = pack_bf16(ab[1][2], ab[1][3]);
 #pragma unroll
-            for (int nc = 0; nc < 6; ++nc) {
+            for (int nc = 0; nc < NC; ++nc) {
                 const __nv_bfloat16 *gt = &sGt[nc * 8 + g][tk0 + 2 * t];
                 mma_bf16_16816(dV[nc], abar, *reinterpret_cast<const uint32_t *>(gt), *reinterpret_cast<const uint32_t *>(gt + 8));
             }
@@ -1016,12 +1019,12 @@ __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const Poole
 #pragma unroll
         for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int nd = 0; nd < 3; ++nd) {
+            for (int nd = 0; nd < ND; ++nd) {
                 atomicAdd(dkb + j * HD + nd * 8 + 2 * t, dK[j][nd][2 * r] * p.scale2);
                 atomicAdd(dkb + j * HD + nd * 8 + 2 * t + 1, dK[j][nd][2 * r + 1] * p.scale2);
             }
 #pragma unroll
-        for (int nc = 0; nc < 6; ++nc) {
+        for (int nc = 0; nc < NC; ++nc) {
             atomicAdd(dvb + nc * 8 + 2 * t, dV[nc][2 * r]);
             atomicAdd(dvb + nc * 8 + 2 * t + 1, dV[nc][2 * r + 1]);
         }
@@ -1037,23 +1040,28 @@ template <typename T, int HD>
 static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStream_t st) {
     const size_t smem = (size_t)p.P * HD * 16;   // kI (P x hd float2) + V (P x 2hd float)
     cudaError_t e;
-    if (which == 0 && std::is_same<T, __nv_bfloat16>::value && HD == kMmaHD && p.P <= kMmaPmax && pooled_use_mma() &&
+    constexpr bool kMmaHd = HD == 24 || HD == 32;
+    constexpr int MH = kMmaHd ? HD : 24;   // instantiate the tensor-core kernels only for the head sizes they support
+    if (which == 0 && std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
         p.ldq % 2 == 0 && p.ldkv % 2 == 0 && p.ldo % 2 == 0) {
-        pooled_attn_fwd_mma_kernel<<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, 0, st>>>(p);
+        pooled_attn_fwd_mma_kernel<MH><<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, 0, st>>>(p);
     } else if (which == 0) {
         auto k = pooled_attn_fwd_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);
-    } else if (which == 1 && std::is_same<T, __nv_bfloat16>::value && HD == kMmaHD && p.P <= kMmaPmax && pooled_use_mma() &&
+    } else if (which == 1 && std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
                p.ldq % 2 == 0 && p.ldkv % 2 == 0 && p.lddo % 2 == 0 && p.lddq % 2 == 0) {
-        pooled_attn_bwd_q_mma_kernel<<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, 0, st>>>(p);
+        const size_t bq = sizeof(__nv_bfloat16) * (2 * kMmaPmax * kMmaKS + 2 * MH * kMmaVS + kMmaPmax * (2 * MH + 8));
+        auto k = pooled_attn_bwd_q_mma_kernel<MH>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bq)) != cudaSuccess) return e;
+        k<<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, bq, st>>>(p);
     } else if (which == 1) {
         auto k = pooled_attn_bwd_q_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);
-    } else if (std::is_same<T, __nv_bfloat16>::value && HD == kMmaHD && p.P <= kMmaPmax && pooled_use_mma() &&
+    } else if (std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
                p.ldq % 2 == 0 && p.ldkv % 2 == 0) {
-        pooled_attn_bwd_kv_mma_kernel<<<dim3((p.N + kKvSlab - 1) / kKvSlab, p.h, p.Bn), 224, 0, st>>>(p);
+        pooled_attn_bwd_kv_mma_kernel<MH><<<dim3((p.N + kKvSlab - 1) / kKvSlab, p.h, p.Bn), 224, 0, st>>>(p);
     } else {
         if (HD % 4 == 0 && 2 * p.P <= 256) {
             const int threads = ((2 * p.P + 31) / 32) * 32;

@@ -427,13 +427,12 @@ def test_cuda_graph_train_step_matches_eager():
 
 
 def test_pooled_attention_tensor_core_forward_matches_fp32_path():
-    """bf16 / hd 24 / P <= 112 takes the mma.sync forward kernel: output and (through the shared saved tensors) all
+    """bf16 / hd 24 or 32 / P <= 112 takes the mma.sync kernels: output and (through the shared saved tensors) all
     gradients agree with the fp32 FMA kernels at the bf16 tolerance; ragged token count, P = 100 (not a multiple of 16),
     and P = 7 (a single, mostly masked k-step)."""
     from mlagg_unet_b200 import attention as att
     g = torch.Generator().manual_seed(23)
-    for Bn, N, h, P in [(2, 700, 2, 100), (1, 37, 1, 7), (1, 256, 3, 112)]:
-        hd = 24
+    for Bn, N, h, P, hd in [(2, 700, 2, 100, 24), (1, 37, 1, 7, 24), (1, 256, 3, 112, 24), (2, 333, 2, 64, 32)]:
         C = 2 * h * hd
         q0 = torch.randn(Bn, N, C, generator=g).cuda()
         kv0 = torch.randn(Bn, P, 2 * C, generator=g).cuda()
