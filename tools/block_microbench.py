@@ -1,7 +1,7 @@
 """BASELINE config 2, block part: MLLABlock(dim=256, heads=4, mlp_ratio=2, pooled 8x8) forward and forward+backward on
-(10, 256, sqrt(L), sqrt(L)) inputs, L = 1k .. 64k, fp32 and bf16 autocast, CUDA-event timing; the reference's CPU path
-(oracle.mlagg.mlla_block_forward, fp32, all host threads) is timed beside it at the smallest sizes."""
-import json, os, sys, time
+(10, 256, sqrt(L), sqrt(L)) inputs, L = 1k .. 64k, fp32 and bf16 autocast, CUDA-event timing.  (The CPU reference arm
+lives in bench.py -- oracle/ is only imported by tests/, smoke() and bench.py.)"""
+import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mlagg_unet_b200.mlagg import MLLABlock
@@ -32,13 +32,4 @@ for side in (32, 64, 128, 256):
             y.float().sum().backward()
         row[name + "_fwd_ms"] = round(t_ms(fwd), 3)
         row[name + "_fwd_bwd_ms"] = round(t_ms(fb), 3)
-    if side <= 64:   # CPU reference path (oracle), forward only
-        from oracle.mlagg import mlla_block_forward
-        p = {k: v.detach().cpu() for k, v in blk.named_parameters()}
-        xc = x.detach().cpu().contiguous()
-        torch.set_num_threads(os.cpu_count() or 1)
-        with torch.no_grad():
-            mlla_block_forward(p, xc, 4, side // 8)
-            t = time.perf_counter(); mlla_block_forward(p, xc, 4, side // 8); row["cpu_oracle_fwd_ms"] = round((time.perf_counter() - t) * 1e3, 1)
-        row["cpu_threads"] = torch.get_num_threads()
     print(json.dumps(row))
