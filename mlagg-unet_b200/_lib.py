@@ -116,3 +116,37 @@ def ptr(t):
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- per-step arena of zero-initialised fp32 scratch.  Every backward wrapper needs small zero-filled accumulators (bias /
+# weight gradients, column sums, scalar sums): ~350 separate fill kernels per train step.  While a trainer step is running
+# they are carved out of one buffer that is cleared by a single memset at the start of the step; outside a step (tests,
+# direct module use) `zeros` is plain torch.zeros.
+_ARENA = {"buf": None, "off": 0, "active": False}
+_ARENA_FLOATS, _ARENA_MAX_REQ = 4 << 20, 1 << 16
+
+
+def arena_begin(device):
+    import torch
+    if _ARENA["buf"] is None or _ARENA["buf"].device != torch.device(device):
+        _ARENA["buf"] = torch.empty(_ARENA_FLOATS, device=device, dtype=torch.float32)
+    _ARENA["buf"].zero_()
+    _ARENA["off"], _ARENA["active"] = 0, True
+
+
+def arena_end():
+    _ARENA["active"] = False
+
+
+def zeros(shape, device):
+    """fp32 zeros of `shape`: a 256-byte aligned slice of the step arena when one is active, else torch.zeros."""
+    import math
+    import torch
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    n = math.prod(shape)
+    if _ARENA["active"] and n <= _ARENA_MAX_REQ and _ARENA["buf"].device == torch.device(device):
+        off = _ARENA["off"]
+        if off + n <= _ARENA_FLOATS:
+            _ARENA["off"] = off + (n + 63) // 64 * 64
+            return _ARENA["buf"][off:off + n].view(shape)
+    return torch.zeros(shape, device=device, dtype=torch.float32)

@@ -62,8 +62,8 @@ class _LocalDiffAttn(torch.autograd.Function):
         dt, es = q_.dtype, q_.element_size()
         dout = dout.to(dt).contiguous()
         dq, dkv = torch.empty_like(q_), torch.empty_like(kv_)
-        dw = torch.zeros_like(w_)
-        dlam = torch.zeros(1, device=q_.device, dtype=torch.float32)
+        dw = _lib.zeros(w_.shape, q_.device)
+        dlam = _lib.zeros(1, q_.device)
         L = _lib.lib()
         ws = torch.empty(L.mlagg_local_diffattn_ws_bytes(Bn, H, W, h, hd) // 4, device=q_.device, dtype=torch.float32)
         with torch.cuda.device(q_.device), _lib.timed("local_diffattn_bwd", 2):
@@ -118,8 +118,8 @@ class _PooledDiffAttn(torch.autograd.Function):
         dout = dout.to(dt).contiguous()
         dq = torch.empty_like(q_)
         dkv = torch.zeros(Bn, P, 2 * C, device=q_.device, dtype=torch.float32)
-        dw = torch.zeros_like(w_)
-        dlam = torch.zeros(1, device=q_.device, dtype=torch.float32)
+        dw = _lib.zeros(w_.shape, q_.device)
+        dlam = _lib.zeros(1, q_.device)
         L = _lib.lib()
         ws = torch.empty(L.mlagg_pooled_diffattn_ws_bytes(Bn, N, h, hd) // 4, device=q_.device, dtype=torch.float32)
         with torch.cuda.device(q_.device), _lib.timed("pooled_diffattn_bwd", 2):

@@ -44,8 +44,8 @@ class _DWConv3x3(torch.autograd.Function):
         Bn, N, C = xin.shape
         dy = dy.to(xin.dtype).contiguous()
         dz, dx = torch.empty_like(xin), torch.empty_like(xin)
-        dw = torch.zeros(C, 9, device=xin.device, dtype=torch.float32)
-        db = torch.zeros(C, device=xin.device, dtype=torch.float32) if b32 is not None else None
+        dw = _lib.zeros((C, 9), xin.device)
+        db = _lib.zeros(C, xin.device) if b32 is not None else None
         with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2):
             rc = _lib.lib().mlagg_dwconv3x3_bwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy), _lib.ptr(dz),
                                                 _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), Bn, H, W, C, int(silu),
@@ -134,8 +134,8 @@ class _LayerNorm(torch.autograd.Function):
         M = xin.numel() // C
         dy = dy.to(odt).contiguous()
         dx = torch.empty_like(xin)
-        dw = torch.zeros(C, device=xin.device, dtype=torch.float32)
-        db = torch.zeros(C, device=xin.device, dtype=torch.float32) if bdt is not None else None
+        dw = _lib.zeros(C, xin.device)
+        db = _lib.zeros(C, xin.device) if bdt is not None else None
         with torch.cuda.device(xin.device), _lib.timed("layernorm_bwd"):
             rc = _lib.lib().mlagg_layernorm_bwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dy),
                                                 _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), M, C, _DT[xin.dtype], _DT[odt],
@@ -163,7 +163,7 @@ def colsum(x2d):
     if x2d.dtype not in _DT or x2d.stride(1) != 1:
         x2d = _io(x2d).contiguous()
     M, C = x2d.shape
-    out = torch.zeros(C, device=x2d.device, dtype=torch.float32)
+    out = _lib.zeros(C, x2d.device)
     with torch.cuda.device(x2d.device), _lib.timed("colsum"):
         rc = _lib.lib().mlagg_colsum(_lib.ptr(x2d), _lib.ptr(out), M, C, x2d.stride(0), _DT[x2d.dtype], _lib.stream_ptr())
     _lib.check(rc, "mlagg_colsum")
@@ -275,8 +275,8 @@ class _InstNorm(torch.autograd.Function):
             dyt = dyt.contiguous()
         dx = torch.empty_like(xt)
         sums = torch.empty(Bn, C, 2, device=xt.device, dtype=torch.float32)
-        dw = torch.zeros(C, device=xt.device, dtype=torch.float32) if w32 is not None else None
-        db = torch.zeros(C, device=xt.device, dtype=torch.float32) if b32 is not None else None
+        dw = _lib.zeros(C, xt.device) if w32 is not None else None
+        db = _lib.zeros(C, xt.device) if b32 is not None else None
         with torch.cuda.device(xt.device), _lib.timed("instnorm_bwd", 3):
             rc = _lib.lib().mlagg_instnorm_bwd(_lib.ptr(xt), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(stats), _lib.ptr(dyt),
                                                _lib.ptr(dx), _lib.ptr(sums), _lib.ptr(dw), _lib.ptr(db), Bn, H * W, C, act,

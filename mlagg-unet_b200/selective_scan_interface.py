@@ -132,7 +132,7 @@ class MSMMScanFn(torch.autograd.Function):
         dout = dout.float().contiguous()
         du = torch.empty(Bn, 4, Di, L, device=xrow.device, dtype=torch.float32)
         dxr, dxc = torch.zeros_like(xr), torch.zeros_like(xc)
-        dW, db, dA, dD = torch.zeros_like(W), torch.zeros_like(b), torch.zeros_like(A), torch.zeros_like(D)
+        dW, db, dA, dD = (_lib.zeros(t.shape, t.device) for t in (W, b, A, D))
         lens = (ctypes.c_int * len(ctx.stage_lens))(*ctx.stage_lens)
         L_ = _lib.lib()
         with torch.cuda.device(xrow.device), _lib.timed("scan_bwd"):

@@ -234,7 +234,9 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
 
     # ---- one training step (nnUNetTrainer.train_step, :833-863)
     def _forward_loss(self, data, target):
-        from . import ops
+        from . import _lib, ops
+        if self.device.type == "cuda":
+            _lib.arena_begin(self.device)   # one memset instead of ~350 zero-fill kernels for the backward accumulators
         ops.refresh_cast_cache()      # one multi-tensor fp32 -> bf16 copy of the parameters instead of a cast per layer
         with torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
             return self.loss(self.network(data), target)
@@ -264,11 +266,12 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
     def _step_math(self, data, target):
         """forward -> DiceCE-DS loss -> backward -> gradient all-reduce -> clip(12) -> AdamW; capturable in a CUDA graph."""
         self._drop_grads()
-        from . import ops
+        from . import _lib, ops
         l = self._forward_loss(data, target)
         l.backward()
         ops.release_cast_cache()
         self._reduce_clip_step()
+        _lib.arena_end()
         return l.detach()
 
     def _bind_flat_grads(self):
@@ -322,7 +325,9 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             self._side_stream_warmup(lambda: self._step_math(st["data"], st["target"]))
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             from . import ops
+            from . import _lib
             with torch.cuda.graph(ga):
+                _lib.arena_begin(self.device)
                 ops.refresh_cast_cache()
                 with torch.autocast("cuda", dtype=self.amp_dtype):
                     outs = self.network(st["data"])
@@ -333,6 +338,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             with torch.cuda.graph(gb, pool=ga.pool()):
                 torch.autograd.backward(outs, grad_tensors=st["douts"])
             ops.release_cast_cache()
+            _lib.arena_end()
             st["grads"] = [p.grad for p in self._params]     # written in place by every replay of graph B
             self._graph = (ga, gb)
         with torch.no_grad():
@@ -389,6 +395,8 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         l = self._forward_loss(data, target)
         params = self._params
         self.grad_scaler.scale(l).backward()
+        from . import _lib
+        _lib.arena_end()
         if self.is_ddp:
             for p in params:
                 dist.all_reduce(p.grad, op=dist.ReduceOp.AVG)
