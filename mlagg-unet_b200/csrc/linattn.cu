@@ -418,6 +418,14 @@ __device__ __forceinline__ float2 la_unpack(uint32_t v) {
 }
 __device__ __forceinline__ uint32_t la_lds32(const __nv_bfloat16 *p) { return *reinterpret_cast<const uint32_t *>(p); }
 
+// 8x8 b16 tile held in fragment layout (lane (g, t): row g, columns 2t, 2t+1) -> its transpose in the same layout: turns a
+// [token][channel] register tile into the [channel][token] operand a contraction over tokens needs, without shared memory
+__device__ __forceinline__ uint32_t la_trans(uint32_t v) {
+    uint32_t d;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(v));
+    return d;
+}
+
 constexpr int kLmTok = 256;      // tokens per block of the token-parallel mma kernels (4 warps x 4 tiles of 16)
 
 // One token row pair set of a warp tile in fragment layout: rows (g, g+8), pairs pi = 0 .. HD/8-1 at columns 8*pi + 2t.
@@ -461,10 +469,12 @@ __device__ __forceinline__ void la_frag_rope_a(const LaFrag<HD> &f, uint32_t (&a
 }
 
 // ---- forward 1: S = (1/N) sum rope(phi k) (x) v, kmean = (1/N) sum phi k        (k = tokens)
+// A warp owns 16 tokens at a time: k and v rows are read in fragment layout, phi / RoPE happen in registers, and
+// movmatrix turns the [token][channel] tiles into the [channel][token] A operand and the [token][channel] B operand --
+// no shared-memory staging, no block-wide barriers inside the token loop.
 template <int HD>
 __global__ void __launch_bounds__(kLTok) linattn_state_mma_kernel(const LinAttnParams p) {
-    constexpr int TS = kLTok + 8;                               // row stride of the transposed tiles (bf16)
-    __shared__ __align__(16) __nv_bfloat16 sKt[HD][TS], sPt[HD][TS], sVt[HD][TS];
+    __shared__ float red[HD * HD + HD];
     const int b = blockIdx.z, hh = blockIdx.y, N = p.H * p.W;
     const int n0 = blockIdx.x * p.chunk, n1 = min(N, n0 + p.chunk);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -476,48 +486,34 @@ __global__ void __launch_bounds__(kLTok) linattn_state_mma_kernel(const LinAttnP
         for (int nt = 0; nt < HD / 8; ++nt) S[mt][nt][0] = S[mt][nt][1] = S[mt][nt][2] = S[mt][nt][3] = 0.f;
     }
     const uint32_t ones = (g == 0) ? la_pack(1.f, 1.f) : 0u;     // B operand whose column 0 is all ones
-    for (int t0 = n0; t0 < n1; t0 += kLTok) {
-        const int n = t0 + threadIdx.x;
-        {   // thread = token: phi, RoPE in fp32, transposed bf16 tiles
-            float x[HD], y[HD];
-            const bool in = n < n1;
-            const long long tok = (long long)b * N + (in ? n : 0);
-            la_load<HD>(static_cast<const __nv_bfloat16 *>(p.k) + tok * p.ldk + hh * HD, x);
+    for (int nb = n0 + warp * 16; nb < n1; nb += 64) {
+        const int nr[2] = {nb + g, nb + g + 8};
+        const bool ok[2] = {nr[0] < n1, nr[1] < n1};
+        LaFrag<HD> f;
+        la_frag_load<HD>(p, static_cast<const __nv_bfloat16 *>(p.k), p.ldk, hh, b, nr, ok, t, f);
+        uint32_t kt[2][HD / 8], pt[2][HD / 8], vt[2][HD / 8];     // transposed 8x8 tiles: [token half][channel group]
 #pragma unroll
-            for (int c = 0; c < HD; ++c) x[c] = in ? la_phi(x[c]) : 0.f;
-            float cs[HD];
-            la_angles<HD>(p, hh, in ? n : 0, cs);
-            la_rope<HD>(x, cs, y);
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int c = 0; c < HD; ++c) {
-                sPt[c][threadIdx.x] = __float2bfloat16_rn(x[c]);
-                sKt[c][threadIdx.x] = __float2bfloat16_rn(y[c]);
+            for (int pi = 0; pi < HD / 8; ++pi) {
+                const float2 x = f.phi[r][pi], c = f.cs[r][pi];
+                kt[r][pi] = la_trans(la_pack(c.x * x.x - c.y * x.y, c.y * x.x + c.x * x.y));
+                pt[r][pi] = la_trans(la_pack(x.x, x.y));
+                const uint32_t vv = ok[r] ? la_lds32(static_cast<const __nv_bfloat16 *>(p.v) + ((long long)b * N + nr[r]) * p.ldv +
+                                                     hh * HD + 8 * pi + 2 * t)
+                                          : 0u;
+                vt[r][pi] = la_trans(vv);
             }
-            la_load<HD>(static_cast<const __nv_bfloat16 *>(p.v) + tok * p.ldv + hh * HD, x);
 #pragma unroll
-            for (int c = 0; c < HD; ++c) sVt[c][threadIdx.x] = __float2bfloat16_rn(in ? x[c] : 0.f);
+        for (int mt = 0; mt < HD / 16; ++mt) {
+            const uint32_t a[4] = {kt[0][2 * mt], kt[0][2 * mt + 1], kt[1][2 * mt], kt[1][2 * mt + 1]};
+#pragma unroll
+            for (int nt = 0; nt < HD / 8; ++nt) la_mma(S[mt][nt], a, vt[0][nt], vt[1][nt]);
+            const uint32_t ap[4] = {pt[0][2 * mt], pt[0][2 * mt + 1], pt[1][2 * mt], pt[1][2 * mt + 1]};
+            la_mma(KM[mt], ap, ones, ones);
         }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-            const int tk = 16 * (warp + 4 * kk);
-#pragma unroll
-            for (int mt = 0; mt < HD / 16; ++mt) {
-                const int d0 = mt * 16 + g;
-                const uint32_t a[4] = {la_lds32(&sKt[d0][tk + 2 * t]), la_lds32(&sKt[d0 + 8][tk + 2 * t]),
-                                       la_lds32(&sKt[d0][tk + 8 + 2 * t]), la_lds32(&sKt[d0 + 8][tk + 8 + 2 * t])};
-#pragma unroll
-                for (int nt = 0; nt < HD / 8; ++nt)
-                    la_mma(S[mt][nt], a, la_lds32(&sVt[nt * 8 + g][tk + 2 * t]), la_lds32(&sVt[nt * 8 + g][tk + 8 + 2 * t]));
-                const uint32_t ap[4] = {la_lds32(&sPt[d0][tk + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 2 * t]),
-                                        la_lds32(&sPt[d0][tk + 8 + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 8 + 2 * t])};
-                la_mma(KM[mt], ap, ones, ones);
-            }
-        }
-        __syncthreads();
     }
     // fold the four warps' partial sums through shared memory, then one scaled atomic per element
-    float *red = reinterpret_cast<float *>(&sKt[0][0]);
     for (int i = threadIdx.x; i < HD * HD + HD; i += kLTok) red[i] = 0.f;
     __syncthreads();
 #pragma unroll
@@ -598,10 +594,9 @@ __global__ void __launch_bounds__(128) linattn_apply_mma_kernel(const LinAttnPar
 // ---- backward 1: dq; dS = (1/N) sum rope(phi q) (x) z dO, dkmean = (1/N) sum c phi q     (k = hd, then k = tokens)
 template <int HD>
 __global__ void __launch_bounds__(128) linattn_bwd_q_mma_kernel(const LinAttnParams p) {
-    constexpr int GT = 64, TS = GT + 8;                         // tokens per group (4 warps x 16), transposed row stride
+    constexpr int GT = 64;                                      // tokens per iteration (4 warps x 16)
     __shared__ __align__(16) __nv_bfloat16 sS[HD][HD + 8], sSt[HD][HD + 8];
-    __shared__ __align__(16) __nv_bfloat16 sQt[HD][TS], sPt[HD][TS], sDt[HD][TS];
-    __shared__ float sKm[HD], sc[GT];
+    __shared__ float sKm[HD], red[HD * HD + HD];
     const int b = blockIdx.z, hh = blockIdx.y, N = p.H * p.W;
     const long long bh = (long long)b * p.h + hh;
     const int n0 = blockIdx.x * p.chunk, n1 = min(N, n0 + p.chunk);
@@ -661,24 +656,6 @@ __global__ void __launch_bounds__(128) linattn_bwd_q_mma_kernel(const LinAttnPar
             dz[r] += __shfl_xor_sync(0xffffffffu, dz[r], 2);
             cden[r] = -z[r] * z[r] * dz[r];
         }
-        // transposed operands of the token contraction: q_rope, phi q, dt as [channel][token of the group]; c per token
-        {
-            const int tl[2] = {warp * 16 + g, warp * 16 + g + 8};
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-#pragma unroll
-                for (int pi = 0; pi < HD / 8; ++pi) {
-                    const float2 qr = la_unpack(a[pi >> 1][2 * (pi & 1) + r]);
-                    sQt[8 * pi + 2 * t][tl[r]] = __float2bfloat16_rn(qr.x);
-                    sQt[8 * pi + 2 * t + 1][tl[r]] = __float2bfloat16_rn(qr.y);
-                    sPt[8 * pi + 2 * t][tl[r]] = __float2bfloat16_rn(f.phi[r][pi].x);
-                    sPt[8 * pi + 2 * t + 1][tl[r]] = __float2bfloat16_rn(f.phi[r][pi].y);
-                    sDt[8 * pi + 2 * t][tl[r]] = __float2bfloat16_rn(dt[pi][2 * r]);
-                    sDt[8 * pi + 2 * t + 1][tl[r]] = __float2bfloat16_rn(dt[pi][2 * r + 1]);
-                }
-                if (t == 0) sc[tl[r]] = cden[r];
-            }
-        }
         // d q_rope = dt S^T  (k = hd over e), rotate back, normaliser term, elu'
         {
             uint32_t da[HD / 16][4];
@@ -709,27 +686,29 @@ __global__ void __launch_bounds__(128) linattn_bwd_q_mma_kernel(const LinAttnPar
                 }
             }
         }
-        __syncthreads();
-        {   // dS += q_rope^T dt, dkmean += (phi q)^T c over this warp's 16 tokens of the group
-            const int tk = warp * 16;
-            const uint32_t cb0 = (g == 0) ? la_pack(sc[tk + 2 * t], sc[tk + 2 * t + 1]) : 0u;
-            const uint32_t cb1 = (g == 0) ? la_pack(sc[tk + 8 + 2 * t], sc[tk + 8 + 2 * t + 1]) : 0u;
+        {   // dS += q_rope^T dt, dkmean += (phi q)^T c over this warp's 16 tokens: movmatrix-transposed register tiles
+            uint32_t dtt[2][HD / 8], ptt[2][HD / 8];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int pi = 0; pi < HD / 8; ++pi) {
+                    dtt[r][pi] = la_trans(la_pack(dt[pi][2 * r], dt[pi][2 * r + 1]));
+                    ptt[r][pi] = la_trans(la_pack(f.phi[r][pi].x, f.phi[r][pi].y));
+                }
+            // B operand with c in column 0: lane (g = 0, t) needs c of tokens 2t, 2t+1 (rows g) and 8+2t, 9+2t (rows g+8)
+            const float c00 = __shfl_sync(0xffffffffu, cden[0], 8 * t), c01 = __shfl_sync(0xffffffffu, cden[0], 8 * t + 4);
+            const float c10 = __shfl_sync(0xffffffffu, cden[1], 8 * t), c11 = __shfl_sync(0xffffffffu, cden[1], 8 * t + 4);
+            const uint32_t cb0 = (g == 0) ? la_pack(c00, c01) : 0u, cb1 = (g == 0) ? la_pack(c10, c11) : 0u;
 #pragma unroll
             for (int mt = 0; mt < HD / 16; ++mt) {
-                const int d0 = mt * 16 + g;
-                const uint32_t aq[4] = {la_lds32(&sQt[d0][tk + 2 * t]), la_lds32(&sQt[d0 + 8][tk + 2 * t]),
-                                        la_lds32(&sQt[d0][tk + 8 + 2 * t]), la_lds32(&sQt[d0 + 8][tk + 8 + 2 * t])};
+                const uint32_t aq[4] = {la_trans(a[mt][0]), la_trans(a[mt][2]), la_trans(a[mt][1]), la_trans(a[mt][3])};
 #pragma unroll
-                for (int nt = 0; nt < HD / 8; ++nt)
-                    la_mma(dS[mt][nt], aq, la_lds32(&sDt[nt * 8 + g][tk + 2 * t]), la_lds32(&sDt[nt * 8 + g][tk + 8 + 2 * t]));
-                const uint32_t ap[4] = {la_lds32(&sPt[d0][tk + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 2 * t]),
-                                        la_lds32(&sPt[d0][tk + 8 + 2 * t]), la_lds32(&sPt[d0 + 8][tk + 8 + 2 * t])};
+                for (int nt = 0; nt < HD / 8; ++nt) la_mma(dS[mt][nt], aq, dtt[0][nt], dtt[1][nt]);
+                const uint32_t ap[4] = {ptt[0][2 * mt], ptt[0][2 * mt + 1], ptt[1][2 * mt], ptt[1][2 * mt + 1]};
                 la_mma(dKM[mt], ap, cb0, cb1);
             }
         }
-        __syncthreads();
     }
-    float *red = reinterpret_cast<float *>(&sQt[0][0]);   // HD * HD + HD floats fit in the three transposed tiles
     for (int i = threadIdx.x; i < HD * HD + HD; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
 #pragma unroll
