@@ -184,7 +184,33 @@ int mlagg_msmm_scan_bwd(const float *xrow, const float *xcol, const float *xdbl_
                         const float *Wdt, const float *dt_bias, const float *A, const float *Ds, const float *dout,
                         const float *ckpt, float *du, float *dxdbl_row, float *dxdbl_col, float *dWdt,
                         float *ddt_bias, float *dA, float *dDs, int batch, int d_inner, int dstate, int dt_rank,
-                        int nstages, const int *stage_lens, mlagg_stream_t stream);
+                        int nstages, const int *stage_lens, int dout_walks, mlagg_stream_t stream);
+/* dout_walks = 0: dout is (batch, 4, d_inner, L), one plane per direction (the layout of `out`);
+ * dout_walks = 1: dout is (batch, 2, d_inner, L) = the gradient of the MERGED output y in row-major (plane 0, read by
+ *                 directions 0, 2) and column-major (plane 1, directions 1, 3) walk order -- what the cross-merge's
+ *                 backward (MambaSkip.py:454-471) would broadcast into four planes. */
+
+/* --------------------------------------------------------------------------------------------
+ * Walk packing around the fused MSMM scan: the cross-scan / cross-merge index maps of MambaSkip.py:414-422 and :454-471
+ * as one tile-transpose pass each, between the TOKENS-MAJOR activations the rest of the block uses and the
+ * channels-major fp32 planes in walk order the scan kernels read and write.  The sequence is the concatenation of
+ * nstages (<= 8) images of H_s x W_s tokens (HOST arrays Hs, Ws), L = sum H_s*W_s.  Walk position p visits token p
+ * (col_walk = 0) or, inside stage s with local position q, token soff_s + (q % H_s) * W_s + q / H_s (col_walk = 1).
+ *   mlagg_walk_pack  : dst[b][c][p] = (float) src[b][token(p)][c0 + c],  c < nc
+ *       src (batch, L, .) of `dtype`, row stride ld_src and batch stride bs_src in ELEMENTS; dst fp32, plane stride L,
+ *       batch stride bs_dst elements.
+ *   mlagg_walk_unpack: dst[b][token(p)][c0 + c] (+)= src0[b][c][p] (+ src1[b][c][p]) for c < nc; columns
+ *       nc <= c < nc_pad receive 0 (+ old value when accumulating).  src0 / src1 (nullable) fp32 planes with the same
+ *       batch stride bs_src; dst (batch, L, .) of `dtype`, strides ld_dst / bs_dst; accumulate != 0 adds to dst.
+ * Forward use: x, x_dbl -> xrow / xcol / xdbl_row / xdbl_col;  out -> y = out0 + out2 + colmajor_to_rowmajor(out1 + out3).
+ * Backward use: dy -> dout (dout_walks = 1);  du, dxdbl_row / dxdbl_col -> dx, dx_dbl.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_walk_pack(const void *src, int dtype, long long ld_src, long long bs_src, int c0, int nc, float *dst,
+                    long long bs_dst, int batch, int nstages, const int *host_Hs, const int *host_Ws, int col_walk,
+                    mlagg_stream_t stream);
+int mlagg_walk_unpack(const float *src0, const float *src1, long long bs_src, int nc, int nc_pad, void *dst, int dtype,
+                      long long ld_dst, long long bs_dst, int c0, int batch, int nstages, const int *host_Hs,
+                      const int *host_Ws, int col_walk, int accumulate, mlagg_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension of tokens-major activations, fp32 math, fp32 or bf16 input and output.

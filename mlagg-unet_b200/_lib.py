@@ -23,7 +23,9 @@ SIGNATURES = {
     "mlagg_selective_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 6 + [c_p]),
     "mlagg_selective_scan_bwd": (c_i, [c_p] * 16 + [c_i] * 6 + [c_p]),
     "mlagg_msmm_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 5 + [c_p, c_p]),
-    "mlagg_msmm_scan_bwd": (c_i, [c_p] * 17 + [c_i] * 5 + [c_p, c_p]),
+    "mlagg_msmm_scan_bwd": (c_i, [c_p] * 17 + [c_i] * 5 + [c_p, c_i, c_p]),
+    "mlagg_walk_pack": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_i, c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p]),
+    "mlagg_walk_unpack": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_p, c_i, c_ll, c_ll, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "mlagg_layernorm_fwd": (c_i, [c_p] * 6 + [c_ll, c_i, c_f, c_i, c_i, c_p]),
     "mlagg_layernorm_bwd": (c_i, [c_p] * 8 + [c_ll, c_i, c_i, c_i, c_p]),
     "mlagg_linattn_state_bytes": (c_sz, [c_i] * 3),

@@ -10,6 +10,12 @@
 namespace mlagg {
 cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
+cudaError_t walk_pack_dispatch(const void *src, int dtype, long long ld_src, long long bs_src, int c0, int nc, float *dst,
+                               long long bs_dst, int batch, int nstages, const int *Hs, const int *Ws, int col,
+                               cudaStream_t st);
+cudaError_t walk_unpack_dispatch(const float *src0, const float *src1, long long bs_src, int nc, int nc_pad, void *dst,
+                                 int dtype, long long ld_dst, long long bs_dst, int c0, int batch, int nstages,
+                                 const int *Hs, const int *Ws, int col, int accumulate, cudaStream_t st);
 
 cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, void *y, int Bn, int H, int W,
                                    int C, int act, int dtype, cudaStream_t st);
@@ -387,17 +393,48 @@ extern "C" int mlagg_msmm_scan_bwd(const float *xrow, const float *xcol, const f
                                    const float *dout, const float *ckpt, float *du, float *dxdbl_row,
                                    float *dxdbl_col, float *dWdt, float *ddt_bias, float *dA, float *dDs, int batch,
                                    int d_inner, int dstate, int dt_rank, int nstages, const int *stage_lens,
-                                   mlagg_stream_t stream) {
+                                   int dout_walks, mlagg_stream_t stream) {
     ScanParams p;
     int rc = msmm_fill(p, xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, batch, d_inner, dstate, dt_rank,
                        nstages, stage_lens);
     if (rc) return rc;
+    p.dout_walks = dout_walks ? 1 : 0;
     if (!dout || !ckpt || !du || !dxdbl_row || !dxdbl_col || !dWdt || !dA) return MLAGG_ERR_NULL;
     if ((Ds && !dDs) || (dt_bias && !ddt_bias)) return MLAGG_ERR_NULL;
     if (!aligned(ckpt, 16)) return MLAGG_ERR_ALIGN;
     p.dout = dout; p.ckpt_in = ckpt; p.du = du; p.dxdbl_row = dxdbl_row; p.dxdbl_col = dxdbl_col; p.dWdt = dWdt;
     p.dA = dA; p.dD = Ds ? dDs : nullptr; p.dbias = dt_bias ? ddt_bias : nullptr;
     cudaError_t e = scan_bwd_dispatch(p, false, 4, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_walk_pack(const void *src, int dtype, long long ld_src, long long bs_src, int c0, int nc,
+                               float *dst, long long bs_dst, int batch, int nstages, const int *host_Hs,
+                               const int *host_Ws, int col_walk, mlagg_stream_t stream) {
+    if (!src || !dst || !host_Hs || !host_Ws) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || nc <= 0 || c0 < 0 || nstages <= 0 || nstages > 8 || ld_src < c0 + nc)
+        return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    if (!aligned(src, dtype == MLAGG_F32 ? 4 : 2) || !aligned(dst, 4)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = walk_pack_dispatch(src, dtype, ld_src, bs_src, c0, nc, dst, bs_dst, batch, nstages, host_Hs, host_Ws,
+                                       col_walk ? 1 : 0, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) return MLAGG_ERR_BAD_SHAPE;
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_walk_unpack(const float *src0, const float *src1, long long bs_src, int nc, int nc_pad, void *dst,
+                                 int dtype, long long ld_dst, long long bs_dst, int c0, int batch, int nstages,
+                                 const int *host_Hs, const int *host_Ws, int col_walk, int accumulate,
+                                 mlagg_stream_t stream) {
+    if (!src0 || !dst || !host_Hs || !host_Ws) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || nc <= 0 || nc_pad < nc || c0 < 0 || nstages <= 0 || nstages > 8 ||
+        ld_dst < c0 + nc_pad)
+        return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    if (!aligned(dst, dtype == MLAGG_F32 ? 4 : 2) || !aligned(src0, 4) || (src1 && !aligned(src1, 4))) return MLAGG_ERR_ALIGN;
+    cudaError_t e = walk_unpack_dispatch(src0, src1, bs_src, nc, nc_pad, dst, dtype, ld_dst, bs_dst, c0, batch, nstages,
+                                         host_Hs, host_Ws, col_walk ? 1 : 0, accumulate ? 1 : 0, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) return MLAGG_ERR_BAD_SHAPE;
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

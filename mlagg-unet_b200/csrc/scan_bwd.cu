@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(256, 1) scan_bwd_kernel(const ScanParams p) {
         const int C35 = p.Rk + 2 * kN;
         const int dloc0 = blockIdx.x * R + 8 * h;
         const float *ub, *db = nullptr, *Bb, *Cb, *dtb = nullptr;
-        const float *gb = p.dout + rowoff;
+        const float *gb = (fused && p.dout_walks)
+                              ? p.dout + (((size_t)b * 2 + (kdir & 1)) * p.dpg + dloc0) * (size_t)L
+                              : p.dout + rowoff;
         float *dBg, *dCg, *ddtg = nullptr;
         if (fused) {
             ub = ((kdir & 1) ? p.xcol : p.xrow) + ((size_t)b * p.dpg + dloc0) * L;

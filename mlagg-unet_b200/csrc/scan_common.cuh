@@ -37,6 +37,7 @@ struct ScanParams {
     const float *xdbl_row, *xdbl_col;                      // (B, 2, Rk + 2N, L): directions {0,2} / {1,3}
     const float *Wdt;                                      // (4 * Di, Rk)
     float *dxdbl_row, *dxdbl_col, *dWdt;                   // bwd, accumulated into
+    int dout_walks;                                        // bwd: dout is (B, 2, Di, L) in row / column walk order
 };
 
 // position read by scan position t of a mirrored direction (per-stage reversal), fused mode

@@ -1,0 +1,237 @@
+// walk.cu -- the two layout changes around the MSMM selective scan as single passes:
+//   pack   : tokens-major (B, L, C) activations  ->  channels-major fp32 planes (B, nc, L) in WALK order
+//   unpack : channels-major fp32 planes (B, nc, L) in walk order (optionally the sum of two planes)  ->  tokens-major
+// L is the stage-concatenated sequence (fine -> coarse); a walk is row-major (position p reads token p) or, per stage
+// (H, W), column-major (position soff + q reads token soff + (q % H) * W + q / H) -- the index maps of the reference's
+// cross-scan / cross-merge (variants/mamba/MambaSkip.py:414-422 and :454-471); the mirrored directions 2, 3 are handled
+// inside the scan kernels.  These kernels replace, per train step, the transpose().contiguous(), per-stage
+// reshape/transpose/cat, fp32 cast, direction-sum and slice-backward (zero-fill + copy + add) kernels torch ran for
+// `SS2D_skip.forward_corev0` and its autograd graph: ~40 launches and ~5 ms -> 13 launches.
+// HBM-bound 64-position x 32-channel tile transposes through shared memory: token rows are read / written as 64..128-byte
+// pieces (8 threads x 4 channels), planes as 128-byte warp rows.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mlagg {
+
+constexpr int kWalkMaxStages = 8;
+constexpr int kWalkTP = 64;    // positions per tile
+constexpr int kWalkTC = 32;    // channels per tile
+
+struct WalkGeom {
+    int nstage;
+    int soff[kWalkMaxStages + 1];
+    int H[kWalkMaxStages], W[kWalkMaxStages];
+};
+
+__device__ __forceinline__ int walk_token(const WalkGeom &g, int p, int col) {
+    if (!col) return p;
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kWalkMaxStages; ++i) s += (i < g.nstage && p >= g.soff[i]) ? 1 : 0;
+    const int q = p - g.soff[s], H = g.H[s];
+    return g.soff[s] + (q % H) * g.W[s] + q / H;
+}
+
+template <typename T>
+__device__ __forceinline__ float wk_ld(const T *p);
+template <>
+__device__ __forceinline__ float wk_ld<float>(const float *p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float wk_ld<__nv_bfloat16>(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void wk_st(T *p, float v);
+template <>
+__device__ __forceinline__ void wk_st<float>(float *p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void wk_st<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename T>
+__device__ __forceinline__ void wk_ld4(const T *p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void wk_ld4<float>(const float *p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void wk_ld4<__nv_bfloat16>(const __nv_bfloat16 *p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+    v[0] = __uint_as_float(t.x << 16), v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16), v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+template <typename T>
+__device__ __forceinline__ void wk_st4(T *p, const float (&v)[4]);
+template <>
+__device__ __forceinline__ void wk_st4<float>(float *p, const float (&v)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <>
+__device__ __forceinline__ void wk_st4<__nv_bfloat16>(__nv_bfloat16 *p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 raw;
+    raw.x = *reinterpret_cast<uint32_t *>(&a);
+    raw.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = raw;
+}
+
+// src (B, L, >= c0 + nc) tokens-major, row stride ld_src, batch stride bs_src (elements)  ->  dst[b][c][p], c < nc, fp32,
+// batch stride bs_dst.  VEC: 4-channel vector loads are legal (alignment checked by the dispatcher).
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) walk_pack_kernel(const T *__restrict__ src, long long ld_src, long long bs_src,
+                                                        int c0, int nc, float *__restrict__ dst, long long bs_dst, int L,
+                                                        int col, WalkGeom g) {
+    __shared__ float tile[kWalkTC][kWalkTP + 1];
+    const int p0 = blockIdx.x * kWalkTP, cb = blockIdx.y * kWalkTC, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cg = tid & 7, c = cb + 4 * cg;
+    const T *sb = src + (long long)b * bs_src + c0 + c;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int pos = pass * 32 + (tid >> 3), p = p0 + pos;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p < L && c < nc) {
+            const T *r = sb + (long long)walk_token(g, p, col) * ld_src;
+            if (VEC && c + 4 <= nc) {
+                wk_ld4<T>(r, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c + j < nc) v[j] = wk_ld<T>(r + j);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile[4 * cg + j][pos] = v[j];
+    }
+    __syncthreads();
+    float *db = dst + (long long)b * bs_dst;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cl = 4 * warp + j, cc = cb + cl;
+        if (cc < nc) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int p = p0 + half * 32 + lane;
+                if (p < L) db[(long long)cc * L + p] = tile[cl][half * 32 + lane];
+            }
+        }
+    }
+}
+
+// dst[b][token(p)][c0 + c] (+)= src0[b][c][p] (+ src1[b][c][p]) for c < nc, and 0 for nc <= c < nc_pad.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) walk_unpack_kernel(const float *__restrict__ src0, const float *__restrict__ src1,
+                                                          long long bs_src, int nc, int nc_pad, T *__restrict__ dst,
+                                                          long long ld_dst, long long bs_dst, int c0, int L, int col,
+                                                          int accumulate, WalkGeom g) {
+    __shared__ float tile[kWalkTC][kWalkTP + 1];
+    const int p0 = blockIdx.x * kWalkTP, cb = blockIdx.y * kWalkTC, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *s0 = src0 + (long long)b * bs_src, *s1 = src1 ? src1 + (long long)b * bs_src : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cl = 4 * warp + j, cc = cb + cl;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int p = p0 + half * 32 + lane;
+            float v = 0.f;
+            if (cc < nc && p < L) {
+                v = __ldg(s0 + (long long)cc * L + p);
+                if (s1) v += __ldg(s1 + (long long)cc * L + p);
+            }
+            tile[cl][half * 32 + lane] = v;
+        }
+    }
+    __syncthreads();
+    const int cg = tid & 7, c = cb + 4 * cg;
+    T *dbase = dst + (long long)b * bs_dst + c0 + c;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int pos = pass * 32 + (tid >> 3), p = p0 + pos;
+        if (p < L && c < nc_pad) {
+            T *r = dbase + (long long)walk_token(g, p, col) * ld_dst;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = tile[4 * cg + j][pos];
+            if (VEC && c + 4 <= nc_pad) {
+                if (accumulate) {
+                    float o[4];
+                    wk_ld4<T>(r, o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] += o[j];
+                }
+                wk_st4<T>(r, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (c + j < nc_pad) wk_st<T>(r + j, accumulate ? v[j] + wk_ld<T>(r + j) : v[j]);
+            }
+        }
+    }
+}
+
+static bool walk_geom(WalkGeom &g, int nstages, const int *Hs, const int *Ws, long long *L) {
+    if (nstages <= 0 || nstages > kWalkMaxStages || !Hs || !Ws) return false;
+    long long off = 0;
+    g.nstage = nstages;
+    for (int s = 0; s < kWalkMaxStages; ++s) {
+        g.soff[s] = (int)off;
+        g.H[s] = g.W[s] = 1;
+        if (s < nstages) {
+            if (Hs[s] <= 0 || Ws[s] <= 0) return false;
+            g.H[s] = Hs[s], g.W[s] = Ws[s];
+            off += (long long)Hs[s] * Ws[s];
+        }
+    }
+    g.soff[kWalkMaxStages] = (int)off;
+    for (int s = nstages; s < kWalkMaxStages; ++s) g.soff[s] = (int)off;
+    *L = off;
+    return off > 0 && off <= 0x7fffffff;
+}
+
+// returns cudaErrorInvalidValue for shapes the caller should have rejected
+cudaError_t walk_pack_dispatch(const void *src, int dtype, long long ld_src, long long bs_src, int c0, int nc, float *dst,
+                               long long bs_dst, int batch, int nstages, const int *Hs, const int *Ws, int col,
+                               cudaStream_t st) {
+    WalkGeom g;
+    long long L;
+    if (!walk_geom(g, nstages, Hs, Ws, &L)) return cudaErrorInvalidValue;
+    const dim3 grid((unsigned)((L + kWalkTP - 1) / kWalkTP), (unsigned)((nc + kWalkTC - 1) / kWalkTC), (unsigned)batch);
+    const size_t es = dtype == 0 ? 4 : 2;
+    const bool vec = (c0 % 4 == 0) && (ld_src % 4 == 0) && (bs_src % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(src) % (4 * es)) == 0);
+    if (dtype == 0) {
+        const float *s = static_cast<const float *>(src);
+        if (vec) walk_pack_kernel<float, true><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
+        else walk_pack_kernel<float, false><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
+    } else {
+        const __nv_bfloat16 *s = static_cast<const __nv_bfloat16 *>(src);
+        if (vec) walk_pack_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
+        else walk_pack_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t walk_unpack_dispatch(const float *src0, const float *src1, long long bs_src, int nc, int nc_pad, void *dst,
+                                 int dtype, long long ld_dst, long long bs_dst, int c0, int batch, int nstages,
+                                 const int *Hs, const int *Ws, int col, int accumulate, cudaStream_t st) {
+    WalkGeom g;
+    long long L;
+    if (!walk_geom(g, nstages, Hs, Ws, &L)) return cudaErrorInvalidValue;
+    const dim3 grid((unsigned)((L + kWalkTP - 1) / kWalkTP), (unsigned)((nc_pad + kWalkTC - 1) / kWalkTC), (unsigned)batch);
+    const size_t es = dtype == 0 ? 4 : 2;
+    const bool vec = (c0 % 4 == 0) && (ld_dst % 4 == 0) && (bs_dst % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dst) % (4 * es)) == 0);
+    if (dtype == 0) {
+        float *d = static_cast<float *>(dst);
+        if (vec) walk_unpack_kernel<float, true><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
+        else walk_unpack_kernel<float, false><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
+    } else {
+        __nv_bfloat16 *d = static_cast<__nv_bfloat16 *>(dst);
+        if (vec) walk_unpack_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
+        else walk_unpack_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace mlagg

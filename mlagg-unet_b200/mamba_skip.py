@@ -25,8 +25,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
-from .selective_scan_interface import msmm_scan, selective_scan_fn
+from .ops import _Linear, dwconv3x3_tokens, layer_norm_tokens, linear_tokens
+from .selective_scan_interface import msmm_scan, msmm_scan_tokens, selective_scan_fn, xdbl_pad
 from .thirdparty_shims import DropPath, _inst_norm
 
 
@@ -144,7 +144,20 @@ class SS2D_skip(nn.Module):
 
     def forward_core_tokens(self, xc, hw):
         """Fused path: the cross-scan, dt projection and un-permutation of forward_corev0 (reference :405-473) happen
-        inside the scan kernels' operand addressing; torch only supplies two walk orders of x and the x_proj GEMMs."""
+        inside the scan kernels' operand addressing; the walk orders of x / x_dbl and the cross-merge are single
+        tile-transpose kernels (csrc/walk.cu); torch supplies ONE x_proj GEMM on the tokens (a permutation along L
+        commutes with a per-token projection, App. A.3)."""
+        R, N = self.dt_rank, self.d_state
+        Wx = self.x_proj_weight                                                 # (4, R+2N, Di)
+        pad = Wx.new_zeros(xdbl_pad(R + 2 * N) - 2 * (R + 2 * N), Wx.shape[2])
+        W_all = torch.cat([Wx[0], Wx[2], pad, Wx[1], Wx[3], pad], dim=0)        # [row walk: dirs 0, 2 | column walk: 1, 3]
+        xdbl = _Linear.apply(xc, W_all, None)                                   # (B, L, 2 P), autocast dtype
+        return msmm_scan_tokens(xc, xdbl, self.dt_projs_weight.reshape(-1, R), self.dt_projs_bias.reshape(-1),
+                                -torch.exp(self.A_logs.float()), self.Ds, hw)
+
+    def forward_core_planes(self, xc, hw):
+        """Same computation with torch building the walk planes (transpose / per-stage reshape / cat) around
+        `msmm_scan`; kept as the parity partner of `forward_core_tokens` in the tests."""
         Bn, L, Di = xc.shape
         R, N = self.dt_rank, self.d_state
         xrow = xc.transpose(1, 2).contiguous()                                  # (B, Di, L) row-major walk

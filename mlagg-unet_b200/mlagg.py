@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens
+from .ops import GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
 
@@ -228,6 +228,8 @@ class BasicLayer(nn.Module):
                 t = torch.utils.checkpoint.checkpoint(blk.forward_tokens, t, H, W, use_reentrant=False)
             else:
                 t = blk.forward_tokens(t, H, W)
+        if t.requires_grad:
+            t = GradContiguous.apply(t)      # the stage's backward runs on a tokens-major contiguous gradient
         return t.reshape(Bn, H, W, C).permute(0, 3, 1, 2)
 
 

@@ -206,6 +206,35 @@ def _cast_param(t, dtype):
     return t.to(dtype)
 
 
+def _rows2d(t):
+    """(..., C) -> (M, C) VIEW with unit column stride and one uniform row stride, or None when that needs a copy."""
+    if t.dim() < 2 or t.stride(-1) != 1:
+        return None
+    ld = t.stride(-2)
+    if ld < t.shape[-1]:
+        return None
+    n = t.shape[-2]
+    for d in range(t.dim() - 3, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != n * ld:
+            return None
+        n *= t.shape[d]
+    return t.as_strided((n, t.shape[-1]), (ld, 1), t.storage_offset())
+
+
+class GradContiguous(torch.autograd.Function):
+    """Identity whose backward hands on a CONTIGUOUS gradient.  The gradient arriving at a stage output comes from conv
+    backward passes in whatever memory format they chose; left alone, every residual add / mask multiply of the stage
+    inherits those strides (un-vectorised strided kernels, 5x slower) and every Linear backward re-packs its own copy."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.contiguous()
+
+
 class _Linear(torch.autograd.Function):
     """y = x W^T + b with the GEMMs on cuBLAS (library GEMMs) in the autocast dtype and the bias
     gradient as ONE HBM-bound column-sum pass (csrc/reduce.cu) instead of autograd's generic reduction."""
@@ -214,8 +243,16 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
         xc, wc = x.to(cdt), _cast_param(weight, cdt)
+        bc = _cast_param(bias, cdt)
+        x2 = _rows2d(xc)
         with torch.autocast("cuda", enabled=False):
-            y = torch.nn.functional.linear(xc, wc, _cast_param(bias, cdt))
+            if x2 is None:
+                y = torch.nn.functional.linear(xc, wc, bc)
+            else:
+                # 2-D GEMM on the (tokens, Cin) view, row stride = the parent's width: channel slices of a wider
+                # activation (the halves of MLLABlock's `chunk`) are consumed in place and the bias stays in the GEMM
+                # epilogue (F.linear on a strided 3-D input runs matmul + a separate un-vectorised bias add)
+                y = (torch.mm(x2, wc.t()) if bc is None else torch.addmm(bc, x2, wc.t())).view(*xc.shape[:-1], wc.shape[0])
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
         return y
@@ -225,8 +262,9 @@ class _Linear(torch.autograd.Function):
         xc, wc = ctx.saved_tensors
         xdt, wdt, bdt = ctx.meta
         Cout, Cin = wc.shape
-        dy2 = dy.to(wc.dtype).reshape(-1, Cout)
-        x2 = xc.reshape(-1, Cin)
+        dy2 = dy.to(wc.dtype)
+        dy2 = _rows2d(dy2) if _rows2d(dy2) is not None else dy2.reshape(-1, Cout)
+        x2 = _rows2d(xc) if _rows2d(xc) is not None else xc.reshape(-1, Cin)
         with torch.autocast("cuda", enabled=False):
             dx = torch.mm(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
             dw = torch.mm(dy2.t(), x2).to(wdt) if ctx.needs_input_grad[1] else None

@@ -75,18 +75,61 @@ def test_fused_msmm_scan_equals_materialised_cross_scan():
         m.Ds.add_(0.3 * torch.randn_like(m.Ds))
     xc = torch.randn(2, L, m.d_inner, device="cuda")
     res = {}
-    for name, fn in (("fused", m.forward_core_tokens), ("plain", m.forward_core_tokens_unfused)):
+    for name, fn in (("fused", m.forward_core_tokens), ("planes", m.forward_core_planes),
+                     ("plain", m.forward_core_tokens_unfused)):
         x = xc.clone().requires_grad_()
         m.zero_grad()
         y = fn(x, hw)
         torch.manual_seed(1)
         (y * torch.randn_like(y)).sum().backward()
         res[name] = (y.detach(), x.grad, {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
-    assert rel_err(res["fused"][0], res["plain"][0]) < TOL32
-    assert rel_err(res["fused"][1], res["plain"][1]) < TOL32
-    assert set(res["fused"][2]) == set(res["plain"][2])
-    for n in res["plain"][2]:
-        assert rel_err(res["fused"][2][n], res["plain"][2][n]) < TOL32, n
+    for k in ("fused", "planes"):
+        assert rel_err(res[k][0], res["plain"][0]) < TOL32, k
+        assert rel_err(res[k][1], res["plain"][1]) < TOL32, k
+        assert set(res[k][2]) == set(res["plain"][2]), k
+        for n in res["plain"][2]:
+            assert rel_err(res[k][2][n], res["plain"][2][n]) < TOL32, (k, n)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_walk_pack_unpack_match_the_cross_scan_index_maps(dtype):
+    """mlagg_walk_pack / mlagg_walk_unpack against the reference's index maps (MambaSkip.py:414-422, :454-471) restated
+    with torch gathers: bit-exact moves (bf16 -> fp32 widening is exact); odd channel counts, a channel offset that
+    defeats the vector path, zero-filled padding columns, two-plane sums and accumulation."""
+    import ctypes
+    from mlagg_unet_b200 import _lib
+    from mlagg_unet_b200.mamba_skip import cross_scan_maps
+    torch.manual_seed(11)
+    hw = [(9, 7), (5, 6), (1, 3), (2, 2)]
+    L = sum(h * w for h, w in hw)
+    Bn, C = 3, 45
+    ns = len(hw)
+    Hs, Ws = (ctypes.c_int * ns)(*[h for h, _ in hw]), (ctypes.c_int * ns)(*[w for _, w in hw])
+    idx, inv = cross_scan_maps(hw, "cuda")
+    code = {torch.float32: 0, torch.bfloat16: 1}[dtype]
+    Lb, st = _lib.lib(), _lib.stream_ptr()
+    src = torch.randn(Bn, L, C, device="cuda").to(dtype)
+    for c0, nc in ((0, C), (4, 37), (3, 10), (8, 36)):
+        for col in (0, 1):
+            dst = torch.full((Bn, nc, L), float("nan"), device="cuda")
+            _lib.check(Lb.mlagg_walk_pack(src.data_ptr(), code, C, L * C, c0, nc, dst.data_ptr(), nc * L, Bn, ns, Hs, Ws,
+                                          col, st), "pack")
+            ref = src[:, :, c0:c0 + nc].float().index_select(1, idx[col]).transpose(1, 2)
+            assert torch.equal(dst, ref), (c0, nc, col)
+    # unpack: sum of two planes, scatter back to tokens, then accumulate the other walk on top
+    a, b = torch.randn(2, Bn, 2, 30, L, device="cuda").unbind(0)              # planes 0 / 1 of a (B, 2, 30, L) tensor
+    for c0, nc, ncp, ld in ((0, 30, 32, 40), (5, 30, 30, 35), (4, 30, 36, 40)):
+        dst = torch.full((Bn, L, ld), 7.0, device="cuda").to(dtype)
+        want = dst.float().clone()
+        for col, acc in ((0, 0), (1, 1)):
+            _lib.check(Lb.mlagg_walk_unpack(a[:, col].data_ptr(), b[:, col].data_ptr(), 2 * 30 * L, nc, ncp,
+                                            dst.data_ptr(), code, ld, L * ld, c0, Bn, ns, Hs, Ws, col, acc, st), "unpack")
+            tok = (a[:, col] + b[:, col]).index_select(2, inv[col]).transpose(1, 2)          # (B, L, 30) token order
+            blk = torch.zeros(Bn, L, ncp, device="cuda")
+            blk[..., :nc] = tok
+            prev = want[..., c0:c0 + ncp] if acc else 0.0
+            want[..., c0:c0 + ncp] = (prev + blk).to(dtype).float()
+        assert torch.equal(dst.float(), want), (c0, nc, ncp, ld)
 
 
 def test_vss_conv_layer_matches_reference():
