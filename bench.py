@@ -118,6 +118,9 @@ def main():
     ap.add_argument("--profile-step", action="store_true",
                     help="one extra (eagerly launched) step between cudaProfilerStart/Stop, for "
                          "`ncu --profile-from-start off` launch lists (profiles/README.md)")
+    ap.add_argument("--trace-step", default=None, metavar="CSV",
+                    help="one extra eagerly launched step under torch.profiler (CUPTI activity records, no replay): "
+                         "writes every kernel launch of the step with its duration, in launch order")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -198,6 +201,18 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         _lib.STATS["events"] = None
+    if a.trace_step and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            tr.train_step(resident, sync=False)
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
+                      and not e.name.lower().startswith(("memcpy", "memset"))), key=lambda e: e.time_range.start)
+        with open(a.trace_step, "w") as f:
+            f.write('"ID","Kernel Name","Metric Unit","Metric Value"\n')
+            for i, e in enumerate(evs):
+                f.write('"%d","%s","us","%.3f"\n' % (i, e.name.replace('"', "'"), e.device_time))
     # per-kernel CUDA events need Python between the launches: the same K steps once more, eagerly (not part of `value`);
     # the graph replays exactly this launch sequence, so the launch count is taken here too
     ms_eager, launches, ev, _ = timed(resident, False, a.steps, events=True)

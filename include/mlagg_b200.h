@@ -94,6 +94,20 @@ int mlagg_dwconv3x3_fwd(const void *x, const float *weight, const float *bias, v
 int mlagg_dwconv3x3_bwd(const void *x, const float *weight, const float *bias, const void *dy, void *dz_ws,
                         void *dx, float *dweight, float *dbias, int batch, int H, int W, int C, int act_silu,
                         int dtype, mlagg_stream_t stream);
+/* Strided variants: pixel stride ld* and image stride bs* in ELEMENTS for every activation operand (ld >= C; multiples of 4
+ * when C % 4 == 0), so channel slices of wider activations (the v half of the kv projection for LePE, :680/:782; the first
+ * half of ConvolutionalGLU's fc1 output, MambaSkip.py:567-575) and the per-stage segments of the stage-concatenated MSMM
+ * sequence (MambaSkip.py:521-523) are read and written in place.  `residual` (nullable, same shape as y) is added to the
+ * result after the activation: y = act(conv(x) + b) + residual -- the `attn_out + lepe(v)` of :716/:759.
+ * The backward takes dy with its own strides, a CONTIGUOUS dz workspace, and stores dx with (lddx, bsdx). */
+int mlagg_dwconv3x3_fwd_strided(const void *x, const float *weight, const float *bias, const void *residual, void *y,
+                                int batch, int H, int W, int C, long long ldx, long long bsx, long long ldr,
+                                long long bsr, long long ldy, long long bsy, int act_silu, int dtype,
+                                mlagg_stream_t stream);
+int mlagg_dwconv3x3_bwd_strided(const void *x, const float *weight, const float *bias, const void *dy, void *dz_ws,
+                                void *dx, float *dweight, float *dbias, int batch, int H, int W, int C, long long ldx,
+                                long long bsx, long long lddy, long long bsdy, long long lddx, long long bsdx,
+                                int act_silu, int dtype, mlagg_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * Depthwise causal conv1d: y[b,c,t] = bias[c] + sum_j weight[c,j] * x[b,c,t-(K-1)+j]  (+ SiLU), K <= 4.
@@ -286,6 +300,27 @@ int mlagg_avgpool_tokens_fwd(const void *x, void *y, int batch, int H, int W, in
                              int dtype, mlagg_stream_t stream);
 int mlagg_avgpool_tokens_bwd(const void *x, const void *dy, void *dx, int batch, int H, int W, int C, int pH, int pW,
                              int act_gelu, int dtype, mlagg_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Element-wise seams of the MLAgg block (contiguous tensors of `dtype`, n % 4 == 0, 16-byte (fp32) / 8-byte (bf16) aligned).
+ *   mlagg_residual_scale : out = x + scale[b] * y -- `shortcut + drop_path(branch)`, nnUNetTrainer_MLAgg_2D_dt_MS.py:907-908
+ *       (timm DropPath: scale[b] = Bernoulli(keep) / keep per sample, fp32 (batch); NULL = 1).  x NULL = 0, which is the
+ *       backward of the branch input (dbranch = scale[b] * dout).  per_sample = n / batch, % 4 == 0.
+ *   mlagg_silu_gate_fwd  : out = t * silu(z) -- `x * act_res` with act_res = SiLU(act_proj(.)), :881, :907.
+ *   mlagg_silu_gate_bwd  : dt = dout * silu(z), dz = dout * t * silu'(z).
+ *   mlagg_diff_lambda_fwd: out[0] = exp(<lq1, lk1>) - exp(<lq2, lk2>) + lambda_init (:700-702, :745-747), out[1], out[2] =
+ *       the two exponentials (saved for the backward); vectors of n fp32.
+ *   mlagg_diff_lambda_bwd: grads (4, n) fp32 = d out[0] / d (lq1, lk1, lq2, lk2) * dlam[0], plain stores.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_residual_scale(const void *x, const void *y, const float *scale, void *out, long long n, long long per_sample,
+                         int dtype, mlagg_stream_t stream);
+int mlagg_silu_gate_fwd(const void *t, const void *z, void *out, long long n, int dtype, mlagg_stream_t stream);
+int mlagg_silu_gate_bwd(const void *t, const void *z, const void *dout, void *dt, void *dz, long long n, int dtype,
+                        mlagg_stream_t stream);
+int mlagg_diff_lambda_fwd(const float *lq1, const float *lk1, const float *lq2, const float *lk2, int n,
+                          float lambda_init, float *out, mlagg_stream_t stream);
+int mlagg_diff_lambda_bwd(const float *lq1, const float *lk1, const float *lq2, const float *lk2, const float *saved,
+                          const float *dlam, int n, float *grads, mlagg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -24,6 +24,11 @@ SIGNATURES = {
     "mlagg_selective_scan_bwd": (c_i, [c_p] * 16 + [c_i] * 6 + [c_p]),
     "mlagg_msmm_scan_fwd": (c_i, [c_p] * 10 + [c_i] * 5 + [c_p, c_p]),
     "mlagg_msmm_scan_bwd": (c_i, [c_p] * 17 + [c_i] * 5 + [c_p, c_i, c_p]),
+    "mlagg_residual_scale": (c_i, [c_p] * 4 + [c_ll, c_ll, c_i, c_p]),
+    "mlagg_silu_gate_fwd": (c_i, [c_p] * 3 + [c_ll, c_i, c_p]),
+    "mlagg_silu_gate_bwd": (c_i, [c_p] * 5 + [c_ll, c_i, c_p]),
+    "mlagg_diff_lambda_fwd": (c_i, [c_p] * 4 + [c_i, c_f, c_p, c_p]),
+    "mlagg_diff_lambda_bwd": (c_i, [c_p] * 6 + [c_i, c_p, c_p]),
     "mlagg_walk_pack": (c_i, [c_p, c_i, c_ll, c_ll, c_i, c_i, c_p, c_ll, c_i, c_i, c_p, c_p, c_i, c_p]),
     "mlagg_walk_unpack": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_p, c_i, c_ll, c_ll, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "mlagg_layernorm_fwd": (c_i, [c_p] * 6 + [c_ll, c_i, c_f, c_i, c_i, c_p]),
@@ -38,6 +43,8 @@ SIGNATURES = {
     "mlagg_colsum": (c_i, [c_p, c_p, c_ll, c_i, c_ll, c_i, c_p]),
     "mlagg_dwconv3x3_fwd": (c_i, [c_p] * 4 + [c_i] * 6 + [c_p]),
     "mlagg_dwconv3x3_bwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
+    "mlagg_dwconv3x3_fwd_strided": (c_i, [c_p] * 5 + [c_i] * 4 + [c_ll] * 6 + [c_i, c_i, c_p]),
+    "mlagg_dwconv3x3_bwd_strided": (c_i, [c_p] * 8 + [c_i] * 4 + [c_ll] * 6 + [c_i, c_i, c_p]),
     "mlagg_causal_conv1d_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),
     "mlagg_causal_conv1d_bwd": (c_i, [c_p] * 7 + [c_i] * 5 + [c_p]),
     "mlagg_pooled_diffattn_ws_bytes": (c_sz, [c_i] * 4),

@@ -27,7 +27,38 @@ def rmsnorm_affine(x, weight, eps):
     return y.type_as(x) * weight
 
 
+class _DiffLambda(torch.autograd.Function):
+    """C ABI: mlagg_diff_lambda_fwd / _bwd (csrc/ew.cu): one one-warp kernel each way instead of 8 + 14."""
+
+    @staticmethod
+    def forward(ctx, lq1, lk1, lq2, lk2):
+        n = lq1.numel()
+        out = torch.empty(3, device=lq1.device, dtype=torch.float32)
+        with torch.cuda.device(lq1.device), _lib.timed("diff_lambda"):
+            rc = _lib.lib().mlagg_diff_lambda_fwd(lq1.data_ptr(), lk1.data_ptr(), lq2.data_ptr(), lk2.data_ptr(), n,
+                                                  LAMBDA_INIT, out.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "mlagg_diff_lambda_fwd")
+        ctx.save_for_backward(lq1, lk1, lq2, lk2, out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        lq1, lk1, lq2, lk2, out = ctx.saved_tensors
+        n = lq1.numel()
+        g = g.detach().float().reshape(1).contiguous()
+        grads = torch.empty(4, n, device=lq1.device, dtype=torch.float32)
+        with torch.cuda.device(lq1.device), _lib.timed("diff_lambda"):
+            rc = _lib.lib().mlagg_diff_lambda_bwd(lq1.data_ptr(), lk1.data_ptr(), lq2.data_ptr(), lk2.data_ptr(),
+                                                  out.data_ptr(), g.data_ptr(), n, grads.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "mlagg_diff_lambda_bwd")
+        return tuple(grads[i].view_as(lq1) for i in range(4))
+
+
 def diff_lambda(lq1, lk1, lq2, lk2):
+    """exp(<lq1, lk1>) - exp(<lq2, lk2>) + lambda_init (reference :700-702, :745-747) as a 0-dim fp32 tensor"""
+    ts = (lq1, lk1, lq2, lk2)
+    if all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in ts):
+        return _DiffLambda.apply(*ts)
     return torch.exp(torch.sum(lq1 * lk1).float()) - torch.exp(torch.sum(lq2 * lk2).float()) + LAMBDA_INIT
 
 

@@ -10,6 +10,12 @@
 namespace mlagg {
 cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
+cudaError_t residual_scale_dispatch(const void *x, const void *y, const float *s, void *out, long long n,
+                                    long long per_sample, int dtype, cudaStream_t st);
+cudaError_t silu_gate_dispatch(const void *t, const void *z, const void *g, void *o1, void *o2, long long n, int dtype,
+                               bool bwd, cudaStream_t st);
+cudaError_t diff_lambda_dispatch(const float *q1, const float *k1, const float *q2, const float *k2, int n, float init,
+                                 float *out, const float *dlam, float *grads, cudaStream_t st);
 cudaError_t walk_pack_dispatch(const void *src, int dtype, long long ld_src, long long bs_src, int c0, int nc, float *dst,
                                long long bs_dst, int batch, int nstages, const int *Hs, const int *Ws, int col,
                                cudaStream_t st);
@@ -17,10 +23,12 @@ cudaError_t walk_unpack_dispatch(const float *src0, const float *src1, long long
                                  int dtype, long long ld_dst, long long bs_dst, int c0, int batch, int nstages,
                                  const int *Hs, const int *Ws, int col, int accumulate, cudaStream_t st);
 
-cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, void *y, int Bn, int H, int W,
-                                   int C, int act, int dtype, cudaStream_t st);
+cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, const void *res, void *y, int Bn, int H,
+                                   int W, int C, long long ldx, long long bsx, long long ldr, long long bsr,
+                                   long long ldy, long long bsy, int act, int dtype, cudaStream_t st);
 cudaError_t dwconv3x3_bwd_dispatch(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
-                                   float *dw, float *db, int Bn, int H, int W, int C, int act, int dtype,
+                                   float *dw, float *db, int Bn, int H, int W, int C, long long ldx, long long bsx,
+                                   long long lddy, long long bsdy, long long lddx, long long bsdx, int act, int dtype,
                                    cudaStream_t st);
 cudaError_t causal_conv1d_fwd_dispatch(const float *x, const float *w, const float *b, float *y, int rows, int C,
                                        int L, int K, int act, cudaStream_t st);
@@ -188,26 +196,53 @@ static int dwconv_check(const void *x, const float *w, const void *y, int batch,
     return MLAGG_OK;
 }
 
-extern "C" int mlagg_dwconv3x3_fwd(const void *x, const float *weight, const float *bias, void *y, int batch, int H,
-                                   int W, int C, int act_silu, int dtype, mlagg_stream_t stream) {
+static bool dw_strides_ok(int C, long long ld, long long bs) { return ld >= C && bs >= 0 && (C % 4 != 0 || (ld % 4 == 0 && bs % 4 == 0)); }
+
+extern "C" int mlagg_dwconv3x3_fwd_strided(const void *x, const float *weight, const float *bias, const void *residual,
+                                           void *y, int batch, int H, int W, int C, long long ldx, long long bsx,
+                                           long long ldr, long long bsr, long long ldy, long long bsy, int act_silu,
+                                           int dtype, mlagg_stream_t stream) {
     int rc = dwconv_check(x, weight, y, batch, H, W, C, dtype);
     if (rc) return rc;
-    if (bias && !aligned(bias, C % 4 ? 4 : 16)) return MLAGG_ERR_ALIGN;
-    cudaError_t e = dwconv3x3_fwd_dispatch(x, weight, bias, y, batch, H, W, C, act_silu, dtype, (cudaStream_t)stream);
+    if (!dw_strides_ok(C, ldx, bsx) || !dw_strides_ok(C, ldy, bsy) || (residual && !dw_strides_ok(C, ldr, bsr)))
+        return MLAGG_ERR_BAD_SHAPE;
+    const size_t a = C % 4 != 0 ? (dtype == MLAGG_F32 ? 4 : 2) : (dtype == MLAGG_F32 ? 16 : 8);
+    if ((bias && !aligned(bias, C % 4 ? 4 : 16)) || (residual && !aligned(residual, a))) return MLAGG_ERR_ALIGN;
+    cudaError_t e = dwconv3x3_fwd_dispatch(x, weight, bias, residual, y, batch, H, W, C, ldx, bsx, ldr, bsr, ldy, bsy,
+                                           act_silu, dtype, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_dwconv3x3_fwd(const void *x, const float *weight, const float *bias, void *y, int batch, int H,
+                                   int W, int C, int act_silu, int dtype, mlagg_stream_t stream) {
+    const long long bs = (long long)H * W * C;
+    return mlagg_dwconv3x3_fwd_strided(x, weight, bias, nullptr, y, batch, H, W, C, C, bs, C, bs, C, bs, act_silu, dtype,
+                                       stream);
+}
+
+extern "C" int mlagg_dwconv3x3_bwd_strided(const void *x, const float *weight, const float *bias, const void *dy,
+                                           void *dz_ws, void *dx, float *dweight, float *dbias, int batch, int H, int W,
+                                           int C, long long ldx, long long bsx, long long lddy, long long bsdy,
+                                           long long lddx, long long bsdx, int act_silu, int dtype,
+                                           mlagg_stream_t stream) {
+    int rc = dwconv_check(x, weight, dx, batch, H, W, C, dtype);
+    if (rc) return rc;
+    if (!dy || !dz_ws || !dweight) return MLAGG_ERR_NULL;
+    if (!dw_strides_ok(C, ldx, bsx) || !dw_strides_ok(C, lddy, bsdy) || !dw_strides_ok(C, lddx, bsdx))
+        return MLAGG_ERR_BAD_SHAPE;
+    const size_t a = C % 4 != 0 ? (dtype == MLAGG_F32 ? 4 : 2) : (dtype == MLAGG_F32 ? 16 : 8);
+    if (!aligned(dy, a) || !aligned(dz_ws, a) || (bias && !aligned(bias, C % 4 ? 4 : 16))) return MLAGG_ERR_ALIGN;
+    cudaError_t e = dwconv3x3_bwd_dispatch(x, weight, bias, dy, dz_ws, dx, dweight, dbias, batch, H, W, C, ldx, bsx, lddy,
+                                           bsdy, lddx, bsdx, act_silu, dtype, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 
 extern "C" int mlagg_dwconv3x3_bwd(const void *x, const float *weight, const float *bias, const void *dy,
                                    void *dz_ws, void *dx, float *dweight, float *dbias, int batch, int H, int W,
                                    int C, int act_silu, int dtype, mlagg_stream_t stream) {
-    int rc = dwconv_check(x, weight, dx, batch, H, W, C, dtype);
-    if (rc) return rc;
-    if (!dy || !dz_ws || !dweight) return MLAGG_ERR_NULL;
-    const size_t a = C % 4 != 0 ? (dtype == MLAGG_F32 ? 4 : 2) : (dtype == MLAGG_F32 ? 16 : 8);
-    if (!aligned(dy, a) || !aligned(dz_ws, a) || (bias && !aligned(bias, C % 4 ? 4 : 16))) return MLAGG_ERR_ALIGN;
-    cudaError_t e = dwconv3x3_bwd_dispatch(x, weight, bias, dy, dz_ws, dx, dweight, dbias, batch, H, W, C, act_silu,
-                                           dtype, (cudaStream_t)stream);
-    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+    const long long bs = (long long)H * W * C;
+    return mlagg_dwconv3x3_bwd_strided(x, weight, bias, dy, dz_ws, dx, dweight, dbias, batch, H, W, C, C, bs, C, bs, C, bs,
+                                       act_silu, dtype, stream);
 }
 
 extern "C" int mlagg_causal_conv1d_fwd(const float *x, const float *weight, const float *bias, float *y, int batch,
@@ -435,6 +470,60 @@ extern "C" int mlagg_walk_unpack(const float *src0, const float *src1, long long
     cudaError_t e = walk_unpack_dispatch(src0, src1, bs_src, nc, nc_pad, dst, dtype, ld_dst, bs_dst, c0, batch, nstages,
                                          host_Hs, host_Ws, col_walk ? 1 : 0, accumulate ? 1 : 0, (cudaStream_t)stream);
     if (e == cudaErrorInvalidValue) return MLAGG_ERR_BAD_SHAPE;
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+static int ew_check(const void *a, const void *b, const void *c, long long n, int dtype) {
+    if (!a || !b || !c) return MLAGG_ERR_NULL;
+    if (n <= 0 || n % 4 != 0) return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    const size_t al = dtype == MLAGG_F32 ? 16 : 8;
+    if (!aligned(a, al) || !aligned(b, al) || !aligned(c, al)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_residual_scale(const void *x, const void *y, const float *scale, void *out, long long n,
+                                    long long per_sample, int dtype, mlagg_stream_t stream) {
+    int rc = ew_check(y, out, x ? x : y, n, dtype);
+    if (rc) return rc;
+    if (per_sample <= 0 || per_sample % 4 != 0 || n % per_sample != 0) return MLAGG_ERR_BAD_SHAPE;
+    cudaError_t e = residual_scale_dispatch(x, y, scale, out, n, per_sample, dtype, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_silu_gate_fwd(const void *t, const void *z, void *out, long long n, int dtype,
+                                   mlagg_stream_t stream) {
+    int rc = ew_check(t, z, out, n, dtype);
+    if (rc) return rc;
+    cudaError_t e = silu_gate_dispatch(t, z, nullptr, out, nullptr, n, dtype, false, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_silu_gate_bwd(const void *t, const void *z, const void *dout, void *dt, void *dz, long long n,
+                                   int dtype, mlagg_stream_t stream) {
+    int rc = ew_check(t, z, dout, n, dtype);
+    if (rc) return rc;
+    rc = ew_check(dt, dz, dz, n, dtype);
+    if (rc) return rc;
+    cudaError_t e = silu_gate_dispatch(t, z, dout, dt, dz, n, dtype, true, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_diff_lambda_fwd(const float *lq1, const float *lk1, const float *lq2, const float *lk2, int n,
+                                     float lambda_init, float *out, mlagg_stream_t stream) {
+    if (!lq1 || !lk1 || !lq2 || !lk2 || !out) return MLAGG_ERR_NULL;
+    if (n <= 0) return MLAGG_ERR_BAD_SHAPE;
+    cudaError_t e = diff_lambda_dispatch(lq1, lk1, lq2, lk2, n, lambda_init, out, nullptr, nullptr, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_diff_lambda_bwd(const float *lq1, const float *lk1, const float *lq2, const float *lk2,
+                                     const float *saved, const float *dlam, int n, float *grads,
+                                     mlagg_stream_t stream) {
+    if (!lq1 || !lk1 || !lq2 || !lk2 || !saved || !dlam || !grads) return MLAGG_ERR_NULL;
+    if (n <= 0) return MLAGG_ERR_BAD_SHAPE;
+    cudaError_t e = diff_lambda_dispatch(lq1, lk1, lq2, lk2, n, 0.f, const_cast<float *>(saved), dlam, grads,
+                                         (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

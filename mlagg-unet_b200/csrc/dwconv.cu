@@ -58,6 +58,12 @@ struct Row3 {
     const void *p[3];
 };
 
+// pixel (ld*) and image (bs*) strides in elements of the input, the output and the optional second input
+// (forward: residual added to the result; weight-gradient pass: dy).  Contiguous tokens-major data: ld = C, bs = H*W*C.
+struct DwLay {
+    long long ldx, bsx, ldy, bsy, ldr, bsr;
+};
+
 template <typename T>
 __device__ __forceinline__ void dw_col(const Row3 &rows, int wc, int W, int C, float4 (&o)[3]) {
     const bool in = wc >= 0 && wc < W;
@@ -85,8 +91,8 @@ __device__ __forceinline__ float4 dw_window(const float4 &b, const float (&wr)[4
 
 template <typename T, bool FLIP, int ACT>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x, const float *__restrict__ w,
-                                                        const float *__restrict__ bias, T *__restrict__ y, int Bn,
-                                                        int H, int W, int C) {
+                                                        const float *__restrict__ bias, const T *__restrict__ res,
+                                                        T *__restrict__ y, int Bn, int H, int W, int C, DwLay lay) {
     const int cv = C >> 2;
     const int SW = (W + kStrip - 1) / kStrip;
     const long long total = (long long)Bn * H * SW * cv;
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x,
     const int w0 = (int)(s % SW) * kStrip;
     s /= SW;
     const int hr = (int)(s % H);
-    const long long img = (s / H) * H;   // first row of this image, in rows
+    const long long bimg = s / H;        // image index
     float wr[4][9];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -108,20 +114,27 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x,
 #pragma unroll
     for (int dr = 0; dr < 3; ++dr) {
         const int rr = hr + dr - 1;
-        rows.p[dr] = (rr >= 0 && rr < H) ? static_cast<const void *>(x + ((img + rr) * W) * C + c) : nullptr;
+        rows.p[dr] = (rr >= 0 && rr < H) ? static_cast<const void *>(x + bimg * lay.bsx + ((long long)rr * W) * lay.ldx + c)
+                                         : nullptr;
     }
-    T *yr = y + ((img + hr) * W) * C + c;
+    T *yr = y + bimg * lay.bsy + ((long long)hr * W) * lay.ldy + c;
+    const T *rsr = res ? res + bimg * lay.bsr + ((long long)hr * W) * lay.ldr + c : nullptr;
     const int w1 = min(W, w0 + kStrip);
+    const int ldx = (int)lay.ldx;
     float4 A[3], Bc[3], Cc[3];
-    dw_col<T>(rows, w0 - 1, W, C, A);
-    dw_col<T>(rows, w0, W, C, Bc);
+    dw_col<T>(rows, w0 - 1, W, ldx, A);
+    dw_col<T>(rows, w0, W, ldx, Bc);
     auto step = [&](int wc, const float4 (&L)[3], const float4 (&M)[3], float4 (&R)[3]) {
-        dw_col<T>(rows, wc + 1, W, C, R);
+        dw_col<T>(rows, wc + 1, W, ldx, R);
         float4 acc = dw_window(bv, wr, L, M, R);
         if (ACT == 1) {
             acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w);
         }
-        st4<T>(yr + (long long)wc * C, acc);
+        if (rsr) {
+            const float4 r4 = ld4<T>(rsr + (long long)wc * lay.ldr);
+            acc.x += r4.x; acc.y += r4.y; acc.z += r4.z; acc.w += r4.w;
+        }
+        st4<T>(yr + (long long)wc * lay.ldy, acc);
     };
     for (int wc = w0; wc < w1; wc += 3) {
         step(wc, A, Bc, Cc);
@@ -145,20 +158,23 @@ __device__ __forceinline__ void st1<float>(float *p, float v) { *p = v; }
 template <>
 __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
-// mode 0: y = act(conv(x)+b); mode 1 (FLIP): y = conv_flipped(x); mode 2: dz = dy * act'(conv(x)+b) and dw/db atomics
+// mode 0: y = act(conv(x)+b) [+ res]; mode 1 (FLIP): y = conv_flipped(x); mode 2: dz = dy * act'(conv(x)+b) and dw/db
+// atomics (dy addressed through lay.ldr / lay.bsr)
 template <typename T, int ACT>
 __global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                                const float *__restrict__ bias,
                                                                const T *__restrict__ dy, T *__restrict__ y,
                                                                float *__restrict__ dw, float *__restrict__ db, int Bn,
-                                                               int H, int W, int C, int mode) {
+                                                               int H, int W, int C, int mode, DwLay lay) {
     const long long total = (long long)Bn * H * W * C;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % C);
         const long long pix = idx / C;
         const int wc = (int)(pix % W), hr = (int)((pix / W) % H);
-        const T *xb = x + (pix - (long long)hr * W - wc) * C + c;
+        const long long bimg = pix / ((long long)H * W);
+        const long long lpix = (long long)hr * W + wc;
+        const T *xb = x + bimg * lay.bsx + c;
         float acc = (mode != 1 && bias) ? __ldg(bias + c) : 0.f;
         float xn[9];
 #pragma unroll
@@ -168,18 +184,21 @@ __global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restri
                 const int p = 3 * (dr + 1) + (dc + 1);
                 const int rr = hr + dr, cc = wc + dc;
                 const bool ok = rr >= 0 && rr < H && cc >= 0 && cc < W;
-                xn[p] = ok ? ld1<T>(xb + ((long long)rr * W + cc) * C) : 0.f;
+                xn[p] = ok ? ld1<T>(xb + ((long long)rr * W + cc) * lay.ldx) : 0.f;
                 acc = fmaf(__ldg(w + c * 9 + (mode == 1 ? 8 - p : p)), xn[p], acc);
             }
+        T *yp = y + bimg * lay.bsy + lpix * lay.ldy + c;
         if (mode == 2) {
-            float g = ld1<T>(dy + pix * C + c);
+            float g = ld1<T>(dy + bimg * lay.bsr + lpix * lay.ldr + c);
             if (ACT == 1) g *= silu_grad(acc);
-            st1<T>(y + pix * C + c, g);
+            st1<T>(yp, g);
 #pragma unroll
             for (int p = 0; p < 9; ++p) atomicAdd(dw + c * 9 + p, g * xn[p]);
             if (db) atomicAdd(db + c, g);
         } else {
-            st1<T>(y + pix * C + c, (ACT == 1 && mode == 0) ? silu_f(acc) : acc);
+            float o = (ACT == 1 && mode == 0) ? silu_f(acc) : acc;
+            if (mode == 0 && dy) o += ld1<T>(dy + bimg * lay.bsr + lpix * lay.ldr + c);   // residual rides in `dy`
+            st1<T>(yp, o);
         }
     }
 }
@@ -195,8 +214,9 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restric
                                                               const float *__restrict__ bias,
                                                               const T *__restrict__ dy, T *__restrict__ dz,
                                                               float *__restrict__ dw, float *__restrict__ db,
-                                                              int Bn, int H, int W, int C, int strips_per_lane) {
-    extern __shared__ float red[];  // [PP][cv][40]
+                                                              int Bn, int H, int W, int C, int strips_per_lane,
+                                                              DwLay lay) {
+    extern __shared__ float red[];  // [PP][cv][40]    (x: lay.ldx/bsx, dy: lay.ldr/bsr, dz: lay.ldy/bsy)
     const int cv = C >> 2;
     const int PP = blockDim.x / cv;
     const int cvi = threadIdx.x % cv, pl = threadIdx.x / cv;
@@ -223,26 +243,30 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restric
             const int w0 = (int)(s % SW) * kStripW;
             s /= SW;
             const int hr = (int)(s % H);
-            const long long img = (s / H) * H;
+            const long long bimg = s / H;
             Row3 rows;
 #pragma unroll
             for (int dr = 0; dr < 3; ++dr) {
                 const int rr = hr + dr - 1;
-                rows.p[dr] = (rr >= 0 && rr < H) ? static_cast<const void *>(x + ((img + rr) * W) * C + c) : nullptr;
+                rows.p[dr] = (rr >= 0 && rr < H)
+                                 ? static_cast<const void *>(x + bimg * lay.bsx + ((long long)rr * W) * lay.ldx + c)
+                                 : nullptr;
             }
-            const long long rowoff = ((img + hr) * W) * C + c;
+            const T *gyr = dy + bimg * lay.bsr + ((long long)hr * W) * lay.ldr + c;
+            T *dzr = dz + bimg * lay.bsy + ((long long)hr * W) * lay.ldy + c;
             const int w1 = min(W, w0 + kStripW);
+            const int ldx = (int)lay.ldx;
             float4 A[3], Bc[3], Cc[3];
-            dw_col<T>(rows, w0 - 1, W, C, A);
-            dw_col<T>(rows, w0, W, C, Bc);
+            dw_col<T>(rows, w0 - 1, W, ldx, A);
+            dw_col<T>(rows, w0, W, ldx, Bc);
             auto step = [&](int wc, const float4 (&L)[3], const float4 (&M)[3], float4 (&R)[3]) {
-                dw_col<T>(rows, wc + 1, W, C, R);
-                float4 g = ld4<T>(dy + rowoff + (long long)wc * C);
+                dw_col<T>(rows, wc + 1, W, ldx, R);
+                float4 g = ld4<T>(gyr + (long long)wc * lay.ldr);
                 if (ACT == 1) {
                     const float4 z = dw_window(bv, wr, L, M, R);
                     g.x *= silu_grad(z.x); g.y *= silu_grad(z.y); g.z *= silu_grad(z.z); g.w *= silu_grad(z.w);
                 }
-                st4<T>(dz + rowoff + (long long)wc * C, g);
+                st4<T>(dzr + (long long)wc * lay.ldy, g);
                 ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w;
 #pragma unroll
                 for (int dr = 0; dr < 3; ++dr) {
@@ -378,47 +402,58 @@ __global__ void __launch_bounds__(256) causal_conv1d_bwd_kernel(const float *__r
 }
 
 // ------------------------------------------------------------------ host launchers
+static DwLay dw_contig(int H, int W, int C) {
+    const long long bs = (long long)H * W * C;
+    return DwLay{C, bs, C, bs, C, bs};
+}
+
 template <typename T>
-static cudaError_t dwconv_fwd_t(const void *x, const float *w, const float *b, void *y, int Bn, int H, int W, int C,
-                                int act, bool flip, cudaStream_t st) {
-    const T *xp0 = static_cast<const T *>(x);
-    T *yp0 = static_cast<T *>(y);
+static cudaError_t dwconv_fwd_t(const void *x, const float *w, const float *b, const void *res, void *y, int Bn, int H,
+                                int W, int C, int act, bool flip, DwLay lay, cudaStream_t st) {
+    const T *xp = static_cast<const T *>(x), *rp = static_cast<const T *>(res);
+    T *yp = static_cast<T *>(y);
     if (C % 4 != 0) {
         long long nb1 = ((long long)Bn * H * W * C + 255) / 256;
         if (nb1 > 148LL * 32) nb1 = 148LL * 32;
-        if (act && !flip) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xp0, w, b, nullptr, yp0, nullptr, nullptr, Bn, H, W, C, 0);
-        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xp0, w, b, nullptr, yp0, nullptr, nullptr, Bn, H, W, C, flip ? 1 : 0);
+        if (act && !flip) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xp, w, b, rp, yp, nullptr, nullptr, Bn, H, W, C, 0, lay);
+        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xp, w, b, flip ? nullptr : rp, yp, nullptr, nullptr, Bn, H, W, C, flip ? 1 : 0, lay);
         return cudaGetLastError();
     }
     const long long total = (long long)Bn * H * ((W + kStrip - 1) / kStrip) * (C / 4);   // one thread per strip
     const int blocks = (int)((total + 255) / 256);
-    const T *xp = static_cast<const T *>(x);
-    T *yp = static_cast<T *>(y);
-    if (flip) dwconv3x3_kernel<T, true, 0><<<blocks, 256, 0, st>>>(xp, w, nullptr, yp, Bn, H, W, C);
-    else if (act) dwconv3x3_kernel<T, false, 1><<<blocks, 256, 0, st>>>(xp, w, b, yp, Bn, H, W, C);
-    else dwconv3x3_kernel<T, false, 0><<<blocks, 256, 0, st>>>(xp, w, b, yp, Bn, H, W, C);
+    if (flip) dwconv3x3_kernel<T, true, 0><<<blocks, 256, 0, st>>>(xp, w, nullptr, nullptr, yp, Bn, H, W, C, lay);
+    else if (act) dwconv3x3_kernel<T, false, 1><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
+    else dwconv3x3_kernel<T, false, 0><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
     return cudaGetLastError();
 }
 
-cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, void *y, int Bn, int H, int W,
-                                   int C, int act, int dtype, cudaStream_t st) {
-    return dtype == 0 ? dwconv_fwd_t<float>(x, w, b, y, Bn, H, W, C, act, false, st)
-                      : dwconv_fwd_t<__nv_bfloat16>(x, w, b, y, Bn, H, W, C, act, false, st);
+// x (ldx, bsx), residual (ldr, bsr; nullable), y (ldy, bsy)
+cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, const void *res, void *y, int Bn, int H,
+                                   int W, int C, long long ldx, long long bsx, long long ldr, long long bsr,
+                                   long long ldy, long long bsy, int act, int dtype, cudaStream_t st) {
+    const DwLay lay{ldx, bsx, ldy, bsy, ldr, bsr};
+    return dtype == 0 ? dwconv_fwd_t<float>(x, w, b, res, y, Bn, H, W, C, act, false, lay, st)
+                      : dwconv_fwd_t<__nv_bfloat16>(x, w, b, res, y, Bn, H, W, C, act, false, lay, st);
 }
 
 template <typename T>
 static cudaError_t dwconv_bwd_t(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
-                                float *dw, float *db, int Bn, int H, int W, int C, int act, cudaStream_t st) {
+                                float *dw, float *db, int Bn, int H, int W, int C, int act, DwLay lx, long long lddx,
+                                long long bsdx, cudaStream_t st) {
+    // pass 1: x (lx.ldx/bsx), dy (lx.ldr/bsr) -> dz contiguous workspace; pass 2: dz -> dx (lddx, bsdx)
+    const DwLay c0 = dw_contig(H, W, C);
+    const DwLay l1{lx.ldx, lx.bsx, c0.ldy, c0.bsy, lx.ldr, lx.bsr};
+    const DwLay l2{c0.ldx, c0.bsx, lddx, bsdx, c0.ldr, c0.bsr};
     if (C % 4 != 0) {
         long long nb1 = ((long long)Bn * H * W * C + 255) / 256;
         if (nb1 > 148LL * 32) nb1 = 148LL * 32;
         const T *xq = static_cast<const T *>(x), *gq = static_cast<const T *>(dy);
         T *zq = static_cast<T *>(dz);
-        if (act) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2);
-        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2);
+        if (act) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2, l1);
+        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2, l1);
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return e1;
-        return dwconv_fwd_t<T>(dz, w, nullptr, dx, Bn, H, W, C, 0, true, st);
+        return dwconv_fwd_t<T>(dz, w, nullptr, nullptr, dx, Bn, H, W, C, 0, true, l2, st);
     }
     const int cv = C / 4;
     const int PP = max(1, 256 / cv);
@@ -434,21 +469,24 @@ static cudaError_t dwconv_bwd_t(const void *x, const float *w, const float *b, c
     if (act) {
         auto k = dwconv3x3_bwd_w_kernel<T, 1>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb);
+        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb, l1);
     } else {
         auto k = dwconv3x3_bwd_w_kernel<T, 0>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb);
+        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb, l1);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return dwconv_fwd_t<T>(dz, w, nullptr, dx, Bn, H, W, C, 0, true, st);
+    return dwconv_fwd_t<T>(dz, w, nullptr, nullptr, dx, Bn, H, W, C, 0, true, l2, st);
 }
 
+// x (ldx, bsx), dy (lddy, bsdy), dz: contiguous workspace, dx (lddx, bsdx)
 cudaError_t dwconv3x3_bwd_dispatch(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
-                                   float *dw, float *db, int Bn, int H, int W, int C, int act, int dtype,
+                                   float *dw, float *db, int Bn, int H, int W, int C, long long ldx, long long bsx,
+                                   long long lddy, long long bsdy, long long lddx, long long bsdx, int act, int dtype,
                                    cudaStream_t st) {
-    return dtype == 0 ? dwconv_bwd_t<float>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, st)
-                      : dwconv_bwd_t<__nv_bfloat16>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, st);
+    const DwLay lx{ldx, bsx, 0, 0, lddy, bsdy};
+    return dtype == 0 ? dwconv_bwd_t<float>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, lx, lddx, bsdx, st)
+                      : dwconv_bwd_t<__nv_bfloat16>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, lx, lddx, bsdx, st);
 }
 
 cudaError_t causal_conv1d_fwd_dispatch(const float *x, const float *w, const float *b, float *y, int rows, int C,

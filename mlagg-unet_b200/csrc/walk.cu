@@ -7,8 +7,8 @@
 // inside the scan kernels.  These kernels replace, per train step, the transpose().contiguous(), per-stage
 // reshape/transpose/cat, fp32 cast, direction-sum and slice-backward (zero-fill + copy + add) kernels torch ran for
 // `SS2D_skip.forward_corev0` and its autograd graph: ~40 launches and ~5 ms -> 13 launches.
-// HBM-bound 64-position x 32-channel tile transposes through shared memory: token rows are read / written as 64..128-byte
-// pieces (8 threads x 4 channels), planes as 128-byte warp rows.
+// HBM-bound tile transposes through shared memory (tile shapes below): token rows are read / written as 8- or 16-byte
+// pieces per thread, planes as 64- or 128-byte row segments.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -16,8 +16,16 @@
 namespace mlagg {
 
 constexpr int kWalkMaxStages = 8;
-constexpr int kWalkTP = 64;    // positions per tile
-constexpr int kWalkTC = 32;    // channels per tile
+// tile = TC channels x TP positions, TC * TP = 2048: (32, 64) for narrow operands, (128, 16) when a token row is wider than
+// 32 channels -- a warp then moves one whole token row (up to 512 B), which matters for the column walk where consecutive
+// positions are W tokens apart (64-byte pieces per token measured 4x slower than the row walk).
+
+// shared-memory row of tile channel cl: identity for TC = 32 (conflict-free with 8 threads per position); for TC = 128 a
+// warp writes the 4 x 32 channels of one position, so channel 4 cg + j goes to row 32 j + cg (odd row stride 17)
+template <int TC>
+__device__ __forceinline__ int walk_row(int cl) {
+    return TC == 32 ? cl : ((cl & 3) * 32 + (cl >> 2));
+}
 
 struct WalkGeom {
     int nstage;
@@ -77,18 +85,19 @@ __device__ __forceinline__ void wk_st4<__nv_bfloat16>(__nv_bfloat16 *p, const fl
 
 // src (B, L, >= c0 + nc) tokens-major, row stride ld_src, batch stride bs_src (elements)  ->  dst[b][c][p], c < nc, fp32,
 // batch stride bs_dst.  VEC: 4-channel vector loads are legal (alignment checked by the dispatcher).
-template <typename T, bool VEC>
+template <typename T, bool VEC, int TC>
 __global__ void __launch_bounds__(256) walk_pack_kernel(const T *__restrict__ src, long long ld_src, long long bs_src,
                                                         int c0, int nc, float *__restrict__ dst, long long bs_dst, int L,
                                                         int col, WalkGeom g) {
-    __shared__ float tile[kWalkTC][kWalkTP + 1];
-    const int p0 = blockIdx.x * kWalkTP, cb = blockIdx.y * kWalkTC, b = blockIdx.z;
+    constexpr int TP = 2048 / TC, TPP = TC / 4, PPP = 256 / TPP;   // threads per position, positions per pass
+    __shared__ float tile[TC][TP + 1];
+    const int p0 = blockIdx.x * TP, cb = blockIdx.y * TC, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cg = tid & 7, c = cb + 4 * cg;
+    const int cg = tid % TPP, c = cb + 4 * cg;
     const T *sb = src + (long long)b * bs_src + c0 + c;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int pos = pass * 32 + (tid >> 3), p = p0 + pos;
+    for (int pass = 0; pass < TP / PPP; ++pass) {
+        const int pos = pass * PPP + tid / TPP, p = p0 + pos;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (p < L && c < nc) {
             const T *r = sb + (long long)walk_token(g, p, col) * ld_src;
@@ -101,58 +110,82 @@ __global__ void __launch_bounds__(256) walk_pack_kernel(const T *__restrict__ sr
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tile[4 * cg + j][pos] = v[j];
+        for (int j = 0; j < 4; ++j) tile[walk_row<TC>(4 * cg + j)][pos] = v[j];
     }
     __syncthreads();
     float *db = dst + (long long)b * bs_dst;
+    if (TP >= 32) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int cl = 4 * warp + j, cc = cb + cl;
-        if (cc < nc) {
+        for (int j = 0; j < TC / 8; ++j) {
+            const int cl = (TC / 8) * warp + j, cc = cb + cl;
+            if (cc < nc) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int p = p0 + half * 32 + lane;
-                if (p < L) db[(long long)cc * L + p] = tile[cl][half * 32 + lane];
+                for (int half = 0; half < TP / 32; ++half) {
+                    const int p = p0 + half * 32 + lane;
+                    if (p < L) db[(long long)cc * L + p] = tile[walk_row<TC>(cl)][half * 32 + lane];
+                }
             }
+        }
+    } else {   // TP == 16: a warp writes two channel rows of 16 positions (64 B each) per step
+#pragma unroll
+        for (int j = 0; j < TC / 16; ++j) {
+            const int cl = (TC / 8) * warp + 2 * j + (lane >> 4), cc = cb + cl;
+            const int p = p0 + (lane & 15);
+            if (cc < nc && p < L) db[(long long)cc * L + p] = tile[walk_row<TC>(cl)][lane & 15];
         }
     }
 }
 
 // dst[b][token(p)][c0 + c] (+)= src0[b][c][p] (+ src1[b][c][p]) for c < nc, and 0 for nc <= c < nc_pad.
-template <typename T, bool VEC>
+template <typename T, bool VEC, int TC>
 __global__ void __launch_bounds__(256) walk_unpack_kernel(const float *__restrict__ src0, const float *__restrict__ src1,
                                                           long long bs_src, int nc, int nc_pad, T *__restrict__ dst,
                                                           long long ld_dst, long long bs_dst, int c0, int L, int col,
                                                           int accumulate, WalkGeom g) {
-    __shared__ float tile[kWalkTC][kWalkTP + 1];
-    const int p0 = blockIdx.x * kWalkTP, cb = blockIdx.y * kWalkTC, b = blockIdx.z;
+    constexpr int TP = 2048 / TC, TPP = TC / 4, PPP = 256 / TPP;
+    __shared__ float tile[TC][TP + 1];
+    const int p0 = blockIdx.x * TP, cb = blockIdx.y * TC, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *s0 = src0 + (long long)b * bs_src, *s1 = src1 ? src1 + (long long)b * bs_src : nullptr;
+    if (TP >= 32) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int cl = 4 * warp + j, cc = cb + cl;
+        for (int j = 0; j < TC / 8; ++j) {
+            const int cl = (TC / 8) * warp + j, cc = cb + cl;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int p = p0 + half * 32 + lane;
+            for (int half = 0; half < TP / 32; ++half) {
+                const int p = p0 + half * 32 + lane;
+                float v = 0.f;
+                if (cc < nc && p < L) {
+                    v = __ldg(s0 + (long long)cc * L + p);
+                    if (s1) v += __ldg(s1 + (long long)cc * L + p);
+                }
+                tile[walk_row<TC>(cl)][half * 32 + lane] = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < TC / 16; ++j) {
+            const int cl = (TC / 8) * warp + 2 * j + (lane >> 4), cc = cb + cl;
+            const int p = p0 + (lane & 15);
             float v = 0.f;
             if (cc < nc && p < L) {
                 v = __ldg(s0 + (long long)cc * L + p);
                 if (s1) v += __ldg(s1 + (long long)cc * L + p);
             }
-            tile[cl][half * 32 + lane] = v;
+            tile[walk_row<TC>(cl)][lane & 15] = v;
         }
     }
     __syncthreads();
-    const int cg = tid & 7, c = cb + 4 * cg;
+    const int cg = tid % TPP, c = cb + 4 * cg;
     T *dbase = dst + (long long)b * bs_dst + c0 + c;
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int pos = pass * 32 + (tid >> 3), p = p0 + pos;
+    for (int pass = 0; pass < TP / PPP; ++pass) {
+        const int pos = pass * PPP + tid / TPP, p = p0 + pos;
         if (p < L && c < nc_pad) {
             T *r = dbase + (long long)walk_token(g, p, col) * ld_dst;
             float v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = tile[4 * cg + j][pos];
+            for (int j = 0; j < 4; ++j) v[j] = tile[walk_row<TC>(4 * cg + j)][pos];
             if (VEC && c + 4 <= nc_pad) {
                 if (accumulate) {
                     float o[4];
@@ -196,19 +229,24 @@ cudaError_t walk_pack_dispatch(const void *src, int dtype, long long ld_src, lon
     WalkGeom g;
     long long L;
     if (!walk_geom(g, nstages, Hs, Ws, &L)) return cudaErrorInvalidValue;
-    const dim3 grid((unsigned)((L + kWalkTP - 1) / kWalkTP), (unsigned)((nc + kWalkTC - 1) / kWalkTC), (unsigned)batch);
+    const int TC = nc > 32 ? 128 : 32, TP = 2048 / TC;
+    const dim3 grid((unsigned)((L + TP - 1) / TP), (unsigned)((nc + TC - 1) / TC), (unsigned)batch);
     const size_t es = dtype == 0 ? 4 : 2;
     const bool vec = (c0 % 4 == 0) && (ld_src % 4 == 0) && (bs_src % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(src) % (4 * es)) == 0);
-    if (dtype == 0) {
-        const float *s = static_cast<const float *>(src);
-        if (vec) walk_pack_kernel<float, true><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
-        else walk_pack_kernel<float, false><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
-    } else {
-        const __nv_bfloat16 *s = static_cast<const __nv_bfloat16 *>(src);
-        if (vec) walk_pack_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
-        else walk_pack_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(s, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g);
-    }
+#define MLAGG_PACK(T_, V_, C_) \
+    walk_pack_kernel<T_, V_, C_><<<grid, 256, 0, st>>>(static_cast<const T_ *>(src), ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g)
+#define MLAGG_PACK_T(T_)                                  \
+    do {                                                  \
+        if (vec && TC == 128) MLAGG_PACK(T_, true, 128);  \
+        else if (vec) MLAGG_PACK(T_, true, 32);           \
+        else if (TC == 128) MLAGG_PACK(T_, false, 128);   \
+        else MLAGG_PACK(T_, false, 32);                   \
+    } while (0)
+    if (dtype == 0) MLAGG_PACK_T(float);
+    else MLAGG_PACK_T(__nv_bfloat16);
+#undef MLAGG_PACK_T
+#undef MLAGG_PACK
     return cudaGetLastError();
 }
 
@@ -218,19 +256,25 @@ cudaError_t walk_unpack_dispatch(const float *src0, const float *src1, long long
     WalkGeom g;
     long long L;
     if (!walk_geom(g, nstages, Hs, Ws, &L)) return cudaErrorInvalidValue;
-    const dim3 grid((unsigned)((L + kWalkTP - 1) / kWalkTP), (unsigned)((nc_pad + kWalkTC - 1) / kWalkTC), (unsigned)batch);
+    const int TC = nc_pad > 32 ? 128 : 32, TP = 2048 / TC;
+    const dim3 grid((unsigned)((L + TP - 1) / TP), (unsigned)((nc_pad + TC - 1) / TC), (unsigned)batch);
     const size_t es = dtype == 0 ? 4 : 2;
     const bool vec = (c0 % 4 == 0) && (ld_dst % 4 == 0) && (bs_dst % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(dst) % (4 * es)) == 0);
-    if (dtype == 0) {
-        float *d = static_cast<float *>(dst);
-        if (vec) walk_unpack_kernel<float, true><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
-        else walk_unpack_kernel<float, false><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
-    } else {
-        __nv_bfloat16 *d = static_cast<__nv_bfloat16 *>(dst);
-        if (vec) walk_unpack_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
-        else walk_unpack_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, d, ld_dst, bs_dst, c0, (int)L, col, accumulate, g);
-    }
+#define MLAGG_UNPACK(T_, V_, C_)                                                                                        \
+    walk_unpack_kernel<T_, V_, C_><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, static_cast<T_ *>(dst), ld_dst, \
+                                                         bs_dst, c0, (int)L, col, accumulate, g)
+#define MLAGG_UNPACK_T(T_)                                  \
+    do {                                                    \
+        if (vec && TC == 128) MLAGG_UNPACK(T_, true, 128);  \
+        else if (vec) MLAGG_UNPACK(T_, true, 32);           \
+        else if (TC == 128) MLAGG_UNPACK(T_, false, 128);   \
+        else MLAGG_UNPACK(T_, false, 32);                   \
+    } while (0)
+    if (dtype == 0) MLAGG_UNPACK_T(float);
+    else MLAGG_UNPACK_T(__nv_bfloat16);
+#undef MLAGG_UNPACK_T
+#undef MLAGG_UNPACK
     return cudaGetLastError();
 }
 

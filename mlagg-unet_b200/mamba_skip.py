@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import _Linear, dwconv3x3_tokens, layer_norm_tokens, linear_tokens
+from .ops import _Linear, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
 from .selective_scan_interface import msmm_scan, msmm_scan_tokens, selective_scan_fn, xdbl_pad
 from .thirdparty_shims import DropPath, _inst_norm
 
@@ -206,15 +206,10 @@ class SS2D_skip(nn.Module):
     def forward(self, x, B, H, W, L_split, **kwargs):
         """x (B, L_cat, d_model), stages concatenated fine -> coarse along L."""
         hw = list(zip(H, W))
-        x = self.in_proj(x)
-        parts, off = [], 0
-        for s, (h, w) in enumerate(hw):
-            conv = self.conv2d[s]
-            parts.append(dwconv3x3_tokens(x[:, off:off + h * w].contiguous(), conv.weight, conv.bias, h, w, silu=True))
-            off += h * w
-        y = self.forward_core_tokens(torch.cat(parts, dim=1), hw)
+        x = linear_tokens(x, self.in_proj)
+        y = self.forward_core_tokens(dwconv3x3_stages(x, hw, self.conv2d, silu=True), hw)
         assert y.dtype == torch.float32
-        out = self.out_proj(layer_norm_tokens(y, self.out_norm))
+        out = linear_tokens(layer_norm_tokens(y, self.out_norm), self.out_proj)
         return self.dropout(out) if self.dropout is not None else out
 
 
@@ -224,7 +219,7 @@ class DWConv(nn.Module):
         self.dwconv = nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, bias=True, groups=dim)
 
     def forward(self, x, H, W, silu=False):
-        return dwconv3x3_tokens(x.contiguous(), self.dwconv.weight, self.dwconv.bias, H, W, silu=silu)
+        return dwconv3x3_tokens(x, self.dwconv.weight, self.dwconv.bias, H, W, silu=silu)   # x may be a channel slice
 
 
 class ConvolutionalGLU(nn.Module):
@@ -274,7 +269,7 @@ class VSS_Conv_Block(nn.Module):
         hd = self.hidden_dim
         # tokens-major (B, L, hd): NHWC views of the inputs (free when they are channels_last), first hd channels
         m = torch.cat([t.permute(0, 2, 3, 1)[..., :hd].reshape(Bn, L_split[s], hd) for s, t in enumerate(inputs)], dim=1)
-        m = m + self.drop_path(self.self_attention(layer_norm_tokens(m, self.ln_1), Bn, H, W, L_split))
+        m = residual_drop_path(m, self.self_attention(layer_norm_tokens(m, self.ln_1), Bn, H, W, L_split), self.drop_path)
         m = layer_norm_tokens(m, self.norm2)
         outs, off = [], 0
         for s, t in enumerate(inputs):

@@ -22,7 +22,8 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens
+from .ops import (GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path,
+                  silu_gate)
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
 
@@ -129,7 +130,8 @@ class AggregatedAttention(nn.Module):
                 t = self.pool(self.act(t).transpose(1, 2).reshape(Bn, C, H, W)).flatten(2).transpose(1, 2)
             o = att.pooled_diff_attention(q, linear_tokens(layer_norm_tokens(t, self.norm), self.kv), lam,
                                           self.subln.weight, h, hd, self.scale)
-        return o + dwconv3x3_tokens(v_local.contiguous(), self.lepe.weight, self.lepe.bias, H, W)
+        # LePE on the v half of the kv projection, read in place, with the attention output added in the same pass
+        return dwconv3x3_tokens(v_local, self.lepe.weight, self.lepe.bias, H, W, residual=o)
 
 
 class Attention(nn.Module):
@@ -181,15 +183,16 @@ class MLLABlock(nn.Module):
         """tokens-major (B, N, C) -> (B, N, C)"""
         shortcut = t
         t = layer_norm_tokens(t, self.norm1)
-        gate = self.act(linear_tokens(t, self.act_proj))
+        gate = linear_tokens(t, self.act_proj)                  # SiLU applied inside the gate kernel below
         t = dwconv3x3_tokens(linear_tokens(t, self.in_proj), self.dwc.weight, self.dwc.bias, H, W, silu=True)
         if self.sr_ratio == 1:
             t = self.attn(t, H, W)
         else:
             a, b = torch.chunk(t, 2, dim=-1)
             t = torch.cat([self.attn[0](a, H, W), self.attn[1](b, H, W)], dim=-1)
-        t = shortcut + self.drop_path(linear_tokens(t * gate, self.out_proj))
-        return t + self.drop_path(self.mlp(layer_norm_tokens(t, self.norm2)))
+        t = silu_gate(t, gate) if isinstance(self.act, nn.SiLU) else t * self.act(gate)
+        t = residual_drop_path(shortcut, linear_tokens(t, self.out_proj), self.drop_path)
+        return residual_drop_path(t, self.mlp(layer_norm_tokens(t, self.norm2)), self.drop_path)
 
     def forward(self, x):
         H, W = self.input_resolution

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import attention as att
 from .mlagg import Mlp
-from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens
+from .ops import dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path, silu_gate
 from .thirdparty_shims import DropPath
 
 
@@ -46,7 +46,7 @@ class LinearAttention(nn.Module):
         """x (B, N, C) -> (B, N, C)"""
         H, W = self.input_resolution
         o = att.linear_attention_qk(linear_tokens(x, self.qk), x, H, W, self.num_heads)
-        return o + dwconv3x3_tokens(x.contiguous(), self.lepe.weight, self.lepe.bias, H, W)
+        return dwconv3x3_tokens(x, self.lepe.weight, self.lepe.bias, H, W, residual=o)
 
     def extra_repr(self):
         return f"dim={self.dim}, num_heads={self.num_heads}"
@@ -74,15 +74,15 @@ class MLLABlock(nn.Module):
         H, W = self.input_resolution
         Bn, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
-        x = x + dwconv3x3_tokens(x.contiguous(), self.cpe1.weight, self.cpe1.bias, H, W)
+        x = dwconv3x3_tokens(x, self.cpe1.weight, self.cpe1.bias, H, W, residual=x)
         shortcut = x
         t = layer_norm_tokens(x, self.norm1)
-        gate = self.act(linear_tokens(t, self.act_proj))
+        gate = linear_tokens(t, self.act_proj)                  # SiLU applied inside the gate kernel below
         t = dwconv3x3_tokens(linear_tokens(t, self.in_proj), self.dwc.weight, self.dwc.bias, H, W, silu=True)
         t = self.attn(t)
-        x = shortcut + self.drop_path(linear_tokens(t.to(gate.dtype) * gate, self.out_proj))
-        x = x + dwconv3x3_tokens(x.contiguous(), self.cpe2.weight, self.cpe2.bias, H, W)
-        return x + self.drop_path(self.mlp(layer_norm_tokens(x, self.norm2)))
+        x = residual_drop_path(shortcut, linear_tokens(silu_gate(t.to(gate.dtype), gate), self.out_proj), self.drop_path)
+        x = dwconv3x3_tokens(x, self.cpe2.weight, self.cpe2.bias, H, W, residual=x)
+        return residual_drop_path(x, self.mlp(layer_norm_tokens(x, self.norm2)), self.drop_path)
 
     def extra_repr(self):
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "

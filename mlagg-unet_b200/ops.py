@@ -18,45 +18,145 @@ def _io(x):
     return x if x.dtype in _DT else x.float()
 
 
+def _tok_strides(t, C):
+    """(pixel stride, image stride) of a tokens-major (B, N, C) view the stencil kernels can address in place, or None:
+    unit channel stride, strides that keep the 4-channel vectors aligned."""
+    if t.dim() != 3 or t.stride(2) != 1 or t.stride(1) < C:
+        return None
+    ld, bs = t.stride(1), t.stride(0)
+    if C % 4 == 0 and (ld % 4 or bs % 4 or (t.data_ptr() % (4 * t.element_size()))):
+        return None
+    return ld, bs
+
+
+def _tok_operand(t, C):
+    """t as the kernels take it (fp32 / bf16) plus its (ld, bs); copies only when the view cannot be addressed in place"""
+    t = _io(t)
+    st = _tok_strides(t, C)
+    if st is None:
+        t = t.contiguous()
+        st = (t.stride(1), t.stride(0))
+    return t, st
+
+
 class _DWConv3x3(torch.autograd.Function):
+    """C ABI: mlagg_dwconv3x3_fwd_strided / _bwd_strided.  y = act(conv(x) + b) [+ residual]"""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, H, W, silu):
+    def forward(ctx, x, weight, bias, H, W, silu, residual):
         if not x.is_cuda:
             raise _lib.MlaggError("dwconv3x3_tokens: CUDA tensor required (no CPU fallback in the product path)")
         Bn, N, C = x.shape
         assert N == H * W and weight.shape == (C, 1, 3, 3)
-        xin = _io(x).contiguous()
+        xin, (ldx, bsx) = _tok_operand(x, C)
         w32 = weight.detach().float().contiguous()
         b32 = None if bias is None else bias.detach().float().contiguous()
-        y = torch.empty_like(xin)
+        res, (ldr, bsr) = (None, (C, N * C))
+        if residual is not None:
+            assert residual.shape == x.shape
+            res, (ldr, bsr) = _tok_operand(residual.to(xin.dtype), C)
+        y = torch.empty(Bn, N, C, device=x.device, dtype=xin.dtype)
         with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd"):
-            rc = _lib.lib().mlagg_dwconv3x3_fwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), Bn, H, W, C,
-                                                int(silu), _DT[xin.dtype], _lib.stream_ptr())
-        _lib.check(rc, "mlagg_dwconv3x3_fwd")
+            rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(res),
+                                                        _lib.ptr(y), Bn, H, W, C, ldx, bsx, ldr, bsr, C, N * C, int(silu),
+                                                        _DT[xin.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dwconv3x3_fwd_strided")
         ctx.save_for_backward(xin, w32, b32)
-        ctx.meta = (H, W, bool(silu), x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        ctx.meta = (H, W, bool(silu), x.dtype, weight.dtype, None if bias is None else bias.dtype, (ldx, bsx),
+                    None if residual is None else residual.dtype)
         return y.to(x.dtype)
 
     @staticmethod
     def backward(ctx, dy):
         xin, w32, b32 = ctx.saved_tensors
-        H, W, silu, xdt, wdt, bdt = ctx.meta
+        H, W, silu, xdt, wdt, bdt, (ldx, bsx), rdt = ctx.meta
         Bn, N, C = xin.shape
-        dy = dy.to(xin.dtype).contiguous()
-        dz, dx = torch.empty_like(xin), torch.empty_like(xin)
+        dy, (ldg, bsg) = _tok_operand(dy.to(xin.dtype), C)
+        dz = torch.empty(Bn, N, C, device=xin.device, dtype=xin.dtype)
+        dx = torch.empty_like(dz)
         dw = _lib.zeros((C, 9), xin.device)
         db = _lib.zeros(C, xin.device) if b32 is not None else None
         with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2):
-            rc = _lib.lib().mlagg_dwconv3x3_bwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy), _lib.ptr(dz),
-                                                _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), Bn, H, W, C, int(silu),
-                                                _DT[xin.dtype], _lib.stream_ptr())
-        _lib.check(rc, "mlagg_dwconv3x3_bwd")
-        return (dx.to(xdt), dw.view(C, 1, 3, 3).to(wdt), None if db is None else db.to(bdt), None, None, None)
+            rc = _lib.lib().mlagg_dwconv3x3_bwd_strided(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy),
+                                                        _lib.ptr(dz), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), Bn, H, W,
+                                                        C, ldx, bsx, ldg, bsg, C, N * C, int(silu), _DT[xin.dtype],
+                                                        _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dwconv3x3_bwd_strided")
+        return (dx.to(xdt), dw.view(C, 1, 3, 3).to(wdt), None if db is None else db.to(bdt), None, None, None,
+                None if rdt is None else dy.to(rdt))
 
 
-def dwconv3x3_tokens(x, weight, bias, H, W, silu=False):
-    """x (B, H*W, C) -> depthwise 3x3 (pad 1) [+ SiLU]; weight is the nn.Conv2d(C, C, 3, groups=C) parameter."""
-    return _DWConv3x3.apply(x, weight, bias, H, W, silu)
+def dwconv3x3_tokens(x, weight, bias, H, W, silu=False, residual=None):
+    """x (B, H*W, C) -> depthwise 3x3 (pad 1) [+ SiLU] [+ residual]; weight is the nn.Conv2d(C, C, 3, groups=C)
+    parameter.  x / residual may be channel slices of wider activations (read in place)."""
+    return _DWConv3x3.apply(x, weight, bias, H, W, silu, residual)
+
+
+class _DWConv3x3Stages(torch.autograd.Function):
+    """Per-stage depthwise 3x3 + SiLU on the stage-concatenated sequence x (B, L, C), L = sum H_s W_s, each stage with its
+    own Conv2d parameters (reference MambaSkip.py:521-523: split, permute, conv2d[i], act[i], flatten, cat): the stage
+    segments are read and written in place through the image stride L*C -- no split / contiguous / cat copies, and the
+    backward writes one dx instead of autograd's zero-fill + copy + add per stage."""
+
+    @staticmethod
+    def forward(ctx, x, hw, silu, *params):
+        if not x.is_cuda:
+            raise _lib.MlaggError("dwconv3x3_stages: CUDA tensor required (no CPU fallback in the product path)")
+        Bn, L, C = x.shape
+        ns = len(hw)
+        ws, bs_ = params[:ns], params[ns:]
+        xin = _io(x).contiguous()
+        y = torch.empty_like(xin)
+        w32 = [w.detach().float().contiguous() for w in ws]
+        b32 = [None if b is None else b.detach().float().contiguous() for b in bs_]
+        es, off = xin.element_size(), 0
+        with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd", ns):
+            for s, (h, w) in enumerate(hw):
+                rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(xin.data_ptr() + off * C * es, _lib.ptr(w32[s]),
+                                                            _lib.ptr(b32[s]), None, y.data_ptr() + off * C * es, Bn, h, w,
+                                                            C, C, L * C, C, L * C, C, L * C, int(silu), _DT[xin.dtype],
+                                                            _lib.stream_ptr())
+                _lib.check(rc, "mlagg_dwconv3x3_fwd_strided")
+                off += h * w
+        assert off == L
+        ctx.save_for_backward(xin, *w32, *[b for b in b32 if b is not None])
+        ctx.meta = (tuple(hw), bool(silu), x.dtype, [w.dtype for w in ws], [None if b is None else b.dtype for b in bs_])
+        return y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        hw, silu, xdt, wdts, bdts = ctx.meta
+        ns = len(hw)
+        saved = ctx.saved_tensors
+        xin, w32 = saved[0], saved[1:1 + ns]
+        it = iter(saved[1 + ns:])
+        b32 = [None if d is None else next(it) for d in bdts]
+        Bn, L, C = xin.shape
+        dy = dy.to(xin.dtype).contiguous()
+        dx = torch.empty_like(xin)
+        es, off = xin.element_size(), 0
+        dws, dbs = [], []
+        with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2 * ns):
+            for s, (h, w) in enumerate(hw):
+                dz = torch.empty(Bn, h * w, C, device=xin.device, dtype=xin.dtype)
+                dw = _lib.zeros((C, 9), xin.device)
+                db = _lib.zeros(C, xin.device) if b32[s] is not None else None
+                o = off * C * es
+                rc = _lib.lib().mlagg_dwconv3x3_bwd_strided(xin.data_ptr() + o, _lib.ptr(w32[s]), _lib.ptr(b32[s]),
+                                                            dy.data_ptr() + o, _lib.ptr(dz), dx.data_ptr() + o,
+                                                            _lib.ptr(dw), _lib.ptr(db), Bn, h, w, C, C, L * C, C, L * C, C,
+                                                            L * C, int(silu), _DT[xin.dtype], _lib.stream_ptr())
+                _lib.check(rc, "mlagg_dwconv3x3_bwd_strided")
+                dws.append(dw.view(C, 1, 3, 3).to(wdts[s]))
+                dbs.append(None if db is None else db.to(bdts[s]))
+                off += h * w
+        return (dx.to(xdt), None, None, *dws, *dbs)
+
+
+def dwconv3x3_stages(x, hw, convs, silu=True):
+    """x (B, sum H_s W_s, C); convs[s] = nn.Conv2d(C, C, 3, padding=1, groups=C) of stage s."""
+    hw = tuple((int(h), int(w)) for h, w in hw)
+    return _DWConv3x3Stages.apply(x, hw, silu, *[c.weight for c in convs], *[c.bias for c in convs])
 
 
 class _CausalConv1d(torch.autograd.Function):
@@ -372,3 +472,87 @@ class _AvgPoolTokens(torch.autograd.Function):
 def avgpool_tokens(x, H, W, pH, pW, gelu=False):
     """x (B, H*W, C) -> adaptive average pool to (B, pH*pW, C) of gelu(x) (gelu=True) or x, torch bin semantics."""
     return _AvgPoolTokens.apply(x, H, W, pH, pW, gelu)
+
+
+def _ew_ok(*ts):
+    """operands the element-wise kernels take directly: CUDA, same fp32 / bf16 dtype and shape, contiguous, numel % 4 == 0"""
+    t0 = ts[0]
+    return (t0.is_cuda and t0.dtype in _DT and t0.numel() % 4 == 0 and t0.numel() > 0
+            and all(t.dtype == t0.dtype and t.shape == t0.shape and t.is_contiguous() for t in ts))
+
+
+class _ResidualScale(torch.autograd.Function):
+    """C ABI: mlagg_residual_scale.  out = x + scale[b] * y."""
+
+    @staticmethod
+    def forward(ctx, x, y, scale):
+        out = torch.empty_like(x)
+        n = x.numel()
+        with torch.cuda.device(x.device), _lib.timed("residual_scale"):
+            rc = _lib.lib().mlagg_residual_scale(_lib.ptr(x), _lib.ptr(y), _lib.ptr(scale), _lib.ptr(out), n,
+                                                 n // x.shape[0], _DT[x.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_residual_scale")
+        ctx.save_for_backward(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (scale,) = ctx.saved_tensors
+        if not _ew_ok(g):
+            g = g.contiguous()
+        n = g.numel()
+        dy = torch.empty_like(g)
+        with torch.cuda.device(g.device), _lib.timed("residual_scale"):
+            rc = _lib.lib().mlagg_residual_scale(None, _lib.ptr(g), _lib.ptr(scale), _lib.ptr(dy), n, n // g.shape[0],
+                                                 _DT[g.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_residual_scale")
+        return g, dy, None
+
+
+def residual_drop_path(x, y, drop_path):
+    """`x + drop_path(y)` (reference nnUNetTrainer_MLAgg_2D_dt_MS.py:907-908, MambaSkip.py:733,745): a plain add when the
+    module is the identity, else ONE pass with the per-sample keep mask / keep as a (B) fp32 vector."""
+    p = float(getattr(drop_path, "drop_prob", 0.0) or 0.0)
+    if p == 0.0 or not drop_path.training:
+        return x + drop_path(y)
+    if not (_ew_ok(x, y) and (x.numel() // x.shape[0]) % 4 == 0):
+        return x + drop_path(y)
+    keep = 1.0 - p
+    scale = torch.empty(x.shape[0], device=x.device, dtype=torch.float32).bernoulli_(keep)
+    if keep > 0.0 and getattr(drop_path, "scale_by_keep", True):
+        scale.div_(keep)
+    return _ResidualScale.apply(x, y, scale)
+
+
+class _SiluGate(torch.autograd.Function):
+    """C ABI: mlagg_silu_gate_fwd / _bwd.  out = t * silu(z)."""
+
+    @staticmethod
+    def forward(ctx, t, z):
+        out = torch.empty_like(t)
+        with torch.cuda.device(t.device), _lib.timed("silu_gate_fwd"):
+            rc = _lib.lib().mlagg_silu_gate_fwd(_lib.ptr(t), _lib.ptr(z), _lib.ptr(out), t.numel(), _DT[t.dtype],
+                                                _lib.stream_ptr())
+        _lib.check(rc, "mlagg_silu_gate_fwd")
+        ctx.save_for_backward(t, z)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        t, z = ctx.saved_tensors
+        g = g.to(t.dtype).contiguous()
+        dt, dz = torch.empty_like(t), torch.empty_like(z)
+        with torch.cuda.device(t.device), _lib.timed("silu_gate_bwd"):
+            rc = _lib.lib().mlagg_silu_gate_bwd(_lib.ptr(t), _lib.ptr(z), _lib.ptr(g), _lib.ptr(dt), _lib.ptr(dz),
+                                                t.numel(), _DT[t.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_silu_gate_bwd")
+        return dt, dz
+
+
+def silu_gate(t, z):
+    """t * silu(z) in one pass (the block's output gate, reference :881 / :907)."""
+    if z.dtype != t.dtype:
+        z = z.to(t.dtype)
+    if not _ew_ok(t, z):
+        return t * torch.nn.functional.silu(z)
+    return _SiluGate.apply(t, z)

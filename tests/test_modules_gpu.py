@@ -491,3 +491,103 @@ def test_pooled_attention_tensor_core_forward_matches_fp32_path():
         for a, b in zip(outs[torch.float32], outs[torch.bfloat16]):
             assert torch.isfinite(b).all()
             assert rel_err(b.cpu(), a.cpu()) < TOL16, (N, P)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_elementwise_seams_match_torch(dtype):
+    """mlagg_residual_scale / mlagg_silu_gate_* / mlagg_diff_lambda_* against the torch expressions of the reference
+    (nnUNetTrainer_MLAgg_2D_dt_MS.py:881, :907-908, :700-702), forward and backward."""
+    from mlagg_unet_b200.attention import LAMBDA_INIT, diff_lambda
+    from mlagg_unet_b200.ops import _ResidualScale, silu_gate
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    torch.manual_seed(3)
+    x, y, g = (torch.randn(3, 50, 24, device="cuda").to(dtype) for _ in range(3))
+    scale = torch.tensor([0.0, 1.25, 1.25], device="cuda")
+    xa, ya = x.clone().requires_grad_(), y.clone().requires_grad_()
+    out = _ResidualScale.apply(xa, ya, scale)
+    out.backward(g)
+    ref = x.double() + scale.double().view(3, 1, 1) * y.double()
+    assert rel_err(out.double(), ref) < tol
+    assert torch.equal(xa.grad, g)
+    assert rel_err(ya.grad.double(), scale.double().view(3, 1, 1) * g.double()) < tol
+    # gate
+    ta, za = x.clone().requires_grad_(), (2 * y).clone().requires_grad_()
+    o = silu_gate(ta, za)
+    o.backward(g)
+    td, zd = x.double().requires_grad_(), (2 * y).double().requires_grad_()
+    od = td * torch.nn.functional.silu(zd)
+    od.backward(g.double())
+    assert rel_err(o.double(), od) < tol
+    assert rel_err(ta.grad.double(), td.grad) < tol and rel_err(za.grad.double(), zd.grad) < tol
+    # lambda (always fp32 parameters)
+    if dtype == torch.float32:
+        ps = [(0.3 * torch.randn(24, device="cuda")).requires_grad_() for _ in range(4)]
+        lam = diff_lambda(*ps)
+        (3.0 * lam).backward()
+        pd = [p.detach().double().requires_grad_() for p in ps]
+        lamd = torch.exp(torch.sum(pd[0] * pd[1])) - torch.exp(torch.sum(pd[2] * pd[3])) + LAMBDA_INIT
+        (3.0 * lamd).backward()
+        assert lam.shape == () and abs(float(lam) - float(lamd)) < 1e-5 * abs(float(lamd))
+        for p, q in zip(ps, pd):
+            assert rel_err(p.grad.double(), q.grad) < TOL32
+
+
+def _dwconv_ref(x, w, b, H, W, silu):
+    """fp64 torch restatement on the NCHW view: x (B, H*W, C) -> (B, H*W, C)"""
+    Bn, N, C = x.shape
+    y = torch.nn.functional.conv2d(x.transpose(1, 2).reshape(Bn, C, H, W), w, b, padding=1, groups=C)
+    if silu:
+        y = torch.nn.functional.silu(y)
+    return y.flatten(2).transpose(1, 2)
+
+
+@pytest.mark.parametrize("C", [8, 6])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dwconv_strided_operands_and_residual(C, dtype):
+    """mlagg_dwconv3x3_*_strided: the input and the residual are channel slices of wider activations (LePE on the v half
+    of kv, reference :680/:782 + the add of :716), forward and all gradients against fp64 torch; C = 6 takes the scalar
+    kernels."""
+    from mlagg_unet_b200.ops import dwconv3x3_tokens
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    torch.manual_seed(7)
+    Bn, H, W = 2, 7, 5
+    wide = torch.randn(Bn, H * W, 2 * C, device="cuda").to(dtype).requires_grad_()
+    rwide = torch.randn(Bn, H * W, 2 * C, device="cuda").to(dtype).requires_grad_()
+    w = (0.3 * torch.randn(C, 1, 3, 3, device="cuda")).requires_grad_()
+    b = (0.1 * torch.randn(C, device="cuda")).requires_grad_()
+    y = dwconv3x3_tokens(wide[..., C:], w, b, H, W, silu=True, residual=rwide[..., :C])
+    g = torch.randn_like(y)
+    y.backward(g)
+    wd, rd, ww, bb = (t.detach().double().requires_grad_() for t in (wide, rwide, w, b))
+    yd = _dwconv_ref(wd[..., C:], ww, bb, H, W, True) + rd[..., :C]
+    yd.backward(g.double())
+    assert rel_err(y.double(), yd) < tol
+    for got, want in ((wide.grad, wd.grad), (rwide.grad, rd.grad), (w.grad, ww.grad), (b.grad, bb.grad)):
+        assert rel_err(got.double(), want) < tol
+
+
+@pytest.mark.parametrize("C", [8, 6])
+def test_dwconv_stages_in_place_segments(C):
+    """dwconv3x3_stages (MambaSkip.py:521-523) against per-stage fp64 torch convolutions: outputs, dx and every stage's
+    parameter gradients."""
+    from mlagg_unet_b200.ops import dwconv3x3_stages
+    torch.manual_seed(9)
+    hw = [(6, 5), (3, 4), (1, 2)]
+    L = sum(h * w for h, w in hw)
+    convs = [torch.nn.Conv2d(C, C, 3, padding=1, groups=C).cuda() for _ in hw]
+    x = torch.randn(3, L, C, device="cuda", requires_grad=True)
+    y = dwconv3x3_stages(x, hw, convs, silu=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xd = x.detach().double().requires_grad_()
+    parts, off, pd = [], 0, []
+    for (h, w), cv in zip(hw, convs):
+        ww, bb = cv.weight.detach().double().requires_grad_(), cv.bias.detach().double().requires_grad_()
+        pd.append((ww, bb))
+        parts.append(_dwconv_ref(xd[:, off:off + h * w], ww, bb, h, w, True))
+        off += h * w
+    yd = torch.cat(parts, 1)
+    yd.backward(g.double())
+    assert rel_err(y.double(), yd) < TOL32 and rel_err(x.grad.double(), xd.grad) < TOL32
+    for cv, (ww, bb) in zip(convs, pd):
+        assert rel_err(cv.weight.grad.double(), ww.grad) < TOL32 and rel_err(cv.bias.grad.double(), bb.grad) < TOL32
