@@ -314,6 +314,11 @@ int mlagg_avgpool_tokens_bwd(const void *x, const void *dy, void *dx, int batch,
  * ------------------------------------------------------------------------------------------ */
 int mlagg_residual_scale(const void *x, const void *y, const float *scale, void *out, long long n, long long per_sample,
                          int dtype, mlagg_stream_t stream);
+/* y[pix][c] += bias[c] IN PLACE on a channels_last / tokens-major (pixels, C) map of n elements, C % 4 == 0 -- the bias of
+ * the conv stages' nn.Conv2d / nn.ConvTranspose2d (nnUNetTrainer_MLAgg_2D_dt_MS.py:230-366, MambaSkip.py:712-716), which torch
+ * adds after the cuDNN call with an un-vectorised broadcast kernel and differentiates with its generic reduction; the
+ * gradient here is mlagg_colsum. */
+int mlagg_bias_add_cl(void *y, const float *bias, long long n, int C, int dtype, mlagg_stream_t stream);
 int mlagg_silu_gate_fwd(const void *t, const void *z, void *out, long long n, int dtype, mlagg_stream_t stream);
 int mlagg_silu_gate_bwd(const void *t, const void *z, const void *dout, void *dt, void *dz, long long n, int dtype,
                         mlagg_stream_t stream);

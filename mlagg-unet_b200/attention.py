@@ -62,6 +62,14 @@ def diff_lambda(lq1, lk1, lq2, lk2):
     return torch.exp(torch.sum(lq1 * lk1).float()) - torch.exp(torch.sum(lq2 * lk2).float()) + LAMBDA_INIT
 
 
+def _rows(t):
+    """tokens-major (B, N, C) view usable by the C ABI: unit channel stride, one uniform row stride over B*N."""
+    if t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1) or (t.stride(1) * t.element_size()) % 16 \
+            or t.data_ptr() % 16:
+        t = t.contiguous()
+    return t
+
+
 class _LocalDiffAttn(torch.autograd.Function):
     """C ABI: mlagg_local_diffattn_fwd / _bwd (csrc/local_attn.cu)."""
 
@@ -91,7 +99,7 @@ class _LocalDiffAttn(torch.autograd.Function):
         H, W, h, hd, scale, qdt, kvdt, lamdt, wdt = ctx.meta
         Bn, N, C = q_.shape
         dt, es = q_.dtype, q_.element_size()
-        dout = dout.to(dt).contiguous()
+        dout = _rows(dout.to(dt))          # a half of the concatenated block gradient is read in place (lddo)
         dq, dkv = torch.empty_like(q_), torch.empty_like(kv_)
         dw = _lib.zeros(w_.shape, q_.device)
         dlam = _lib.zeros(1, q_.device)
@@ -100,8 +108,8 @@ class _LocalDiffAttn(torch.autograd.Function):
         with torch.cuda.device(q_.device), _lib.timed("local_diffattn_bwd", 2):
             rc = L.mlagg_local_diffattn_bwd(q_.data_ptr(), kv_.data_ptr(), kv_.data_ptr() + C * es, w_.data_ptr(),
                                             dout.data_ptr(), dq.data_ptr(), dkv.data_ptr(), dkv.data_ptr() + C * es,
-                                            dw.data_ptr(), dlam.data_ptr(), ws.data_ptr(), Bn, H, W, h, hd, C, 2 * C, C, C,
-                                            2 * C, scale, lam_.data_ptr(), 1e-5, 1.0 - LAMBDA_INIT, _DT[dt],
+                                            dw.data_ptr(), dlam.data_ptr(), ws.data_ptr(), Bn, H, W, h, hd, C, 2 * C,
+                                            dout.stride(1), C, 2 * C, scale, lam_.data_ptr(), 1e-5, 1.0 - LAMBDA_INIT, _DT[dt],
                                             _lib.stream_ptr())
         _lib.check(rc, "mlagg_local_diffattn_bwd")
         return dq.to(qdt), dkv.to(kvdt), dlam.reshape(()).to(lamdt), dw.to(wdt), None, None, None, None, None
@@ -146,7 +154,7 @@ class _PooledDiffAttn(torch.autograd.Function):
         Bn, N, C = q_.shape
         P = kv_.shape[1]
         dt, es = q_.dtype, q_.element_size()
-        dout = dout.to(dt).contiguous()
+        dout = _rows(dout.to(dt))
         dq = torch.empty_like(q_)
         dkv = torch.zeros(Bn, P, 2 * C, device=q_.device, dtype=torch.float32)
         dw = _lib.zeros(w_.shape, q_.device)
@@ -157,7 +165,7 @@ class _PooledDiffAttn(torch.autograd.Function):
             rc = L.mlagg_pooled_diffattn_bwd(q_.data_ptr(), kv_.data_ptr(), kv_.data_ptr() + C * es, w_.data_ptr(),
                                              lse.data_ptr(), dout.data_ptr(), dq.data_ptr(), dkv.data_ptr(),
                                              dkv.data_ptr() + C * 4, dw.data_ptr(), dlam.data_ptr(), ws.data_ptr(), Bn, N,
-                                             P, h, hd, C, 2 * C, C, C, 2 * C, scale, lam_.data_ptr(), 1e-5,
+                                             P, h, hd, C, 2 * C, dout.stride(1), C, 2 * C, scale, lam_.data_ptr(), 1e-5,
                                              1.0 - LAMBDA_INIT, _DT[dt], _lib.stream_ptr())
         _lib.check(rc, "mlagg_pooled_diffattn_bwd")
         return dq.to(qdt), dkv.to(kvdt), dlam.reshape(()).to(lamdt), dw.to(wdt), None, None, None
@@ -209,14 +217,6 @@ def rope_table_separable(H, W, C, device, base=10000.0):
         ang = torch.cat([torch.arange(H).unsqueeze(-1) * theta, torch.arange(W).unsqueeze(-1) * theta], dim=0)
         _ROPE_SEP[key] = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).float().contiguous().to(device)
     return _ROPE_SEP[key]
-
-
-def _rows(t):
-    """tokens-major (B, N, C) view usable by the C ABI: unit channel stride, one uniform row stride over B*N."""
-    if t.stride(2) != 1 or t.stride(0) != t.shape[1] * t.stride(1) or (t.stride(1) * t.element_size()) % 16 \
-            or t.data_ptr() % 16:
-        t = t.contiguous()
-    return t
 
 
 class _LinAttn(torch.autograd.Function):

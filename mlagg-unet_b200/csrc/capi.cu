@@ -12,6 +12,7 @@ cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStr
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
 cudaError_t residual_scale_dispatch(const void *x, const void *y, const float *s, void *out, long long n,
                                     long long per_sample, int dtype, cudaStream_t st);
+cudaError_t bias_add_cl_dispatch(void *y, const float *b, long long n, int C, int dtype, cudaStream_t st);
 cudaError_t silu_gate_dispatch(const void *t, const void *z, const void *g, void *o1, void *o2, long long n, int dtype,
                                bool bwd, cudaStream_t st);
 cudaError_t diff_lambda_dispatch(const float *q1, const float *k1, const float *q2, const float *k2, int n, float init,
@@ -488,6 +489,16 @@ extern "C" int mlagg_residual_scale(const void *x, const void *y, const float *s
     if (rc) return rc;
     if (per_sample <= 0 || per_sample % 4 != 0 || n % per_sample != 0) return MLAGG_ERR_BAD_SHAPE;
     cudaError_t e = residual_scale_dispatch(x, y, scale, out, n, per_sample, dtype, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_bias_add_cl(void *y, const float *bias, long long n, int C, int dtype, mlagg_stream_t stream) {
+    int rc = ew_check(y, y, y, n, dtype);
+    if (rc) return rc;
+    if (!bias) return MLAGG_ERR_NULL;
+    if (C <= 0 || C % 4 != 0 || n % C != 0) return MLAGG_ERR_BAD_SHAPE;
+    if (!aligned(bias, 16)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = bias_add_cl_dispatch(y, bias, n, C, dtype, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

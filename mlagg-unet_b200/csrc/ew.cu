@@ -119,6 +119,25 @@ __global__ void __launch_bounds__(32) diff_lambda_bwd_kernel(const float *__rest
     }
 }
 
+__device__ __forceinline__ float4 ew_ld4_rw(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 ew_ld4_rw(const __nv_bfloat16 *p) {
+    const uint2 t = *reinterpret_cast<const uint2 *>(p);
+    return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
+                       __uint_as_float(t.y & 0xffff0000u));
+}
+
+// y[pix][c] += b[c] in place on a channels_last / tokens-major map (C % 4 == 0)
+template <typename T>
+__global__ void __launch_bounds__(256) bias_add_cl_kernel(T *__restrict__ y, const float *__restrict__ b, long long n4,
+                                                          int C4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 bv = __ldg(reinterpret_cast<const float4 *>(b) + (i % C4));
+        float4 a = ew_ld4_rw(y + 4 * i);      // plain (coherent) load: the same address is written below
+        a.x += bv.x, a.y += bv.y, a.z += bv.z, a.w += bv.w;
+        ew_st4<T>(y + 4 * i, a);
+    }
+}
+
 static int ew_blocks(long long n4) {
     long long b = (n4 + 255) / 256;
     const long long cap = 148LL * 16;
@@ -132,6 +151,13 @@ cudaError_t residual_scale_dispatch(const void *x, const void *y, const float *s
         residual_scale_kernel<float><<<ew_blocks(n4), 256, 0, st>>>(static_cast<const float *>(x), static_cast<const float *>(y), s, static_cast<float *>(out), n4, per4);
     else
         residual_scale_kernel<__nv_bfloat16><<<ew_blocks(n4), 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(x), static_cast<const __nv_bfloat16 *>(y), s, static_cast<__nv_bfloat16 *>(out), n4, per4);
+    return cudaGetLastError();
+}
+
+cudaError_t bias_add_cl_dispatch(void *y, const float *b, long long n, int C, int dtype, cudaStream_t st) {
+    const long long n4 = n / 4;
+    if (dtype == 0) bias_add_cl_kernel<float><<<ew_blocks(n4), 256, 0, st>>>(static_cast<float *>(y), b, n4, C / 4);
+    else bias_add_cl_kernel<__nv_bfloat16><<<ew_blocks(n4), 256, 0, st>>>(static_cast<__nv_bfloat16 *>(y), b, n4, C / 4);
     return cudaGetLastError();
 }
 

@@ -16,9 +16,12 @@
 namespace mlagg {
 
 constexpr int kWalkMaxStages = 8;
-// tile = TC channels x TP positions, TC * TP = 2048: (32, 64) for narrow operands, (128, 16) when a token row is wider than
-// 32 channels -- a warp then moves one whole token row (up to 512 B), which matters for the column walk where consecutive
-// positions are W tokens apart (64-byte pieces per token measured 4x slower than the row walk).
+// tile = TC channels x TP positions, TC * TP = 2048.  Shipped: (32, 64).  Measured at the config-3 shape (B = 10,
+// L = 34 000, 96 channels, bf16 tokens -> fp32 planes), row / column walk: pack 39 / 150 us, unpack (two planes summed)
+// 86 / 176 us.  The column walk is slower because consecutive positions are W tokens apart (every 64-byte token piece sits
+// in a different DRAM page).  The (128, 16) shape -- a warp moves one whole token row -- was tried to fix that and is
+// slower on BOTH walks (54 / 202 and 122 / 249 us): the fp32 plane side carries twice the bytes of the bf16 token side and
+// its rows shrink to 64-byte segments.  The templates keep the TC parameter; the dispatchers use 32.
 
 // shared-memory row of tile channel cl: identity for TC = 32 (conflict-free with 8 threads per position); for TC = 128 a
 // warp writes the 4 x 32 channels of one position, so channel 4 cg + j goes to row 32 j + cg (odd row stride 17)
@@ -229,7 +232,7 @@ cudaError_t walk_pack_dispatch(const void *src, int dtype, long long ld_src, lon
     WalkGeom g;
     long long L;
     if (!walk_geom(g, nstages, Hs, Ws, &L)) return cudaErrorInvalidValue;
-    const int TC = nc > 32 ? 128 : 32, TP = 2048 / TC;
+    const int TC = 32, TP = 2048 / TC;
     const dim3 grid((unsigned)((L + TP - 1) / TP), (unsigned)((nc + TC - 1) / TC), (unsigned)batch);
     const size_t es = dtype == 0 ? 4 : 2;
     const bool vec = (c0 % 4 == 0) && (ld_src % 4 == 0) && (bs_src % 4 == 0) &&
@@ -256,7 +259,7 @@ cudaError_t walk_unpack_dispatch(const float *src0, const float *src1, long long
     WalkGeom g;
     long long L;
     if (!walk_geom(g, nstages, Hs, Ws, &L)) return cudaErrorInvalidValue;
-    const int TC = nc_pad > 32 ? 128 : 32, TP = 2048 / TC;
+    const int TC = 32, TP = 2048 / TC;
     const dim3 grid((unsigned)((L + TP - 1) / TP), (unsigned)((nc_pad + TC - 1) / TC), (unsigned)batch);
     const size_t es = dtype == 0 ? 4 : 2;
     const bool vec = (c0 % 4 == 0) && (ld_dst % 4 == 0) && (bs_dst % 4 == 0) &&

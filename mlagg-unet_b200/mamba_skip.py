@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import _Linear, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
+from .ops import Conv2dCL, _Linear, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
 from .selective_scan_interface import msmm_scan, msmm_scan_tokens, selective_scan_fn, xdbl_pad
 from .thirdparty_shims import DropPath, _inst_norm
 
@@ -242,6 +242,21 @@ class ConvolutionalGLU(nn.Module):
         return self.drop(linear_tokens(self.drop(a * v), self.fc2))
 
 
+class _SplitLast(torch.autograd.Function):
+    """x[..., :k], x[..., k:] as views; the backward is ONE concatenation.  Autograd's own slice gradients are two zero-filled
+    full-size tensors (contiguous in the logical NCHW order, which then drags every accumulation into the stage output's
+    channels_last gradient onto strided kernels) plus two copies and an add."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        ctx.k = k
+        return x[..., :k], x[..., k:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        return torch.cat([ga, gb], dim=-1), None
+
+
 class VSS_Conv_Block(nn.Module):
     def __init__(self, feature_dims, hidden_dim: int = 0, drop_path: float = 0,
                  norm_layer: Callable[..., nn.Module] = partial(nn.LayerNorm, eps=1e-6), attn_drop_rate: float = 0,
@@ -257,7 +272,7 @@ class VSS_Conv_Block(nn.Module):
                                                     act_layer=nn.SiLU) for _ in feature_dims])
         self.conv_dims = [d - hidden_dim for d in feature_dims]
         self.conv_branches = nn.ModuleList([
-            nn.Sequential(nn.Conv2d(cd, cd, kernel_size=3, stride=1, padding=1), nn.InstanceNorm2d(cd, affine=True),
+            nn.Sequential(Conv2dCL(cd, cd, kernel_size=3, stride=1, padding=1), nn.InstanceNorm2d(cd, affine=True),
                           nn.SiLU()) for cd in self.conv_dims])
 
     def forward(self, inputs):
@@ -267,17 +282,21 @@ class VSS_Conv_Block(nn.Module):
         W = [t.shape[3] for t in inputs]
         L_split = [h * w for h, w in zip(H, W)]
         hd = self.hidden_dim
-        # tokens-major (B, L, hd): NHWC views of the inputs (free when they are channels_last), first hd channels
-        m = torch.cat([t.permute(0, 2, 3, 1)[..., :hd].reshape(Bn, L_split[s], hd) for s, t in enumerate(inputs)], dim=1)
+        # NHWC views of the inputs (free when they are channels_last), split into the first hd channels -> tokens-major
+        # (B, L, hd) for the scan branch, and the rest -> conv branch
+        halves = [_SplitLast.apply(t.permute(0, 2, 3, 1), hd) for t in inputs]
+        m = torch.cat([a.reshape(Bn, L_split[s], hd) for s, (a, _) in enumerate(halves)], dim=1)
         m = residual_drop_path(m, self.self_attention(layer_norm_tokens(m, self.ln_1), Bn, H, W, L_split), self.drop_path)
         m = layer_norm_tokens(m, self.norm2)
         outs, off = [], 0
         for s, t in enumerate(inputs):
-            ms = m[:, off:off + L_split[s]]
+            # one packed copy per stage: with a uniform row stride the fc1 GEMM keeps its bias epilogue, the residual is
+            # the one-pass kernel, and the Linear backward needs no re-pack of its saved input
+            ms = m[:, off:off + L_split[s]].contiguous()
             off += L_split[s]
-            ms = ms + self.drop_path(self.mlps[s](ms, H[s], W[s]))
+            ms = residual_drop_path(ms, self.mlps[s](ms, H[s], W[s]), self.drop_path)
             br = self.conv_branches[s]                                                 # Conv2d, InstanceNorm2d, SiLU
-            cb = _inst_norm(br[1], br[0](t[:, hd:]), "silu").permute(0, 2, 3, 1)       # NHWC view
+            cb = _inst_norm(br[1], br[0](halves[s][1].permute(0, 3, 1, 2)), "silu").permute(0, 2, 3, 1)   # NHWC view
             outs.append(torch.cat([ms.reshape(Bn, H[s], W[s], hd), cb], dim=-1).permute(0, 3, 1, 2))  # channels_last
         return outs
 

@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import (GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path,
+from .ops import (Conv2dCL, ConvTranspose2dCL, GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path,
                   silu_gate)
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
@@ -255,8 +255,8 @@ class project(nn.Module):
     def __init__(self, in_dim, out_dim, stride, padding, activate, norm, last=False):
         super().__init__()
         self.out_dim, self.last = out_dim, last
-        self.conv1 = nn.Conv2d(in_dim, out_dim, kernel_size=3, stride=stride, padding=padding)
-        self.conv2 = nn.Conv2d(out_dim, out_dim, kernel_size=3, stride=1, padding=1)
+        self.conv1 = Conv2dCL(in_dim, out_dim, kernel_size=3, stride=stride, padding=padding)
+        self.conv2 = Conv2dCL(out_dim, out_dim, kernel_size=3, stride=1, padding=1)
         self.activate = activate()
         self.norm1 = norm(out_dim)
         if not last:
@@ -313,7 +313,7 @@ class MedNeXtBlock(nn.Module):
         super().__init__()
         assert dim == "2d" and norm_type == "group" and not grn, "MLAgg-UNet builds the 2-D GroupNorm variant"
         self.do_res, self.dim, self.grn = do_res, dim, grn
-        self.conv1 = nn.Conv2d(in_channels, in_channels, kernel_size, stride=1, padding=kernel_size // 2,
+        self.conv1 = Conv2dCL(in_channels, in_channels, kernel_size, stride=1, padding=kernel_size // 2,
                                groups=in_channels if n_groups is None else n_groups)
         self.norm = nn.GroupNorm(num_groups=in_channels, num_channels=in_channels)
         self.conv2 = nn.Conv2d(in_channels, exp_r * in_channels, kernel_size=1)
@@ -332,8 +332,8 @@ class MedNeXtDownBlock(MedNeXtBlock):
                          grn=grn)
         self.resample_do_res = do_res
         if do_res:
-            self.res_conv = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=2)
-        self.conv1 = nn.Conv2d(in_channels, in_channels, kernel_size, stride=2, padding=kernel_size // 2,
+            self.res_conv = Conv2dCL(in_channels, out_channels, kernel_size=1, stride=2)
+        self.conv1 = Conv2dCL(in_channels, in_channels, kernel_size, stride=2, padding=kernel_size // 2,
                                groups=in_channels)
 
     def forward(self, x, dummy_tensor=None):
@@ -348,8 +348,8 @@ class PatchExpand(nn.Module):
         assert dim == "2d" and norm_type == "group"
         self.resample_do_res, self.dim = do_res, dim
         if do_res:
-            self.res_conv = nn.ConvTranspose2d(in_channels, out_channels, kernel_size=1, stride=2)
-        self.conv1 = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=2, padding=kernel_size // 2)
+            self.res_conv = ConvTranspose2dCL(in_channels, out_channels, kernel_size=1, stride=2)
+        self.conv1 = ConvTranspose2dCL(in_channels, out_channels, kernel_size, stride=2, padding=kernel_size // 2)
         self.norm = nn.GroupNorm(num_groups=in_channels, num_channels=in_channels)
 
     def forward(self, x, dummy_tensor=None):

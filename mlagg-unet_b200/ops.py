@@ -556,3 +556,55 @@ def silu_gate(t, z):
     if not _ew_ok(t, z):
         return t * torch.nn.functional.silu(z)
     return _SiluGate.apply(t, z)
+
+
+class _BiasAddCL(torch.autograd.Function):
+    """C ABI: mlagg_bias_add_cl (in place on the fresh conv output) / mlagg_colsum for the gradient."""
+
+    @staticmethod
+    def forward(ctx, y, bias):
+        C = y.shape[1]
+        b32 = bias.detach().float().contiguous()
+        with torch.cuda.device(y.device), _lib.timed("bias_add_cl"):
+            rc = _lib.lib().mlagg_bias_add_cl(_lib.ptr(y), _lib.ptr(b32), y.numel(), C, _DT[y.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_bias_add_cl")
+        ctx.mark_dirty(y)
+        ctx.bdt = bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        C = g.shape[1]
+        gt = g.permute(0, 2, 3, 1)
+        if gt.is_contiguous() and g.dtype in _DT:
+            db = colsum(gt.reshape(-1, C))
+        else:
+            db = g.float().sum((0, 2, 3))
+        return g, db.to(ctx.bdt)
+
+
+def _conv_bias_cl(y, bias):
+    """y (B, C, H, W) = bias-free conv output; adds `bias` per channel.  Channels_last fp32 / bf16 CUDA maps with C % 4 == 0
+    take the one-pass kernel (and the column-sum bias gradient); anything else the plain broadcast add."""
+    if (bias is not None and y.is_cuda and y.dim() == 4 and y.dtype in _DT and y.shape[1] % 4 == 0 and y.numel() > 0
+            and y.permute(0, 2, 3, 1).is_contiguous() and y._base is None):
+        return _BiasAddCL.apply(y, bias)
+    return y if bias is None else y + bias.to(y.dtype).view(1, -1, 1, 1)
+
+
+class Conv2dCL(torch.nn.Conv2d):
+    """nn.Conv2d (same parameters / state_dict) whose bias is applied by `_conv_bias_cl` after a bias-free cuDNN call."""
+
+    def forward(self, x):
+        if self.bias is None or not x.is_cuda:
+            return super().forward(x)
+        return _conv_bias_cl(self._conv_forward(x, self.weight, None), self.bias)
+
+
+class ConvTranspose2dCL(torch.nn.ConvTranspose2d):
+    def forward(self, x, output_size=None):
+        if self.bias is None or not x.is_cuda or output_size is not None:
+            return super().forward(x, output_size)
+        y = torch.nn.functional.conv_transpose2d(x, self.weight, None, self.stride, self.padding, self.output_padding,
+                                                 self.groups, self.dilation)
+        return _conv_bias_cl(y, self.bias)

@@ -162,3 +162,32 @@ def test_sliding_window_steps_and_gaussian_follow_the_reference():
     g = inf.compute_gaussian((32, 48))
     assert g.shape == (32, 48) and g.max() == 1.0 and g[16, 24] == 1.0 and g.min() > 0
     assert inf._mirror_sets(None) == [()] and inf._mirror_sets((0, 1)) == [(), (2,), (3,), (2, 3)]
+
+
+def test_rows2d_views_and_padded_xproj_layout():
+    """Host logic of the strided-GEMM path and of the tokens-major x_proj layout (no kernels involved)."""
+    from mlagg_unet_b200.ops import _rows2d
+    from mlagg_unet_b200.selective_scan_interface import xdbl_pad
+    t = torch.arange(3 * 10 * 16, dtype=torch.float32).reshape(3, 10, 16)
+    a, b = t.chunk(2, dim=-1)
+    v = _rows2d(b)
+    assert v.shape == (30, 8) and v.stride() == (16, 1) and v.data_ptr() == b.data_ptr()
+    assert torch.equal(v, b.reshape(30, 8))
+    assert _rows2d(t).shape == (30, 16) and _rows2d(t[:, :5]) is None          # batch stride does not collapse
+    assert _rows2d(t.transpose(1, 2)) is None and _rows2d(t[0]).shape == (10, 16)
+    assert xdbl_pad(35) == 72 and xdbl_pad(34) == 68 and xdbl_pad(33) == 68     # 2 directions x (R + 2N), 4-aligned
+
+
+def test_walk_token_formula_is_the_cross_scan_map():
+    """csrc/walk.cu visits token soff + (q % H) * W + q / H at column-walk position soff + q; that is direction 1 of the
+    cross-scan index maps (reference MambaSkip.py:414-422), which the golden fixtures already pin."""
+    from mlagg_unet_b200.mamba_skip import _scan_maps_cpu
+    hw = ((5, 3), (2, 4), (1, 1), (3, 2))
+    idx, inv = _scan_maps_cpu(hw)
+    toks, off = [], 0
+    for H, W in hw:
+        toks += [off + (q % H) * W + q // H for q in range(H * W)]
+        off += H * W
+    assert idx[1].tolist() == toks and idx[0].tolist() == list(range(off))
+    assert idx[3].tolist() != toks and sorted(toks) == list(range(off))
+    assert all(inv[1][t] == p for p, t in enumerate(toks))

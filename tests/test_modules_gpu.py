@@ -591,3 +591,25 @@ def test_dwconv_stages_in_place_segments(C):
     assert rel_err(y.double(), yd) < TOL32 and rel_err(x.grad.double(), xd.grad) < TOL32
     for cv, (ww, bb) in zip(convs, pd):
         assert rel_err(cv.weight.grad.double(), ww.grad) < TOL32 and rel_err(cv.bias.grad.double(), bb.grad) < TOL32
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_conv_bias_channels_last_matches_torch(transposed):
+    """Conv2dCL / ConvTranspose2dCL (bias through mlagg_bias_add_cl, bias gradient through mlagg_colsum) against the
+    stock modules on the same parameters: output, input gradient, weight and bias gradients (fp32, channels_last)."""
+    from mlagg_unet_b200.ops import Conv2dCL, ConvTranspose2dCL
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(13)
+    if transposed:
+        ours, ref = ConvTranspose2dCL(8, 12, 3, stride=2, padding=1).cuda(), torch.nn.ConvTranspose2d(8, 12, 3, stride=2, padding=1).cuda()
+    else:
+        ours, ref = Conv2dCL(8, 12, 3, stride=2, padding=1).cuda(), torch.nn.Conv2d(8, 12, 3, stride=2, padding=1).cuda()
+    ref.load_state_dict(ours.state_dict())
+    x = torch.randn(3, 8, 10, 14, device="cuda").contiguous(memory_format=torch.channels_last)
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    ya, yb = ours(xa), ref(xb)
+    g = torch.randn_like(yb)
+    ya.backward(g)
+    yb.backward(g)
+    assert rel_err(ya, yb) < TOL32 and rel_err(xa.grad, xb.grad) < TOL32
+    assert rel_err(ours.weight.grad, ref.weight.grad) < TOL32 and rel_err(ours.bias.grad, ref.bias.grad) < TOL32
