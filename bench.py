@@ -250,7 +250,7 @@ def main():
         pass
     if dom in kern:
         ach = alg[dom] / (kern[dom]["ms_avg"] * 1e-3) / 1e9
-        roof = {"kernel": "mlagg::scan_bwd_kernel (selective-scan backward, mamba interface, fp32 I/O)", "bound": "hbm",
+        roof = {"kernel": "mlagg::scan_bwd_kernel (selective-scan backward in the fused MSMM operand mode, fp32 I/O; algorithmic bytes counted at the mamba interface, SURVEY.md 8d)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": kern[dom]["ms_avg"],

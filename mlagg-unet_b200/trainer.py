@@ -134,6 +134,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         self.network = self.optimizer = self.lr_scheduler = self.loss = None
         self.use_cuda_graph = os.environ.get("MLAGG_CUDA_GRAPH", "1") != "0"
         self._graph = self._graph_key = self._static = self._flat_grad = self._params = self._flat_views = None
+        self._flat_slices = None
         self._eager_steps = 0
 
     # ---- reference static API
@@ -252,7 +253,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         grads = [p.grad for p in self._params] if grads is None else grads
         parts = [(g if g.stride() == p.stride() else torch.empty_like(p).copy_(g)).as_strided((g.numel(),), (1,))
                  for g, p in zip(grads, self._params)]
-        torch.cat(parts, out=self._flat_grad)
+        torch._foreach_copy_(self._flat_slices, parts)       # multi-tensor copy: 0.15 ms for 108 MB (torch.cat(out=): 0.55 ms)
         if self.is_ddp:
             dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
             self._flat_grad.div_(dist.get_world_size())
@@ -277,13 +278,14 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
     def _bind_flat_grads(self):
         self._params = [p for p in self.network.parameters() if p.requires_grad]
         self._flat_grad = torch.zeros(sum(p.numel() for p in self._params), device=self.device, dtype=torch.float32)
-        self._flat_views, off = [], 0
+        self._flat_views, self._flat_slices, off = [], [], 0
         for p in self._params:
             dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
             assert p.dtype == torch.float32 and dense, "flat gradient views need dense fp32 parameters"
             # same strides as the parameter (channels_last conv weights): autograd's gradient layout contract gives
             # .grad the parameter's strides, and fused AdamW pairs elements by memory order
             self._flat_views.append(self._flat_grad[off:off + p.numel()].as_strided(p.size(), p.stride()))
+            self._flat_slices.append(self._flat_grad[off:off + p.numel()])
             off += p.numel()
 
     def _alloc_static(self, batch):
