@@ -314,6 +314,12 @@ int mlagg_avgpool_tokens_bwd(const void *x, const void *dy, void *dx, int batch,
  * ------------------------------------------------------------------------------------------ */
 int mlagg_residual_scale(const void *x, const void *y, const float *scale, void *out, long long n, long long per_sample,
                          int dtype, mlagg_stream_t stream);
+/* dst[b][r][0:cols] = src[b][r][0:cols], b < batch, r < rows, for row-strided views of tokens-major activations (row stride
+ * ld*, batch stride bs*, in ELEMENTS; unit column stride): the channel split of the MSMM inputs (`x[:, :hidden]` /
+ * `x[:, hidden:]`, MambaSkip.py:724-727), the per-stage split / concatenation of the token sequence (:728-746) and the
+ * gradients of both, without intermediate zero-filled tensors. */
+int mlagg_copy_rows(const void *src, long long ld_src, long long bs_src, void *dst, long long ld_dst, long long bs_dst,
+                    int batch, long long rows, int cols, int dtype, mlagg_stream_t stream);
 /* y[pix][c] += bias[c] IN PLACE on a channels_last / tokens-major (pixels, C) map of n elements, C % 4 == 0 -- the bias of
  * the conv stages' nn.Conv2d / nn.ConvTranspose2d (nnUNetTrainer_MLAgg_2D_dt_MS.py:230-366, MambaSkip.py:712-716), which torch
  * adds after the cuDNN call with an un-vectorised broadcast kernel and differentiates with its generic reduction; the

@@ -12,6 +12,8 @@ cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStr
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
 cudaError_t residual_scale_dispatch(const void *x, const void *y, const float *s, void *out, long long n,
                                     long long per_sample, int dtype, cudaStream_t st);
+cudaError_t copy_rows_dispatch(const void *src, long long ld_s, long long bs_s, void *dst, long long ld_d, long long bs_d,
+                               int batch, long long rows, int cols, int dtype, cudaStream_t st);
 cudaError_t bias_add_cl_dispatch(void *y, const float *b, long long n, int C, int dtype, cudaStream_t st);
 cudaError_t silu_gate_dispatch(const void *t, const void *z, const void *g, void *o1, void *o2, long long n, int dtype,
                                bool bwd, cudaStream_t st);
@@ -489,6 +491,19 @@ extern "C" int mlagg_residual_scale(const void *x, const void *y, const float *s
     if (rc) return rc;
     if (per_sample <= 0 || per_sample % 4 != 0 || n % per_sample != 0) return MLAGG_ERR_BAD_SHAPE;
     cudaError_t e = residual_scale_dispatch(x, y, scale, out, n, per_sample, dtype, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_copy_rows(const void *src, long long ld_src, long long bs_src, void *dst, long long ld_dst,
+                               long long bs_dst, int batch, long long rows, int cols, int dtype, mlagg_stream_t stream) {
+    if (!src || !dst) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || rows <= 0 || cols <= 0 || ld_src < cols || ld_dst < cols || bs_src < 0 || bs_dst < 0)
+        return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    const size_t es = dtype == MLAGG_F32 ? 4 : 2;
+    if (!aligned(src, es) || !aligned(dst, es)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = copy_rows_dispatch(src, ld_src, bs_src, dst, ld_dst, bs_dst, batch, rows, cols, dtype,
+                                       (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

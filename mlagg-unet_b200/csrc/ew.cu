@@ -138,6 +138,28 @@ __global__ void __launch_bounds__(256) bias_add_cl_kernel(T *__restrict__ y, con
     }
 }
 
+// dst[b][r][0:cols] = src[b][r][0:cols] for row-strided views (ld*, bs* in elements): channel slices and stage segments
+// of tokens-major activations packed / scattered without torch's generic strided-copy kernel (~1 TB/s on these shapes)
+template <typename T, int V>
+__global__ void __launch_bounds__(256) copy_rows_kernel(const T *__restrict__ src, long long ld_s, long long bs_s,
+                                                        T *__restrict__ dst, long long ld_d, long long bs_d,
+                                                        long long rows, int colsv) {
+    const T *sb = src + (long long)blockIdx.y * bs_s;
+    T *db = dst + (long long)blockIdx.y * bs_d;
+    const long long n = rows * colsv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / colsv;
+        const int c = (int)(i % colsv) * V;
+        if (V == 1) {
+            db[r * ld_d + c] = sb[r * ld_s + c];
+        } else if (sizeof(T) * V == 16) {
+            *reinterpret_cast<uint4 *>(db + r * ld_d + c) = __ldg(reinterpret_cast<const uint4 *>(sb + r * ld_s + c));
+        } else {
+            *reinterpret_cast<uint2 *>(db + r * ld_d + c) = __ldg(reinterpret_cast<const uint2 *>(sb + r * ld_s + c));
+        }
+    }
+}
+
 static int ew_blocks(long long n4) {
     long long b = (n4 + 255) / 256;
     const long long cap = 148LL * 16;
@@ -158,6 +180,39 @@ cudaError_t bias_add_cl_dispatch(void *y, const float *b, long long n, int C, in
     const long long n4 = n / 4;
     if (dtype == 0) bias_add_cl_kernel<float><<<ew_blocks(n4), 256, 0, st>>>(static_cast<float *>(y), b, n4, C / 4);
     else bias_add_cl_kernel<__nv_bfloat16><<<ew_blocks(n4), 256, 0, st>>>(static_cast<__nv_bfloat16 *>(y), b, n4, C / 4);
+    return cudaGetLastError();
+}
+
+cudaError_t copy_rows_dispatch(const void *src, long long ld_s, long long bs_s, void *dst, long long ld_d, long long bs_d,
+                               int batch, long long rows, int cols, int dtype, cudaStream_t st) {
+    const size_t es = dtype == 0 ? 4 : 2;
+    // widest vector (in elements) that divides cols and every stride and keeps both bases aligned
+    int V = (int)(16 / es);
+    auto ok = [&](int v) {
+        const size_t bytes = v * es;
+        return cols % v == 0 && ld_s % v == 0 && ld_d % v == 0 && bs_s % v == 0 && bs_d % v == 0 &&
+               reinterpret_cast<uintptr_t>(src) % bytes == 0 && reinterpret_cast<uintptr_t>(dst) % bytes == 0;
+    };
+    while (V > 1 && !ok(V)) V /= 2;
+    if (V * es < 8) V = 1;                                   // 8- and 16-byte vectors, else scalar
+    const long long n = rows * (cols / V);
+    long long bx = (n + 255) / 256;
+    const long long cap = (148LL * 16 + batch - 1) / batch;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    const dim3 grid((unsigned)bx, (unsigned)batch);
+#define MLAGG_COPY(T_, V_) \
+    copy_rows_kernel<T_, V_><<<grid, 256, 0, st>>>(static_cast<const T_ *>(src), ld_s, bs_s, static_cast<T_ *>(dst), ld_d, bs_d, rows, cols / V_)
+    if (dtype == 0) {
+        if (V == 4) MLAGG_COPY(float, 4);
+        else if (V == 2) MLAGG_COPY(float, 2);
+        else MLAGG_COPY(float, 1);
+    } else {
+        if (V == 8) MLAGG_COPY(__nv_bfloat16, 8);
+        else if (V == 4) MLAGG_COPY(__nv_bfloat16, 4);
+        else MLAGG_COPY(__nv_bfloat16, 1);
+    }
+#undef MLAGG_COPY
     return cudaGetLastError();
 }
 
