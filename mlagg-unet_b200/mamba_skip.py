@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import Conv2dCL, _Linear, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
+from .ops import CatStages, Conv2dCL, JoinLast, SplitLast, SplitStages, _Linear, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
 from .selective_scan_interface import msmm_scan, msmm_scan_tokens, selective_scan_fn, xdbl_pad
 from .thirdparty_shims import DropPath, _inst_norm
 
@@ -242,21 +242,6 @@ class ConvolutionalGLU(nn.Module):
         return self.drop(linear_tokens(self.drop(a * v), self.fc2))
 
 
-class _SplitLast(torch.autograd.Function):
-    """x[..., :k], x[..., k:] as views; the backward is ONE concatenation.  Autograd's own slice gradients are two zero-filled
-    full-size tensors (contiguous in the logical NCHW order, which then drags every accumulation into the stage output's
-    channels_last gradient onto strided kernels) plus two copies and an add."""
-
-    @staticmethod
-    def forward(ctx, x, k):
-        ctx.k = k
-        return x[..., :k], x[..., k:]
-
-    @staticmethod
-    def backward(ctx, ga, gb):
-        return torch.cat([ga, gb], dim=-1), None
-
-
 class VSS_Conv_Block(nn.Module):
     def __init__(self, feature_dims, hidden_dim: int = 0, drop_path: float = 0,
                  norm_layer: Callable[..., nn.Module] = partial(nn.LayerNorm, eps=1e-6), attn_drop_rate: float = 0,
@@ -284,20 +269,19 @@ class VSS_Conv_Block(nn.Module):
         hd = self.hidden_dim
         # NHWC views of the inputs (free when they are channels_last), split into the first hd channels -> tokens-major
         # (B, L, hd) for the scan branch, and the rest -> conv branch
-        halves = [_SplitLast.apply(t.permute(0, 2, 3, 1), hd) for t in inputs]
-        m = torch.cat([a.reshape(Bn, L_split[s], hd) for s, (a, _) in enumerate(halves)], dim=1)
+        halves = [SplitLast.apply(t.permute(0, 2, 3, 1), hd) for t in inputs]
+        m = CatStages.apply(*[a.flatten(1, 2) for a, _ in halves])         # (B, H, W, hd) -> (B, H W, hd): views
         m = residual_drop_path(m, self.self_attention(layer_norm_tokens(m, self.ln_1), Bn, H, W, L_split), self.drop_path)
-        m = layer_norm_tokens(m, self.norm2)
-        outs, off = [], 0
+        # one packed copy per stage: with a uniform row stride the fc1 GEMM keeps its bias epilogue, the residual is the
+        # one-pass kernel, and the Linear backward needs no re-pack of its saved input
+        stage_tokens = SplitStages.apply(layer_norm_tokens(m, self.norm2), tuple(L_split))
+        outs = []
         for s, t in enumerate(inputs):
-            # one packed copy per stage: with a uniform row stride the fc1 GEMM keeps its bias epilogue, the residual is
-            # the one-pass kernel, and the Linear backward needs no re-pack of its saved input
-            ms = m[:, off:off + L_split[s]].contiguous()
-            off += L_split[s]
+            ms = stage_tokens[s]
             ms = residual_drop_path(ms, self.mlps[s](ms, H[s], W[s]), self.drop_path)
             br = self.conv_branches[s]                                                 # Conv2d, InstanceNorm2d, SiLU
             cb = _inst_norm(br[1], br[0](halves[s][1].permute(0, 3, 1, 2)), "silu").permute(0, 2, 3, 1)   # NHWC view
-            outs.append(torch.cat([ms.reshape(Bn, H[s], W[s], hd), cb], dim=-1).permute(0, 3, 1, 2))  # channels_last
+            outs.append(JoinLast.apply(ms.reshape(Bn, H[s], W[s], hd), cb).permute(0, 3, 1, 2))      # channels_last
         return outs
 
 

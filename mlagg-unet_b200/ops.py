@@ -608,3 +608,116 @@ class ConvTranspose2dCL(torch.nn.ConvTranspose2d):
         y = torch.nn.functional.conv_transpose2d(x, self.weight, None, self.stride, self.padding, self.output_padding,
                                                  self.groups, self.dilation)
         return _conv_bias_cl(y, self.bias)
+
+
+# ---- strided row copies (C ABI: mlagg_copy_rows) for the channel / stage splits and joins around the MSMM -------------------
+def _rows3(t):
+    """t (B, R, C) or (B, H, W, C) view with unit channel stride whose pixel dims collapse to one row stride ->
+    (ptr-carrying tensor, B, R, C, ld, bs) or None"""
+    if t.dim() == 4:
+        if t.stride(3) != 1 or t.stride(1) != t.shape[2] * t.stride(2):
+            return None
+        return t, t.shape[0], t.shape[1] * t.shape[2], t.shape[3], t.stride(2), t.stride(0)
+    if t.dim() == 3 and t.stride(2) == 1:
+        return t, t.shape[0], t.shape[1], t.shape[2], t.stride(1), t.stride(0)
+    return None
+
+
+def copy_rows_(dst, src):
+    """dst[...] = src[...] for two equally shaped row-strided views (see `_rows3`); falls back to Tensor.copy_ for
+    anything the kernel does not address (other dtypes, CPU, non-collapsible views)."""
+    a, b = _rows3(dst), _rows3(src)
+    if (a is None or b is None or not dst.is_cuda or dst.dtype not in _DT or src.dtype != dst.dtype
+            or a[1:4] != b[1:4] or dst.numel() == 0 or min(a[4], b[4]) < a[3]):
+        dst.copy_(src)
+        return dst
+    with torch.cuda.device(dst.device), _lib.timed("copy_rows"):
+        rc = _lib.lib().mlagg_copy_rows(src.data_ptr(), b[4], b[5], dst.data_ptr(), a[4], a[5], a[1], a[2], a[3],
+                                        _DT[dst.dtype], _lib.stream_ptr())
+    _lib.check(rc, "mlagg_copy_rows")
+    return dst
+
+
+class SplitLast(torch.autograd.Function):
+    """x[..., :k], x[..., k:] as views; the backward assembles ONE gradient with two strided row copies.  Autograd's own
+    slice gradients are two zero-filled full-size tensors (contiguous in the logical NCHW order, which then drags every
+    accumulation into the stage output's channels_last gradient onto strided kernels) plus two copies and an add."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        ctx.k = k
+        return x[..., :k], x[..., k:]
+
+    @staticmethod
+    def backward(ctx, ga, gb):
+        out = torch.empty(ga.shape[:-1] + (ga.shape[-1] + gb.shape[-1],), device=ga.device, dtype=ga.dtype)
+        copy_rows_(out[..., :ctx.k], ga)
+        copy_rows_(out[..., ctx.k:], gb.to(ga.dtype))
+        return out, None
+
+
+class JoinLast(torch.autograd.Function):
+    """torch.cat([a, b], dim=-1) of two (B, H, W, .) maps with strided row copies; the gradients are views."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.k = a.shape[-1]
+        out = torch.empty(a.shape[:-1] + (a.shape[-1] + b.shape[-1],), device=a.device, dtype=a.dtype)
+        copy_rows_(out[..., :ctx.k], a)
+        copy_rows_(out[..., ctx.k:], b.to(a.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[..., :ctx.k], g[..., ctx.k:]
+
+
+class CatStages(torch.autograd.Function):
+    """per-stage token maps (B, L_s, C) (row-strided views allowed) -> the stage-concatenated sequence (B, sum L_s, C);
+    the gradients are views of the sequence gradient."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        Bn, C = parts[0].shape[0], parts[0].shape[2]
+        ctx.lens = [p.shape[1] for p in parts]
+        out = torch.empty(Bn, sum(ctx.lens), C, device=parts[0].device, dtype=parts[0].dtype)
+        off = 0
+        for p, n in zip(parts, ctx.lens):
+            copy_rows_(out[:, off:off + n], p.to(out.dtype))
+            off += n
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for n in ctx.lens:
+            outs.append(g[:, off:off + n])
+            off += n
+        return tuple(outs)
+
+
+class SplitStages(torch.autograd.Function):
+    """the inverse: (B, sum L_s, C) -> packed per-stage (B, L_s, C) tensors (uniform row stride: the per-token GEMMs keep
+    their bias epilogue); the backward writes the stage gradients into ONE sequence gradient (no zero-filled
+    full-size tensor per stage, no adds)."""
+
+    @staticmethod
+    def forward(ctx, x, lens):
+        ctx.lens = tuple(lens)
+        outs, off = [], 0
+        for n in ctx.lens:
+            o = torch.empty(x.shape[0], n, x.shape[2], device=x.device, dtype=x.dtype)
+            copy_rows_(o, x[:, off:off + n])
+            outs.append(o)
+            off += n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        Bn, C = gs[0].shape[0], gs[0].shape[2]
+        out = torch.empty(Bn, sum(ctx.lens), C, device=gs[0].device, dtype=gs[0].dtype)
+        off = 0
+        for g, n in zip(gs, ctx.lens):
+            copy_rows_(out[:, off:off + n], g.to(out.dtype))
+            off += n
+        return out, None

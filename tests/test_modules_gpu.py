@@ -614,3 +614,47 @@ def test_conv_bias_channels_last_matches_torch(transposed):
     yb.backward(g)
     assert rel_err(ya, yb) < TOL32 and rel_err(xa.grad, xb.grad) < TOL32
     assert rel_err(ours.weight.grad, ref.weight.grad) < TOL32 and rel_err(ours.bias.grad, ref.bias.grad) < TOL32
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_strided_row_copies_and_split_join_functions(dtype):
+    """mlagg_copy_rows behind SplitLast / JoinLast / CatStages / SplitStages (the channel and stage splits / joins of
+    VSS_Conv_Block, MambaSkip.py:724-746) against the torch slicing / cat expressions: values bit-exact, gradients equal."""
+    from mlagg_unet_b200.ops import CatStages, JoinLast, SplitLast, SplitStages, copy_rows_
+    torch.manual_seed(17)
+    # raw copies: odd widths (scalar path), 8- and 16-byte vectors, batch strides
+    for cols, wide in ((5, 9), (12, 20), (16, 48), (6, 6)):
+        src = torch.randn(3, 11, wide, device="cuda").to(dtype)
+        dst = torch.full((3, 11, wide + 4), 9.0, device="cuda").to(dtype)
+        copy_rows_(dst[..., 4:4 + cols], src[..., wide - cols:])
+        want = torch.full((3, 11, wide + 4), 9.0, device="cuda").to(dtype)
+        want[..., 4:4 + cols] = src[..., wide - cols:]
+        assert torch.equal(dst, want), (cols, wide)
+    hw, hd, Bn = [(6, 5), (3, 4), (2, 1)], 8, 2
+    Cs = [20, 28, 44]
+    xs = [torch.randn(Bn, c, h, w, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last) for c, (h, w) in zip(Cs, hw)]
+
+    def run(native):
+        ins = [x.clone().requires_grad_() for x in xs]
+        if native:
+            halves = [SplitLast.apply(t.permute(0, 2, 3, 1), hd) for t in ins]
+            m = CatStages.apply(*[a.flatten(1, 2) for a, _ in halves])
+            parts = SplitStages.apply(m * 2, tuple(h * w for h, w in hw))
+            outs = [JoinLast.apply(p.reshape(Bn, h, w, hd), 3 * b).permute(0, 3, 1, 2)
+                    for p, (_, b), (h, w) in zip(parts, halves, hw)]
+        else:
+            tn = [t.permute(0, 2, 3, 1) for t in ins]
+            m = torch.cat([t[..., :hd].reshape(Bn, h * w, hd) for t, (h, w) in zip(tn, hw)], dim=1)
+            m2, off, outs = m * 2, 0, []
+            for t, (h, w) in zip(tn, hw):
+                outs.append(torch.cat([m2[:, off:off + h * w].reshape(Bn, h, w, hd), 3 * t[..., hd:]], dim=-1).permute(0, 3, 1, 2))
+                off += h * w
+        torch.manual_seed(5)
+        loss = sum((o.float() * torch.randn(o.shape, device="cuda")).sum() for o in outs)
+        loss.backward()
+        return [o.detach() for o in outs], [t.grad for t in ins]
+
+    oa, ga = run(True)
+    ob, gb = run(False)
+    for a, b in zip(oa + ga, ob + gb):
+        assert torch.equal(a, b)

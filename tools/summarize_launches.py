@@ -14,7 +14,7 @@ for r in rows[1:]:
     agg[name][1] += v
 tot = sum(v[1] for v in agg.values())
 OURS = ("scan_", "dwconv", "causal_conv1d", "pooled_attn", "local_attn", "layernorm_", "in_sums", "in_apply", "in_finalize",
-        "in_param", "colsum", "avgpool", "linattn", "walk_", "residual_scale", "silu_gate", "diff_lambda")
+        "in_param", "colsum", "avgpool", "linattn", "walk_", "residual_scale", "silu_gate", "diff_lambda", "copy_rows", "bias_add_cl")
 ours = {k: v for k, v in agg.items() if any(t in k for t in OURS) and "at::native" not in k}
 print(f"{sum(v[0] for v in agg.values())} launches, {tot:.2f} ms summed device time (cold-cache, serialised: compare SHARES)")
 print(f"libmlagg_b200.so kernels: {sum(v[0] for v in ours.values())} launches, {sum(v[1] for v in ours.values()):.2f} ms = "
