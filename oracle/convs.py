@@ -7,7 +7,8 @@ Depthwise convolutions of the hot path:
   * causal_conv1d -- named by north_star; not called by the shipped trainer.  The
     arithmetic lives in the un-vendored `causal-conv1d` package (reference README.md:49); its
     published definition y[b,c,t] = bias[c] + sum_j w[c,j] x[b,c,t-(k-1)+j] is restated.
-    PARITY UNPINNED against that package (absent everywhere).
+    PARITY UNPINNED against that package (absent everywhere); pinned instead to the causal conv1d + SiLU inside
+    Hugging Face transformers' `MambaMixer.slow_forward` (tests/test_oracle_pin_hf.py, forward and gradients).
 Nothing under mlagg-unet_b200/ imports this module.
 """
 from __future__ import annotations

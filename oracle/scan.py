@@ -5,7 +5,11 @@ CPU restatement of the selective scan that `SS2D_skip.forward_corev0` calls
 The arithmetic lives in the un-vendored, un-pinned `mamba-ssm` package
 (`selective_scan_fn` / `selective_scan_ref`; reference README.md:49-50); what is
 restated here is that package's published S6 recurrence and
-its analytic gradient (App. A.2).  PARITY UNPINNED against mamba-ssm itself.
+its analytic gradient (App. A.2).  PARITY UNPINNED against mamba-ssm itself (the package is absent everywhere).
+What it IS pinned to: (i) Hugging Face transformers' `MambaMixer.slow_forward` -- an independent torch
+restatement of the same definition that ships in the image -- forward and every gradient, 2e-5
+(tests/test_oracle_pin_hf.py); (ii) through the CUDA path, vLLM's `selective_scan_fwd`, mamba-ssm's forward
+kernel carried into vLLM (tests/test_scan_gpu.py::test_forward_matches_mamba_ssm_derived_cuda_kernel).
 
 Three layers, each checking the next:
   * `selective_scan_loop`   -- plain torch, one python iteration per time step (small L only);
