@@ -97,25 +97,23 @@ int mlagg_dwconv3x3_bwd(const void *x, const float *weight, const float *bias, c
 /* Strided variants: pixel stride ld* and image stride bs* in ELEMENTS for every activation operand (ld >= C; multiples of 4
  * when C % 4 == 0), so channel slices of wider activations (the v half of the kv projection for LePE, :680/:782; the first
  * half of ConvolutionalGLU's fc1 output, MambaSkip.py:567-575) and the per-stage segments of the stage-concatenated MSMM
- * sequence (MambaSkip.py:521-523) are read and written in place.  `residual` (nullable, same shape as y) is added to the
- * result after the activation: y = act(conv(x) + b) + residual -- the `attn_out + lepe(v)` of :716/:759.
- * The backward takes dy with its own strides, a CONTIGUOUS dz workspace, and stores dx with (lddx, bsdx). */
+ * sequence (MambaSkip.py:521-523) are read and written in place.  `residual` (nullable, same shape as y) is combined with
+ * the result after the activation: residual_mul = 0: y = act(conv(x) + b) + residual -- the `attn_out + lepe(v)` of
+ * :716/:759; residual_mul = 1: y = act(conv(x) + b) * residual -- the `act(dwconv(x)) * v` of ConvolutionalGLU,
+ * MambaSkip.py:574.
+ * The backward takes dy with its own strides, a CONTIGUOUS dz workspace, and stores dx with (lddx, bsdx).  With `mul`
+ * (the forward's multiplicative `residual`, strides ldm / bsm; nullable) it also stores dmul = dy * act(conv(x) + b) with
+ * the same strides and differentiates through the product -- so ConvolutionalGLU's gradient lands in the two halves of
+ * ONE fc1-output gradient (dx -> first half, dmul -> second half). */
 int mlagg_dwconv3x3_fwd_strided(const void *x, const float *weight, const float *bias, const void *residual, void *y,
                                 int batch, int H, int W, int C, long long ldx, long long bsx, long long ldr,
-                                long long bsr, long long ldy, long long bsy, int act_silu, int dtype,
+                                long long bsr, long long ldy, long long bsy, int act_silu, int residual_mul, int dtype,
                                 mlagg_stream_t stream);
 int mlagg_dwconv3x3_bwd_strided(const void *x, const float *weight, const float *bias, const void *dy, void *dz_ws,
                                 void *dx, float *dweight, float *dbias, int batch, int H, int W, int C, long long ldx,
                                 long long bsx, long long lddy, long long bsdy, long long lddx, long long bsdx,
-                                int act_silu, int dtype, mlagg_stream_t stream);
-
-/* --------------------------------------------------------------------------------------------
- * Depthwise causal conv1d: y[b,c,t] = bias[c] + sum_j weight[c,j] * x[b,c,t-(K-1)+j]  (+ SiLU), K <= 4.
- * Replaces causal_conv1d_fn(x, weight, bias, activation) of the causal-conv1d package (a pip dependency of
- * mamba_ssm, reference README.md:49; named by north_star, not called by nnUNetTrainer_MLAgg_2D_dt_MS: F3).
- *   x, y, dy, dx : (batch, C, L) fp32;  weight (C, K) fp32;  bias (C) fp32 nullable
- *   dweight / dbias are ACCUMULATED INTO (zero-fill first).
- * ------------------------------------------------------------------------------------------ */
+                                const void *mul, void *dmul, long long ldm, long long bsm, int act_silu, int dtype,
+                                mlagg_stream_t stream);
 int mlagg_causal_conv1d_fwd(const float *x, const float *weight, const float *bias, float *y, int batch, int C,
                             int L, int K, int act_silu, mlagg_stream_t stream);
 int mlagg_causal_conv1d_bwd(const float *x, const float *weight, const float *bias, const float *dy, float *dx,

@@ -45,8 +45,8 @@ SIGNATURES = {
     "mlagg_colsum": (c_i, [c_p, c_p, c_ll, c_i, c_ll, c_i, c_p]),
     "mlagg_dwconv3x3_fwd": (c_i, [c_p] * 4 + [c_i] * 6 + [c_p]),
     "mlagg_dwconv3x3_bwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
-    "mlagg_dwconv3x3_fwd_strided": (c_i, [c_p] * 5 + [c_i] * 4 + [c_ll] * 6 + [c_i, c_i, c_p]),
-    "mlagg_dwconv3x3_bwd_strided": (c_i, [c_p] * 8 + [c_i] * 4 + [c_ll] * 6 + [c_i, c_i, c_p]),
+    "mlagg_dwconv3x3_fwd_strided": (c_i, [c_p] * 5 + [c_i] * 4 + [c_ll] * 6 + [c_i, c_i, c_i, c_p]),
+    "mlagg_dwconv3x3_bwd_strided": (c_i, [c_p] * 8 + [c_i] * 4 + [c_ll] * 6 + [c_p, c_p, c_ll, c_ll] + [c_i, c_i, c_p]),
     "mlagg_causal_conv1d_fwd": (c_i, [c_p] * 4 + [c_i] * 5 + [c_p]),
     "mlagg_causal_conv1d_bwd": (c_i, [c_p] * 7 + [c_i] * 5 + [c_p]),
     "mlagg_pooled_diffattn_ws_bytes": (c_sz, [c_i] * 4),

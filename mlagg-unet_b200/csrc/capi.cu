@@ -28,11 +28,11 @@ cudaError_t walk_unpack_dispatch(const float *src0, const float *src1, long long
 
 cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, const void *res, void *y, int Bn, int H,
                                    int W, int C, long long ldx, long long bsx, long long ldr, long long bsr,
-                                   long long ldy, long long bsy, int act, int dtype, cudaStream_t st);
+                                   long long ldy, long long bsy, int act, int res_mul, int dtype, cudaStream_t st);
 cudaError_t dwconv3x3_bwd_dispatch(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
                                    float *dw, float *db, int Bn, int H, int W, int C, long long ldx, long long bsx,
-                                   long long lddy, long long bsdy, long long lddx, long long bsdx, int act, int dtype,
-                                   cudaStream_t st);
+                                   long long lddy, long long bsdy, long long lddx, long long bsdx, const void *mulv,
+                                   void *dmul, long long ldm, long long bsm, int act, int dtype, cudaStream_t st);
 cudaError_t causal_conv1d_fwd_dispatch(const float *x, const float *w, const float *b, float *y, int rows, int C,
                                        int L, int K, int act, cudaStream_t st);
 cudaError_t causal_conv1d_bwd_dispatch(const float *x, const float *w, const float *b, const float *dy, float *dx,
@@ -204,7 +204,7 @@ static bool dw_strides_ok(int C, long long ld, long long bs) { return ld >= C &&
 extern "C" int mlagg_dwconv3x3_fwd_strided(const void *x, const float *weight, const float *bias, const void *residual,
                                            void *y, int batch, int H, int W, int C, long long ldx, long long bsx,
                                            long long ldr, long long bsr, long long ldy, long long bsy, int act_silu,
-                                           int dtype, mlagg_stream_t stream) {
+                                           int residual_mul, int dtype, mlagg_stream_t stream) {
     int rc = dwconv_check(x, weight, y, batch, H, W, C, dtype);
     if (rc) return rc;
     if (!dw_strides_ok(C, ldx, bsx) || !dw_strides_ok(C, ldy, bsy) || (residual && !dw_strides_ok(C, ldr, bsr)))
@@ -212,22 +212,22 @@ extern "C" int mlagg_dwconv3x3_fwd_strided(const void *x, const float *weight, c
     const size_t a = C % 4 != 0 ? (dtype == MLAGG_F32 ? 4 : 2) : (dtype == MLAGG_F32 ? 16 : 8);
     if ((bias && !aligned(bias, C % 4 ? 4 : 16)) || (residual && !aligned(residual, a))) return MLAGG_ERR_ALIGN;
     cudaError_t e = dwconv3x3_fwd_dispatch(x, weight, bias, residual, y, batch, H, W, C, ldx, bsx, ldr, bsr, ldy, bsy,
-                                           act_silu, dtype, (cudaStream_t)stream);
+                                           act_silu, residual_mul, dtype, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 
 extern "C" int mlagg_dwconv3x3_fwd(const void *x, const float *weight, const float *bias, void *y, int batch, int H,
                                    int W, int C, int act_silu, int dtype, mlagg_stream_t stream) {
     const long long bs = (long long)H * W * C;
-    return mlagg_dwconv3x3_fwd_strided(x, weight, bias, nullptr, y, batch, H, W, C, C, bs, C, bs, C, bs, act_silu, dtype,
+    return mlagg_dwconv3x3_fwd_strided(x, weight, bias, nullptr, y, batch, H, W, C, C, bs, C, bs, C, bs, act_silu, 0, dtype,
                                        stream);
 }
 
 extern "C" int mlagg_dwconv3x3_bwd_strided(const void *x, const float *weight, const float *bias, const void *dy,
                                            void *dz_ws, void *dx, float *dweight, float *dbias, int batch, int H, int W,
                                            int C, long long ldx, long long bsx, long long lddy, long long bsdy,
-                                           long long lddx, long long bsdx, int act_silu, int dtype,
-                                           mlagg_stream_t stream) {
+                                           long long lddx, long long bsdx, const void *mul, void *dmul, long long ldm,
+                                           long long bsm, int act_silu, int dtype, mlagg_stream_t stream) {
     int rc = dwconv_check(x, weight, dx, batch, H, W, C, dtype);
     if (rc) return rc;
     if (!dy || !dz_ws || !dweight) return MLAGG_ERR_NULL;
@@ -235,8 +235,14 @@ extern "C" int mlagg_dwconv3x3_bwd_strided(const void *x, const float *weight, c
         return MLAGG_ERR_BAD_SHAPE;
     const size_t a = C % 4 != 0 ? (dtype == MLAGG_F32 ? 4 : 2) : (dtype == MLAGG_F32 ? 16 : 8);
     if (!aligned(dy, a) || !aligned(dz_ws, a) || (bias && !aligned(bias, C % 4 ? 4 : 16))) return MLAGG_ERR_ALIGN;
+    if (mul) {
+        if (!dmul) return MLAGG_ERR_NULL;
+        if (!dw_strides_ok(C, ldm, bsm)) return MLAGG_ERR_BAD_SHAPE;
+        if (!aligned(mul, a) || !aligned(dmul, a)) return MLAGG_ERR_ALIGN;
+    }
     cudaError_t e = dwconv3x3_bwd_dispatch(x, weight, bias, dy, dz_ws, dx, dweight, dbias, batch, H, W, C, ldx, bsx, lddy,
-                                           bsdy, lddx, bsdx, act_silu, dtype, (cudaStream_t)stream);
+                                           bsdy, lddx, bsdx, mul, mul ? dmul : nullptr, ldm, bsm, act_silu, dtype,
+                                           (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 
@@ -245,7 +251,7 @@ extern "C" int mlagg_dwconv3x3_bwd(const void *x, const float *weight, const flo
                                    int C, int act_silu, int dtype, mlagg_stream_t stream) {
     const long long bs = (long long)H * W * C;
     return mlagg_dwconv3x3_bwd_strided(x, weight, bias, dy, dz_ws, dx, dweight, dbias, batch, H, W, C, C, bs, C, bs, C, bs,
-                                       act_silu, dtype, stream);
+                                       nullptr, nullptr, 0, 0, act_silu, dtype, stream);
 }
 
 extern "C" int mlagg_causal_conv1d_fwd(const float *x, const float *weight, const float *bias, float *y, int batch,

@@ -62,6 +62,8 @@ struct Row3 {
 // (forward: residual added to the result; weight-gradient pass: dy).  Contiguous tokens-major data: ld = C, bs = H*W*C.
 struct DwLay {
     long long ldx, bsx, ldy, bsy, ldr, bsr;
+    int rmul;              // forward: the second input MULTIPLIES the activated result (ConvolutionalGLU's a * v) instead of adding
+    long long ldm, bsm;    // weight-gradient pass: strides of the multiplier v and of its gradient dv (same layout)
 };
 
 template <typename T>
@@ -89,7 +91,7 @@ __device__ __forceinline__ float4 dw_window(const float4 &b, const float (&wr)[4
     return acc;
 }
 
-template <typename T, bool FLIP, int ACT>
+template <typename T, bool FLIP, int ACT, bool RMUL>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                         const float *__restrict__ bias, const T *__restrict__ res,
                                                         T *__restrict__ y, int Bn, int H, int W, int C, DwLay lay) {
@@ -132,7 +134,11 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const T *__restrict__ x,
         }
         if (rsr) {
             const float4 r4 = ld4<T>(rsr + (long long)wc * lay.ldr);
-            acc.x += r4.x; acc.y += r4.y; acc.z += r4.z; acc.w += r4.w;
+            if (RMUL) {
+                acc.x *= r4.x; acc.y *= r4.y; acc.z *= r4.z; acc.w *= r4.w;
+            } else {
+                acc.x += r4.x; acc.y += r4.y; acc.z += r4.z; acc.w += r4.w;
+            }
         }
         st4<T>(yr + (long long)wc * lay.ldy, acc);
     };
@@ -165,7 +171,8 @@ __global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restri
                                                                const float *__restrict__ bias,
                                                                const T *__restrict__ dy, T *__restrict__ y,
                                                                float *__restrict__ dw, float *__restrict__ db, int Bn,
-                                                               int H, int W, int C, int mode, DwLay lay) {
+                                                               int H, int W, int C, int mode, DwLay lay,
+                                                               const T *__restrict__ mulv, T *__restrict__ dmul) {
     const long long total = (long long)Bn * H * W * C;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -190,6 +197,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restri
         T *yp = y + bimg * lay.bsy + lpix * lay.ldy + c;
         if (mode == 2) {
             float g = ld1<T>(dy + bimg * lay.bsr + lpix * lay.ldr + c);
+            if (mulv) {   // y = act(z) * v:  dv = g act(z),  g <- g v
+                st1<T>(dmul + bimg * lay.bsm + lpix * lay.ldm + c, g * (ACT == 1 ? silu_f(acc) : acc));
+                g *= ld1<T>(mulv + bimg * lay.bsm + lpix * lay.ldm + c);
+            }
             if (ACT == 1) g *= silu_grad(acc);
             st1<T>(yp, g);
 #pragma unroll
@@ -197,7 +208,10 @@ __global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restri
             if (db) atomicAdd(db + c, g);
         } else {
             float o = (ACT == 1 && mode == 0) ? silu_f(acc) : acc;
-            if (mode == 0 && dy) o += ld1<T>(dy + bimg * lay.bsr + lpix * lay.ldr + c);   // residual rides in `dy`
+            if (mode == 0 && dy) {                                                        // second input rides in `dy`
+                const float r = ld1<T>(dy + bimg * lay.bsr + lpix * lay.ldr + c);
+                o = lay.rmul ? o * r : o + r;
+            }
             st1<T>(yp, o);
         }
     }
@@ -209,13 +223,14 @@ __global__ void __launch_bounds__(256) dwconv3x3_scalar_kernel(const T *__restri
 // 3x3 window of x in registers (same walk as the forward kernel).
 constexpr int kStripW = 32;
 
-template <typename T, int ACT>
+template <typename T, int ACT, bool MUL>
 __global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                               const float *__restrict__ bias,
                                                               const T *__restrict__ dy, T *__restrict__ dz,
                                                               float *__restrict__ dw, float *__restrict__ db,
                                                               int Bn, int H, int W, int C, int strips_per_lane,
-                                                              DwLay lay) {
+                                                              DwLay lay, const T *__restrict__ mulv,
+                                                              T *__restrict__ dmul) {
     extern __shared__ float red[];  // [PP][cv][40]    (x: lay.ldx/bsx, dy: lay.ldr/bsr, dz: lay.ldy/bsy)
     const int cv = C >> 2;
     const int PP = blockDim.x / cv;
@@ -254,6 +269,8 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restric
             }
             const T *gyr = dy + bimg * lay.bsr + ((long long)hr * W) * lay.ldr + c;
             T *dzr = dz + bimg * lay.bsy + ((long long)hr * W) * lay.ldy + c;
+            const T *mvr = MUL ? mulv + bimg * lay.bsm + ((long long)hr * W) * lay.ldm + c : nullptr;
+            T *dmr = MUL ? dmul + bimg * lay.bsm + ((long long)hr * W) * lay.ldm + c : nullptr;
             const int w1 = min(W, w0 + kStripW);
             const int ldx = (int)lay.ldx;
             float4 A[3], Bc[3], Cc[3];
@@ -262,9 +279,18 @@ __global__ void __launch_bounds__(256) dwconv3x3_bwd_w_kernel(const T *__restric
             auto step = [&](int wc, const float4 (&L)[3], const float4 (&M)[3], float4 (&R)[3]) {
                 dw_col<T>(rows, wc + 1, W, ldx, R);
                 float4 g = ld4<T>(gyr + (long long)wc * lay.ldr);
-                if (ACT == 1) {
+                if (ACT == 1 || MUL) {
                     const float4 z = dw_window(bv, wr, L, M, R);
-                    g.x *= silu_grad(z.x); g.y *= silu_grad(z.y); g.z *= silu_grad(z.z); g.w *= silu_grad(z.w);
+                    if (MUL) {   // y = act(z) * v:  dv = g act(z),  g <- g v
+                        const float4 v4 = ld4<T>(mvr + (long long)wc * lay.ldm);
+                        float4 a4 = z;
+                        if (ACT == 1) { a4.x = silu_f(z.x); a4.y = silu_f(z.y); a4.z = silu_f(z.z); a4.w = silu_f(z.w); }
+                        st4<T>(dmr + (long long)wc * lay.ldm, make_float4(g.x * a4.x, g.y * a4.y, g.z * a4.z, g.w * a4.w));
+                        g.x *= v4.x; g.y *= v4.y; g.z *= v4.z; g.w *= v4.w;
+                    }
+                    if (ACT == 1) {
+                        g.x *= silu_grad(z.x); g.y *= silu_grad(z.y); g.z *= silu_grad(z.z); g.w *= silu_grad(z.w);
+                    }
                 }
                 st4<T>(dzr + (long long)wc * lay.ldy, g);
                 ab[0] += g.x; ab[1] += g.y; ab[2] += g.z; ab[3] += g.w;
@@ -404,7 +430,7 @@ __global__ void __launch_bounds__(256) causal_conv1d_bwd_kernel(const float *__r
 // ------------------------------------------------------------------ host launchers
 static DwLay dw_contig(int H, int W, int C) {
     const long long bs = (long long)H * W * C;
-    return DwLay{C, bs, C, bs, C, bs};
+    return DwLay{C, bs, C, bs, C, bs, 0, C, bs};
 }
 
 template <typename T>
@@ -415,23 +441,26 @@ static cudaError_t dwconv_fwd_t(const void *x, const float *w, const float *b, c
     if (C % 4 != 0) {
         long long nb1 = ((long long)Bn * H * W * C + 255) / 256;
         if (nb1 > 148LL * 32) nb1 = 148LL * 32;
-        if (act && !flip) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xp, w, b, rp, yp, nullptr, nullptr, Bn, H, W, C, 0, lay);
-        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xp, w, b, flip ? nullptr : rp, yp, nullptr, nullptr, Bn, H, W, C, flip ? 1 : 0, lay);
+        if (act && !flip) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xp, w, b, rp, yp, nullptr, nullptr, Bn, H, W, C, 0, lay, nullptr, nullptr);
+        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xp, w, b, flip ? nullptr : rp, yp, nullptr, nullptr, Bn, H, W, C, flip ? 1 : 0, lay, nullptr, nullptr);
         return cudaGetLastError();
     }
     const long long total = (long long)Bn * H * ((W + kStrip - 1) / kStrip) * (C / 4);   // one thread per strip
     const int blocks = (int)((total + 255) / 256);
-    if (flip) dwconv3x3_kernel<T, true, 0><<<blocks, 256, 0, st>>>(xp, w, nullptr, nullptr, yp, Bn, H, W, C, lay);
-    else if (act) dwconv3x3_kernel<T, false, 1><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
-    else dwconv3x3_kernel<T, false, 0><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
+    if (flip) dwconv3x3_kernel<T, true, 0, false><<<blocks, 256, 0, st>>>(xp, w, nullptr, nullptr, yp, Bn, H, W, C, lay);
+    else if (lay.rmul && rp) {   // multiplicative second input: own instantiations, the others keep their code
+        if (act) dwconv3x3_kernel<T, false, 1, true><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
+        else dwconv3x3_kernel<T, false, 0, true><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
+    } else if (act) dwconv3x3_kernel<T, false, 1, false><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
+    else dwconv3x3_kernel<T, false, 0, false><<<blocks, 256, 0, st>>>(xp, w, b, rp, yp, Bn, H, W, C, lay);
     return cudaGetLastError();
 }
 
 // x (ldx, bsx), residual (ldr, bsr; nullable), y (ldy, bsy)
 cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b, const void *res, void *y, int Bn, int H,
                                    int W, int C, long long ldx, long long bsx, long long ldr, long long bsr,
-                                   long long ldy, long long bsy, int act, int dtype, cudaStream_t st) {
-    const DwLay lay{ldx, bsx, ldy, bsy, ldr, bsr};
+                                   long long ldy, long long bsy, int act, int res_mul, int dtype, cudaStream_t st) {
+    const DwLay lay{ldx, bsx, ldy, bsy, ldr, bsr, res_mul ? 1 : 0, 0, 0};
     return dtype == 0 ? dwconv_fwd_t<float>(x, w, b, res, y, Bn, H, W, C, act, false, lay, st)
                       : dwconv_fwd_t<__nv_bfloat16>(x, w, b, res, y, Bn, H, W, C, act, false, lay, st);
 }
@@ -439,18 +468,20 @@ cudaError_t dwconv3x3_fwd_dispatch(const void *x, const float *w, const float *b
 template <typename T>
 static cudaError_t dwconv_bwd_t(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
                                 float *dw, float *db, int Bn, int H, int W, int C, int act, DwLay lx, long long lddx,
-                                long long bsdx, cudaStream_t st) {
+                                long long bsdx, const void *mulv, void *dmul, cudaStream_t st) {
     // pass 1: x (lx.ldx/bsx), dy (lx.ldr/bsr) -> dz contiguous workspace; pass 2: dz -> dx (lddx, bsdx)
     const DwLay c0 = dw_contig(H, W, C);
-    const DwLay l1{lx.ldx, lx.bsx, c0.ldy, c0.bsy, lx.ldr, lx.bsr};
-    const DwLay l2{c0.ldx, c0.bsx, lddx, bsdx, c0.ldr, c0.bsr};
+    const DwLay l1{lx.ldx, lx.bsx, c0.ldy, c0.bsy, lx.ldr, lx.bsr, 0, lx.ldm, lx.bsm};
+    const DwLay l2{c0.ldx, c0.bsx, lddx, bsdx, c0.ldr, c0.bsr, 0, 0, 0};
+    const T *mv = static_cast<const T *>(mulv);
+    T *dm = static_cast<T *>(dmul);
     if (C % 4 != 0) {
         long long nb1 = ((long long)Bn * H * W * C + 255) / 256;
         if (nb1 > 148LL * 32) nb1 = 148LL * 32;
         const T *xq = static_cast<const T *>(x), *gq = static_cast<const T *>(dy);
         T *zq = static_cast<T *>(dz);
-        if (act) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2, l1);
-        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2, l1);
+        if (act) dwconv3x3_scalar_kernel<T, 1><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2, l1, mv, dm);
+        else dwconv3x3_scalar_kernel<T, 0><<<(int)nb1, 256, 0, st>>>(xq, w, b, gq, zq, dw, db, Bn, H, W, C, 2, l1, mv, dm);
         cudaError_t e1 = cudaGetLastError();
         if (e1 != cudaSuccess) return e1;
         return dwconv_fwd_t<T>(dz, w, nullptr, nullptr, dx, Bn, H, W, C, 0, true, l2, st);
@@ -466,15 +497,15 @@ static cudaError_t dwconv_bwd_t(const void *x, const float *w, const float *b, c
     const T *xp = static_cast<const T *>(x), *gp = static_cast<const T *>(dy);
     T *zp = static_cast<T *>(dz);
     cudaError_t e;
-    if (act) {
-        auto k = dwconv3x3_bwd_w_kernel<T, 1>;
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb, l1);
-    } else {
-        auto k = dwconv3x3_bwd_w_kernel<T, 0>;
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb, l1);
-    }
+    auto launch = [&](auto k) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e2 != cudaSuccess) return e2;
+        k<<<blocks, threads, smem, st>>>(xp, w, b, gp, zp, dw, db, Bn, H, W, C, ppb, l1, mv, dm);
+        return cudaSuccess;
+    };
+    if (mv) e = act ? launch(dwconv3x3_bwd_w_kernel<T, 1, true>) : launch(dwconv3x3_bwd_w_kernel<T, 0, true>);
+    else e = act ? launch(dwconv3x3_bwd_w_kernel<T, 1, false>) : launch(dwconv3x3_bwd_w_kernel<T, 0, false>);
+    if (e != cudaSuccess) return e;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     return dwconv_fwd_t<T>(dz, w, nullptr, nullptr, dx, Bn, H, W, C, 0, true, l2, st);
 }
@@ -482,11 +513,11 @@ static cudaError_t dwconv_bwd_t(const void *x, const float *w, const float *b, c
 // x (ldx, bsx), dy (lddy, bsdy), dz: contiguous workspace, dx (lddx, bsdx)
 cudaError_t dwconv3x3_bwd_dispatch(const void *x, const float *w, const float *b, const void *dy, void *dz, void *dx,
                                    float *dw, float *db, int Bn, int H, int W, int C, long long ldx, long long bsx,
-                                   long long lddy, long long bsdy, long long lddx, long long bsdx, int act, int dtype,
-                                   cudaStream_t st) {
-    const DwLay lx{ldx, bsx, 0, 0, lddy, bsdy};
-    return dtype == 0 ? dwconv_bwd_t<float>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, lx, lddx, bsdx, st)
-                      : dwconv_bwd_t<__nv_bfloat16>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, lx, lddx, bsdx, st);
+                                   long long lddy, long long bsdy, long long lddx, long long bsdx, const void *mulv,
+                                   void *dmul, long long ldm, long long bsm, int act, int dtype, cudaStream_t st) {
+    const DwLay lx{ldx, bsx, 0, 0, lddy, bsdy, 0, ldm, bsm};
+    return dtype == 0 ? dwconv_bwd_t<float>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, lx, lddx, bsdx, mulv, dmul, st)
+                      : dwconv_bwd_t<__nv_bfloat16>(x, w, b, dy, dz, dx, dw, db, Bn, H, W, C, act, lx, lddx, bsdx, mulv, dmul, st);
 }
 
 cudaError_t causal_conv1d_fwd_dispatch(const float *x, const float *w, const float *b, float *y, int rows, int C,

@@ -16,7 +16,8 @@
 namespace mlagg {
 
 constexpr int kWalkMaxStages = 8;
-// tile = TC channels x TP positions, TC * TP = 2048.  Shipped: (32, 64).  Measured at the config-3 shape (B = 10,
+// 1-D tiles (row walk; the column walk uses the 2-D tiles further down): TC channels x TP positions, TC * TP = 2048.
+// Shipped: (32, 64).  Measured at the config-3 shape (B = 10,
 // L = 34 000, 96 channels, bf16 tokens -> fp32 planes), row / column walk: pack 39 / 150 us, unpack (two planes summed)
 // 86 / 176 us.  The column walk is slower because consecutive positions are W tokens apart (every 64-byte token piece sits
 // in a different DRAM page).  The (128, 16) shape -- a warp moves one whole token row -- was tried to fix that and is
@@ -34,7 +35,28 @@ struct WalkGeom {
     int nstage;
     int soff[kWalkMaxStages + 1];
     int H[kWalkMaxStages], W[kWalkMaxStages];
+    int toff[kWalkMaxStages + 1];    // cumulative count of kColTI x kColTJ pixel tiles per stage (column walk)
 };
+
+// Column walk, 2-D tiles.  In column-major order position soff + j * H + i visits token soff + i * W + j, so a run of
+// consecutive positions is a column of the image (tokens W apart: every token piece in another DRAM page -- the 1-D tiles
+// above ran the column walk 4x slower than the row walk).  A tile of kColTI rows x kColTJ columns has both sides in runs:
+// the token side reads / writes kColTJ consecutive tokens per image row, the plane side kColTI consecutive positions per
+// image column.
+constexpr int kColTI = 32, kColTJ = 8, kColTC = 32;
+constexpr int kColCS = kColTJ * (kColTI + 1) + 1;   // floats per channel in shared memory: = 1 mod 8 keeps both phases conflict-free
+
+struct ColTile {
+    int soff, H, W, i0, j0;
+};
+__device__ __forceinline__ ColTile col_tile(const WalkGeom &g, int tile) {
+    int s = 0;
+#pragma unroll
+    for (int i = 1; i < kWalkMaxStages; ++i) s += (i < g.nstage && tile >= g.toff[i]) ? 1 : 0;
+    const int lt = tile - g.toff[s];
+    const int ntj = (g.W[s] + kColTJ - 1) / kColTJ;
+    return ColTile{g.soff[s], g.H[s], g.W[s], (lt / ntj) * kColTI, (lt % ntj) * kColTJ};
+}
 
 __device__ __forceinline__ int walk_token(const WalkGeom &g, int p, int col) {
     if (!col) return p;
@@ -206,6 +228,108 @@ __global__ void __launch_bounds__(256) walk_unpack_kernel(const float *__restric
     }
 }
 
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) walk_pack_col2d_kernel(const T *__restrict__ src, long long ld_src, long long bs_src,
+                                                              int c0, int nc, float *__restrict__ dst, long long bs_dst,
+                                                              int L, WalkGeom g) {
+    __shared__ float tile[kColTC * kColCS];
+    const ColTile t = col_tile(g, blockIdx.x);
+    const int cb = blockIdx.y * kColTC, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cg = tid & 7, c = cb + 4 * cg;
+    const T *sb = src + (long long)b * bs_src + c0 + c;
+#pragma unroll
+    for (int pass = 0; pass < kColTI * kColTJ / 32; ++pass) {
+        const int pp = pass * 32 + (tid >> 3), ii = pp / kColTJ, jj = pp % kColTJ;     // j fastest: consecutive tokens
+        const int i = t.i0 + ii, j = t.j0 + jj;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < t.H && j < t.W && c < nc) {
+            const T *r = sb + (long long)(t.soff + i * t.W + j) * ld_src;
+            if (VEC && c + 4 <= nc) {
+                wk_ld4<T>(r, v);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c + k < nc) v[k] = wk_ld<T>(r + k);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tile[(4 * cg + k) * kColCS + jj * (kColTI + 1) + ii] = v[k];
+    }
+    __syncthreads();
+    float *db = dst + (long long)b * bs_dst;
+    const int i = t.i0 + lane;
+#pragma unroll
+    for (int k = 0; k < kColTC / 8; ++k) {
+        const int cl = (kColTC / 8) * warp + k, cc = cb + cl;
+        if (cc < nc && i < t.H) {
+#pragma unroll
+            for (int jj = 0; jj < kColTJ; ++jj) {
+                const int j = t.j0 + jj;
+                if (j < t.W) db[(long long)cc * L + t.soff + j * t.H + i] = tile[cl * kColCS + jj * (kColTI + 1) + lane];
+            }
+        }
+    }
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) walk_unpack_col2d_kernel(const float *__restrict__ src0,
+                                                                const float *__restrict__ src1, long long bs_src, int nc,
+                                                                int nc_pad, T *__restrict__ dst, long long ld_dst,
+                                                                long long bs_dst, int c0, int L, int accumulate,
+                                                                WalkGeom g) {
+    __shared__ float tile[kColTC * kColCS];
+    const ColTile t = col_tile(g, blockIdx.x);
+    const int cb = blockIdx.y * kColTC, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *s0 = src0 + (long long)b * bs_src, *s1 = src1 ? src1 + (long long)b * bs_src : nullptr;
+    {
+        const int i = t.i0 + lane;
+#pragma unroll
+        for (int k = 0; k < kColTC / 8; ++k) {
+            const int cl = (kColTC / 8) * warp + k, cc = cb + cl;
+#pragma unroll
+            for (int jj = 0; jj < kColTJ; ++jj) {
+                const int j = t.j0 + jj;
+                float v = 0.f;
+                if (cc < nc && i < t.H && j < t.W) {
+                    const long long o = (long long)cc * L + t.soff + j * t.H + i;
+                    v = __ldg(s0 + o);
+                    if (s1) v += __ldg(s1 + o);
+                }
+                tile[cl * kColCS + jj * (kColTI + 1) + lane] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int cg = tid & 7, c = cb + 4 * cg;
+    T *dbase = dst + (long long)b * bs_dst + c0 + c;
+#pragma unroll
+    for (int pass = 0; pass < kColTI * kColTJ / 32; ++pass) {
+        const int pp = pass * 32 + (tid >> 3), ii = pp / kColTJ, jj = pp % kColTJ;
+        const int i = t.i0 + ii, j = t.j0 + jj;
+        if (i < t.H && j < t.W && c < nc_pad) {
+            T *r = dbase + (long long)(t.soff + i * t.W + j) * ld_dst;
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = tile[(4 * cg + k) * kColCS + jj * (kColTI + 1) + ii];
+            if (VEC && c + 4 <= nc_pad) {
+                if (accumulate) {
+                    float o[4];
+                    wk_ld4<T>(r, o);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] += o[k];
+                }
+                wk_st4<T>(r, v);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c + k < nc_pad) wk_st<T>(r + k, accumulate ? v[k] + wk_ld<T>(r + k) : v[k]);
+            }
+        }
+    }
+}
+
 static bool walk_geom(WalkGeom &g, int nstages, const int *Hs, const int *Ws, long long *L) {
     if (nstages <= 0 || nstages > kWalkMaxStages || !Hs || !Ws) return false;
     long long off = 0;
@@ -221,8 +345,14 @@ static bool walk_geom(WalkGeom &g, int nstages, const int *Hs, const int *Ws, lo
     }
     g.soff[kWalkMaxStages] = (int)off;
     for (int s = nstages; s < kWalkMaxStages; ++s) g.soff[s] = (int)off;
+    long long tiles = 0;
+    for (int s = 0; s <= kWalkMaxStages; ++s) {
+        g.toff[s] = (int)tiles;
+        if (s < nstages)
+            tiles += (long long)((g.H[s] + kColTI - 1) / kColTI) * ((g.W[s] + kColTJ - 1) / kColTJ);
+    }
     *L = off;
-    return off > 0 && off <= 0x7fffffff;
+    return off > 0 && off <= 0x7fffffff && tiles <= 0x7fffffff;
 }
 
 // returns cudaErrorInvalidValue for shapes the caller should have rejected
@@ -237,6 +367,19 @@ cudaError_t walk_pack_dispatch(const void *src, int dtype, long long ld_src, lon
     const size_t es = dtype == 0 ? 4 : 2;
     const bool vec = (c0 % 4 == 0) && (ld_src % 4 == 0) && (bs_src % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(src) % (4 * es)) == 0);
+    if (col) {
+        const dim3 g2((unsigned)g.toff[kWalkMaxStages], (unsigned)((nc + kColTC - 1) / kColTC), (unsigned)batch);
+        if (dtype == 0) {
+            const float *sp = static_cast<const float *>(src);
+            if (vec) walk_pack_col2d_kernel<float, true><<<g2, 256, 0, st>>>(sp, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, g);
+            else walk_pack_col2d_kernel<float, false><<<g2, 256, 0, st>>>(sp, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, g);
+        } else {
+            const __nv_bfloat16 *sp = static_cast<const __nv_bfloat16 *>(src);
+            if (vec) walk_pack_col2d_kernel<__nv_bfloat16, true><<<g2, 256, 0, st>>>(sp, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, g);
+            else walk_pack_col2d_kernel<__nv_bfloat16, false><<<g2, 256, 0, st>>>(sp, ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, g);
+        }
+        return cudaGetLastError();
+    }
 #define MLAGG_PACK(T_, V_, C_) \
     walk_pack_kernel<T_, V_, C_><<<grid, 256, 0, st>>>(static_cast<const T_ *>(src), ld_src, bs_src, c0, nc, dst, bs_dst, (int)L, col, g)
 #define MLAGG_PACK_T(T_)                                  \
@@ -264,6 +407,19 @@ cudaError_t walk_unpack_dispatch(const float *src0, const float *src1, long long
     const size_t es = dtype == 0 ? 4 : 2;
     const bool vec = (c0 % 4 == 0) && (ld_dst % 4 == 0) && (bs_dst % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(dst) % (4 * es)) == 0);
+    if (col) {
+        const dim3 g2((unsigned)g.toff[kWalkMaxStages], (unsigned)((nc_pad + kColTC - 1) / kColTC), (unsigned)batch);
+        if (dtype == 0) {
+            float *dp = static_cast<float *>(dst);
+            if (vec) walk_unpack_col2d_kernel<float, true><<<g2, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, dp, ld_dst, bs_dst, c0, (int)L, accumulate, g);
+            else walk_unpack_col2d_kernel<float, false><<<g2, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, dp, ld_dst, bs_dst, c0, (int)L, accumulate, g);
+        } else {
+            __nv_bfloat16 *dp = static_cast<__nv_bfloat16 *>(dst);
+            if (vec) walk_unpack_col2d_kernel<__nv_bfloat16, true><<<g2, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, dp, ld_dst, bs_dst, c0, (int)L, accumulate, g);
+            else walk_unpack_col2d_kernel<__nv_bfloat16, false><<<g2, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, dp, ld_dst, bs_dst, c0, (int)L, accumulate, g);
+        }
+        return cudaGetLastError();
+    }
 #define MLAGG_UNPACK(T_, V_, C_)                                                                                        \
     walk_unpack_kernel<T_, V_, C_><<<grid, 256, 0, st>>>(src0, src1, bs_src, nc, nc_pad, static_cast<T_ *>(dst), ld_dst, \
                                                          bs_dst, c0, (int)L, col, accumulate, g)

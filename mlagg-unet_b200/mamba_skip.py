@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import CatStages, Conv2dCL, JoinLast, SplitLast, SplitStages, _Linear, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
+from .ops import CatStages, Conv2dCL, JoinLast, SplitLast, SplitStages, _Linear, conv_glu_core, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
 from .selective_scan_interface import msmm_scan, msmm_scan_tokens, selective_scan_fn, xdbl_pad
 from .thirdparty_shims import DropPath, _inst_norm
 
@@ -234,12 +234,14 @@ class ConvolutionalGLU(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, H, W):
-        a, v = linear_tokens(x, self.fc1).chunk(2, dim=-1)
+        h = linear_tokens(x, self.fc1)
         if isinstance(self.act, nn.SiLU):
-            a = self.dwconv(a, H, W, silu=True)  # SiLU fused into the stencil
+            # conv + SiLU + the product with the v half in one kernel, both halves of h read in place
+            av = conv_glu_core(h, self.dwconv.dwconv.weight, self.dwconv.dwconv.bias, H, W, silu=True)
         else:
-            a = self.act(self.dwconv(a, H, W))
-        return self.drop(linear_tokens(self.drop(a * v), self.fc2))
+            a, v = h.chunk(2, dim=-1)
+            av = self.act(self.dwconv(a, H, W)) * v
+        return self.drop(linear_tokens(self.drop(av), self.fc2))
 
 
 class VSS_Conv_Block(nn.Module):

@@ -59,7 +59,7 @@ class _DWConv3x3(torch.autograd.Function):
         with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd"):
             rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(res),
                                                         _lib.ptr(y), Bn, H, W, C, ldx, bsx, ldr, bsr, C, N * C, int(silu),
-                                                        _DT[xin.dtype], _lib.stream_ptr())
+                                                        0, _DT[xin.dtype], _lib.stream_ptr())
         _lib.check(rc, "mlagg_dwconv3x3_fwd_strided")
         ctx.save_for_backward(xin, w32, b32)
         ctx.meta = (H, W, bool(silu), x.dtype, weight.dtype, None if bias is None else bias.dtype, (ldx, bsx),
@@ -79,8 +79,8 @@ class _DWConv3x3(torch.autograd.Function):
         with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2):
             rc = _lib.lib().mlagg_dwconv3x3_bwd_strided(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy),
                                                         _lib.ptr(dz), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), Bn, H, W,
-                                                        C, ldx, bsx, ldg, bsg, C, N * C, int(silu), _DT[xin.dtype],
-                                                        _lib.stream_ptr())
+                                                        C, ldx, bsx, ldg, bsg, C, N * C, None, None, 0, 0, int(silu),
+                                                        _DT[xin.dtype], _lib.stream_ptr())
         _lib.check(rc, "mlagg_dwconv3x3_bwd_strided")
         return (dx.to(xdt), dw.view(C, 1, 3, 3).to(wdt), None if db is None else db.to(bdt), None, None, None,
                 None if rdt is None else dy.to(rdt))
@@ -90,6 +90,60 @@ def dwconv3x3_tokens(x, weight, bias, H, W, silu=False, residual=None):
     """x (B, H*W, C) -> depthwise 3x3 (pad 1) [+ SiLU] [+ residual]; weight is the nn.Conv2d(C, C, 3, groups=C)
     parameter.  x / residual may be channel slices of wider activations (read in place)."""
     return _DWConv3x3.apply(x, weight, bias, H, W, silu, residual)
+
+
+class _ConvGLUCore(torch.autograd.Function):
+    """ConvolutionalGLU between fc1 and fc2 (reference MambaSkip.py:572-574): h = fc1(x) (B, N, 2 hid) ->
+    act(dwconv(h[..., :hid])) * h[..., hid:] in ONE kernel on the two halves of h in place; the backward writes the
+    gradients of both halves into one (B, N, 2 hid) tensor (C ABI: mlagg_dwconv3x3_fwd_strided with residual_mul = 1,
+    mlagg_dwconv3x3_bwd_strided with mul / dmul)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, H, W, silu):
+        if not h.is_cuda:
+            raise _lib.MlaggError("conv_glu_core: CUDA tensor required (no CPU fallback in the product path)")
+        Bn, N, C2 = h.shape
+        C = C2 // 2
+        assert N == H * W and C2 == 2 * C and weight.shape == (C, 1, 3, 3)
+        hin = _io(h).contiguous()
+        w32 = weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty(Bn, N, C, device=h.device, dtype=hin.dtype)
+        es = hin.element_size()
+        with torch.cuda.device(h.device), _lib.timed("dwconv3x3_fwd"):
+            rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(hin.data_ptr(), _lib.ptr(w32), _lib.ptr(b32), hin.data_ptr() + C * es,
+                                                        _lib.ptr(y), Bn, H, W, C, C2, N * C2, C2, N * C2, C, N * C,
+                                                        int(silu), 1, _DT[hin.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dwconv3x3_fwd_strided")
+        ctx.save_for_backward(hin, w32, b32)
+        ctx.meta = (H, W, bool(silu), h.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return y.to(h.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        hin, w32, b32 = ctx.saved_tensors
+        H, W, silu, hdt, wdt, bdt = ctx.meta
+        Bn, N, C2 = hin.shape
+        C = C2 // 2
+        dy, (ldg, bsg) = _tok_operand(dy.to(hin.dtype), C)
+        dz = torch.empty(Bn, N, C, device=hin.device, dtype=hin.dtype)
+        dh = torch.empty_like(hin)
+        dw = _lib.zeros((C, 9), hin.device)
+        db = _lib.zeros(C, hin.device) if b32 is not None else None
+        es = hin.element_size()
+        with torch.cuda.device(hin.device), _lib.timed("dwconv3x3_bwd", 2):
+            rc = _lib.lib().mlagg_dwconv3x3_bwd_strided(hin.data_ptr(), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy),
+                                                        _lib.ptr(dz), dh.data_ptr(), _lib.ptr(dw), _lib.ptr(db), Bn, H, W,
+                                                        C, C2, N * C2, ldg, bsg, C2, N * C2, hin.data_ptr() + C * es,
+                                                        dh.data_ptr() + C * es, C2, N * C2, int(silu), _DT[hin.dtype],
+                                                        _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dwconv3x3_bwd_strided")
+        return dh.to(hdt), dw.view(C, 1, 3, 3).to(wdt), None if db is None else db.to(bdt), None, None, None
+
+
+def conv_glu_core(h, weight, bias, H, W, silu=True):
+    """h (B, H*W, 2 hid) = fc1 output -> act(dwconv3x3(h[..., :hid])) * h[..., hid:]  (B, H*W, hid)"""
+    return _ConvGLUCore.apply(h, weight, bias, H, W, silu)
 
 
 class _DWConv3x3Stages(torch.autograd.Function):
@@ -114,7 +168,7 @@ class _DWConv3x3Stages(torch.autograd.Function):
             for s, (h, w) in enumerate(hw):
                 rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(xin.data_ptr() + off * C * es, _lib.ptr(w32[s]),
                                                             _lib.ptr(b32[s]), None, y.data_ptr() + off * C * es, Bn, h, w,
-                                                            C, C, L * C, C, L * C, C, L * C, int(silu), _DT[xin.dtype],
+                                                            C, C, L * C, C, L * C, C, L * C, int(silu), 0, _DT[xin.dtype],
                                                             _lib.stream_ptr())
                 _lib.check(rc, "mlagg_dwconv3x3_fwd_strided")
                 off += h * w
@@ -145,7 +199,8 @@ class _DWConv3x3Stages(torch.autograd.Function):
                 rc = _lib.lib().mlagg_dwconv3x3_bwd_strided(xin.data_ptr() + o, _lib.ptr(w32[s]), _lib.ptr(b32[s]),
                                                             dy.data_ptr() + o, _lib.ptr(dz), dx.data_ptr() + o,
                                                             _lib.ptr(dw), _lib.ptr(db), Bn, h, w, C, C, L * C, C, L * C, C,
-                                                            L * C, int(silu), _DT[xin.dtype], _lib.stream_ptr())
+                                                            L * C, None, None, 0, 0, int(silu), _DT[xin.dtype],
+                                                            _lib.stream_ptr())
                 _lib.check(rc, "mlagg_dwconv3x3_bwd_strided")
                 dws.append(dw.view(C, 1, 3, 3).to(wdts[s]))
                 dbs.append(None if db is None else db.to(bdts[s]))

@@ -100,7 +100,7 @@ def test_walk_pack_unpack_match_the_cross_scan_index_maps(dtype):
     from mlagg_unet_b200 import _lib
     from mlagg_unet_b200.mamba_skip import cross_scan_maps
     torch.manual_seed(11)
-    hw = [(9, 7), (5, 6), (1, 3), (2, 2)]
+    hw = [(9, 7), (70, 19), (1, 3), (2, 2)]          # the second stage spans 3 x 3 of the column walk's 32 x 8 pixel tiles
     L = sum(h * w for h, w in hw)
     Bn, C = 3, 45
     ns = len(hw)
@@ -658,3 +658,27 @@ def test_strided_row_copies_and_split_join_functions(dtype):
     ob, gb = run(False)
     for a, b in zip(oa + ga, ob + gb):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("hid", [8, 7])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_glu_core_matches_torch(hid, dtype):
+    """act(dwconv(h[..., :hid])) * h[..., hid:] (ConvolutionalGLU, MambaSkip.py:572-574) as one kernel with both halves of
+    the fc1 output addressed in place, against fp64 torch: output, dh (both halves), dweight, dbias; hid = 7 takes the
+    scalar kernels."""
+    from mlagg_unet_b200.ops import conv_glu_core
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    torch.manual_seed(23)
+    Bn, H, W = 2, 6, 9
+    h = torch.randn(Bn, H * W, 2 * hid, device="cuda").to(dtype).requires_grad_()
+    w = (0.3 * torch.randn(hid, 1, 3, 3, device="cuda")).requires_grad_()
+    b = (0.1 * torch.randn(hid, device="cuda")).requires_grad_()
+    y = conv_glu_core(h, w, b, H, W, silu=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    hd_, wd, bd = (t.detach().double().requires_grad_() for t in (h, w, b))
+    yd = _dwconv_ref(hd_[..., :hid], wd, bd, H, W, True) * hd_[..., hid:]
+    yd.backward(g.double())
+    assert rel_err(y.double(), yd) < tol
+    for got, want in ((h.grad, hd_.grad), (w.grad, wd.grad), (b.grad, bd.grad)):
+        assert rel_err(got.double(), want) < tol
