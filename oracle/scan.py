@@ -170,3 +170,47 @@ def selective_scan_oracle(u, delta, A, B, C, D=None, z=None, delta_bias=None, de
         _, last = scan_fwd_c(u, delta, A, B, C, D, delta_bias, delta_softplus, fp64, True)
         return out, last
     return out
+
+
+def selective_scan_chunked(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, chunks=4):
+    """Chunk-parallel form of the same recurrence ("next" item 1) -- a MATH PROTOTYPE for the round-2 kernels,
+    test infrastructure like everything else here.  L is cut into `chunks` pieces:
+      pass A (parallel over chunks)   local scan of every chunk from a zero state -> y_local, h_end_local, and the running
+                                      sums S_t of delta inside the chunk;
+      pass B (sequential, K steps)    h_start[k+1] = exp(A * S_total[k]) * h_start[k] + h_end_local[k];
+      pass C (parallel over all t)    y_t += sum_n C_t,n * exp(A_n * S_t) * h_start[k],n      (no recurrence).
+    Returns exactly what `selective_scan_loop` returns (any dtype; differentiable through autograd)."""
+    dt = torch.float64 if A.dtype == torch.float64 else torch.float32
+    u_, dl = u.to(dt), delta.to(dt)
+    if delta_bias is not None:
+        dl = dl + delta_bias.to(dt)[..., None]
+    if delta_softplus:
+        dl = F.softplus(dl)
+    Bn, Dm, L = u_.shape
+    if B.dim() == 3:
+        B = B.unsqueeze(1)
+    if C.dim() == 3:
+        C = C.unsqueeze(1)
+    rep = Dm // B.shape[1]
+    Bx = B.to(dt).repeat_interleave(rep, dim=1)                    # (Bn, D, N, L)
+    Cx = C.to(dt).repeat_interleave(rep, dim=1)
+    bounds = [round(i * L / chunks) for i in range(chunks + 1)]
+    h_start = u_.new_zeros(Bn, Dm, A.shape[1])
+    ys = []
+    for k in range(chunks):
+        t0, t1 = bounds[k], bounds[k + 1]
+        if t1 == t0:
+            continue
+        # pass A: local scan from zero (delta already activated: no bias / softplus again)
+        y_loc, h_end = selective_scan_loop(u_[:, :, t0:t1], dl[:, :, t0:t1], A.to(dt), Bx[..., t0:t1], Cx[..., t0:t1],
+                                           None, None, None, False, return_last_state=True)
+        S = torch.cumsum(dl[:, :, t0:t1], dim=-1)                  # inclusive running sum of delta inside the chunk
+        # pass C: carried-state term, one exponential per (channel, state, step), no dependence between steps
+        P = torch.exp(A.to(dt)[None, :, :, None] * S[:, :, None, :])            # (Bn, D, N, Lc)
+        ys.append(y_loc + (Cx[..., t0:t1] * P * h_start[..., None]).sum(2))
+        # pass B: chain the chunk states
+        h_start = P[..., -1] * h_start + h_end
+    y = torch.cat(ys, dim=-1)
+    if D is not None:
+        y = y + u_ * D.to(dt)[..., None]
+    return y.to(u.dtype)
