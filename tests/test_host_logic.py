@@ -191,3 +191,21 @@ def test_walk_token_formula_is_the_cross_scan_map():
     assert idx[1].tolist() == toks and idx[0].tolist() == list(range(off))
     assert idx[3].tolist() != toks and sorted(toks) == list(range(off))
     assert all(inv[1][t] == p for p, t in enumerate(toks))
+
+
+def test_stride_probes_for_in_place_operands():
+    """`_tok_strides` / `_rows3` decide whether a view is handed to the kernels in place or copied first: channel slices
+    and stage segments qualify, transposed or misaligned views do not."""
+    from mlagg_unet_b200.ops import _rows3, _tok_strides
+    t = torch.zeros(2, 30, 16)
+    assert _tok_strides(t, 16) == (16, 480)
+    assert _tok_strides(t[..., 8:], 8) == (16, 480)                 # v half of a kv projection
+    assert _tok_strides(t[:, 5:15], 16) == (16, 480)                # a stage segment keeps the parent's image stride
+    assert _tok_strides(t[..., 2:10], 8) is None                    # 4-channel vectors would be misaligned
+    assert _tok_strides(t[..., 2:9], 7) == (16, 480)                # scalar kernels (C % 4 != 0) take any offset
+    assert _tok_strides(t.transpose(1, 2), 30) is None
+    x = torch.zeros(2, 12, 5, 6).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)    # (B, H, W, C) view
+    r = _rows3(x[..., 4:])
+    assert r is not None and r[1:] == (2, 30, 8, 12, 360)
+    assert _rows3(x.permute(0, 2, 1, 3)) is None                    # rows no longer collapse to one stride
+    assert _rows3(torch.zeros(2, 7, 3)[:, 1:5])[1:] == (2, 4, 3, 3, 21)
