@@ -1,7 +1,8 @@
 """Generate tests/golden/*.pt by RUNNING THE REFERENCE'S OWN MODULE SOURCE in this container.
 
 Usage (only where /root/reference exists -- it does not exist on the GPU box):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # all round-1 fixtures
+    python tests/golden/make_golden.py --hd24     # round 2: the hd = 24 / P = 100 attention + block fixtures only
 
 Method: the reference package cannot be imported (batchgenerators, timm, monai,
 mamba_ssm ... are absent), but the three hot-path files are pure torch once their third-party import
@@ -73,8 +74,38 @@ def grads(out, wrt):
     return [g.detach().clone() for g in torch.autograd.grad(loss, wrt, allow_unused=True)]
 
 
+def hd24(mlagg):
+    """Round 2: fixtures at the SHIPPED attention geometry (hd = 24, P = 100; reference :71-89 gives every stage hd 24):
+    the two AggregatedAttention branches with h = 2 and one stage-0-shaped MLLABlock (dim 96, heads 2 -> h = 1)."""
+    torch.manual_seed(24)
+    H, W, dim, h = 10, 10, 96, 2                       # branch dim 96 = 2 * h * 24; sr 1 -> P = N = 100
+    for local in (True, False):
+        att = mlagg["AggregatedAttention"](dim, (H, W), num_heads=h, local=local, sr_ratio=1).eval()
+        x = torch.randn(2, H * W, dim, requires_grad=True)
+        y = att(x, H, W)
+        g = grads(y, [x] + list(att.parameters()))
+        torch.save({"H": H, "W": W, "dim": dim, "num_heads": h, "sr_ratio": 1, "local": local,
+                    "state": sd(att), "input": x.detach(), "output": y.detach(), "grad_input": g[0],
+                    "grad_params": {n_: g_ for (n_, _), g_ in zip(att.named_parameters(), g[1:])}},
+                   f"{HERE}/mlagg_attention_{'local' if local else 'pooled'}_hd24.pt")
+    H, W, dim, heads, sr = 20, 20, 96, 2, 2            # stage-0 block of the shipped network: pooled 10 x 10 = 100
+    blk = mlagg["MLLABlock"](dim, (H, W), heads, mlp_ratio=2, sr_ratio=sr, drop_path=0.05).eval()
+    x = torch.randn(2, dim, H, W, requires_grad=True)
+    y = blk(x)
+    g = grads(y, [x] + list(blk.parameters()))
+    torch.save({"H": H, "W": W, "dim": dim, "num_heads": heads, "sr_ratio": sr, "state": sd(blk),
+                "input": x.detach(), "output": y.detach(), "grad_input": g[0],
+                "grad_params": {n_: g_ for (n_, _), g_ in zip(blk.named_parameters(), g[1:])}},
+               f"{HERE}/mlagg_block_hd24.pt")
+
+
 def main():
     torch.set_num_threads(8)
+    if "--hd24" in sys.argv:          # add the round-2 fixtures without rewriting the round-1 files
+        mamba = load_reference(f"{REF}/variants/mamba/MambaSkip.py")
+        hd24(load_reference(f"{REF}/nnUNetTrainer_MLAgg_2D_dt_MS.py", "import sys\nimport torch.utils.checkpoint",
+                            {"VSS_Conv_Layer": mamba["VSS_Conv_Layer"]}))
+        return
     mamba = load_reference(f"{REF}/variants/mamba/MambaSkip.py")
     mlagg = load_reference(f"{REF}/nnUNetTrainer_MLAgg_2D_dt_MS.py", "import sys\nimport torch.utils.checkpoint",
                            {"VSS_Conv_Layer": mamba["VSS_Conv_Layer"]})

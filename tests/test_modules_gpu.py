@@ -31,10 +31,11 @@ def _check_param_grads(module, golden_grads, tol=TOL32, fp64_grads=None):
         if fp64_grads is not None and n in fp64_grads:
             # lambda_* receive ONE scalar: a signed sum over every (token, head pair, neighbour) with heavy
             # cancellation -- fp32 dot-product rounding is amplified; 5e-4 there, 1e-4 everywhere else
-            assert rel_err(p.grad.cpu(), fp64_grads[n]) < (5 * tol if n.startswith("lambda_") else tol), n
+            assert rel_err(p.grad.cpu(), fp64_grads[n]) < (5 * tol if "lambda_" in n else tol), n
             assert rel_err(ref, fp64_grads[n]) < 10 * tol, n  # the golden itself agrees with fp64 to fp32 noise
         else:
-            assert rel_err(p.grad.cpu(), ref) < tol, n
+            # lambda_* against an fp32 golden: the golden's own cancelling sum carries 1e-4-level noise (test_oracle_golden)
+            assert rel_err(p.grad.cpu(), ref) < (10 * tol if "lambda_" in n else tol), n
 
 
 def _fp64_attention_grads(g):
@@ -147,8 +148,9 @@ def test_vss_conv_layer_matches_reference():
     _check_param_grads(m, g["grad_params"])
 
 
-@pytest.mark.parametrize("kind", ["local", "pooled"])
+@pytest.mark.parametrize("kind", ["local", "pooled", "local_hd24", "pooled_hd24"])
 def test_aggregated_attention_matches_reference(kind):
+    """`*_hd24`: the shipped geometry (hd = 24, P = 100), generated from the reference source in round 2"""
     from mlagg_unet_b200.mlagg import AggregatedAttention
     g = load_golden(f"mlagg_attention_{kind}.pt")
     m = AggregatedAttention(g["dim"], (g["H"], g["W"]), num_heads=g["num_heads"], local=g["local"],
@@ -162,9 +164,10 @@ def test_aggregated_attention_matches_reference(kind):
     _check_param_grads(m, g["grad_params"], fp64_grads=_fp64_attention_grads(g))
 
 
-def test_mlagg_block_matches_reference_fp32_and_bf16():
+@pytest.mark.parametrize("name", ["mlagg_block.pt", "mlagg_block_hd24.pt"])
+def test_mlagg_block_matches_reference_fp32_and_bf16(name):
     from mlagg_unet_b200.mlagg import MLLABlock
-    g = load_golden("mlagg_block.pt")
+    g = load_golden(name)
     m = MLLABlock(g["dim"], (g["H"], g["W"]), g["num_heads"], mlp_ratio=2, sr_ratio=g["sr_ratio"], drop_path=0.05)
     m = m.cuda().eval()
     m.load_state_dict(g["state"], strict=True)
@@ -175,9 +178,20 @@ def test_mlagg_block_matches_reference_fp32_and_bf16():
     _loss(y).backward()
     assert rel_err(x.grad.cpu(), g["grad_input"]) < TOL32
     _check_param_grads(m, g["grad_params"])
+    # bf16 autocast: forward AND backward (input gradient + every parameter gradient) at 2e-2
+    m.zero_grad(set_to_none=True)
+    x16 = g["input"].cuda().requires_grad_()
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        y16 = m(g["input"].cuda())
+        y16 = m(x16)
     assert rel_err(y16.float().cpu(), g["output"]) < TOL16
+    _loss(y16.float()).backward()
+    assert rel_err(x16.grad.float().cpu(), g["grad_input"]) < TOL16
+    for n, p in m.named_parameters():
+        ref = g["grad_params"].get(n)
+        if ref is None or float(ref.abs().max()) < 1e-5:
+            continue
+        # lambda_*: one scalar each, a cancelling sum over every token (see _check_param_grads)
+        assert rel_err(p.grad.float().cpu(), ref) < (5 * TOL16 if "lambda_" in n else 2 * TOL16), n
 
 
 def test_linear_attention_and_mlla_block_match_reference():
