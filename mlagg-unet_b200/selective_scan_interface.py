@@ -22,9 +22,16 @@ def _f32c(t):
     return None if t is None else t.detach().float().contiguous()
 
 
+def _wants_grad(*ts):
+    """Decided OUTSIDE Function.apply: inside `forward` grad mode is always off and Parameters passed in directly keep
+    requires_grad = True under torch.no_grad(), which would make inference write (and allocate) the state checkpoints."""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
 class SelectiveScanFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, return_last_state=False,
+                need_grad=True):
         if not u.is_cuda:
             raise _lib.MlaggError("selective_scan_fn: CUDA tensors required (no CPU fallback in the product path)")
         if A.is_complex() or B.dim() not in (3, 4) or C.dim() != B.dim():
@@ -37,7 +44,6 @@ class SelectiveScanFn(torch.autograd.Function):
             B32, C32 = B32.unsqueeze(1), C32.unsqueeze(1)
         Bn, Dm, L = u32.shape
         N, G = A32.shape[1], B32.shape[1]
-        need_grad = any(t is not None and t.requires_grad for t in (u, delta, A, B, C, D, delta_bias))
         L_ = _lib.lib()
         out = torch.empty_like(u32)
         ckpt = None
@@ -82,13 +88,14 @@ class SelectiveScanFn(torch.autograd.Function):
         dt = ctx.in_dtypes
         cast = lambda g, d: None if g is None else g.to(d)
         return (cast(du, dt[0]), cast(dd, dt[1]), cast(dA, dt[2]), cast(dB, dt[3]), cast(dC, dt[4]),
-                cast(dD, dt[5]), cast(db, dt[6]), None, None)
+                cast(dD, dt[5]), cast(db, dt[6]), None, None, None)
 
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                       return_last_state=False):
     """out = S6 scan of u (plus D*u), optionally gated by silu(z); see module docstring."""
-    res = SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, return_last_state)
+    res = SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, return_last_state,
+                                _wants_grad(u, delta, A, B, C, D, delta_bias))
     out, last = res if return_last_state else (res, None)
     if z is not None:
         out = out * F.silu(z)
@@ -100,7 +107,7 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
 # --------------------------------------------------------------------------------------------------------------------
 class MSMMScanFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, stage_lens):
+    def forward(ctx, xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, stage_lens, need_grad=True):
         if not xrow.is_cuda:
             raise _lib.MlaggError("msmm_scan: CUDA tensors required (no CPU fallback in the product path)")
         ctx.in_dtypes = tuple(t.dtype for t in (xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds))
@@ -109,7 +116,6 @@ class MSMMScanFn(torch.autograd.Function):
         N, R = A_.shape[1], W_.shape[1]
         assert sum(stage_lens) == L and xr_.shape == (Bn, 2, R + 2 * N, L) and xc_.shape == xr_.shape
         lens = (ctypes.c_int * len(stage_lens))(*[int(v) for v in stage_lens])
-        need_grad = any(t.requires_grad for t in (xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds))
         L_ = _lib.lib()
         out = torch.empty(Bn, 4, Di, L, device=xrow.device, dtype=torch.float32)
         ckpt = None
@@ -144,13 +150,14 @@ class MSMMScanFn(torch.autograd.Function):
         _lib.check(rc, "mlagg_msmm_scan_bwd")
         dt = ctx.in_dtypes
         return ((du[:, 0] + du[:, 2]).to(dt[0]), (du[:, 1] + du[:, 3]).to(dt[1]), dxr.to(dt[2]), dxc.to(dt[3]),
-                dW.to(dt[4]), db.to(dt[5]), dA.to(dt[6]), dD.to(dt[7]), None)
+                dW.to(dt[4]), db.to(dt[5]), dA.to(dt[6]), dD.to(dt[7]), None, None)
 
 
 def msmm_scan(xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, stage_lens):
     """4-direction multi-scale selective scan on un-permuted operands; see include/mlagg_b200.h (mlagg_msmm_scan_fwd).
     Returns out (B, 4, Di, L): direction k in row-major (k even) / column-major (k odd) order, mirroring undone."""
-    return MSMMScanFn.apply(xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, tuple(stage_lens))
+    return MSMMScanFn.apply(xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds, tuple(stage_lens),
+                            _wants_grad(xrow, xcol, xdbl_row, xdbl_col, Wdt, dt_bias, A, Ds))
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -175,7 +182,7 @@ def xdbl_pad(c35):
 
 class MSMMTokensFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xc, xdbl, Wdt, dt_bias, A, Ds, hw):
+    def forward(ctx, xc, xdbl, Wdt, dt_bias, A, Ds, hw, need_grad=True):
         if not xc.is_cuda:
             raise _lib.MlaggError("msmm_scan_tokens: CUDA tensors required (no CPU fallback in the product path)")
         ctx.in_dtypes = tuple(t.dtype for t in (xc, xdbl, Wdt, dt_bias, A, Ds))
@@ -197,7 +204,6 @@ class MSMMTokensFn(torch.autograd.Function):
         xcol = torch.empty_like(xrow)
         xr = torch.empty(Bn, 2, C35, L, device=dev, dtype=torch.float32)
         xcl = torch.empty_like(xr)
-        need_grad = any(t.requires_grad for t in (xc, xdbl, Wdt, dt_bias, A, Ds))
         out = torch.empty(Bn, 4, Di, L, device=dev, dtype=torch.float32)
         ckpt = None
         if need_grad:
@@ -269,11 +275,11 @@ class MSMMTokensFn(torch.autograd.Function):
                     rc = L_.mlagg_walk_unpack(dxd[col].data_ptr(), None, 2 * C35 * L, 2 * C35, P, dxdbl.data_ptr(),
                                               _DT[dxdbl.dtype], 2 * P, L * 2 * P, col * P, Bn, ns, Hs, Ws, col, 0, st)
                     _lib.check(rc, "mlagg_walk_unpack")
-        return (dxc.to(dt[0]), dxdbl.to(dt[1]), dW.to(dt[2]), db.to(dt[3]), dA.to(dt[4]), dD.to(dt[5]), None)
+        return (dxc.to(dt[0]), dxdbl.to(dt[1]), dW.to(dt[2]), db.to(dt[3]), dA.to(dt[4]), dD.to(dt[5]), None, None)
 
 
 def msmm_scan_tokens(xc, xdbl, Wdt, dt_bias, A, Ds, hw):
     """xc (B, L, Di): conv + SiLU output, tokens-major, stages concatenated; xdbl (B, L, 2 P), P = xdbl_pad(R + 2 N): the
     x_proj output with columns [direction 0 | direction 2 | pad | direction 1 | direction 3 | pad]; hw = [(H_s, W_s)].
     Returns the merged scan output y (B, L, Di) fp32 (reference MambaSkip.py:405-473)."""
-    return MSMMTokensFn.apply(xc, xdbl, Wdt, dt_bias, A, Ds, tuple(hw))
+    return MSMMTokensFn.apply(xc, xdbl, Wdt, dt_bias, A, Ds, tuple(hw), _wants_grad(xc, xdbl, Wdt, dt_bias, A, Ds))

@@ -159,7 +159,10 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         return DeepSupervisionDiceCE(len(self._get_deep_supervision_scales()), self.plans.batch_dice, self.is_ddp)
 
     def configure_optimizers(self):
-        params = [p for p in self.network.parameters() if p.requires_grad]
+        # ALL parameters, in registration order, like the reference (`AdamW(self.network.parameters(), ...)`, :137-140):
+        # the frozen `dummy_tensor` keeps its slot, so `optimizer_state` indices are interchangeable with the
+        # reference's checkpoints in both directions (it never gets a gradient there either, so it has no state)
+        params = list(self.network.parameters())
         cuda = self.device.type == "cuda"
         # fused + capturable: the step (and the learning rate, kept as a device scalar) can live inside a CUDA graph
         lr = torch.tensor(self.initial_lr, device=self.device, dtype=torch.float32) if cuda else self.initial_lr
@@ -209,7 +212,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         if dist.is_available() and dist.is_initialized() and dist.get_rank() != 0:
             return
         net = self.network.module if hasattr(self.network, "module") else self.network
-        torch.save({"network_weights": net.state_dict(), "optimizer_state": self.optimizer.state_dict(),
+        torch.save({"network_weights": net.state_dict(), "optimizer_state": self._portable_optimizer_state(),
                     "grad_scaler_state": self.grad_scaler.state_dict() if self.grad_scaler is not None else None,
                     "logging": {}, "_best_ema": None, "current_epoch": self.current_epoch + 1,
                     "init_args": {"configuration": "2d_bs10", "fold": 0}, "trainer_name": self.__class__.__name__,
@@ -228,10 +231,44 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         self.current_epoch = ck.get("current_epoch", 0)
         if load_optimizer and ck.get("optimizer_state") is not None:
             self.optimizer.load_state_dict(ck["optimizer_state"])
+            self._restore_optimizer_flags()
         if self.grad_scaler is not None and ck.get("grad_scaler_state") is not None:
             self.grad_scaler.load_state_dict(ck["grad_scaler_state"])
         self._graph = None                    # captured graphs hold the old optimizer state tensors
         self._eager_steps = 0
+
+    def _portable_optimizer_state(self):
+        """optimizer.state_dict() in the form the reference's plain AdamW writes and expects: python-float lr, the stock
+        foreach / fused / capturable settings, `step` as a CPU scalar tensor (a CUDA `step` trips the assertion of the
+        non-capturable implementation)."""
+        sd = self.optimizer.state_dict()
+        groups = []
+        for g in sd["param_groups"]:
+            g = dict(g)
+            g["lr"] = float(g["lr"])
+            if "initial_lr" in g:
+                g["initial_lr"] = float(g["initial_lr"])
+            g.update(fused=None, capturable=False, foreach=None)
+            groups.append(g)
+        state = {k: {n: (v.detach().float().cpu() if n == "step" and torch.is_tensor(v) else v) for n, v in st.items()}
+                 for k, st in sd["state"].items()}
+        return {"state": state, "param_groups": groups}
+
+    def _restore_optimizer_flags(self):
+        """`load_state_dict` replaces the param groups with the checkpoint's: a reference checkpoint brings a python
+        float `lr` and fused / capturable = False, which a captured step would bake in as constants.  Put back what
+        configure_optimizers set up: lr as a device scalar (the scheduler writes into it), fused + capturable, and
+        `step` counters as device tensors."""
+        if self.device.type != "cuda":
+            return
+        for g in self.optimizer.param_groups:
+            lr = g["lr"]
+            g["lr"] = (lr.to(self.device, torch.float32) if torch.is_tensor(lr)
+                       else torch.tensor(float(lr), device=self.device, dtype=torch.float32))
+            g["fused"], g["capturable"], g["foreach"] = True, True, False
+        for st in self.optimizer.state.values():
+            if "step" in st and not (torch.is_tensor(st["step"]) and st["step"].is_cuda):
+                st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32, device=self.device)
 
     # ---- one training step (nnUNetTrainer.train_step, :833-863)
     def _forward_loss(self, data, target):
@@ -251,17 +288,25 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         it once over NCCL / NVSwitch (108 MB: well under a millisecond, no DDP hooks or buckets), clip the global norm to
         12 with two kernels on the flat buffer, and let AdamW read its gradients as views of that buffer."""
         grads = [p.grad for p in self._params] if grads is None else grads
+        # a parameter the step did not use (e.g. out_1..out_4 after set_deep_supervision_enabled(False)) has no gradient:
+        # its slice of the flat buffer is zero (the reference's clip_grad_norm_ / AdamW skip it; AdamW with a zero
+        # gradient still applies weight decay, so such parameters are ALSO dropped from the step below)
+        missing = [i for i, g in enumerate(grads) if g is None]
+        have = [(g, p, s) for g, p, s in zip(grads, self._params, self._flat_slices) if g is not None]
         parts = [(g if g.stride() == p.stride() else torch.empty_like(p).copy_(g)).as_strided((g.numel(),), (1,))
-                 for g, p in zip(grads, self._params)]
-        torch._foreach_copy_(self._flat_slices, parts)       # multi-tensor copy: 0.15 ms for 108 MB (torch.cat(out=): 0.55 ms)
+                 for g, p, _ in have]
+        torch._foreach_copy_([s for _, _, s in have], parts)   # multi-tensor copy: 0.15 ms for 108 MB (torch.cat(out=): 0.55 ms)
+        for i in missing:
+            self._flat_slices[i].zero_()
         if self.is_ddp:
             dist.all_reduce(self._flat_grad, op=dist.ReduceOp.SUM)
             self._flat_grad.div_(dist.get_world_size())
         # torch.nn.utils.clip_grad_norm_(params, 12): total 2-norm over all gradients == norm of the flat buffer
         coef = torch.clamp(12.0 / (torch.linalg.vector_norm(self._flat_grad) + 1e-6), max=1.0)
         self._flat_grad.mul_(coef)
-        for p, v in zip(self._params, self._flat_views):
-            p.grad = v
+        skip = set(missing)
+        for i, (p, v) in enumerate(zip(self._params, self._flat_views)):
+            p.grad = None if i in skip else v
         self.optimizer.step()
 
     def _step_math(self, data, target):

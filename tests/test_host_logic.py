@@ -58,6 +58,11 @@ def test_state_dict_compatibility_with_reference():
     net.load_state_dict(g["state"], strict=True)
     assert sum(p.numel() for p in net.parameters()) == g["n_params"]
     assert not net.dummy_tensor.requires_grad  # F6: unused parameter must not take part in DDP reduction
+    # parameter ORDER equals the reference's registration order (the golden's state_dict was written by the reference's
+    # own MLLA_Uper): AdamW's `optimizer_state` indexes parameters by position, so checkpoints interchange only then
+    ours = [k for k, _ in net.named_parameters()]
+    ref_order = [k for k in g["state"] if k in set(ours)]
+    assert ours == ref_order
     g = load_golden("msmm_vss_conv_layer.pt")
     VSS_Conv_Layer(g["dims"], g["hidden"], depth=1, drop_path=0.1).load_state_dict(g["state"], strict=True)
     g = load_golden("mlagg_block.pt")

@@ -49,6 +49,54 @@ def test_reference_format_checkpoint_round_trip(tmp_path):
         assert torch.equal(a, b), k
 
 
+def test_reference_optimizer_state_round_trip(tmp_path):
+    """A reference checkpoint carries `optimizer_state` of torch.optim.AdamW over ALL network parameters (reference
+    nnUNetTrainer_MLAgg_2D_dt_MS.py:137-140), `dummy_tensor` included, with a python-float lr and no fused / capturable
+    flags.  It must load, the restored step must still be graph-capturable with the learning rate as a device scalar,
+    and what we save must load back into an optimizer built over the reference's parameter list."""
+    from mlagg_unet_b200.trainer import SyntheticPlan, nnUNetTrainer_MLAgg_2D_dt_MS
+    g = load_golden("mlla_uper_embed8.pt")
+    ref_net = _net()
+    ref_net.load_state_dict(g["state"], strict=True)
+    ref_net.dummy_tensor.requires_grad_(True)                    # as in the reference (:1362)
+    ref_params = list(ref_net.parameters())
+    ref_opt = torch.optim.AdamW(ref_params, 5e-4, weight_decay=3e-5, eps=1e-4)
+    gen = torch.Generator().manual_seed(0)
+    for p in ref_params:
+        if p is not ref_net.dummy_tensor:                        # never used in forward: no gradient, no state
+            p.grad = 1e-3 * torch.randn(p.shape, generator=gen)
+    ref_opt.step()
+    ck = {"network_weights": ref_net.state_dict(), "optimizer_state": ref_opt.state_dict(), "grad_scaler_state": None,
+          "logging": {}, "_best_ema": None, "current_epoch": 3, "init_args": {},
+          "trainer_name": "nnUNetTrainer_MLAgg_2D_dt_MS", "inference_allowed_mirroring_axes": (0, 1)}
+    path = str(tmp_path / "checkpoint_latest.pth")
+    torch.save(ck, path)
+
+    tr = nnUNetTrainer_MLAgg_2D_dt_MS(SyntheticPlan(patch_size=(64, 64), batch_size=2, num_classes=5))
+    tr.build_network_architecture = staticmethod(lambda *a, **k: _net())
+    tr.initialize()
+    tr.load_checkpoint(path)                                     # default load_optimizer=True
+    grp = tr.optimizer.param_groups[0]
+    assert len(grp["params"]) == len(ref_params)
+    assert torch.is_tensor(grp["lr"]) and grp["lr"].is_cuda and grp["capturable"] and grp["fused"]
+    own = list(tr.network.parameters())
+    for i, p in enumerate(ref_params):
+        if p in ref_opt.state:
+            assert torch.equal(tr.optimizer.state[own[i]]["exp_avg"].cpu(), ref_opt.state[p]["exp_avg"]), i
+            assert float(tr.optimizer.state[own[i]]["step"]) == 1.0
+    batch = tr.synthetic_batch(2, device=tr.device)
+    losses = [float(tr.train_step(batch)["loss"]) for _ in range(6)]     # 3 eager steps, capture, replays
+    assert tr._graph is not None and all(np.isfinite(losses))
+    tr.lr_scheduler.step(5)                                      # the scheduler's write reaches the captured step
+    assert abs(float(tr.optimizer.param_groups[0]["lr"]) - (1e-4 + 5 * (5e-4 - 1e-4) / 10)) < 1e-9
+    out = str(tmp_path / "ours.pth")
+    tr.save_checkpoint(out)
+    back = torch.load(out, weights_only=False, map_location="cpu")
+    ref_opt2 = torch.optim.AdamW(ref_params, 5e-4, weight_decay=3e-5, eps=1e-4)
+    ref_opt2.load_state_dict(back["optimizer_state"])            # same group size, same indices
+    assert float(ref_opt2.state[ref_params[0]]["step"]) == 7.0
+
+
 def test_sliding_window_matches_tilewise_restatement():
     from mlagg_unet_b200 import inference as inf
     g = load_golden("mlla_uper_embed8.pt")
