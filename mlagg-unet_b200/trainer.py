@@ -266,9 +266,14 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             g["lr"] = (lr.to(self.device, torch.float32) if torch.is_tensor(lr)
                        else torch.tensor(float(lr), device=self.device, dtype=torch.float32))
             g["fused"], g["capturable"], g["foreach"] = True, True, False
-        for st in self.optimizer.state.values():
+        for p, st in self.optimizer.state.items():
             if "step" in st and not (torch.is_tensor(st["step"]) and st["step"].is_cuda):
                 st["step"] = torch.as_tensor(float(st["step"]), dtype=torch.float32, device=self.device)
+            for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+                # the fused kernel pairs elements by memory order: moments take the parameter's strides (conv weights are
+                # channels_last here, contiguous in a reference checkpoint)
+                if k in st and st[k].stride() != p.stride():
+                    st[k] = torch.empty_like(p).copy_(st[k])
 
     # ---- one training step (nnUNetTrainer.train_step, :833-863)
     def _forward_loss(self, data, target):
