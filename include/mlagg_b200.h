@@ -264,6 +264,34 @@ int mlagg_linattn_bwd(const void *q, const void *k, const void *v, const float *
                       long long lddk, long long lddv, float eps, int dtype, mlagg_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Projection contractions on the 5th-generation tensor cores (csrc/gemm_tc.cu: TMA operand loads, tcgen05.mma with the
+ * accumulator in tensor memory, tcgen05.ld epilogue).  Replace the cuBLAS GEMMs autograd runs for every nn.Linear /
+ * 1x1 convolution of the named path and their two backward GEMMs:
+ *   nnUNetTrainer_MLAgg_2D_dt_MS.py:673-674 (q, kv), :849-850 (in_proj, act_proj), :867 / :902 (out_proj), :176-192 (Mlp:
+ *   fc1 -> GELU -> fc2), :660-661 (sr 1x1 conv); variants/mamba/MambaSkip.py:301 (in_proj), :345 (out_proj), :431 (x_proj as
+ *   ONE tokens-major GEMM), :559-577 (ConvolutionalGLU fc1 / fc2).
+ * All activations / weights are bf16, row-major with unit column stride and a row stride (ld*, in ELEMENTS, multiple of 8;
+ * base pointers 16-byte aligned): channel slices of a wider activation are consumed and produced in place.  fp32
+ * accumulation.  N % 8 == 0 and K % 8 == 0.  act: 0 none, 1 exact GELU, 2 SiLU.  out_dtype: MLAGG_BF16 / MLAGG_F32.
+ *
+ *   mlagg_linear_fwd        y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]);   bias fp32, nullable;
+ *                           pre (nullable, bf16 [M, ldpre]) additionally receives the PRE-activation for the backward.
+ *   mlagg_linear_bwd_data   dx[M,K] = (dy[M,N] . w[N,K]) (*) act'(aux[M,K]);  aux nullable (then act is ignored): the
+ *                           gradient through the activation in FRONT of this layer (Mlp: GELU between fc1 and fc2) is
+ *                           applied in the epilogue.  w is read as stored (MN-major B operand, no transposed copy).
+ *   mlagg_linear_bwd_weight dw[N,K] += dy[M,N]^T . x[M,K];  dw fp32, row stride lddw, ACCUMULATED INTO (zero-fill first);
+ *                           the contraction over the M tokens is split across CTAs and reduced with fp32 vector atomics.
+ * ------------------------------------------------------------------------------------------ */
+int mlagg_linear_fwd(const void *x, long long ldx, const void *w, long long ldw, const float *bias, void *y,
+                     long long ldy, void *pre, long long ldpre, long long M, int N, int K, int act, int out_dtype,
+                     mlagg_stream_t stream);
+int mlagg_linear_bwd_data(const void *dy, long long lddy, const void *w, long long ldw, const void *aux, long long ldaux,
+                          int act, void *dx, long long lddx, long long M, int N, int K, int out_dtype,
+                          mlagg_stream_t stream);
+int mlagg_linear_bwd_weight(const void *dy, long long lddy, const void *x, long long ldx, float *dw, long long lddw,
+                            long long M, int N, int K, mlagg_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * Column sums of a tokens-major matrix: out[c] += sum_m x[m * ld + c]  (out fp32, ACCUMULATED INTO: zero-fill first).
  * Replaces autograd's `grad_output.sum(0)` for the bias gradient of the nn.Linear layers of the hot path
  *   (nnUNetTrainer_MLAgg_2D_dt_MS.py:849-850, :868, :180-186, :673-674; variants/mamba/MambaSkip.py:567,570).

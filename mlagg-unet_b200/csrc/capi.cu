@@ -6,6 +6,7 @@
 
 #include "../../include/mlagg_b200.h"
 #include "scan_common.cuh"
+#include "gemm_tc.cuh"
 
 namespace mlagg {
 cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
@@ -78,6 +79,8 @@ bool linattn_hd_supported(int hd);
 cudaError_t linattn_dispatch(const LinAttnParams &p, int hd, int dtype, int which, cudaStream_t st);
 
 cudaError_t colsum_dispatch(const void *x, float *out, long long M, int C, long long ld, int dtype, cudaStream_t st);
+
+
 
 cudaError_t instnorm_dispatch(const void *x, const void *dy, const float *w, const float *b, void *out, float *stats,
                               float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
@@ -649,6 +652,58 @@ extern "C" int mlagg_linattn_bwd(const void *q, const void *k, const void *v, co
     p.Bn = batch; p.H = H; p.W = W; p.h = heads; p.eps = eps;
     cudaError_t e = cudaMemsetAsync(ws, 0, mlagg_linattn_state_bytes(batch, heads, head_dim), (cudaStream_t)stream);
     if (e == cudaSuccess) e = linattn_dispatch(p, head_dim, dtype, 1, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+// ------------------------------------------------------------------------------------------------ tensor-core GEMMs
+static int gemm_check(const void *a, long long lda, const void *b, long long ldb, const void *o, long long ldo, long long M,
+                      int N, int K, int o_elt) {
+    if (!a || !b || !o) return MLAGG_ERR_NULL;
+    if (M <= 0 || M > 0x7fffffffLL || N <= 0 || K <= 0 || N % 8 != 0 || K % 8 != 0) return MLAGG_ERR_BAD_SHAPE;
+    if (lda % 8 != 0 || ldb % 8 != 0 || ldo * o_elt % 16 != 0) return MLAGG_ERR_BAD_SHAPE;
+    if (!aligned(a, 16) || !aligned(b, 16) || !aligned(o, 16)) return MLAGG_ERR_ALIGN;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_linear_fwd(const void *x, long long ldx, const void *w, long long ldw, const float *bias, void *y,
+                                long long ldy, void *pre, long long ldpre, long long M, int N, int K, int act, int out_dtype,
+                                mlagg_stream_t stream) {
+    if (out_dtype != MLAGG_F32 && out_dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    int rc = gemm_check(x, ldx, w, ldw, y, ldy, M, N, K, out_dtype == MLAGG_F32 ? 4 : 2);
+    if (rc) return rc;
+    if (ldx < K || ldw < K || ldy < N || act < 0 || act > 2) return MLAGG_ERR_BAD_SHAPE;
+    if (pre && (ldpre < N || ldpre % 8 != 0 || !aligned(pre, 16))) return MLAGG_ERR_ALIGN;
+    GemmTcParams p{};
+    p.out = y; p.ldo = ldy; p.pre = pre; p.ldpre = ldpre; p.bias = bias;
+    p.M = (int)M; p.N = N; p.K = K; p.act = act; p.out_f32 = out_dtype == MLAGG_F32;
+    cudaError_t e = gemm_tc_dispatch(x, ldx, 0, w, ldw, 0, p, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_linear_bwd_data(const void *dy, long long lddy, const void *w, long long ldw, const void *aux,
+                                     long long ldaux, int act, void *dx, long long lddx, long long M, int N, int K,
+                                     int out_dtype, mlagg_stream_t stream) {
+    if (out_dtype != MLAGG_F32 && out_dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    int rc = gemm_check(dy, lddy, w, ldw, dx, lddx, M, N, K, out_dtype == MLAGG_F32 ? 4 : 2);
+    if (rc) return rc;
+    if (lddy < N || ldw < K || lddx < K || act < 0 || act > 2) return MLAGG_ERR_BAD_SHAPE;
+    if (aux && (ldaux < K || ldaux % 8 != 0 || !aligned(aux, 16))) return MLAGG_ERR_ALIGN;
+    GemmTcParams p{};                       // D[M, K_in] = dy[M, N_out] . w[N_out, K_in]: contraction over N_out
+    p.out = dx; p.ldo = lddx; p.aux = aux; p.ldaux = ldaux;
+    p.M = (int)M; p.N = K; p.K = N; p.act = aux ? act : 0; p.out_f32 = out_dtype == MLAGG_F32;
+    cudaError_t e = gemm_tc_dispatch(dy, lddy, 0, w, ldw, 1, p, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_linear_bwd_weight(const void *dy, long long lddy, const void *x, long long ldx, float *dw,
+                                       long long lddw, long long M, int N, int K, mlagg_stream_t stream) {
+    int rc = gemm_check(dy, lddy, x, ldx, dw, lddw, M, N, K, 4);
+    if (rc) return rc;
+    if (lddy < N || ldx < K || lddw < K) return MLAGG_ERR_BAD_SHAPE;
+    GemmTcParams p{};                       // D[N_out, K_in] += dy[M, N_out]^T . x[M, K_in]: contraction over the tokens
+    p.out = dw; p.ldo = lddw;
+    p.M = N; p.N = K; p.K = (int)M; p.reduce = 1;
+    cudaError_t e = gemm_tc_dispatch(dy, lddy, 1, x, ldx, 1, p, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

@@ -1,0 +1,382 @@
+// gemm_tc.cu -- the projection contractions of the MLAgg block and the MSMM on the 5th-generation tensor cores.
+//
+// Replaces the cuBLAS GEMMs behind every nn.Linear / 1x1 conv of the named path (reference
+// nnUNetTrainer_MLAgg_2D_dt_MS.py:673-674 q / kv, :849-850 in_proj / act_proj, :867 / :902 out_proj, :176-192 Mlp;
+// MambaSkip.py:301 in_proj, :345 out_proj, :431 x_proj, :559-577 ConvolutionalGLU fc1 / fc2) and their two backward GEMMs.
+//
+//   D[M, N] (+)= A[M, K] . B[N, K]^T          bf16 operands, fp32 accumulation in TENSOR MEMORY
+//
+// One CTA = one 128 x BN output tile (BN <= 256), 6 warps with fixed roles:
+//   warp 0     TMA producer: cp.async.bulk.tensor (SASS UTMALDG) of the A / B k-blocks (64 elements of K = one 128-byte
+//              swizzle atom) into a ring of shared-memory stages, completion on `full` mbarriers; owns the TMEM allocation
+//   warp 1     MMA issuer: ONE elected lane issues tcgen05.mma.cta_group::1.kind::f16 (SASS UTCHMMA), M = 128, N = BN,
+//              K = 16 per instruction, operands straight from the swizzled stages through shared-memory descriptors;
+//              tcgen05.commit releases a stage to the producer (`empty`) and finally hands the accumulator over (`accf`)
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns (SASS LDTM) -> bias / activation / activation-gradient product
+//              -> bf16 or fp32 rows to HBM, or fp32 vector reductions (split-K weight gradients)
+// Both operand majors are supported through the descriptors (no transposed copies anywhere):
+//   K-major   memory [rows][K]  (activations x W^T: forward)          TMA box {64 k, rows}
+//   MN-major  memory [K][rows]  (dY . W: data gradient, B operand;   TMA box {64 rows, 64 k} per 64-row slab
+//                                dY^T . X: weight gradient, A and B)
+// The weight-gradient GEMM contracts over the tokens: gridDim.z CTAs split K, each reduces its partial tile into the
+// fp32 gradient with red.global.add.v4.f32.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace mlagg {
+
+constexpr int kBM = 128, kBK = 64;
+constexpr int kABytes = kBM * kBK * 2;          // 16 KiB per stage
+constexpr int kSlab = 64 * 128;                 // MN-major slab: 64 k-rows x 128 bytes
+
+
+// ---------------------------------------------------------------- PTX wrappers (tcgen05 / TMA)
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading
+// byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in
+// [61,64).  K-major operand: rows of 128 bytes, 8-row groups SBO = 1024 bytes apart (LBO unused).  MN-major operand:
+// k-rows of 128 bytes (64 MN elements), 8-k groups SBO = 1024 bytes apart, 64-element MN slabs LBO bytes apart.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float silu_grad(float x) {
+    const float s = 1.f / (1.f + __expf(-x));
+    return s * (1.f + x * (1.f - s));
+}
+
+template <bool kAmn, bool kBmn>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int BN = p.BN;
+    const int nslabB = (BN + 63) / 64;
+    const int bBytes = kBmn ? nslabB * kSlab : BN * 128;
+    const int stageBytes = kABytes + bBytes;
+    unsigned char *tail = smem + (size_t)p.stages * stageBytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(tail);      // [stages]
+    uint64_t *empty = full + p.stages;                        // [stages]
+    uint64_t *accf = empty + p.stages;                        // [1]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accf + 1);
+    float *bias_s = reinterpret_cast<float *>(tmem_slot + 2); // [BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+    const int kb_total = (p.K + kBK - 1) / kBK;
+    const int kb0 = blockIdx.z * p.kblocks_per_split;
+    const int kb1 = min(kb_total, kb0 + p.kblocks_per_split);
+    const int nkb = kb1 - kb0;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tmap_prefetch(&tmA);
+            tmap_prefetch(&tmB);
+            for (int s = 0; s < p.stages; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            mbar_init(accf, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, tmem_cols);
+    }
+    for (int i = threadIdx.x; i < BN + 32; i += blockDim.x)      // + 32: the epilogue walks the columns in chunks of 32
+        bias_s[i] = (p.bias != nullptr && n0 + i < p.N) ? p.bias[n0 + i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================================================ TMA producer
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                if (i >= p.stages) mbar_wait(&empty[s], ((i / p.stages) & 1) ^ 1);
+                unsigned char *sa = smem + (size_t)s * stageBytes, *sb = sa + kABytes;
+                const int k0 = (kb0 + i) * kBK;
+                mbar_arrive_expect_tx(&full[s], (uint32_t)stageBytes);
+                if (kAmn) {
+                    tma_load_2d(sa, &tmA, m0, k0, &full[s]);
+                    tma_load_2d(sa + kSlab, &tmA, m0 + 64, k0, &full[s]);
+                } else {
+                    tma_load_2d(sa, &tmA, k0, m0, &full[s]);
+                }
+                if (kBmn) {
+                    for (int j = 0; j < nslabB; ++j) tma_load_2d(sb + j * kSlab, &tmB, n0 + 64 * j, k0, &full[s]);
+                } else {
+                    tma_load_2d(sb, &tmB, k0, n0, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 [4,6) = 1, A / B bf16 [7,10) = [10,13) = 1, A / B
+        // major bits 15 / 16 (1 = MN-major), N >> 3 in [17,23), M >> 4 in [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((kAmn ? 1u : 0u) << 15) | ((kBmn ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % p.stages;
+            mbar_wait(&full[s], (i / p.stages) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * stageBytes), sb = sa + kABytes;
+                const int kleft = p.K - (kb0 + i) * kBK;
+                const int ksteps = (min(kleft, kBK) + 15) >> 4;
+                for (int k = 0; k < ksteps; ++k) {
+                    // K-major: 16 elements of K = 32 bytes inside the 128-byte swizzle row; MN-major: 16 k-rows = 2 atoms
+                    const uint64_t ad = kAmn ? smem_desc(sa + k * 2048, kSlab, 1024) : smem_desc(sa + k * 32, 16, 1024);
+                    const uint64_t bd = kBmn ? smem_desc(sb + k * 2048, kSlab, 1024) : smem_desc(sb + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);                 // stage free once these MMAs have read it
+                if (i == nkb - 1) umma_commit(accf);    // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ============================================================ epilogue (TMEM lanes 32 * (warp % 4) ...)
+        const int quad = warp & 3;
+        const int row = m0 + 32 * quad + lane;
+        const bool rok = row < p.M;
+        if (nkb > 0) {
+            mbar_wait(accf, 0);
+            tc_fence_after();
+        }
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(32 * quad) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            const int nbase = n0 + c0;
+            if (p.reduce) {
+                if (rok) {
+                    float *o = reinterpret_cast<float *>(p.out) + (size_t)row * p.ldo + nbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (nbase + j < p.N)     // N is a multiple of 4 (checked on the host)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j),
+                                         "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                         : "memory");
+                    }
+                }
+                continue;
+            }
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bias_s[c0 + j];
+            if (!rok) continue;
+            if (p.pre != nullptr) {
+                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.pre) + (size_t)row * p.ldpre + nbase;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (nbase + j < p.N) {
+                        uint4 w;
+                        __nv_bfloat162 t;
+                        t = __floats2bfloat162_rn(x[j], x[j + 1]);     w.x = *reinterpret_cast<uint32_t *>(&t);
+                        t = __floats2bfloat162_rn(x[j + 2], x[j + 3]); w.y = *reinterpret_cast<uint32_t *>(&t);
+                        t = __floats2bfloat162_rn(x[j + 4], x[j + 5]); w.z = *reinterpret_cast<uint32_t *>(&t);
+                        t = __floats2bfloat162_rn(x[j + 6], x[j + 7]); w.w = *reinterpret_cast<uint32_t *>(&t);
+                        *reinterpret_cast<uint4 *>(o + j) = w;
+                    }
+                }
+            }
+            if (p.aux != nullptr) {      // gradient through the activation of the layer below: x *= act'(aux)
+                const __nv_bfloat16 *a = reinterpret_cast<const __nv_bfloat16 *>(p.aux) + (size_t)row * p.ldaux + nbase;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (nbase + j < p.N) {
+                        const uint4 w = *reinterpret_cast<const uint4 *>(a + j);
+                        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ww[e]));
+                            if (p.act == 1) {
+                                x[j + 2 * e] *= gelu_grad(f.x);
+                                x[j + 2 * e + 1] *= gelu_grad(f.y);
+                            } else if (p.act == 2) {
+                                x[j + 2 * e] *= silu_grad(f.x);
+                                x[j + 2 * e + 1] *= silu_grad(f.y);
+                            }
+                        }
+                    }
+                }
+            } else if (p.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = gelu_f(x[j]);
+            } else if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+            }
+            if (p.out_f32) {
+                float *o = reinterpret_cast<float *>(p.out) + (size_t)row * p.ldo + nbase;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    if (nbase + j < p.N) *reinterpret_cast<float4 *>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+            } else {
+                __nv_bfloat16 *o = reinterpret_cast<__nv_bfloat16 *>(p.out) + (size_t)row * p.ldo + nbase;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (nbase + j < p.N) {
+                        uint4 w;
+                        __nv_bfloat162 t;
+                        t = __floats2bfloat162_rn(x[j], x[j + 1]);     w.x = *reinterpret_cast<uint32_t *>(&t);
+                        t = __floats2bfloat162_rn(x[j + 2], x[j + 3]); w.y = *reinterpret_cast<uint32_t *>(&t);
+                        t = __floats2bfloat162_rn(x[j + 4], x[j + 5]); w.z = *reinterpret_cast<uint32_t *>(&t);
+                        t = __floats2bfloat162_rn(x[j + 6], x[j + 7]); w.w = *reinterpret_cast<uint32_t *>(&t);
+                        *reinterpret_cast<uint4 *>(o + j) = w;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// bf16 matrix [outer][inner] with row stride ld (elements): box {box_inner, box_outer}, 128-byte swizzle, zero fill
+static bool make_map(CUtensorMap *m, const void *base, long long inner, long long outer, long long ld, int box_inner,
+                     int box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t es[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// a_mn / b_mn: 0 = memory [rows][K] (K-major), 1 = memory [K][rows] (MN-major).  Returns cudaErrorNotSupported when the
+// driver entry point for tensor maps is unavailable.
+cudaError_t gemm_tc_dispatch(const void *A, long long lda, int a_mn, const void *B, long long ldb, int b_mn, GemmTcParams p,
+                             cudaStream_t st) {
+    int BN = p.N <= 256 ? (p.N + 15) / 16 * 16 : 256;
+    if (p.N > 256) {   // balance the column tiles: 384 -> 2 x 192, 768 -> 3 x 256, 1536 -> 6 x 256
+        const int nt = (p.N + 255) / 256;
+        BN = ((p.N + nt - 1) / nt + 15) / 16 * 16;
+    }
+    p.BN = BN;
+    const int nslabB = (BN + 63) / 64;
+    const int bBytes = b_mn ? nslabB * kSlab : BN * 128;
+    const int stageBytes = kABytes + bBytes;
+    const int kb_total = (p.K + kBK - 1) / kBK;
+    const int mt = (p.M + kBM - 1) / kBM, nt = (p.N + BN - 1) / BN;
+    int splits = 1;
+    if (p.reduce) {
+        // enough CTAs for two waves, at least 4 k-blocks each
+        splits = max(1, min((2 * sm_count() + mt * nt - 1) / (mt * nt), (kb_total + 3) / 4));
+    }
+    p.kblocks_per_split = (kb_total + splits - 1) / splits;
+    splits = (kb_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    const int budget = p.reduce ? 200 * 1024 : 100 * 1024;     // store mode: two CTAs per SM overlap epilogue and loads
+    p.stages = max(2, min(min(8, budget / stageBytes), max(2, p.kblocks_per_split)));
+    const size_t smem = (size_t)p.stages * stageBytes + (2 * p.stages + 1) * 8 + 8 + (size_t)(BN + 32) * 4 + 1024;
+
+    CUtensorMap tmA, tmB;
+    bool ok = a_mn ? make_map(&tmA, A, p.M, p.K, lda, 64, 64) : make_map(&tmA, A, p.K, p.M, lda, 64, kBM);
+    ok = ok && (b_mn ? make_map(&tmB, B, p.N, p.K, ldb, 64, 64) : make_map(&tmB, B, p.K, p.N, ldb, 64, BN));
+    if (!ok) return cudaErrorNotSupported;
+
+    auto kern = a_mn ? (b_mn ? gemm_tc_kernel<true, true> : gemm_tc_kernel<true, false>)
+                     : (b_mn ? gemm_tc_kernel<false, true> : gemm_tc_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(mt, nt, splits);
+    kern<<<grid, 192, smem, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+}  // namespace mlagg

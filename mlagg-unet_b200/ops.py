@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, gemm
 
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
@@ -391,23 +391,31 @@ class GradContiguous(torch.autograd.Function):
 
 
 class _Linear(torch.autograd.Function):
-    """y = x W^T + b with the GEMMs on cuBLAS (library GEMMs) in the autocast dtype and the bias
-    gradient as ONE HBM-bound column-sum pass (csrc/reduce.cu) instead of autograd's generic reduction."""
+    """y = x W^T + b.  Under bf16 autocast all three GEMMs (forward, data gradient, weight gradient) run on the sm_100a
+    tensor-core kernels of csrc/gemm_tc.cu (TMA + tcgen05.mma + TMEM) behind mlagg_linear_*: bias added from the fp32
+    parameter in the epilogue, W consumed as stored for the data gradient (MN-major operand), fp32 weight gradient
+    reduced across the token split.  fp32 (the 1e-4 parity path) stays on cuBLAS -- a library GEMM in full fp32; the
+    bias gradient is ONE HBM-bound column-sum pass (csrc/reduce.cu) either way."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
         xc, wc = x.to(cdt), _cast_param(weight, cdt)
-        bc = _cast_param(bias, cdt)
         x2 = _rows2d(xc)
-        with torch.autocast("cuda", enabled=False):
-            if x2 is None:
-                y = torch.nn.functional.linear(xc, wc, bc)
-            else:
-                # 2-D GEMM on the (tokens, Cin) view, row stride = the parent's width: channel slices of a wider
-                # activation (the halves of MLLABlock's `chunk`) are consumed in place and the bias stays in the GEMM
-                # epilogue (F.linear on a strided 3-D input runs matmul + a separate un-vectorised bias add)
-                y = (torch.mm(x2, wc.t()) if bc is None else torch.addmm(bc, x2, wc.t())).view(*xc.shape[:-1], wc.shape[0])
+        ctx.tc = bool(cdt == torch.bfloat16 and x2 is not None and gemm.supported(x2, wc))
+        if ctx.tc:
+            y2, _ = gemm.linear_fwd(x2, wc, bias)
+            y = y2.view(*xc.shape[:-1], wc.shape[0])
+        else:
+            bc = _cast_param(bias, cdt)
+            with torch.autocast("cuda", enabled=False):
+                if x2 is None:
+                    y = torch.nn.functional.linear(xc, wc, bc)
+                else:
+                    # 2-D GEMM on the (tokens, Cin) view, row stride = the parent's width: channel slices of a wider
+                    # activation (the halves of MLLABlock's `chunk`) are consumed in place and the bias stays in the GEMM
+                    # epilogue (F.linear on a strided 3-D input runs matmul + a separate un-vectorised bias add)
+                    y = (torch.mm(x2, wc.t()) if bc is None else torch.addmm(bc, x2, wc.t())).view(*xc.shape[:-1], wc.shape[0])
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
         return y
@@ -420,9 +428,13 @@ class _Linear(torch.autograd.Function):
         dy2 = dy.to(wc.dtype)
         dy2 = _rows2d(dy2) if _rows2d(dy2) is not None else dy2.reshape(-1, Cout)
         x2 = _rows2d(xc) if _rows2d(xc) is not None else xc.reshape(-1, Cin)
-        with torch.autocast("cuda", enabled=False):
-            dx = torch.mm(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
-            dw = torch.mm(dy2.t(), x2).to(wdt) if ctx.needs_input_grad[1] else None
+        if ctx.tc and gemm.rows_ok(dy2) and gemm.rows_ok(x2):
+            dx = gemm.linear_bwd_data(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
+            dw = gemm.linear_bwd_weight(dy2, x2).to(wdt) if ctx.needs_input_grad[1] else None
+        else:
+            with torch.autocast("cuda", enabled=False):
+                dx = torch.mm(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
+                dw = torch.mm(dy2.t(), x2).to(wdt) if ctx.needs_input_grad[1] else None
         db = colsum(dy2).to(bdt) if (bdt is not None and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 

@@ -147,7 +147,7 @@ class _OracleScan(torch.autograd.Function):
     def forward(ctx, u, delta, A, B, C, D, delta_bias, delta_softplus, fp64):
         ctx.save_for_backward(u, delta, A, B, C, D, delta_bias)
         ctx.flags = (delta_softplus, fp64)
-        return scan_fwd_c(u, delta, A, B, C, D, delta_bias, delta_softplus, fp64).to(u.device)
+        return scan_fwd_c(u, delta, A, B, C, D, delta_bias, delta_softplus, fp64).to(u.device, u.dtype)
 
     @staticmethod
     def backward(ctx, dout):

