@@ -22,6 +22,8 @@
 // fp32 gradient with red.global.add.v4.f32.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -324,9 +326,13 @@ static bool make_map(CUtensorMap *m, const void *base, long long inner, long lon
     cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t es[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, es,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS && getenv("MLAGG_DEBUG"))
+        fprintf(stderr, "mlagg: cuTensorMapEncodeTiled -> %d (base %p inner %lld outer %lld ld %lld box %d x %d)\n", (int)r,
+                base, inner, outer, ld, box_inner, box_outer);
+    return r == CUDA_SUCCESS;
 }
 
 static int sm_count() {
@@ -366,9 +372,16 @@ cudaError_t gemm_tc_dispatch(const void *A, long long lda, int a_mn, const void 
     const size_t smem = (size_t)p.stages * stageBytes + (2 * p.stages + 1) * 8 + 8 + (size_t)(BN + 32) * 4 + 1024;
 
     CUtensorMap tmA, tmB;
-    bool ok = a_mn ? make_map(&tmA, A, p.M, p.K, lda, 64, 64) : make_map(&tmA, A, p.K, p.M, lda, 64, kBM);
-    ok = ok && (b_mn ? make_map(&tmB, B, p.N, p.K, ldb, 64, 64) : make_map(&tmB, B, p.K, p.N, ldb, 64, BN));
-    if (!ok) return cudaErrorNotSupported;
+    auto encode = [&]() {
+        bool ok = a_mn ? make_map(&tmA, A, p.M, p.K, lda, 64, 64) : make_map(&tmA, A, p.K, p.M, lda, 64, kBM);
+        return ok && (b_mn ? make_map(&tmB, B, p.N, p.K, ldb, 64, 64) : make_map(&tmB, B, p.K, p.N, ldb, 64, BN));
+    };
+    if (!encode()) {
+        // cuTensorMapEncodeTiled is a driver-API call: on a thread that has not touched the runtime yet (autograd's
+        // backward thread) no context is current -- bind the primary context of the current device and try once more
+        cudaFree(nullptr);
+        if (!encode()) return cudaErrorNotSupported;
+    }
 
     auto kern = a_mn ? (b_mn ? gemm_tc_kernel<true, true> : gemm_tc_kernel<true, false>)
                      : (b_mn ? gemm_tc_kernel<false, true> : gemm_tc_kernel<false, false>);
