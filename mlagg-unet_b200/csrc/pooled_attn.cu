@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
         const bool ok[2] = {nr[0] < p.N, nr[1] < p.N};
         // ---- RMSNorm backward on the saved O0 | O1 (accumulator layout: row r, columns nc*8 + 2t, +1)
         float dO[NC][4];
-        float D0[2], D1[2], lse0[2], lse1[2];
+        float lse0[2], lse1[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const long long tok = (long long)b * p.N + (ok[r] ? nr[r] : 0);
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                 }
             d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
             d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-            D0[r] = d0, D1[r] = d1;
+            (void)d0;
             lse0[r] = ok[r] ? p.lse[(tok * p.h + m) * 2 + 0] : 0.f;
             lse1[r] = ok[r] ? p.lse[(tok * p.h + m) * 2 + 1] : 0.f;
             if (ok[r]) {
@@ -756,10 +756,6 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
 #pragma unroll
                     for (int nc = 0; nc < NC; ++nc)
                         *reinterpret_cast<float2 *>(wdO + nc * 8 + 2 * t) = make_float2(dO[nc][2 * r], dO[nc][2 * r + 1]);
-                    if (t == 0) {
-                        p.ws_D[(tok * p.h + m) * 2 + 0] = d0;
-                        p.ws_D[(tok * p.h + m) * 2 + 1] = d1;
-                    }
                 }
             }
         }
@@ -797,8 +793,34 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                 qa[1][2 + r] = (HD > 24 && ok[r]) ? *reinterpret_cast<const uint32_t *>(qp + 24 + 2 * t) : 0u;
             }
             const float ls[2] = {j == 0 ? lse0[0] : lse1[0], j == 0 ? lse0[1] : lse1[1]};
-            const float Dj[2] = {j == 0 ? D0[0] : D1[0], j == 0 ? D0[1] : D1[1]};
             const float sgn = j == 0 ? 1.f : -lam;
+            // D_j = sum_p A_j[p] dab[p], formed from the SAME probabilities and the SAME (bf16-operand) dab values that
+            // dS_j = A_j (dab - D_j) uses below, so that sum_p dS_j[p] = 0 holds to rounding.  (Round 1 took D_j = dO . O_j
+            // from the fp32 dO and the saved O_j: mathematically equal, but dab is computed from bf16-rounded dO, and
+            // wherever the softmax is nearly uniform -- stage 0 / 1, logits damped by the double scale -- dab - D_j is a
+            // difference of nearly equal numbers: dq came out at 3 - 8x its own magnitude in error against fp64,
+            // tests/test_parity_shipped_gpu.py.)
+            float Dj[2] = {0.f, 0.f};
+#pragma unroll
+            for (int nt = 0; nt < kMmaNT; ++nt) {
+                float S[4] = {0.f, 0.f, 0.f, 0.f};
+                const __nv_bfloat16 *kr = &sK[j][nt * 8 + g][2 * t];
+                mma_bf16_16816(S, qa[0], *reinterpret_cast<const uint32_t *>(kr), *reinterpret_cast<const uint32_t *>(kr + 8));
+                mma_bf16_16816(S, qa[1], *reinterpret_cast<const uint32_t *>(kr + 16), *reinterpret_cast<const uint32_t *>(kr + 24));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = e >> 1;
+                    const bool in = nt * 8 + 2 * t + (e & 1) < p.P;
+                    const float a = in ? ex2_approx(S[e] * qs - ls[r]) : 0.f;
+                    Dj[r] = fmaf(a, dab[nt][e], Dj[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                Dj[r] += __shfl_xor_sync(0xffffffffu, Dj[r], 1);
+                Dj[r] += __shfl_xor_sync(0xffffffffu, Dj[r], 2);
+                if (p.ws_D && ok[r] && t == 0) p.ws_D[(((long long)b * p.N + nr[r]) * p.h + m) * 2 + j] = Dj[r];
+            }
             float dq[ND][4];
 #pragma unroll
             for (int nd = 0; nd < ND; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
