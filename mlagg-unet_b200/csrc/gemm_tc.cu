@@ -298,6 +298,248 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------- persistent store-mode kernel (forward, data gradient)
+// One CTA per SM walks the output tiles of ONE column block (n fixed, m strided) when the whole B operand of that block
+// fits in shared memory: W is then loaded ONCE per CTA ("resident") and only activation tiles stream through the TMA ring;
+// otherwise (m, n) tiles are walked in row-major order and B streams with A.  Two TMEM accumulators alternate, so the
+// epilogue of tile i (tcgen05.ld -> bias / activation -> bf16 -> 128-byte-swizzled staging slab -> TMA store, SASS
+// UTMASTG) overlaps the loads and MMAs of tile i + 1.  A is K-major (activations / output gradients); B is K-major
+// (forward: W[N][K]) or MN-major (data gradient: W[K][N] as stored).
+struct GemmStoreCfg {
+    int nt, mt, ctas_per_n, resident, bBytes, kb_total, stages;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+
+template <bool kBmn>
+__global__ void __launch_bounds__(192, 1) gemm_tc_store_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmO,
+                                                               const __grid_constant__ CUtensorMap tmP,
+                                                               const GemmTcParams p, const GemmStoreCfg c) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    const int BN = p.BN;
+    const int nslabB = (BN + 63) / 64;
+    const int stageBytes = kABytes + (c.resident ? 0 : c.bBytes);
+    unsigned char *ring = smem;
+    unsigned char *resB = ring + (size_t)c.stages * stageBytes;                       // [kb_total][bBytes] when resident
+    unsigned char *stag = resB + (c.resident ? (size_t)c.kb_total * c.bBytes : 0);    // [2][128 rows][128 B]
+    unsigned char *tail = stag + 2 * kABytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(tail);   // [stages]
+    uint64_t *empty = full + c.stages;                     // [stages]
+    uint64_t *accf = empty + c.stages;                     // [2] accumulator complete
+    uint64_t *acce = accf + 2;                             // [2] accumulator drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acce + 2);
+    float *bias_s = reinterpret_cast<float *>(tmem_slot + 2);   // [BN + 64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile walk: resident -> n fixed per CTA, m = mfirst + i * mstep; streaming -> t = cta + i * grid, (m, n) = (t / nt, t % nt)
+    const int nfix = c.resident ? (int)(blockIdx.x % c.nt) : 0;
+    const int mfirst = c.resident ? (int)(blockIdx.x / c.nt) : 0;
+    const int ntiles = c.resident ? (c.mt > mfirst ? (c.mt - mfirst + c.ctas_per_n - 1) / c.ctas_per_n : 0)
+                                  : ((c.mt * c.nt > (int)blockIdx.x) ? (c.mt * c.nt - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+    auto tile_mn = [&](int i, int &m0, int &n0) {
+        if (c.resident) {
+            m0 = (mfirst + i * c.ctas_per_n) * kBM;
+            n0 = nfix * BN;
+        } else {
+            const int t = blockIdx.x + i * gridDim.x;
+            m0 = (t / c.nt) * kBM;
+            n0 = (t % c.nt) * BN;
+        }
+    };
+    uint32_t acc_cols = 32;
+    while ((int)acc_cols < BN) acc_cols <<= 1;
+    const uint32_t tmem_cols = 2 * acc_cols;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tmap_prefetch(&tmA);
+            tmap_prefetch(&tmB);
+            tmap_prefetch(&tmO);
+            for (int s = 0; s < c.stages; ++s) {
+                mbar_init(&full[s], 1);
+                mbar_init(&empty[s], 1);
+            }
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&accf[b], 1);
+                mbar_init(&acce[b], 4);
+            }
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, tmem_cols);
+    }
+    if (c.resident) {
+        for (int i = threadIdx.x; i < BN + 64; i += blockDim.x)
+            bias_s[i] = (p.bias != nullptr && nfix * BN + i < p.N) ? p.bias[nfix * BN + i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================================================ TMA producer
+        if (lane == 0) {
+            int kc = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                int m0, n0;
+                tile_mn(i, m0, n0);
+                const bool loadB = !c.resident || i == 0;
+                for (int kb = 0; kb < c.kb_total; ++kb, ++kc) {
+                    const int s = kc % c.stages;
+                    if (kc >= c.stages) mbar_wait(&empty[s], ((kc / c.stages) & 1) ^ 1);
+                    unsigned char *sa = ring + (size_t)s * stageBytes;
+                    unsigned char *sb = c.resident ? resB + (size_t)kb * c.bBytes : sa + kABytes;
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(kABytes + (loadB ? c.bBytes : 0)));
+                    tma_load_2d(sa, &tmA, kb * kBK, m0, &full[s]);
+                    if (loadB) {
+                        if (kBmn) {
+                            for (int j = 0; j < nslabB; ++j) tma_load_2d(sb + j * kSlab, &tmB, n0 + 64 * j, kb * kBK, &full[s]);
+                        } else {
+                            tma_load_2d(sb, &tmB, kb * kBK, n0, &full[s]);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((kBmn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                               ((uint32_t)(kBM >> 4) << 24);
+        int kc = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int buf = i & 1;
+            if (i >= 2) mbar_wait(&acce[buf], ((i >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t dtm = tmem_base + buf * acc_cols;
+            for (int kb = 0; kb < c.kb_total; ++kb, ++kc) {
+                const int s = kc % c.stages;
+                mbar_wait(&full[s], (kc / c.stages) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(ring + (size_t)s * stageBytes);
+                    const uint32_t sb = c.resident ? smem_u32(resB + (size_t)kb * c.bBytes) : sa + kABytes;
+                    const int ksteps = (min(p.K - kb * kBK, kBK) + 15) >> 4;
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t ad = smem_desc(sa + k * 32, 16, 1024);
+                        const uint64_t bd = kBmn ? smem_desc(sb + k * 2048, kSlab, 1024) : smem_desc(sb + k * 32, 16, 1024);
+                        umma_bf16(dtm, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == c.kb_total - 1) umma_commit(&accf[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ============================================================ epilogue warps (TMEM lanes 32 * (warp % 4) ...)
+        const int quad = warp & 3;
+        const int rloc = 32 * quad + lane;                     // row inside the tile = TMEM lane
+        const bool issuer = (warp == 2 && lane == 0);
+        int slabc = 0;                                          // staging slabs issued so far (2 buffers round-robin)
+        for (int i = 0; i < ntiles; ++i) {
+            int m0, n0;
+            tile_mn(i, m0, n0);
+            const int buf = i & 1;
+            if (!c.resident) {                                  // bias of this tile's column block
+                named_bar_sync(3, 128);
+                for (int j = threadIdx.x - 64; j < BN + 64; j += 128)
+                    bias_s[j] = (p.bias != nullptr && n0 + j < p.N) ? p.bias[n0 + j] : 0.f;
+                named_bar_sync(3, 128);
+            }
+            mbar_wait(&accf[buf], (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + buf * acc_cols + ((uint32_t)(32 * quad) << 16);
+            const bool rok = m0 + rloc < p.M;
+            const int npass = p.pre != nullptr ? 2 : 1;         // pass 0 of 2: the pre-activation goes to `pre`
+            for (int pass = 0; pass < npass; ++pass) {
+                const bool to_pre = npass == 2 && pass == 0;
+                for (int c0 = 0; c0 < BN; c0 += 64, ++slabc) {
+                    unsigned char *sg = stag + (slabc & 1) * kABytes + rloc * 128;
+                    if (issuer) bulk_wait_read<1>();            // the store that used this buffer two slabs ago has been read
+                    named_bar_sync(1, 128);
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const int cc = c0 + 32 * hf;
+                        if (cc >= BN) break;                    // (uniform) nothing beyond the accumulator's columns
+                        uint32_t v[32];
+                        tmem_ld32(trow + (uint32_t)cc, v);
+                        float x[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bias_s[cc + j];
+                        if (!to_pre) {
+                            if (p.aux != nullptr) {
+                                if (rok) {
+                                    const __nv_bfloat16 *a = reinterpret_cast<const __nv_bfloat16 *>(p.aux) +
+                                                             (size_t)(m0 + rloc) * p.ldaux + n0 + cc;
+#pragma unroll
+                                    for (int j = 0; j < 32; j += 8) {
+                                        if (n0 + cc + j < p.N) {
+                                            const uint4 w = *reinterpret_cast<const uint4 *>(a + j);
+                                            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                                            for (int e = 0; e < 4; ++e) {
+                                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ww[e]));
+                                                if (p.act == 1) {
+                                                    x[j + 2 * e] *= gelu_grad(f.x);
+                                                    x[j + 2 * e + 1] *= gelu_grad(f.y);
+                                                } else if (p.act == 2) {
+                                                    x[j + 2 * e] *= silu_grad(f.x);
+                                                    x[j + 2 * e + 1] *= silu_grad(f.y);
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                            } else if (p.act == 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) x[j] = gelu_f(x[j]);
+                            } else if (p.act == 2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+                            }
+                        }
+                        // 16-byte chunk ch of row r sits at ch ^ (r & 7): the TMA store's 128-byte swizzle, and
+                        // conflict-free for a warp whose lanes are 32 consecutive rows
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const int ch = (4 * hf + (j >> 3)) ^ (rloc & 7);
+                            *reinterpret_cast<uint4 *>(sg + ch * 16) = make_uint4(pack2(x[j], x[j + 1]), pack2(x[j + 2], x[j + 3]),
+                                                                                  pack2(x[j + 4], x[j + 5]), pack2(x[j + 6], x[j + 7]));
+                        }
+                    }
+                    if (pass == npass - 1 && c0 + 64 >= BN) {   // last TMEM read of this tile: hand the accumulator back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acce[buf]);
+                    }
+                    fence_proxy_async();
+                    named_bar_sync(2, 128);
+                    if (issuer) {
+                        tma_store_2d(to_pre ? &tmP : &tmO, stag + (slabc & 1) * kABytes, n0 + c0, m0);
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        if (issuer) bulk_wait_read<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -345,10 +587,68 @@ static int sm_count() {
     return n;
 }
 
+static bool make_map_out(CUtensorMap *m, const void *base, long long inner, long long outer, long long ld) {
+    return make_map(m, base, inner, outer, ld, 64, kBM);
+}
+
+// persistent store-mode launch (bf16 output); returns cudaErrorInvalidConfiguration when the shape does not fit its plan
+static cudaError_t gemm_tc_store_launch(const void *A, long long lda, const void *B, long long ldb, int b_mn, GemmTcParams p,
+                                        cudaStream_t st) {
+    GemmStoreCfg c{};
+    int BN = p.N <= 256 ? (p.N + 15) / 16 * 16 : 256;
+    if (p.N > 256) {
+        const int nt = (p.N + 255) / 256;
+        BN = ((p.N + nt - 1) / nt + 63) / 64 * 64;       // several column blocks: whole 64-column store slabs
+    }
+    p.BN = BN;
+    c.nt = (p.N + BN - 1) / BN;
+    c.mt = (p.M + kBM - 1) / kBM;
+    c.kb_total = (p.K + kBK - 1) / kBK;
+    c.bBytes = b_mn ? ((BN + 63) / 64) * kSlab : BN * 128;
+    const int sms = sm_count();
+    const long long resBytes = (long long)c.kb_total * c.bBytes;
+    c.resident = resBytes <= 112 * 1024 && c.nt <= sms;
+    const int fixed = 2 * kABytes + 2048 + (BN + 64) * 4 + 1024;
+    const int budget = 227 * 1024 - fixed - (c.resident ? (int)resBytes : 0);
+    const int stageBytes = kABytes + (c.resident ? 0 : c.bBytes);
+    c.stages = min(8, budget / stageBytes);
+    if (c.stages < 2) return cudaErrorInvalidConfiguration;
+    int grid;
+    if (c.resident) {
+        c.ctas_per_n = max(1, min(sms / c.nt, c.mt));
+        grid = c.ctas_per_n * c.nt;
+    } else {
+        c.ctas_per_n = 0;
+        grid = min(sms, c.mt * c.nt);
+    }
+    const size_t smem = (size_t)c.stages * stageBytes + (c.resident ? (size_t)resBytes : 0) + fixed;
+    CUtensorMap tmA, tmB, tmO, tmP;
+    auto encode = [&]() {
+        bool ok = make_map(&tmA, A, p.K, p.M, lda, 64, kBM);
+        ok = ok && (b_mn ? make_map(&tmB, B, p.N, p.K, ldb, 64, 64) : make_map(&tmB, B, p.K, p.N, ldb, 64, BN));
+        ok = ok && make_map_out(&tmO, p.out, p.N, p.M, p.ldo);
+        ok = ok && (p.pre ? make_map_out(&tmP, p.pre, p.N, p.M, p.ldpre) : make_map_out(&tmP, p.out, p.N, p.M, p.ldo));
+        return ok;
+    };
+    if (!encode()) {
+        cudaFree(nullptr);
+        if (!encode()) return cudaErrorNotSupported;
+    }
+    auto kern = b_mn ? gemm_tc_store_kernel<true> : gemm_tc_store_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 192, smem, st>>>(tmA, tmB, tmO, tmP, p, c);
+    return cudaGetLastError();
+}
+
 // a_mn / b_mn: 0 = memory [rows][K] (K-major), 1 = memory [K][rows] (MN-major).  Returns cudaErrorNotSupported when the
 // driver entry point for tensor maps is unavailable.
 cudaError_t gemm_tc_dispatch(const void *A, long long lda, int a_mn, const void *B, long long ldb, int b_mn, GemmTcParams p,
                              cudaStream_t st) {
+    if (!p.reduce && !p.out_f32 && !a_mn && !getenv("MLAGG_GEMM_V1")) {
+        cudaError_t e = gemm_tc_store_launch(A, lda, B, ldb, b_mn, p, st);
+        if (e != cudaErrorInvalidConfiguration) return e;
+    }
     int BN = p.N <= 256 ? (p.N + 15) / 16 * 16 : 256;
     if (p.N > 256) {   // balance the column tiles: 384 -> 2 x 192, 768 -> 3 x 256, 1536 -> 6 x 256
         const int nt = (p.N + 255) / 256;
@@ -362,8 +662,8 @@ cudaError_t gemm_tc_dispatch(const void *A, long long lda, int a_mn, const void 
     const int mt = (p.M + kBM - 1) / kBM, nt = (p.N + BN - 1) / BN;
     int splits = 1;
     if (p.reduce) {
-        // enough CTAs for two waves, at least 4 k-blocks each
-        splits = max(1, min((2 * sm_count() + mt * nt - 1) / (mt * nt), (kb_total + 3) / 4));
+        // about one CTA per SM, at least 8 k-blocks each: every split pays an fp32 reduction of its whole tile
+        splits = max(1, min((sm_count() + mt * nt - 1) / (mt * nt), (kb_total + 7) / 8));
     }
     p.kblocks_per_split = (kb_total + splits - 1) / splits;
     splits = (kb_total + p.kblocks_per_split - 1) / p.kblocks_per_split;

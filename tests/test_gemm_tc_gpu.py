@@ -46,6 +46,13 @@ def test_linear_fwd_activation_and_preactivation(act):
     y, pre = gemm.linear_fwd(x.cuda(), w.cuda(), b.cuda(), act=act, out_dtype=torch.float32, want_pre=True)
     assert rel_err(y.cpu(), f(pre_ref)) < 2e-5
     assert pre.dtype == torch.bfloat16 and rel_err(pre.float().cpu(), pre_ref) < 2 ** -8
+    # bf16 output: the persistent kernel (two TMA-store passes over the accumulator: pre-activation, then activation)
+    for (M2, N2, K2) in ((M, N, K), (4100, 768, 384), (900, 1536, 768)):
+        x, w, b = _mk(M2, N2, K2)
+        pre_ref = x.double() @ w.double().t() + b.double()
+        y16, pre16 = gemm.linear_fwd(x.cuda(), w.cuda(), b.cuda(), act=act, want_pre=True)
+        assert rel_err(y16.float().cpu(), f(pre_ref)) < 2 ** -8
+        assert rel_err(pre16.float().cpu(), pre_ref) < 2 ** -8
 
 
 def test_linear_on_strided_views_in_place():
@@ -91,6 +98,8 @@ def test_linear_bwd_data_applies_the_activation_gradient(act):
     ref = (dy.double() @ w.double()) * dact
     dx = gemm.linear_bwd_data(dy.cuda(), w.cuda(), aux=pre.cuda(), act=act, out_dtype=torch.float32)
     assert rel_err(dx.cpu(), ref) < 2e-5
+    dx16 = gemm.linear_bwd_data(dy.cuda(), w.cuda(), aux=pre.cuda(), act=act)
+    assert rel_err(dx16.float().cpu(), ref) < 2 ** -8
 
 
 def test_linear_autograd_function_uses_the_tensor_core_path_under_autocast():
