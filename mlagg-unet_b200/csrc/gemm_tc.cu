@@ -320,7 +320,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 template <bool kBmn>
-__global__ void __launch_bounds__(192, 1) gemm_tc_store_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO,
                                                                const __grid_constant__ CUtensorMap tmP,
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_store_kernel(const __grid_cons
     unsigned char *ring = smem;
     unsigned char *resB = ring + (size_t)c.stages * stageBytes;                       // [kb_total][bBytes] when resident
     unsigned char *stag = resB + (c.resident ? (size_t)c.kb_total * c.bBytes : 0);    // [2][128 rows][128 B]
-    unsigned char *tail = stag + 2 * kABytes;
+    unsigned char *tail = stag + 4 * kABytes;                                         // 8 warps x 2 x (32 rows x 128 B)
     uint64_t *full = reinterpret_cast<uint64_t *>(tail);   // [stages]
     uint64_t *empty = full + c.stages;                     // [stages]
     uint64_t *accf = empty + c.stages;                     // [2] accumulator complete
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_store_kernel(const __grid_cons
             }
             for (int b = 0; b < 2; ++b) {
                 mbar_init(&accf[b], 1);
-                mbar_init(&acce[b], 4);
+                mbar_init(&acce[b], 8);
             }
             mbar_fence_init();
         }
@@ -443,20 +443,26 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_store_kernel(const __grid_cons
             }
         }
     } else {
-        // ============================================================ epilogue warps (TMEM lanes 32 * (warp % 4) ...)
+        // ============================================================ epilogue: 8 warps, no block-level barriers
+        // warp w reads TMEM lanes 32 * (w % 4) ... (its 32 rows of the tile); warps 2-5 take the even 64-column slabs,
+        // warps 6-9 the odd ones.  Each warp owns two 4 KiB staging buffers and issues its OWN TMA store (box 64 x 32),
+        // so slabs only need __syncwarp: wait until the store that used this buffer two slabs ago has been read, write
+        // the rows (16-byte chunk ch of row r at ch ^ (r & 7): the store's 128-byte swizzle, conflict-free across the
+        // 32 rows of a warp), fence to the async proxy, lane 0 stores.
         const int quad = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const int rloc = 32 * quad + lane;                     // row inside the tile = TMEM lane
-        const bool issuer = (warp == 2 && lane == 0);
-        int slabc = 0;                                          // staging slabs issued so far (2 buffers round-robin)
+        unsigned char *mystag = stag + (size_t)(warp - 2) * 2 * 4096;
+        int slabc = 0;
         for (int i = 0; i < ntiles; ++i) {
             int m0, n0;
             tile_mn(i, m0, n0);
             const int buf = i & 1;
             if (!c.resident) {                                  // bias of this tile's column block
-                named_bar_sync(3, 128);
-                for (int j = threadIdx.x - 64; j < BN + 64; j += 128)
+                named_bar_sync(3, 256);
+                for (int j = threadIdx.x - 64; j < BN + 64; j += 256)
                     bias_s[j] = (p.bias != nullptr && n0 + j < p.N) ? p.bias[n0 + j] : 0.f;
-                named_bar_sync(3, 128);
+                named_bar_sync(3, 256);
             }
             mbar_wait(&accf[buf], (i >> 1) & 1);
             tc_fence_after();
@@ -465,10 +471,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_store_kernel(const __grid_cons
             const int npass = p.pre != nullptr ? 2 : 1;         // pass 0 of 2: the pre-activation goes to `pre`
             for (int pass = 0; pass < npass; ++pass) {
                 const bool to_pre = npass == 2 && pass == 0;
-                for (int c0 = 0; c0 < BN; c0 += 64, ++slabc) {
-                    unsigned char *sg = stag + (slabc & 1) * kABytes + rloc * 128;
-                    if (issuer) bulk_wait_read<1>();            // the store that used this buffer two slabs ago has been read
-                    named_bar_sync(1, 128);
+                for (int c0 = 64 * grp; c0 < BN; c0 += 128, ++slabc) {
+                    unsigned char *sbuf = mystag + (slabc & 1) * 4096;
+                    unsigned char *sg = sbuf + lane * 128;
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         const int cc = c0 + 32 * hf;
@@ -510,30 +517,27 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_store_kernel(const __grid_cons
                                 for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
                             }
                         }
-                        // 16-byte chunk ch of row r sits at ch ^ (r & 7): the TMA store's 128-byte swizzle, and
-                        // conflict-free for a warp whose lanes are 32 consecutive rows
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
-                            const int ch = (4 * hf + (j >> 3)) ^ (rloc & 7);
+                            const int ch = (4 * hf + (j >> 3)) ^ (lane & 7);
                             *reinterpret_cast<uint4 *>(sg + ch * 16) = make_uint4(pack2(x[j], x[j + 1]), pack2(x[j + 2], x[j + 3]),
                                                                                   pack2(x[j + 4], x[j + 5]), pack2(x[j + 6], x[j + 7]));
                         }
                     }
-                    if (pass == npass - 1 && c0 + 64 >= BN) {   // last TMEM read of this tile: hand the accumulator back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acce[buf]);
-                    }
                     fence_proxy_async();
-                    named_bar_sync(2, 128);
-                    if (issuer) {
-                        tma_store_2d(to_pre ? &tmP : &tmO, stag + (slabc & 1) * kABytes, n0 + c0, m0);
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(to_pre ? &tmP : &tmO, sbuf, n0 + c0, m0 + 32 * quad);
                         bulk_commit();
                     }
                 }
             }
+            // every TMEM read of this tile by this warp is complete (tcgen05.wait::ld): hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acce[buf]);
         }
-        if (issuer) bulk_wait_read<0>();
+        if (lane == 0) bulk_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -588,7 +592,7 @@ static int sm_count() {
 }
 
 static bool make_map_out(CUtensorMap *m, const void *base, long long inner, long long outer, long long ld) {
-    return make_map(m, base, inner, outer, ld, 64, kBM);
+    return make_map(m, base, inner, outer, ld, 64, 32);      // one epilogue warp's store: 64 columns x its 32 rows
 }
 
 // persistent store-mode launch (bf16 output); returns cudaErrorInvalidConfiguration when the shape does not fit its plan
@@ -607,8 +611,8 @@ static cudaError_t gemm_tc_store_launch(const void *A, long long lda, const void
     c.bBytes = b_mn ? ((BN + 63) / 64) * kSlab : BN * 128;
     const int sms = sm_count();
     const long long resBytes = (long long)c.kb_total * c.bBytes;
-    c.resident = resBytes <= 112 * 1024 && c.nt <= sms;
-    const int fixed = 2 * kABytes + 2048 + (BN + 64) * 4 + 1024;
+    c.resident = resBytes <= 96 * 1024 && c.nt <= sms;
+    const int fixed = 4 * kABytes + 2048 + (BN + 64) * 4 + 1024;
     const int budget = 227 * 1024 - fixed - (c.resident ? (int)resBytes : 0);
     const int stageBytes = kABytes + (c.resident ? 0 : c.bBytes);
     c.stages = min(8, budget / stageBytes);
@@ -637,7 +641,7 @@ static cudaError_t gemm_tc_store_launch(const void *A, long long lda, const void
     auto kern = b_mn ? gemm_tc_store_kernel<true> : gemm_tc_store_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 192, smem, st>>>(tmA, tmB, tmO, tmP, p, c);
+    kern<<<grid, 320, smem, st>>>(tmA, tmB, tmO, tmP, p, c);
     return cudaGetLastError();
 }
 
