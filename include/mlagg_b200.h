@@ -281,6 +281,8 @@ int mlagg_linattn_bwd(const void *q, const void *k, const void *v, const float *
  *                           applied in the epilogue.  w is read as stored (MN-major B operand, no transposed copy).
  *   mlagg_linear_bwd_weight dw[N,K] += dy[M,N]^T . x[M,K];  dw fp32, row stride lddw, ACCUMULATED INTO (zero-fill first);
  *                           the contraction over the M tokens is split across CTAs and reduced with fp32 vector atomics.
+ *                           db (nullable, fp32 [N], ACCUMULATED INTO) += column sums of dy -- the bias gradient, taken from
+ *                           the same operand tiles by one extra MMA against a tile of ones (replaces mlagg_colsum there).
  * ------------------------------------------------------------------------------------------ */
 int mlagg_linear_fwd(const void *x, long long ldx, const void *w, long long ldw, const float *bias, void *y,
                      long long ldy, void *pre, long long ldpre, long long M, int N, int K, int act, int out_dtype,
@@ -289,7 +291,7 @@ int mlagg_linear_bwd_data(const void *dy, long long lddy, const void *w, long lo
                           int act, void *dx, long long lddx, long long M, int N, int K, int out_dtype,
                           mlagg_stream_t stream);
 int mlagg_linear_bwd_weight(const void *dy, long long lddy, const void *x, long long ldx, float *dw, long long lddw,
-                            long long M, int N, int K, mlagg_stream_t stream);
+                            float *db, long long M, int N, int K, mlagg_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * Column sums of a tokens-major matrix: out[c] += sum_m x[m * ld + c]  (out fp32, ACCUMULATED INTO: zero-fill first).

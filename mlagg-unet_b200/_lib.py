@@ -45,7 +45,7 @@ SIGNATURES = {
     "mlagg_colsum": (c_i, [c_p, c_p, c_ll, c_i, c_ll, c_i, c_p]),
     "mlagg_linear_fwd": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_p, c_ll, c_p, c_ll, c_ll, c_i, c_i, c_i, c_i, c_p]),
     "mlagg_linear_bwd_data": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_ll, c_i, c_i, c_i, c_p]),
-    "mlagg_linear_bwd_weight": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_ll, c_i, c_i, c_p]),
+    "mlagg_linear_bwd_weight": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_p]),
     "mlagg_dwconv3x3_fwd": (c_i, [c_p] * 4 + [c_i] * 6 + [c_p]),
     "mlagg_dwconv3x3_bwd": (c_i, [c_p] * 8 + [c_i] * 6 + [c_p]),
     "mlagg_dwconv3x3_fwd_strided": (c_i, [c_p] * 5 + [c_i] * 4 + [c_ll] * 6 + [c_i, c_i, c_i, c_p]),

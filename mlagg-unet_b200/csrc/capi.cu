@@ -696,12 +696,12 @@ extern "C" int mlagg_linear_bwd_data(const void *dy, long long lddy, const void 
 }
 
 extern "C" int mlagg_linear_bwd_weight(const void *dy, long long lddy, const void *x, long long ldx, float *dw,
-                                       long long lddw, long long M, int N, int K, mlagg_stream_t stream) {
+                                       long long lddw, float *db, long long M, int N, int K, mlagg_stream_t stream) {
     int rc = gemm_check(dy, lddy, x, ldx, dw, lddw, M, N, K, 4);
     if (rc) return rc;
     if (lddy < N || ldx < K || lddw < K) return MLAGG_ERR_BAD_SHAPE;
     GemmTcParams p{};                       // D[N_out, K_in] += dy[M, N_out]^T . x[M, K_in]: contraction over the tokens
-    p.out = dw; p.ldo = lddw;
+    p.out = dw; p.ldo = lddw; p.colsum = db;
     p.M = N; p.N = K; p.K = (int)M; p.reduce = 1;
     cudaError_t e = gemm_tc_dispatch(dy, lddy, 1, x, ldx, 1, p, (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);

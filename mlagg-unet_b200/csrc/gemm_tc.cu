@@ -114,7 +114,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     uint64_t *empty = full + p.stages;                        // [stages]
     uint64_t *accf = empty + p.stages;                        // [1]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accf + 1);
-    float *bias_s = reinterpret_cast<float *>(tmem_slot + 2); // [BN]
+    float *bias_s = reinterpret_cast<float *>(tmem_slot + 2); // [BN + 32]
+    // reduce mode with `colsum`: a 16 x 64 K-major tile of bf16 ones (2 KiB, 1024-byte aligned).  One more MMA per k-step,
+    // D2[128, 16] += A . ones^T, leaves sum_k A[m][k] -- the bias gradient of the layer whose weight gradient this CTA is
+    // computing -- in every column of D2, so the column-sum kernel (145 launches per train step in round 1) disappears.
+    unsigned char *ones_s = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(bias_s + BN + 32) + 1023) & ~uintptr_t(1023));
+    const bool do_colsum = p.colsum != nullptr && blockIdx.y == 0;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
@@ -123,7 +128,11 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     const int kb1 = min(kb_total, kb0 + p.kblocks_per_split);
     const int nkb = kb1 - kb0;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < BN) tmem_cols <<= 1;
+    while ((int)tmem_cols < BN + (p.colsum != nullptr ? 32 : 0)) tmem_cols <<= 1;
+    if (p.colsum != nullptr) {
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) reinterpret_cast<uint32_t *>(ones_s)[i] = 0x3F803F80u;
+        fence_proxy_async();
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -187,6 +196,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                     const uint64_t ad = kAmn ? smem_desc(sa + k * 2048, kSlab, 1024) : smem_desc(sa + k * 32, 16, 1024);
                     const uint64_t bd = kBmn ? smem_desc(sb + k * 2048, kSlab, 1024) : smem_desc(sb + k * 32, 16, 1024);
                     umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+                    if (do_colsum) {
+                        const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((kAmn ? 1u : 0u) << 15) | (2u << 17) |
+                                                ((uint32_t)(kBM >> 4) << 24);      // N = 16, B K-major
+                        umma_bf16(tmem_base + (uint32_t)BN, ad, smem_desc(smem_u32(ones_s), 16, 1024), idesc1,
+                                  (i | k) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(&empty[s]);                 // stage free once these MMAs have read it
                 if (i == nkb - 1) umma_commit(accf);    // accumulator complete
@@ -201,6 +216,11 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         if (nkb > 0) {
             mbar_wait(accf, 0);
             tc_fence_after();
+        }
+        if (do_colsum && nkb > 0) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * quad) << 16) + (uint32_t)BN, v);
+            if (rok) atomicAdd(p.colsum + row, __uint_as_float(v[0]));
         }
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
@@ -673,7 +693,8 @@ cudaError_t gemm_tc_dispatch(const void *A, long long lda, int a_mn, const void 
     splits = (kb_total + p.kblocks_per_split - 1) / p.kblocks_per_split;
     const int budget = p.reduce ? 200 * 1024 : 100 * 1024;     // store mode: two CTAs per SM overlap epilogue and loads
     p.stages = max(2, min(min(8, budget / stageBytes), max(2, p.kblocks_per_split)));
-    const size_t smem = (size_t)p.stages * stageBytes + (2 * p.stages + 1) * 8 + 8 + (size_t)(BN + 32) * 4 + 1024;
+    const size_t smem = (size_t)p.stages * stageBytes + (2 * p.stages + 1) * 8 + 8 + (size_t)(BN + 32) * 4 + 1024 +
+                        (p.colsum ? 3072 : 0);
 
     CUtensorMap tmA, tmB;
     auto encode = [&]() {

@@ -9,6 +9,7 @@ struct GemmTcParams {
     void *pre;                  // optional second output: the pre-activation, bf16 [M][ldpre]
     const void *aux;            // optional bf16 [M][ldaux]: epilogue multiplies by act'(aux)
     const float *bias;          // optional [N]
+    float *colsum;              // reduce mode, optional [M]: += sum over K of A[m][k] (the bias gradient), fp32 atomics
     long long ldo, ldpre, ldaux;
     int M, N, K;
     int BN;                     // UMMA N (multiple of 16, <= 256)

@@ -22,8 +22,8 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import (Conv2dCL, ConvTranspose2dCL, GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path,
-                  silu_gate)
+from .ops import (Conv2dCL, ConvTranspose2dCL, GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens,
+                  mlp_gelu_tokens, residual_drop_path, silu_gate)
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
 
@@ -36,6 +36,8 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
+        if isinstance(self.act, nn.GELU) and self.act.approximate == "none" and (self.drop.p == 0. or not self.training):
+            return mlp_gelu_tokens(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
         return self.drop(linear_tokens(self.drop(self.act(linear_tokens(x, self.fc1))), self.fc2))
 
 
@@ -321,7 +323,17 @@ class MedNeXtBlock(nn.Module):
         self.conv3 = nn.Conv2d(exp_r * in_channels, out_channels, kernel_size=1)
 
     def forward(self, x, dummy_tensor=None):
-        y = _conv1x1_cl(self.conv3, self.act(_conv1x1_cl(self.conv2, _inst_norm(self.norm, self.conv1(x)))))
+        t = _inst_norm(self.norm, self.conv1(x))
+        tk = t.permute(0, 2, 3, 1)
+        if t.is_cuda and tk.is_contiguous() and isinstance(self.act, nn.GELU):
+            # the 1x1-conv pair on the channels_last map == fc1 -> GELU -> fc2 on its tokens (one fused node)
+            Bn, C, H, W = t.shape
+            w2, w3 = self.conv2.weight, self.conv3.weight
+            y = mlp_gelu_tokens(tk.reshape(Bn, H * W, C), w2.view(w2.shape[0], w2.shape[1]), self.conv2.bias,
+                                w3.view(w3.shape[0], w3.shape[1]), self.conv3.bias)
+            y = y.reshape(Bn, H, W, -1).permute(0, 3, 1, 2)
+        else:
+            y = _conv1x1_cl(self.conv3, self.act(_conv1x1_cl(self.conv2, t)))
         return x + y if self.do_res else y
 
 

@@ -430,6 +430,9 @@ class _Linear(torch.autograd.Function):
         x2 = _rows2d(xc) if _rows2d(xc) is not None else xc.reshape(-1, Cin)
         if ctx.tc and gemm.rows_ok(dy2) and gemm.rows_ok(x2):
             dx = gemm.linear_bwd_data(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
+            if ctx.needs_input_grad[1] and bdt is not None and ctx.needs_input_grad[2]:
+                dw, db = gemm.linear_bwd_weight(dy2, x2, want_db=True)      # bias gradient from the same operand tiles
+                return dx, dw.to(wdt), db.to(bdt)
             dw = gemm.linear_bwd_weight(dy2, x2).to(wdt) if ctx.needs_input_grad[1] else None
         else:
             with torch.autocast("cuda", enabled=False):
@@ -437,6 +440,51 @@ class _Linear(torch.autograd.Function):
                 dw = torch.mm(dy2.t(), x2).to(wdt) if ctx.needs_input_grad[1] else None
         db = colsum(dy2).to(bdt) if (bdt is not None and ctx.needs_input_grad[2]) else None
         return dx, dw, db
+
+
+class _MlpFused(torch.autograd.Function):
+    """fc1 -> exact GELU -> fc2 (reference Mlp, nnUNetTrainer_MLAgg_2D_dt_MS.py:176-192; the 1x1-conv pair of MedNeXtBlock
+    :230-324 has the same shape) as ONE autograd node on the tensor-core kernels: GELU is the epilogue of the fc1 GEMM
+    (which also stores the pre-activation), and its gradient is the epilogue of fc2's data-gradient GEMM -- no
+    element-wise kernel on the (tokens, hidden) tensor in either direction."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x2 = _rows2d(x.to(torch.bfloat16))
+        w1c, w2c = _cast_param(w1, torch.bfloat16), _cast_param(w2, torch.bfloat16)
+        h, pre = gemm.linear_fwd(x2, w1c, b1, act="gelu", want_pre=True)
+        y, _ = gemm.linear_fwd(h, w2c, b2)
+        ctx.save_for_backward(x2, pre, h, w1c, w2c)
+        ctx.meta = (x.dtype, x.shape, w1.dtype, w2.dtype, None if b1 is None else b1.dtype, None if b2 is None else b2.dtype)
+        return y.view(*x.shape[:-1], w2c.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, pre, h, w1c, w2c = ctx.saved_tensors
+        xdt, xshape, w1dt, w2dt, b1dt, b2dt = ctx.meta
+        dy2 = dy.to(torch.bfloat16)
+        dy2 = _rows2d(dy2) if _rows2d(dy2) is not None else dy2.reshape(-1, w2c.shape[0])
+        if not gemm.rows_ok(dy2):
+            dy2 = dy2.contiguous()
+        need = ctx.needs_input_grad
+        dpre = gemm.linear_bwd_data(dy2, w2c, aux=pre, act="gelu")            # (dy W2) * gelu'(pre)
+        dw2, db2 = gemm.linear_bwd_weight(dy2, h, want_db=True)
+        dx = gemm.linear_bwd_data(dpre, w1c).view(xshape).to(xdt) if need[0] else None
+        dw1, db1 = gemm.linear_bwd_weight(dpre, x2, want_db=True)
+        return (dx, dw1.to(w1dt), None if b1dt is None else db1.to(b1dt), dw2.to(w2dt), None if b2dt is None else db2.to(b2dt))
+
+
+def mlp_gelu_tokens(x, w1, b1, w2, b2):
+    """fc2(gelu(fc1(x))) for tokens-major x (..., C); weights (hidden, C) / (C_out, hidden) as nn.Linear stores them.
+    The fused tensor-core node under bf16 autocast, else the two Linear nodes with torch's GELU between them."""
+    if (x.is_cuda and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            and x.dim() >= 2 and w1.shape[0] % 8 == 0 and w1.shape[1] % 8 == 0 and w2.shape[0] % 8 == 0
+            and w1.stride(-1) == 1 and w2.stride(-1) == 1):
+        x16 = x.to(torch.bfloat16)
+        x2 = _rows2d(x16)
+        if x2 is not None and gemm.rows_ok(x2):
+            return _MlpFused.apply(x, w1, b1, w2, b2)
+    return _Linear.apply(torch.nn.functional.gelu(_Linear.apply(x, w1, b1)), w2, b2)
 
 
 def linear_tokens(x, lin: torch.nn.Linear):

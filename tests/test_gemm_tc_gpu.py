@@ -82,6 +82,9 @@ def test_linear_bwd_data_and_weight_match_fp64(M, N, K):
     assert rel_err(dx16.float().cpu(), dy.double() @ w.double()) < 2 ** -8
     dw = gemm.linear_bwd_weight(dy.cuda(), x.cuda())
     assert dw.dtype == torch.float32 and rel_err(dw.cpu(), dy.double().t() @ x.double()) < 2e-5
+    dw2, db = gemm.linear_bwd_weight(dy.cuda(), x.cuda(), want_db=True)      # bias gradient from the ones-tile MMA
+    assert rel_err(dw2.cpu(), dy.double().t() @ x.double()) < 2e-5
+    assert db.shape == (N,) and rel_err(db.cpu(), dy.double().sum(0)) < 2e-5
 
 
 @pytest.mark.parametrize("act", ["gelu", "silu"])

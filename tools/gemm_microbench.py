@@ -1,5 +1,6 @@
 """Projection GEMMs of one train step at config 3 (B = 10, 320 x 320): the tcgen05 / TMEM / TMA kernels (mlagg_linear_*)
-beside cuBLAS (torch.mm / addmm, what round 1 shipped) on the same bf16 operands, L2 flushed between launches.
+beside cuBLAS (torch.mm / addmm, what round 1 shipped) on the same bf16 operands.  L2 is flushed between launches by
+READING a 256 MB buffer (a write flush leaves ~126 MB of dirty lines whose write-back is then charged to the timed kernel).
 Per shape: forward (bias epilogue), data gradient, weight gradient; microseconds and algorithmic GB/s
 (operands + result once) against the measured HBM peak."""
 import json
@@ -20,7 +21,7 @@ def t_us(fn, n=20):
         fn()
     tot = 0.0
     for _ in range(n):
-        flush.zero_()
+        flush.max()          # read flush: L2 ends up full of clean lines
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
