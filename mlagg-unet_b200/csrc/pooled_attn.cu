@@ -226,8 +226,6 @@ __global__ void __launch_bounds__(kPTok) pooled_attn_bwd_q_kernel(const PooledAt
 #pragma unroll
             for (int c = 0; c < 2 * HD; c += 4)
                 *reinterpret_cast<float4 *>(wdO + c) = make_float4(g[c], g[c + 1], g[c + 2], g[c + 3]);
-            p.ws_D[(tok * p.h + m) * 2 + 0] = D0;
-            p.ws_D[(tok * p.h + m) * 2 + 1] = D1;
             dlam = -D1;
         }
         // ---- dq_j = scale2 * sum_p dlogit_jp k_jp
@@ -251,6 +249,20 @@ __global__ void __launch_bounds__(kPTok) pooled_attn_bwd_q_kernel(const PooledAt
             }
             return (da.x + da.y) + (db.x + db.y);
         };
+        // D_j = sum_p A_j[p] dab[p] from the same probabilities and dab values the loop below uses (see the tensor-core
+        // kernel): dO . O_j is the same number mathematically, but where the softmax is nearly uniform dab - D_j cancels
+        // to ~1e-3 of dab and the two evaluation orders differ by more than that leaves
+        {
+            float2 Dc = p2(0.f, 0.f);
+            for (int pp = 0; pp < p.P; ++pp) {
+                const float2 d = logits2<HD>(q2, kI + pp * HD);
+                const float dab = dot_v(pp);
+                Dc = __ffma2_rn(p2(ex2_approx(d.x - lse0), ex2_approx(d.y - lse1)), p2(dab, dab), Dc);
+            }
+            D0 = Dc.x, D1 = Dc.y;
+            p.ws_D[(tok * p.h + m) * 2 + 0] = D0;
+            p.ws_D[(tok * p.h + m) * 2 + 1] = D1;
+        }
         float2 dnext = logits2<HD>(q2, kI);
         float dabnext = dot_v(0);
         for (int pp = 0; pp < p.P; ++pp) {

@@ -117,7 +117,7 @@ def test_linear_autograd_function_uses_the_tensor_core_path_under_autocast():
         y = linear_tokens(x, lin)
     dy = torch.randn_like(y)
     y.backward(dy)
-    assert _lib.STATS["launches"] >= 4            # fwd, bwd_data, bwd_weight, colsum went through the C ABI
+    assert _lib.STATS["launches"] >= 3            # fwd, bwd_data, bwd_weight (+ bias gradient) went through the C ABI
     xr = x.detach().bfloat16().double().requires_grad_()
     wr = lin.weight.detach().bfloat16().double().requires_grad_()
     br = lin.bias.detach().double().requires_grad_()
