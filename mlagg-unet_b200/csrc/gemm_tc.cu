@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 // One CTA per SM walks the output tiles of ONE column block (n fixed, m strided) when the whole B operand of that block
 // fits in shared memory: W is then loaded ONCE per CTA ("resident") and only activation tiles stream through the TMA ring;
 // otherwise (m, n) tiles are walked in row-major order and B streams with A.  Two TMEM accumulators alternate, so the
-// epilogue of tile i (tcgen05.ld -> bias / activation -> bf16 -> XOR-swizzled per-warp staging slab -> coalesced
-// 128-byte row-segment stores) overlaps the loads and MMAs of tile i + 1.  A is K-major (activations / output gradients); B is K-major
+// epilogue of tile i (tcgen05.ld -> bias / activation -> bf16 -> 128-byte-swizzled staging slab -> TMA store, SASS
+// UTMASTG) overlaps the loads and MMAs of tile i + 1.  A is K-major (activations / output gradients); B is K-major
 // (forward: W[N][K]) or MN-major (data gradient: W[K][N] as stored).
 struct GemmStoreCfg {
     int nt, mt, ctas_per_n, resident, bBytes, kb_total, stages;
@@ -342,6 +342,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 template <bool kBmn>
 __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmO,
+                                                               const __grid_constant__ CUtensorMap tmP,
                                                                const GemmTcParams p, const GemmStoreCfg c) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
         if (lane == 0) {
             tmap_prefetch(&tmA);
             tmap_prefetch(&tmB);
+            tmap_prefetch(&tmO);
             for (int s = 0; s < c.stages; ++s) {
                 mbar_init(&full[s], 1);
                 mbar_init(&empty[s], 1);
@@ -462,9 +465,10 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
     } else {
         // ============================================================ epilogue: 8 warps, no block-level barriers
         // warp w reads TMEM lanes 32 * (w % 4) ... (its 32 rows of the tile); warps 2-5 take the even 64-column slabs,
-        // warps 6-9 the odd ones.  Each warp owns two 4 KiB staging buffers, so slabs only need __syncwarp: write the rows
-        // (lane = row; 16-byte chunk ch of row r at ch ^ (r & 7): conflict-free for 32 consecutive rows), then read them
-        // back with lanes along the row and store whole 128-byte segments.
+        // warps 6-9 the odd ones.  Each warp owns two 4 KiB staging buffers and issues its OWN TMA store (box 64 x 32),
+        // so slabs only need __syncwarp: wait until the store that used this buffer two slabs ago has been read, write
+        // the rows (16-byte chunk ch of row r at ch ^ (r & 7): the store's 128-byte swizzle, conflict-free across the
+        // 32 rows of a warp), fence to the async proxy, lane 0 stores.
         const int quad = warp & 3;
         const int grp = (warp - 2) >> 2;
         const int rloc = 32 * quad + lane;                     // row inside the tile = TMEM lane
@@ -490,6 +494,8 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
                 for (int c0 = 64 * grp; c0 < BN; c0 += 128, ++slabc) {
                     unsigned char *sbuf = mystag + (slabc & 1) * 4096;
                     unsigned char *sg = sbuf + lane * 128;
+                    if (lane == 0) bulk_wait_read<1>();
+                    __syncwarp();
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
                         const int cc = c0 + 32 * hf;
@@ -538,26 +544,12 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
                                                                                   pack2(x[j + 4], x[j + 5]), pack2(x[j + 6], x[j + 7]));
                         }
                     }
+                    fence_proxy_async();
                     __syncwarp();
-                    // staging -> HBM: lane l moves the 16-byte chunk l % 8 of rows l / 8, l / 8 + 4, ...: every store
-                    // instruction of the warp writes four complete 128-byte row segments.  (A TMA store per warp was
-                    // measured first: the stores queue behind the producer's prefetched loads in the SM's TMA unit and
-                    // the staging buffers came back ~2 us late -- the epilogue, not HBM, paced the kernel.)
-                    {
-                        __nv_bfloat16 *ob = reinterpret_cast<__nv_bfloat16 *>(to_pre ? p.pre : p.out);
-                        const long long ldob = to_pre ? p.ldpre : p.ldo;
-                        const int ch = lane & 7, col = n0 + c0 + 8 * ch;
-                        if (col < p.N && c0 + 8 * ch < BN) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int r = (lane >> 3) + 4 * k;
-                                const int grow = m0 + 32 * quad + r;
-                                const uint4 w = *reinterpret_cast<const uint4 *>(sbuf + r * 128 + ((ch ^ (r & 7)) * 16));
-                                if (grow < p.M) *reinterpret_cast<uint4 *>(ob + (size_t)grow * ldob + col) = w;
-                            }
-                        }
+                    if (lane == 0) {
+                        tma_store_2d(to_pre ? &tmP : &tmO, sbuf, n0 + c0, m0 + 32 * quad);
+                        bulk_commit();
                     }
-                    __syncwarp();
                 }
             }
             // every TMEM read of this tile by this warp is complete (tcgen05.wait::ld): hand the accumulator back
@@ -565,6 +557,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&acce[buf]);
         }
+        if (lane == 0) bulk_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -618,6 +611,10 @@ static int sm_count() {
     return n;
 }
 
+static bool make_map_out(CUtensorMap *m, const void *base, long long inner, long long outer, long long ld) {
+    return make_map(m, base, inner, outer, ld, 64, 32);      // one epilogue warp's store: 64 columns x its 32 rows
+}
+
 // persistent store-mode launch (bf16 output); returns cudaErrorInvalidConfiguration when the shape does not fit its plan
 static cudaError_t gemm_tc_store_launch(const void *A, long long lda, const void *B, long long ldb, int b_mn, GemmTcParams p,
                                         cudaStream_t st) {
@@ -649,10 +646,13 @@ static cudaError_t gemm_tc_store_launch(const void *A, long long lda, const void
         grid = min(sms, c.mt * c.nt);
     }
     const size_t smem = (size_t)c.stages * stageBytes + (c.resident ? (size_t)resBytes : 0) + fixed;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO, tmP;
     auto encode = [&]() {
         bool ok = make_map(&tmA, A, p.K, p.M, lda, 64, kBM);
-        return ok && (b_mn ? make_map(&tmB, B, p.N, p.K, ldb, 64, 64) : make_map(&tmB, B, p.K, p.N, ldb, 64, BN));
+        ok = ok && (b_mn ? make_map(&tmB, B, p.N, p.K, ldb, 64, 64) : make_map(&tmB, B, p.K, p.N, ldb, 64, BN));
+        ok = ok && make_map_out(&tmO, p.out, p.N, p.M, p.ldo);
+        ok = ok && (p.pre ? make_map_out(&tmP, p.pre, p.N, p.M, p.ldpre) : make_map_out(&tmP, p.out, p.N, p.M, p.ldo));
+        return ok;
     };
     if (!encode()) {
         cudaFree(nullptr);
@@ -661,7 +661,7 @@ static cudaError_t gemm_tc_store_launch(const void *A, long long lda, const void
     auto kern = b_mn ? gemm_tc_store_kernel<true> : gemm_tc_store_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 320, smem, st>>>(tmA, tmB, p, c);
+    kern<<<grid, 320, smem, st>>>(tmA, tmB, tmO, tmP, p, c);
     return cudaGetLastError();
 }
 
