@@ -80,6 +80,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 format, cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading
 // byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in
@@ -339,7 +352,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&t);
 }
 
-template <bool kBmn>
+template <bool kBmn, int kAct, bool kPre, bool kAux>
 __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO,
@@ -468,7 +481,9 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
         // warps 6-9 the odd ones.  Each warp owns two 4 KiB staging buffers and issues its OWN TMA store (box 64 x 32),
         // so slabs only need __syncwarp: wait until the store that used this buffer two slabs ago has been read, write
         // the rows (16-byte chunk ch of row r at ch ^ (r & 7): the store's 128-byte swizzle, conflict-free across the
-        // 32 rows of a warp), fence to the async proxy, lane 0 stores.
+        // 32 rows of a warp), fence to the async proxy, lane 0 stores.  The epilogue math is selected at COMPILE time
+        // (kAct / kPre / kAux): with run-time flags inside the 64-element unrolled body the first version executed
+        // ~660 instructions per warp and tile and paced the whole kernel (ncu: profiles/gemm_store_r02_ncu.txt).
         const int quad = warp & 3;
         const int grp = (warp - 2) >> 2;
         const int rloc = 32 * quad + lane;                     // row inside the tile = TMEM lane
@@ -488,25 +503,34 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
             tc_fence_after();
             const uint32_t trow = tmem_base + buf * acc_cols + ((uint32_t)(32 * quad) << 16);
             const bool rok = m0 + rloc < p.M;
-            const int npass = p.pre != nullptr ? 2 : 1;         // pass 0 of 2: the pre-activation goes to `pre`
-            for (int pass = 0; pass < npass; ++pass) {
-                const bool to_pre = npass == 2 && pass == 0;
+#pragma unroll
+            for (int pass = 0; pass < (kPre ? 2 : 1); ++pass) {
+                const bool to_pre = kPre && pass == 0;          // pass 0 of 2: the pre-activation goes to `pre`
                 for (int c0 = 64 * grp; c0 < BN; c0 += 128, ++slabc) {
                     unsigned char *sbuf = mystag + (slabc & 1) * 4096;
                     unsigned char *sg = sbuf + lane * 128;
+                    const bool two = c0 + 32 < BN;              // (uniform) second 32-column half inside the accumulator
+                    uint32_t v[2][32];
+                    tmem_ld32_nowait(trow + (uint32_t)c0, v[0]);
+                    if (two) tmem_ld32_nowait(trow + (uint32_t)(c0 + 32), v[1]);
                     if (lane == 0) bulk_wait_read<1>();
+                    tmem_ld_wait();
                     __syncwarp();
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
+                        if (hf == 1 && !two) break;
                         const int cc = c0 + 32 * hf;
-                        if (cc >= BN) break;                    // (uniform) nothing beyond the accumulator's columns
-                        uint32_t v[32];
-                        tmem_ld32(trow + (uint32_t)cc, v);
                         float x[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bias_s[cc + j];
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bb = *reinterpret_cast<const float4 *>(bias_s + cc + j);
+                            x[j] = __uint_as_float(v[hf][j]) + bb.x;
+                            x[j + 1] = __uint_as_float(v[hf][j + 1]) + bb.y;
+                            x[j + 2] = __uint_as_float(v[hf][j + 2]) + bb.z;
+                            x[j + 3] = __uint_as_float(v[hf][j + 3]) + bb.w;
+                        }
                         if (!to_pre) {
-                            if (p.aux != nullptr) {
+                            if (kAux) {
                                 if (rok) {
                                     const __nv_bfloat16 *a = reinterpret_cast<const __nv_bfloat16 *>(p.aux) +
                                                              (size_t)(m0 + rloc) * p.ldaux + n0 + cc;
@@ -518,21 +542,16 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
 #pragma unroll
                                             for (int e = 0; e < 4; ++e) {
                                                 const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ww[e]));
-                                                if (p.act == 1) {
-                                                    x[j + 2 * e] *= gelu_grad(f.x);
-                                                    x[j + 2 * e + 1] *= gelu_grad(f.y);
-                                                } else if (p.act == 2) {
-                                                    x[j + 2 * e] *= silu_grad(f.x);
-                                                    x[j + 2 * e + 1] *= silu_grad(f.y);
-                                                }
+                                                x[j + 2 * e] *= kAct == 1 ? gelu_grad(f.x) : silu_grad(f.x);
+                                                x[j + 2 * e + 1] *= kAct == 1 ? gelu_grad(f.y) : silu_grad(f.y);
                                             }
                                         }
                                     }
                                 }
-                            } else if (p.act == 1) {
+                            } else if (kAct == 1) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) x[j] = gelu_f(x[j]);
-                            } else if (p.act == 2) {
+                            } else if (kAct == 2) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
                             }
@@ -658,7 +677,19 @@ static cudaError_t gemm_tc_store_launch(const void *A, long long lda, const void
         cudaFree(nullptr);
         if (!encode()) return cudaErrorNotSupported;
     }
-    auto kern = b_mn ? gemm_tc_store_kernel<true> : gemm_tc_store_kernel<false>;
+    using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmTcParams,
+                           const GemmStoreCfg);
+    KernT kern = nullptr;
+    const int act = p.act;
+#define MLAGG_PICK(BMN, ACT, PRE, AUX) \
+    if (b_mn == BMN && act == ACT && (p.pre != nullptr) == PRE && (p.aux != nullptr) == AUX) kern = gemm_tc_store_kernel<BMN, ACT, PRE, AUX>;
+    MLAGG_PICK(false, 0, false, false) MLAGG_PICK(true, 0, false, false)
+    MLAGG_PICK(false, 1, false, false) MLAGG_PICK(false, 2, false, false)
+    MLAGG_PICK(false, 1, true, false) MLAGG_PICK(false, 2, true, false)
+    MLAGG_PICK(true, 1, false, true) MLAGG_PICK(true, 2, false, true)
+    MLAGG_PICK(false, 0, true, false)
+#undef MLAGG_PICK
+    if (kern == nullptr) return cudaErrorInvalidConfiguration;       // combination not instantiated: generic kernel
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, 320, smem, st>>>(tmA, tmB, tmO, tmP, p, c);
