@@ -238,6 +238,13 @@ int mlagg_layernorm_fwd(const void *x, const float *weight, const float *bias, v
 int mlagg_layernorm_bwd(const void *x, const float *weight, const float *mean, const float *rstd, const void *dy,
                         void *dx, float *dweight, float *dbias, long long M, int C, int dt_in, int dt_out,
                         mlagg_stream_t stream);
+/* Same with the gradient that reaches x along the RESIDUAL path added in the same pass: dx = LN'(dy) + dres
+ * (dres (M, C) of dt_in, nullable).  Every pre-norm residual branch of the path -- `x + f(norm(x))` at
+ * nnUNetTrainer_MLAgg_2D_dt_MS.py:877-911 (twice per block) and variants/mamba/MambaSkip.py:738 -- otherwise costs one
+ * full-tensor add in autograd's gradient accumulation. */
+int mlagg_layernorm_bwd_res(const void *x, const float *weight, const float *mean, const float *rstd, const void *dy,
+                            const void *dres, void *dx, float *dweight, float *dbias, long long M, int C, int dt_in,
+                            int dt_out, mlagg_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * elu+1 linear attention core of MLLA (the ops BASELINE.json:north_star names).

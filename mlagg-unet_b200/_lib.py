@@ -35,6 +35,7 @@ SIGNATURES = {
     "mlagg_walk_unpack": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_p, c_i, c_ll, c_ll, c_i, c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "mlagg_layernorm_fwd": (c_i, [c_p] * 6 + [c_ll, c_i, c_f, c_i, c_i, c_p]),
     "mlagg_layernorm_bwd": (c_i, [c_p] * 8 + [c_ll, c_i, c_i, c_i, c_p]),
+    "mlagg_layernorm_bwd_res": (c_i, [c_p] * 9 + [c_ll, c_i, c_i, c_i, c_p]),
     "mlagg_linattn_state_bytes": (c_sz, [c_i] * 3),
     "mlagg_linattn_fwd": (c_i, [c_p] * 6 + [c_i] * 5 + [c_ll] * 4 + [c_f, c_i, c_p]),
     "mlagg_linattn_bwd": (c_i, [c_p] * 10 + [c_i] * 5 + [c_ll] * 7 + [c_f, c_i, c_p]),

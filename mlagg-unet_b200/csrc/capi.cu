@@ -91,7 +91,7 @@ cudaError_t avgpool_dispatch(const void *x, const void *dy, void *out, int Bn, i
 
 cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                                const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
-                               int dt_in, int dt_out, bool bwd, cudaStream_t st);
+                               int dt_in, int dt_out, bool bwd, cudaStream_t st, const void *dres = nullptr);
 
 static thread_local char g_last_err[256] = "";
 
@@ -582,16 +582,23 @@ extern "C" int mlagg_layernorm_fwd(const void *x, const float *weight, const flo
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 
-extern "C" int mlagg_layernorm_bwd(const void *x, const float *weight, const float *mean, const float *rstd,
-                                   const void *dy, void *dx, float *dweight, float *dbias, long long M, int C,
-                                   int dt_in, int dt_out, mlagg_stream_t stream) {
+extern "C" int mlagg_layernorm_bwd_res(const void *x, const float *weight, const float *mean, const float *rstd,
+                                       const void *dy, const void *dres, void *dx, float *dweight, float *dbias,
+                                       long long M, int C, int dt_in, int dt_out, mlagg_stream_t stream) {
     int rc = ln_check(x, weight, M, C, dt_in, dt_out);
     if (rc) return rc;
     if (!mean || !rstd || !dy || !dx || !dweight) return MLAGG_ERR_NULL;
     if (!aligned(dy, dt_out == MLAGG_F32 ? 16 : 8) || !aligned(dx, dt_in == MLAGG_F32 ? 16 : 8)) return MLAGG_ERR_ALIGN;
+    if (dres && !aligned(dres, dt_in == MLAGG_F32 ? 16 : 8)) return MLAGG_ERR_ALIGN;
     cudaError_t e = layernorm_dispatch(x, weight, nullptr, nullptr, const_cast<float *>(mean), const_cast<float *>(rstd),
-                                       dy, dx, dweight, dbias, M, C, 0.f, dt_in, dt_out, true, (cudaStream_t)stream);
+                                       dy, dx, dweight, dbias, M, C, 0.f, dt_in, dt_out, true, (cudaStream_t)stream, dres);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_layernorm_bwd(const void *x, const float *weight, const float *mean, const float *rstd,
+                                   const void *dy, void *dx, float *dweight, float *dbias, long long M, int C,
+                                   int dt_in, int dt_out, mlagg_stream_t stream) {
+    return mlagg_layernorm_bwd_res(x, weight, mean, rstd, dy, nullptr, dx, dweight, dbias, M, C, dt_in, dt_out, stream);
 }
 
 // ------------------------------------------------------------------------------------------------ linear attention

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(320, 1) gemm_tc_store_kernel(const __grid_cons
     uint64_t *accf = empty + c.stages;                     // [2] accumulator complete
     uint64_t *acce = accf + 2;                             // [2] accumulator drained
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acce + 2);
-    float *bias_s = reinterpret_cast<float *>(tmem_slot + 2);   // [BN + 64]
+    float *bias_s = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~uintptr_t(15));   // [BN + 64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // tile walk: resident -> n fixed per CTA, m = mfirst + i * mstep; streaming -> t = cta + i * grid, (m, n) = (t / nt, t % nt)

@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI *__restrict
                                                             const float *__restrict__ mean,
                                                             const float *__restrict__ rstd, const TO *__restrict__ dy,
                                                             TI *__restrict__ dx, float *__restrict__ dw,
-                                                            float *__restrict__ db, long long M, int C) {
+                                                            float *__restrict__ db, long long M, int C,
+                                                            const TI *__restrict__ dres) {
     extern __shared__ float red[];  // [2][C]
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
@@ -147,6 +148,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI *__restrict
                 o.y = rs * (g[i].y - c1 - xh[i].y * c2);
                 o.z = rs * (g[i].z - c1 - xh[i].z * c2);
                 o.w = rs * (g[i].w - c1 - xh[i].w * c2);
+                if (dres != nullptr) {   // gradient arriving at x along the residual path: dx = LN'(dy) + dres in one pass
+                    const float4 rv = ln_ld4<TI>(dres + row * C + c);
+                    o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                }
                 ln_st4<TI>(dx + row * C + c, o);
             }
         }
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TI *__restrict
 template <typename TI, typename TO, int NV>
 static cudaError_t ln_launch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                              const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps, bool bwd,
-                             cudaStream_t st) {
+                             cudaStream_t st, const void *dres) {
     long long blocks = (M + 7) / 8;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (!bwd) {
@@ -177,7 +182,8 @@ static cudaError_t ln_launch(const void *x, const float *w, const float *b, void
                                                                       static_cast<TO *>(y), mean, rstd, M, C, eps);
     } else {
         layernorm_bwd_kernel<TI, TO, NV><<<(int)blocks, 256, 2 * C * sizeof(float), st>>>(
-            static_cast<const TI *>(x), w, mean, rstd, static_cast<const TO *>(dy), static_cast<TI *>(dx), dw, db, M, C);
+            static_cast<const TI *>(x), w, mean, rstd, static_cast<const TO *>(dy), static_cast<TI *>(dx), dw, db, M, C,
+            static_cast<const TI *>(dres));
     }
     return cudaGetLastError();
 }
@@ -185,14 +191,14 @@ static cudaError_t ln_launch(const void *x, const float *w, const float *b, void
 template <typename TI, typename TO>
 static cudaError_t ln_nv(int nv, const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                          const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps, bool bwd,
-                         cudaStream_t st) {
+                         cudaStream_t st, const void *dres) {
     switch (nv) {
-        case 1: return ln_launch<TI, TO, 1>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-        case 2: return ln_launch<TI, TO, 2>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-        case 3: return ln_launch<TI, TO, 3>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-        case 4: return ln_launch<TI, TO, 4>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-        case 5: case 6: return ln_launch<TI, TO, 6>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-        case 7: case 8: return ln_launch<TI, TO, 8>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+        case 1: return ln_launch<TI, TO, 1>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+        case 2: return ln_launch<TI, TO, 2>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+        case 3: return ln_launch<TI, TO, 3>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+        case 4: return ln_launch<TI, TO, 4>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+        case 5: case 6: return ln_launch<TI, TO, 6>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+        case 7: case 8: return ln_launch<TI, TO, 8>(x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -200,13 +206,13 @@ static cudaError_t ln_nv(int nv, const void *x, const float *w, const float *b, 
 // dt_in / dt_out: 0 = fp32, 1 = bf16
 cudaError_t layernorm_dispatch(const void *x, const float *w, const float *b, void *y, float *mean, float *rstd,
                                const void *dy, void *dx, float *dw, float *db, long long M, int C, float eps,
-                               int dt_in, int dt_out, bool bwd, cudaStream_t st) {
+                               int dt_in, int dt_out, bool bwd, cudaStream_t st, const void *dres) {
     const int nv = (C / 4 + 31) / 32;
     using bf = __nv_bfloat16;
-    if (dt_in == 0 && dt_out == 0) return ln_nv<float, float>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-    if (dt_in == 0 && dt_out == 1) return ln_nv<float, bf>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-    if (dt_in == 1 && dt_out == 0) return ln_nv<bf, float>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
-    return ln_nv<bf, bf>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st);
+    if (dt_in == 0 && dt_out == 0) return ln_nv<float, float>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+    if (dt_in == 0 && dt_out == 1) return ln_nv<float, bf>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+    if (dt_in == 1 && dt_out == 0) return ln_nv<bf, float>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
+    return ln_nv<bf, bf>(nv, x, w, b, y, mean, rstd, dy, dx, dw, db, M, C, eps, bwd, st, dres);
 }
 
 }  // namespace mlagg

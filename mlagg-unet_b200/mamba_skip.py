@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import CatStages, Conv2dCL, JoinLast, SplitLast, SplitStages, _Linear, conv_glu_core, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_tokens, linear_tokens, residual_drop_path
+from .ops import CatStages, Conv2dCL, JoinLast, SplitLast, SplitStages, _Linear, conv_glu_core, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_fork, layer_norm_tokens, linear_tokens, residual_drop_path
 from .selective_scan_interface import msmm_scan, msmm_scan_tokens, selective_scan_fn, xdbl_pad
 from .thirdparty_shims import DropPath, _inst_norm
 
@@ -273,7 +273,8 @@ class VSS_Conv_Block(nn.Module):
         # (B, L, hd) for the scan branch, and the rest -> conv branch
         halves = [SplitLast.apply(t.permute(0, 2, 3, 1), hd) for t in inputs]
         m = CatStages.apply(*[a.flatten(1, 2) for a, _ in halves])         # (B, H, W, hd) -> (B, H W, hd): views
-        m = residual_drop_path(m, self.self_attention(layer_norm_tokens(m, self.ln_1), Bn, H, W, L_split), self.drop_path)
+        n1, m = layer_norm_fork(m, self.ln_1)                # m's residual-path gradient is added inside ln_1's backward
+        m = residual_drop_path(m, self.self_attention(n1, Bn, H, W, L_split), self.drop_path)
         # one packed copy per stage: with a uniform row stride the fc1 GEMM keeps its bias epilogue, the residual is the
         # one-pass kernel, and the Linear backward needs no re-pack of its saved input
         stage_tokens = SplitStages.apply(layer_norm_tokens(m, self.norm2), tuple(L_split))

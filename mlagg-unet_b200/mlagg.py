@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import (Conv2dCL, ConvTranspose2dCL, GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_tokens, linear_tokens,
+from .ops import (Conv2dCL, ConvTranspose2dCL, GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_fork, layer_norm_tokens, linear_tokens,
                   mlp_gelu_tokens, residual_drop_path, silu_gate)
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
@@ -183,8 +183,7 @@ class MLLABlock(nn.Module):
 
     def forward_tokens(self, t, H, W):
         """tokens-major (B, N, C) -> (B, N, C)"""
-        shortcut = t
-        t = layer_norm_tokens(t, self.norm1)
+        t, shortcut = layer_norm_fork(t, self.norm1)          # shortcut == input; its gradient is added inside LN's backward
         gate = linear_tokens(t, self.act_proj)                  # SiLU applied inside the gate kernel below
         t = dwconv3x3_tokens(linear_tokens(t, self.in_proj), self.dwc.weight, self.dwc.bias, H, W, silu=True)
         if self.sr_ratio == 1:
@@ -194,7 +193,8 @@ class MLLABlock(nn.Module):
             t = torch.cat([self.attn[0](a, H, W), self.attn[1](b, H, W)], dim=-1)
         t = silu_gate(t, gate) if isinstance(self.act, nn.SiLU) else t * self.act(gate)
         t = residual_drop_path(shortcut, linear_tokens(t, self.out_proj), self.drop_path)
-        return residual_drop_path(t, self.mlp(layer_norm_tokens(t, self.norm2)), self.drop_path)
+        n2, t = layer_norm_fork(t, self.norm2)
+        return residual_drop_path(t, self.mlp(n2), self.drop_path)
 
     def forward(self, x):
         H, W = self.input_resolution

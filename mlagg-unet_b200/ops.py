@@ -258,45 +258,71 @@ def causal_conv1d_fn(x, weight, bias=None, activation=None):
     return _CausalConv1d.apply(x, weight, bias, activation is not None)
 
 
+def _ln_forward(ctx, x, weight, bias, eps, out_dtype):
+    if not x.is_cuda:
+        raise _lib.MlaggError("layer_norm_tokens: CUDA tensor required (no CPU fallback in the product path)")
+    C = x.shape[-1]
+    xin = _io(x).contiguous()
+    odt = out_dtype if out_dtype in _DT else torch.float32
+    w32 = weight.detach().float().contiguous()
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    M = xin.numel() // C
+    y = torch.empty(xin.shape, device=x.device, dtype=odt)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _lib.timed("layernorm_fwd"):
+        rc = _lib.lib().mlagg_layernorm_fwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), _lib.ptr(mean),
+                                            _lib.ptr(rstd), M, C, float(eps), _DT[xin.dtype], _DT[odt],
+                                            _lib.stream_ptr())
+    _lib.check(rc, "mlagg_layernorm_fwd")
+    ctx.save_for_backward(xin, w32, mean, rstd)
+    ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype, odt)
+    return y
+
+
+def _ln_backward(ctx, dy, dres):
+    xin, w32, mean, rstd = ctx.saved_tensors
+    xdt, wdt, bdt, odt = ctx.meta
+    C = xin.shape[-1]
+    M = xin.numel() // C
+    dy = dy.to(odt).contiguous()
+    if dres is not None:
+        dres = dres.to(xin.dtype).contiguous()
+    dx = torch.empty_like(xin)
+    dw = _lib.zeros(C, xin.device)
+    db = _lib.zeros(C, xin.device) if bdt is not None else None
+    with torch.cuda.device(xin.device), _lib.timed("layernorm_bwd"):
+        rc = _lib.lib().mlagg_layernorm_bwd_res(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dy),
+                                                _lib.ptr(dres), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), M, C,
+                                                _DT[xin.dtype], _DT[odt], _lib.stream_ptr())
+    _lib.check(rc, "mlagg_layernorm_bwd_res")
+    return dx.to(xdt), dw.to(wdt), None if db is None else db.to(bdt), None, None
+
+
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, eps, out_dtype):
-        if not x.is_cuda:
-            raise _lib.MlaggError("layer_norm_tokens: CUDA tensor required (no CPU fallback in the product path)")
-        C = x.shape[-1]
-        xin = _io(x).contiguous()
-        odt = out_dtype if out_dtype in _DT else torch.float32
-        w32 = weight.detach().float().contiguous()
-        b32 = None if bias is None else bias.detach().float().contiguous()
-        M = xin.numel() // C
-        y = torch.empty(xin.shape, device=x.device, dtype=odt)
-        mean = torch.empty(M, device=x.device, dtype=torch.float32)
-        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device), _lib.timed("layernorm_fwd"):
-            rc = _lib.lib().mlagg_layernorm_fwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), _lib.ptr(mean),
-                                                _lib.ptr(rstd), M, C, float(eps), _DT[xin.dtype], _DT[odt],
-                                                _lib.stream_ptr())
-        _lib.check(rc, "mlagg_layernorm_fwd")
-        ctx.save_for_backward(xin, w32, mean, rstd)
-        ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype, odt)
-        return y
+        return _ln_forward(ctx, x, weight, bias, eps, out_dtype)
 
     @staticmethod
     def backward(ctx, dy):
-        xin, w32, mean, rstd = ctx.saved_tensors
-        xdt, wdt, bdt, odt = ctx.meta
-        C = xin.shape[-1]
-        M = xin.numel() // C
-        dy = dy.to(odt).contiguous()
-        dx = torch.empty_like(xin)
-        dw = _lib.zeros(C, xin.device)
-        db = _lib.zeros(C, xin.device) if bdt is not None else None
-        with torch.cuda.device(xin.device), _lib.timed("layernorm_bwd"):
-            rc = _lib.lib().mlagg_layernorm_bwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dy),
-                                                _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), M, C, _DT[xin.dtype], _DT[odt],
-                                                _lib.stream_ptr())
-        _lib.check(rc, "mlagg_layernorm_bwd")
-        return dx.to(xdt), dw.to(wdt), None if db is None else db.to(bdt), None, None
+        return _ln_backward(ctx, dy, None)
+
+
+class _LayerNormFork(torch.autograd.Function):
+    """(LN(x), x) for a pre-norm residual branch `x + f(LN(x))`: the second output is x itself, to be used as the
+    shortcut.  Both gradients then arrive at THIS node, and dx = LN'(d_ln) + d_shortcut is one kernel
+    (mlagg_layernorm_bwd_res) instead of the LayerNorm backward plus autograd's accumulation add over the full tensor."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        return _ln_forward(ctx, x, weight, bias, eps, out_dtype), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dshort):
+        if dy is None:                       # the normalised output was not used
+            return dshort, None, None, None, None
+        return _ln_backward(ctx, dy, dshort)
 
 
 def layer_norm_tokens(x, norm: torch.nn.LayerNorm, out_dtype=None):
@@ -309,6 +335,16 @@ def layer_norm_tokens(x, norm: torch.nn.LayerNorm, out_dtype=None):
     if C % 4 != 0 or C > 1024 or norm.weight is None:
         return norm(x)
     return _LayerNorm.apply(x, norm.weight, norm.bias, norm.eps, out_dtype)
+
+
+def layer_norm_fork(x, norm: torch.nn.LayerNorm, out_dtype=None):
+    """(LayerNorm(x), shortcut) with shortcut == x: use the shortcut in the residual add that closes the branch."""
+    if out_dtype is None:
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    C = x.shape[-1]
+    if C % 4 != 0 or C > 1024 or norm.weight is None or not x.requires_grad:
+        return layer_norm_tokens(x, norm, out_dtype), x
+    return _LayerNormFork.apply(x, norm.weight, norm.bias, norm.eps, out_dtype)
 
 
 def colsum(x2d):

@@ -696,3 +696,34 @@ def test_conv_glu_core_matches_torch(hid, dtype):
     assert rel_err(y.double(), yd) < tol
     for got, want in ((h.grad, hd_.grad), (w.grad, wd.grad), (b.grad, bd.grad)):
         assert rel_err(got.double(), want) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, TOL16)])
+def test_layer_norm_fork_adds_the_shortcut_gradient_in_the_same_pass(dtype, tol):
+    """(LN(x), x) with both gradients arriving at one node (mlagg_layernorm_bwd_res) == LayerNorm backward + shortcut"""
+    from mlagg_unet_b200.ops import layer_norm_fork
+    g = torch.Generator().manual_seed(4)
+    C = 96
+    x = torch.randn(3, 41, C, generator=g) * 1.5
+    ln = torch.nn.LayerNorm(C)
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        ln.bias.copy_(torch.randn(C, generator=g))
+    w1, w2 = torch.randn(3, 41, C, generator=g), torch.randn(3, 41, C, generator=g)
+    xr = x.to(dtype).double().requires_grad_()
+    ref = torch.nn.functional.layer_norm(xr, (C,), ln.weight.detach().double(), ln.bias.detach().double(), ln.eps)
+    ((ref * w1.to(dtype).double()).sum() + (xr * w2.to(dtype).double()).sum()).backward()
+    lnc = ln.cuda()
+    xc = x.cuda().to(dtype).requires_grad_()
+    y, short = layer_norm_fork(xc, lnc, out_dtype=dtype)
+    assert short.data_ptr() == xc.data_ptr() and rel_err(y.float().cpu(), ref) < tol
+    ((y * w1.cuda().to(dtype)).sum() + (short * w2.cuda().to(dtype)).sum()).backward()
+    assert rel_err(xc.grad.float().cpu(), xr.grad) < tol
+    # shortcut unused / normalised output unused
+    xc2 = x.cuda().to(dtype).requires_grad_()
+    y2, _ = layer_norm_fork(xc2, lnc, out_dtype=dtype)
+    (y2 * w1.cuda().to(dtype)).sum().backward()
+    xr2 = x.to(dtype).double().requires_grad_()
+    (torch.nn.functional.layer_norm(xr2, (C,), ln.weight.detach().cpu().double(), ln.bias.detach().cpu().double(), ln.eps)
+     * w1.to(dtype).double()).sum().backward()
+    assert rel_err(xc2.grad.float().cpu(), xr2.grad) < tol
