@@ -113,6 +113,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=10)
     ap.add_argument("--size", type=int, default=320)
+    ap.add_argument("--in-channels", type=int, default=1, help="3 for the Endovis17-shaped config 5 (3 x 512 x 512)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: ONE global batch of --batch-per-gpu images split over the ranks exactly as the "
+                         "reference does (nnUNetTrainer.py:295-307: [5, 5], [3, 3, 3, 1]; invalid at 8 ranks, SURVEY 8d)")
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
@@ -156,7 +160,13 @@ def main():
         r = cpu_reference_run(3, 1, a.cpu_sample_batch, a.size)
         cpu_base = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
-    plan = SyntheticPlan(patch_size=(a.size, a.size), batch_size=a.batch_per_gpu)
+    global_batch = a.batch_per_gpu * world
+    if a.strong:
+        from mlagg_unet_b200.trainer import split_batch
+        sizes = split_batch(a.batch_per_gpu, world)
+        assert all(v > 0 for v in sizes), f"the reference's batch split {sizes} is invalid for {world} ranks (SURVEY.md 8d)"
+        global_batch, a.batch_per_gpu = a.batch_per_gpu, sizes[rank]
+    plan = SyntheticPlan(patch_size=(a.size, a.size), batch_size=a.batch_per_gpu, num_input_channels=a.in_channels)
     tr = nnUNetTrainer_MLAgg_2D_dt_MS(plan, device=dev).initialize()
     host = tr.synthetic_batch(seed=rank, pin=True)
     resident = {"data": host["data"].to(dev), "target": [t.to(dev) for t in host["target"]]}
@@ -221,7 +231,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    imgs = a.batch_per_gpu * world * a.steps
+    imgs = global_batch * a.steps
     # roofline of the dominant hot-path kernel: selective-scan backward at the mamba interface
     peaks = {}
     try:
@@ -241,28 +251,44 @@ def main():
         kern[name] = {"launches": len(ts), "ms_avg": sum(ts) / len(ts), "ms_total": sum(ts)}
     dom = "scan_bwd"
     roof = None
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "scan_bwd_r01_ncu.json")))
-        if prof["shape"] == {"batch": a.batch_per_gpu, "dim": D, "groups": G, "dstate": N, "L": Lcat}:
-            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
-    except Exception:
-        pass
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (the newest committed
+    # capture whose shape AND kernel revision match; null otherwise -- a stale figure is worse than none)
+    traffic, traffic_src = None, None
+    for name in ("scan_bwd_r02_ncu.json", "scan_bwd_r01_ncu.json"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if prof["shape"] == {"batch": a.batch_per_gpu, "dim": D, "groups": G, "dstate": N, "L": Lcat}:
+                traffic, traffic_src = prof["dram_bytes_read"] + prof["dram_bytes_write"], "profiles/" + name
+                break
+        except Exception:
+            continue
     if dom in kern:
         ach = alg[dom] / (kern[dom]["ms_avg"] * 1e-3) / 1e9
         roof = {"kernel": "mlagg::scan_bwd_kernel (selective-scan backward in the fused MSMM operand mode, fp32 I/O; algorithmic bytes counted at the mamba interface, SURVEY.md 8d)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": kern[dom]["ms_avg"],
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_src,
+                # the scan is NOT HBM-bound on B200: one MUFU.EX2 per (channel, state, step) at 16 lanes/clk/SM (measured,
+                # profiles/mufu_bench_r01.txt) puts the exponential floor above the HBM floor -- report both
+                "xu_floor": {"exp_per_launch": a.batch_per_gpu * D * N * Lcat * (2 if dom == "scan_bwd" else 1),
+                             "floor_ms": a.batch_per_gpu * D * N * Lcat * (2 if dom == "scan_bwd" else 1)
+                                         / (16.0 * 148 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6) * 1e3 if clocks else None,
+                             "note": "backward recomputes a_t from the 16-step checkpoints: 1 exponential per update "
+                                     "in the recompute sweep, reused by the adjoint sweep; counted 2x with the "
+                                     "softplus / sigmoid helpers"},
                 "also": {k: {"ms_avg": v["ms_avg"], "launches_per_step": v["launches"] / a.steps,
                              **({"achieved_GBps": alg[k] / (v["ms_avg"] * 1e-3) / 1e9} if k in alg else {})}
                          for k, v in kern.items()}}
     line = {
         "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if a.strong else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": a.batch_per_gpu * world, "per_gpu_batch": a.batch_per_gpu,
+        "config": {"workload": WORKLOAD if (a.size, a.in_channels, a.strong) == (320, 1, False) else
+                   f"{'strong-scaling split of one global batch, ' if a.strong else ''}{a.in_channels}x{a.size}x{a.size} "
+                   f"inputs, 14 classes, full train step (fwd + DiceCE-DS loss + bwd + clip + AdamW)",
+                   "global_batch": global_batch, "per_gpu_batch": a.batch_per_gpu,
+                   "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                    "parallelism": f"dp{world}" if world > 1 else "single", "scan_state_dtype": "f32",
                    "cuda_graph": graphed, "eager_ms_per_step_with_kernel_events": ms_eager / a.steps,
                    "l2": "per-step working set (~14 GB of activations) >> 126 MB L2, no flush needed"},

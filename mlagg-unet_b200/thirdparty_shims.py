@@ -158,4 +158,13 @@ class UnetrUpBlock(nn.Module):
         self.conv_block = UnetResBlock2d(2 * out_channels, out_channels, kernel_size, 1)
 
     def forward(self, inp, skip):
-        return self.conv_block(torch.cat((self.transp_conv(inp), skip), dim=1))
+        up = self.transp_conv(inp)
+        a, b = up.permute(0, 2, 3, 1), skip.permute(0, 2, 3, 1)
+        if up.is_cuda and a.is_contiguous() and b.is_contiguous() and up.dtype == skip.dtype:
+            # channel concatenation of two channels_last maps == two row-strided copies (torch.cat falls onto its generic
+            # strided-copy kernel here: 191 us forward and 3 x ~130 us backward at 10 x 96 x 320 x 320)
+            from .ops import JoinLastDense
+            x = JoinLastDense.apply(a, b).permute(0, 3, 1, 2)
+        else:
+            x = torch.cat((up, skip), dim=1)
+        return self.conv_block(x)
