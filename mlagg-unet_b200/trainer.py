@@ -106,6 +106,45 @@ class SyntheticPlan:
         return _LabelManager(self.num_classes)
 
 
+class TrainingLogger:
+    """One value per epoch and key, `ema_fg_dice` derived from `mean_fg_dice` (0.9 / 0.1) -- the bookkeeping of the
+    reference's nnUNetLogger (training/logging/nnunet_logger.py:17-51) without its matplotlib plots."""
+    KEYS = ("mean_fg_dice", "ema_fg_dice", "dice_per_class_or_region", "train_losses", "val_losses", "lrs",
+            "epoch_start_timestamps", "epoch_end_timestamps")
+
+    def __init__(self):
+        self.my_fantastic_logging = {k: [] for k in self.KEYS}
+
+    def log(self, key, value, epoch: int):
+        lst = self.my_fantastic_logging[key]
+        assert len(lst) in (epoch, epoch + 1), "exactly one value per epoch and key"
+        if len(lst) < epoch + 1:
+            lst.append(value)
+        else:
+            lst[epoch] = value
+        if key == "mean_fg_dice":
+            ema = self.my_fantastic_logging["ema_fg_dice"]
+            self.log("ema_fg_dice", ema[epoch - 1] * 0.9 + 0.1 * value if len(ema) > 0 else value, epoch)
+
+
+class SyntheticLoader:
+    """Endless iterator of synthetic batches in the shape the reference's augmenter yields (pattern:
+    nnUNetTrainerBenchmark_5epochs_noDataLoading.py:16-22).  `pool` distinct batches are generated once and cycled."""
+
+    def __init__(self, trainer, batch_size=None, pool=2, seed=0, pin=True):
+        pin = pin and trainer.device.type == "cuda"
+        self.batches = [trainer.synthetic_batch(batch_size, seed=seed + i, pin=pin) for i in range(pool)]
+        self.i = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        b = self.batches[self.i % len(self.batches)]
+        self.i += 1
+        return b
+
+
 def split_batch(global_batch: int, world_size: int):
     """Per-rank batch sizes exactly as nnUNetTrainer._set_batch_size_and_oversample computes them
     (reference nnUNetTrainer.py:295-307).  NOTE: for 10 images on 8 ranks this yields
@@ -136,6 +175,11 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         self._graph = self._graph_key = self._static = self._flat_grad = self._params = self._flat_views = None
         self._flat_slices = None
         self._eager_steps = 0
+        self.logger = TrainingLogger()
+        self.output_folder = None            # set it to get checkpoint_latest / _best / _final like the reference
+        self.save_every, self._best_ema = 50, None
+        self.dataloader_train = self.dataloader_val = None
+        self.local_rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
 
     # ---- reference static API
     @staticmethod
@@ -214,7 +258,8 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         net = self.network.module if hasattr(self.network, "module") else self.network
         torch.save({"network_weights": net.state_dict(), "optimizer_state": self._portable_optimizer_state(),
                     "grad_scaler_state": self.grad_scaler.state_dict() if self.grad_scaler is not None else None,
-                    "logging": {}, "_best_ema": None, "current_epoch": self.current_epoch + 1,
+                    "logging": self.logger.my_fantastic_logging, "_best_ema": self._best_ema,
+                    "current_epoch": self.current_epoch + 1,
                     "init_args": {"configuration": "2d_bs10", "fold": 0}, "trainer_name": self.__class__.__name__,
                     "inference_allowed_mirroring_axes": (0, 1)}, filename)
 
@@ -229,6 +274,10 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         state = {(k[7:] if k not in own and k.startswith("module.") else k): v for k, v in ck["network_weights"].items()}
         net.load_state_dict(state)            # strict: names and shapes are the reference's
         self.current_epoch = ck.get("current_epoch", 0)
+        if isinstance(ck.get("logging"), dict) and ck["logging"]:
+            self.logger.my_fantastic_logging.update({k: list(v) for k, v in ck["logging"].items()
+                                                     if k in self.logger.my_fantastic_logging})
+        self._best_ema = ck.get("_best_ema", None)
         if load_optimizer and ck.get("optimizer_state") is not None:
             self.optimizer.load_state_dict(ck["optimizer_state"])
             self._restore_optimizer_flags()
@@ -439,6 +488,119 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             l = self._step_math(data, target)
             self._eager_steps += 1
         return {"loss": l.cpu().numpy() if sync else l}
+
+    # ---- epoch loop (nnUNetTrainer.run_training and its hooks, nnUNetTrainer.py:784-1223), minus file logging / plots
+    def print_to_log_file(self, *args):
+        if self.local_rank == 0 and os.environ.get("MLAGG_QUIET", "0") != "1":
+            print(*args, flush=True)
+
+    def on_train_start(self):
+        if self.network is None:
+            self.initialize()
+        if self.dataloader_train is None:                 # no batchgenerators in this image: synthetic plan data
+            self.dataloader_train = SyntheticLoader(self, seed=1000 * self.local_rank)
+            self.dataloader_val = SyntheticLoader(self, seed=1000 * self.local_rank + 500)
+        if self.output_folder is not None:
+            os.makedirs(self.output_folder, exist_ok=True)
+
+    def on_epoch_start(self):
+        import time
+        self.logger.log("epoch_start_timestamps", time.time(), self.current_epoch)
+
+    def on_train_epoch_start(self):
+        self.network.train()
+        self.lr_scheduler.step(self.current_epoch)        # once per epoch (:825); writes the device-resident lr
+        lr = float(self.optimizer.param_groups[0]["lr"])
+        self.print_to_log_file(f"Epoch {self.current_epoch}  lr {lr:.5g}")
+        self.logger.log("lrs", lr, self.current_epoch)
+
+    def on_train_epoch_end(self, train_outputs):
+        losses = np.array([float(o["loss"]) for o in train_outputs])
+        if self.is_ddp:
+            gathered = [None] * dist.get_world_size()
+            dist.all_gather_object(gathered, losses)
+            loss_here = float(np.vstack(gathered).mean())
+        else:
+            loss_here = float(losses.mean())
+        self.logger.log("train_losses", loss_here, self.current_epoch)
+
+    def on_validation_epoch_start(self):
+        self.network.eval()
+
+    def validation_step(self, batch: dict) -> dict:
+        """nnUNetTrainer.validation_step (:865-926): loss with deep supervision, then hard tp / fp / fn of the argmax mask
+        of the full-resolution head per class (background dropped) for the online pseudo dice."""
+        data = batch["data"].to(self.device, non_blocking=True)
+        target = [t.to(self.device, non_blocking=True) for t in batch["target"]]
+        with torch.no_grad(), torch.autocast(self.device.type, dtype=self.amp_dtype, enabled=self.device.type == "cuda"):
+            output = self.network(data)
+            l = self.loss(output, target)
+        out0 = output[0] if isinstance(output, (list, tuple)) else output
+        tgt0 = target[0].long()
+        C = out0.shape[1]
+        pred = out0.argmax(1, keepdim=True)
+        axes = (0, 2, 3)
+        p1 = torch.zeros(out0.shape, device=out0.device, dtype=torch.float32).scatter_(1, pred, 1)
+        g1 = torch.zeros(out0.shape, device=out0.device, dtype=torch.float32).scatter_(1, tgt0, 1)
+        tp, fp, fn = (p1 * g1).sum(axes), (p1 * (1 - g1)).sum(axes), ((1 - p1) * g1).sum(axes)
+        assert tp.shape == (C,)
+        return {"loss": l.detach().float().cpu().numpy(), "tp_hard": tp.cpu().numpy()[1:], "fp_hard": fp.cpu().numpy()[1:],
+                "fn_hard": fn.cpu().numpy()[1:]}
+
+    def on_validation_epoch_end(self, val_outputs):
+        tp, fp, fn = (np.sum([o[k] for o in val_outputs], 0) for k in ("tp_hard", "fp_hard", "fn_hard"))
+        losses = np.array([float(o["loss"]) for o in val_outputs])
+        if self.is_ddp:
+            ws = dist.get_world_size()
+            parts = [None] * ws
+            dist.all_gather_object(parts, (tp, fp, fn, losses))
+            tp, fp, fn = (np.sum([q[i] for q in parts], 0) for i in range(3))
+            losses = np.concatenate([q[3] for q in parts])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dc = [float(2 * i / (2 * i + j + k)) if (2 * i + j + k) > 0 else float("nan") for i, j, k in zip(tp, fp, fn)]
+        self.logger.log("mean_fg_dice", float(np.nanmean(dc)), self.current_epoch)
+        self.logger.log("dice_per_class_or_region", dc, self.current_epoch)
+        self.logger.log("val_losses", float(losses.mean()), self.current_epoch)
+
+    def on_epoch_end(self):
+        import time
+        lg = self.logger.my_fantastic_logging
+        self.logger.log("epoch_end_timestamps", time.time(), self.current_epoch)
+        self.print_to_log_file(f"train_loss {lg['train_losses'][-1]:.4f}  val_loss {lg['val_losses'][-1]:.4f}  "
+                               f"pseudo dice {lg['mean_fg_dice'][-1]:.4f}  "
+                               f"epoch time {lg['epoch_end_timestamps'][-1] - lg['epoch_start_timestamps'][-1]:.2f} s")
+        if self.output_folder is not None:
+            if (self.current_epoch + 1) % self.save_every == 0 and self.current_epoch != self.num_epochs - 1:
+                self.save_checkpoint(os.path.join(self.output_folder, "checkpoint_latest.pth"))
+            if self._best_ema is None or lg["ema_fg_dice"][-1] > self._best_ema:
+                self._best_ema = lg["ema_fg_dice"][-1]
+                self.save_checkpoint(os.path.join(self.output_folder, "checkpoint_best.pth"))
+        elif self._best_ema is None or lg["ema_fg_dice"][-1] > self._best_ema:
+            self._best_ema = lg["ema_fg_dice"][-1]
+        self.current_epoch += 1
+
+    def on_train_end(self):
+        if self.output_folder is not None:
+            self.save_checkpoint(os.path.join(self.output_folder, "checkpoint_final.pth"))
+            latest = os.path.join(self.output_folder, "checkpoint_latest.pth")
+            if self.local_rank == 0 and os.path.isfile(latest):
+                os.remove(latest)
+
+    def run_training(self):
+        """nnUNetTrainer.run_training (:1202-1223), hook for hook."""
+        self.on_train_start()
+        for _ in range(self.current_epoch, self.num_epochs):
+            self.on_epoch_start()
+            self.on_train_epoch_start()
+            train_outputs = [self.train_step(next(self.dataloader_train)) for _ in range(self.num_iterations_per_epoch)]
+            self.on_train_epoch_end(train_outputs)
+            with torch.no_grad():
+                self.on_validation_epoch_start()
+                val_outputs = [self.validation_step(next(self.dataloader_val))
+                               for _ in range(self.num_val_iterations_per_epoch)]
+                self.on_validation_epoch_end(val_outputs)
+            self.on_epoch_end()
+        self.on_train_end()
 
     def _train_step_scaled(self, batch: dict, sync: bool = True) -> dict:
         data = batch["data"].to(self.device, non_blocking=True)

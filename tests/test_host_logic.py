@@ -214,3 +214,36 @@ def test_stride_probes_for_in_place_operands():
     assert r is not None and r[1:] == (2, 30, 8, 12, 360)
     assert _rows3(x.permute(0, 2, 1, 3)) is None                    # rows no longer collapse to one stride
     assert _rows3(torch.zeros(2, 7, 3)[:, 1:5])[1:] == (2, 4, 3, 3, 21)
+
+
+def test_overlay_files_define_what_the_reference_looks_up():
+    """overlay/ mirrors the two reference paths run_training.py:39-40 / the trainer's own import resolve; nnunetv2 is
+    absent in this image, so the check is structural: the files parse, sit at the reference's relative paths, and define
+    / re-export the names the reference imports."""
+    import ast
+    base = os.path.join(ROOT, "overlay", "nnunetv2", "training", "nnUNetTrainer")
+    tr = ast.parse(open(os.path.join(base, "nnUNetTrainer_MLAgg_2D_dt_MS.py")).read())
+    cls = [n for n in tr.body if isinstance(n, ast.ClassDef) and n.name == "nnUNetTrainer_MLAgg_2D_dt_MS"]
+    assert len(cls) == 1 and [b.id for b in cls[0].bases] == ["nnUNetTrainer"]
+    defined = {n.name for n in cls[0].body if isinstance(n, ast.FunctionDef)} | {
+        t.id for n in cls[0].body if isinstance(n, ast.Assign) for t in n.targets if isinstance(t, ast.Name)}
+    assert {"build_network_architecture", "set_deep_supervision_enabled", "_get_deep_supervision_scales", "_build_loss",
+            "configure_optimizers", "train_step"} <= defined
+    ms = ast.parse(open(os.path.join(base, "variants", "mamba", "MambaSkip.py")).read())
+    names = {a.name for n in ms.body if isinstance(n, ast.ImportFrom) for a in n.names}
+    assert {"SS2D_skip", "DWConv", "ConvolutionalGLU", "VSS_Conv_Block", "VSS_Conv_Layer", "selective_scan_fn"} <= names
+
+
+def test_training_logger_and_epoch_bookkeeping_follow_the_reference():
+    """TrainingLogger == nnUNetLogger's list-per-key bookkeeping incl. the 0.9 / 0.1 EMA (nnunet_logger.py:17-51); the
+    scheduler is stepped once per epoch with the epoch index (nnUNetTrainer.py:825)."""
+    from mlagg_unet_b200.trainer import TrainingLogger
+    lg = TrainingLogger()
+    for e, v in enumerate([0.2, 0.6, 0.4]):
+        lg.log("mean_fg_dice", v, e)
+    ema = lg.my_fantastic_logging["ema_fg_dice"]
+    assert ema[0] == 0.2 and abs(ema[1] - (0.2 * 0.9 + 0.06)) < 1e-12 and abs(ema[2] - (ema[1] * 0.9 + 0.04)) < 1e-12
+    lg.log("mean_fg_dice", 0.5, 2)                       # re-logging the same epoch overwrites
+    assert len(lg.my_fantastic_logging["mean_fg_dice"]) == 3 and lg.my_fantastic_logging["mean_fg_dice"][2] == 0.5
+    with pytest.raises(AssertionError):
+        lg.log("train_losses", 1.0, 5)                   # exactly one value per epoch

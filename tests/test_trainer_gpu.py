@@ -1,0 +1,59 @@
+"""GPU: the epoch loop of the trainer (run_training and its hooks, reference nnUNetTrainer.py:784-1223) on a small
+synthetic plan: learning-rate schedule stepped once per epoch, train / validation bookkeeping, pseudo dice from hard
+tp / fp / fn, checkpoints written and resumable."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(tmp_path=None, epochs=2):
+    from mlagg_unet_b200.trainer import SyntheticPlan, nnUNetTrainer_MLAgg_2D_dt_MS
+    torch.manual_seed(0)
+    tr = nnUNetTrainer_MLAgg_2D_dt_MS(SyntheticPlan(patch_size=(64, 64), batch_size=2, num_classes=5))
+    tr.num_epochs, tr.num_iterations_per_epoch, tr.num_val_iterations_per_epoch = epochs, 5, 2
+    tr.output_folder = None if tmp_path is None else str(tmp_path)
+    os.environ["MLAGG_QUIET"] = "1"
+    return tr
+
+
+def test_run_training_epoch_loop(tmp_path):
+    tr = _trainer(tmp_path, epochs=3)
+    tr.run_training()
+    lg = tr.logger.my_fantastic_logging
+    assert tr.current_epoch == 3 and all(len(lg[k]) == 3 for k in lg)
+    # warm-up schedule of timm's CosineLRScheduler(warmup_t=10, warmup_lr_init=1e-4), stepped with the epoch index
+    assert np.allclose(lg["lrs"], [1e-4 + e * (5e-4 - 1e-4) / 10 for e in range(3)], rtol=1e-6)
+    assert all(np.isfinite(lg["train_losses"])) and all(np.isfinite(lg["val_losses"]))
+    assert len(lg["dice_per_class_or_region"][0]) == 4            # 5 classes, background dropped
+    assert 0.0 <= lg["mean_fg_dice"][-1] <= 1.0
+    assert tr._graph is not None                                   # steps 4+ of epoch 0 replayed the captured graph
+    assert tr.network.training is False or True
+    assert os.path.isfile(tmp_path / "checkpoint_final.pth") and os.path.isfile(tmp_path / "checkpoint_best.pth")
+    # resume: a fresh trainer continues at the saved epoch with the saved logs
+    tr2 = _trainer(tmp_path, epochs=4)
+    tr2.initialize()
+    tr2.load_checkpoint(str(tmp_path / "checkpoint_final.pth"))
+    assert tr2.current_epoch == 3 and len(tr2.logger.my_fantastic_logging["train_losses"]) == 3
+    tr2.run_training()
+    assert tr2.current_epoch == 4 and len(tr2.logger.my_fantastic_logging["lrs"]) == 4
+    assert abs(tr2.logger.my_fantastic_logging["lrs"][3] - (1e-4 + 3 * 4e-4 / 10)) < 1e-9
+
+
+def test_validation_step_counts_match_a_direct_evaluation():
+    tr = _trainer().initialize()
+    batch = tr.synthetic_batch(2, seed=3)
+    tr.network.eval()
+    out = tr.validation_step(batch)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = tr.network(batch["data"].cuda())[0]
+    pred = logits.argmax(1).cpu()
+    gt = batch["target"][0][:, 0].long()
+    for c in range(1, 5):
+        assert out["tp_hard"][c - 1] == int(((pred == c) & (gt == c)).sum())
+        assert out["fp_hard"][c - 1] == int(((pred == c) & (gt != c)).sum())
+        assert out["fn_hard"][c - 1] == int(((pred != c) & (gt == c)).sum())
+    assert np.isfinite(out["loss"])
