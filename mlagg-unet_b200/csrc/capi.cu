@@ -103,11 +103,9 @@ static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_
 
 // consumer warps per CTA: 8 channels per warp; keep CTAs inside one group and fill >= 148 SMs when possible
 static int pick_warps(int batch, int G, int dpg) {
-    const char *env = getenv("MLAGG_SCAN_WARPS");
-    if (env && *env) return atoi(env);
-    if (dpg >= 32) return 4;
-    if (dpg >= 16) return 2;
-    return 1;
+    (void)batch; (void)G; (void)dpg;
+    const char *env = getenv("MLAGG_SCAN_WARPS");   // 1 or 4 forces the forward kernel's CTA shape; default: the dispatch
+    return (env && *env) ? atoi(env) : 0;           // chooses by grid size (scan_fwd.cu)
 }
 }  // namespace mlagg
 
@@ -431,7 +429,7 @@ extern "C" int mlagg_msmm_scan_fwd(const float *xrow, const float *xcol, const f
     if (!out) return MLAGG_ERR_NULL;
     if (ckpt && !aligned(ckpt, 16)) return MLAGG_ERR_ALIGN;
     p.out = out; p.ckpt = ckpt;
-    cudaError_t e = scan_fwd_dispatch(p, false, 4, (cudaStream_t)stream);
+    cudaError_t e = scan_fwd_dispatch(p, false, pick_warps(batch, 4, d_inner), (cudaStream_t)stream);
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

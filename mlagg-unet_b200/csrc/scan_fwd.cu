@@ -31,8 +31,13 @@ namespace mlagg {
 // helper warps' stores (lane = step, fixed chunk) are conflict-free as well.
 constexpr int kTS = kTT + 4;  // lines per tile: 64 steps + read-ahead padding of the 3-deep software pipeline
 
+// W = scan warps (= helper warps) per CTA, 8 channels each.  W = 4 is the training shape (32 channels of one (batch,
+// group) share the staged B / C tile).  W = 1 is the small-batch / inference shape (sliding-window tiles
+// arrive at B = 1 .. 4): one scan warp + one helper warp per CTA, 4x the CTAs -- at B = 1 the W = 4 grid is 12 CTAs on
+// 148 SMs -- and the 60 KiB of shared memory lets three of them share an SM.
+template <int W_>
 struct FwdCfg {
-    static constexpr int W = 4, R = 32, SP = 3;
+    static constexpr int W = W_, R = 8 * W_, SP = 3;
     static constexpr size_t bytes = (size_t)SP * W * kTS * 128 + (size_t)SP * kTS * 128 +
                                     (size_t)SP * R * kRowF * 4 + 2 * R * 4 + 64 + 2 * SP * 8 + 16;
 };
@@ -44,9 +49,10 @@ __device__ __forceinline__ float ldg_stream(const float *p) {
     return v;
 }
 
-template <bool kFused>
-__global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
-    constexpr int W = FwdCfg::W, R = FwdCfg::R, SP = FwdCfg::SP;
+template <bool kFused, int kW>
+__global__ void __launch_bounds__(64 * kW, 1) scan_fwd_kernel(const ScanParams p) {
+    constexpr int W = FwdCfg<kW>::W, R = FwdCfg<kW>::R, SP = FwdCfg<kW>::SP;
+    constexpr int NQ = 4 / W;      // state quads (B / C chunk pairs) staged by one helper warp
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *pk = reinterpret_cast<float4 *>(smem_raw);         // [SP][W][kTS][8 chunks]
     float4 *bc = pk + SP * W * kTS * 8;                        // [SP][kTS][8 chunks]
@@ -92,13 +98,13 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
             ub = ((kdir & 1) ? p.xcol : p.xrow) + ((size_t)b * p.dpg + dloc0) * L;
             const float *xd = ((kdir & 1) ? p.xdbl_col : p.xdbl_row) + (((size_t)b * 2 + (kdir >> 1)) * C35) * (size_t)L;
             dtb = xd;
-            Bb = xd + (size_t)(p.Rk + h) * L;
-            Cb = xd + (size_t)(p.Rk + kN + h) * L;
+            Bb = xd + (size_t)p.Rk * L;
+            Cb = xd + (size_t)(p.Rk + kN) * L;
         } else {
             ub = p.u + ((size_t)b * p.dim + row0 + 8 * h) * L;
             db = p.delta + ((size_t)b * p.dim + row0 + 8 * h) * L;
-            Bb = p.B + (((size_t)b * p.G + g) * kN + h) * (size_t)L;   // rows h, h+4, h+8, h+12
-            Cb = p.C + (((size_t)b * p.G + g) * kN + h) * (size_t)L;
+            Bb = p.B + (((size_t)b * p.G + g) * kN) * (size_t)L;   // quad q = rows q, q+4, q+8, q+12
+            Cb = p.C + (((size_t)b * p.G + g) * kN) * (size_t)L;
         }
         const bool mirrored = fused && kdir >= 2;
         float *outb = p.out + ((size_t)b * p.dim + row0 + 8 * h) * L;
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
                 wdt[i][rr] = (fused && i < myrows && rr < p.Rk) ? p.Wdt[(size_t)(row0 + 8 * h + i) * p.Rk + rr] : 0.f;
         // the tile in flight: element i = 2 * row + half  ->  step lane + 32 * half.  Loaded values are NOT touched until the
         // next iteration (one tile of scan time later), so the HBM latency is never exposed.
-        float ur[16], dr[16], Br[8], Cr[8], dtr[2][kMaxRk];
+        float ur[16], dr[16], Br[NQ][8], Cr[NQ][8], dtr[2][kMaxRk];   // helper h stages the quads h, h + W, ...
 
         auto fetch = [&](int c) {
             const int t0 = c * kTT;
@@ -132,10 +138,13 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
                     if constexpr (!fused) dr[i] = ok ? ldg_stream(db + (size_t)rw * L + tm) : 0.f;
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    Br[2 * j + hf] = tin ? ldg_stream(Bb + (size_t)(4 * j) * L + tm) : 0.f;
-                    Cr[2 * j + hf] = tin ? ldg_stream(Cb + (size_t)(4 * j) * L + tm) : 0.f;
-                }
+                for (int iq = 0; iq < NQ; ++iq)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rowq = h + W * iq + 4 * j;
+                        Br[iq][2 * j + hf] = tin ? ldg_stream(Bb + (size_t)rowq * L + tm) : 0.f;
+                        Cr[iq][2 * j + hf] = tin ? ldg_stream(Cb + (size_t)rowq * L + tm) : 0.f;
+                    }
             }
         };
         // per-row constants in registers (shared-memory reads here were dependent-load stalls on the helper's path)
@@ -194,11 +203,13 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
             {
                 float4 *bcs = bc + sp * kTS * 8;
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int tl = lane + 32 * k;
-                    bcs[tl * 8 + (h ^ (tl & 7))] = make_float4(Br[k], Br[2 + k], Br[4 + k], Br[6 + k]);
-                    bcs[tl * 8 + ((4 + h) ^ (tl & 7))] = make_float4(Cr[k], Cr[2 + k], Cr[4 + k], Cr[6 + k]);
-                }
+                for (int iq = 0; iq < NQ; ++iq)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int tl = lane + 32 * k, qd = h + W * iq;
+                        bcs[tl * 8 + (qd ^ (tl & 7))] = make_float4(Br[iq][k], Br[iq][2 + k], Br[iq][4 + k], Br[iq][6 + k]);
+                        bcs[tl * 8 + ((4 + qd) ^ (tl & 7))] = make_float4(Cr[iq][k], Cr[iq][2 + k], Cr[iq][4 + k], Cr[iq][6 + k]);
+                    }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&ready[sp]);
@@ -306,15 +317,25 @@ __global__ void __launch_bounds__(256, 1) scan_fwd_kernel(const ScanParams p) {
     }
 }
 
-cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st) {
-    (void)bulk; (void)warps;
-    const size_t smem = FwdCfg::bytes;
-    auto kern = p.fused ? scan_fwd_kernel<true> : scan_fwd_kernel<false>;
+template <int kW>
+static cudaError_t scan_fwd_launch(const ScanParams &p, cudaStream_t st) {
+    const size_t smem = FwdCfg<kW>::bytes;
+    auto kern = p.fused ? scan_fwd_kernel<true, kW> : scan_fwd_kernel<false, kW>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    dim3 grid((p.dpg + 31) / 32, p.G, p.batch);
-    kern<<<grid, 256, smem, st>>>(p);
+    dim3 grid((p.dpg + 8 * kW - 1) / (8 * kW), p.G, p.batch);
+    kern<<<grid, 64 * kW, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+// `warps`: 0 = choose (one scan warp per CTA when the 4-warp grid would leave more than half of the SMs empty), else 1 / 4
+cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st) {
+    (void)bulk;
+    if (warps != 1 && warps != 4) {
+        const long long ctas4 = (long long)((p.dpg + 31) / 32) * p.G * p.batch;
+        warps = ctas4 < 74 ? 1 : 4;
+    }
+    return warps == 1 ? scan_fwd_launch<1>(p, st) : scan_fwd_launch<4>(p, st);
 }
 
 }  // namespace mlagg

@@ -142,3 +142,28 @@ def test_forward_matches_mamba_ssm_derived_cuda_kernel():
         pytest.skip("vllm selective scan unavailable: " + (r.stdout + r.stderr)[-300:])
     _, rel_out, rel_state = lines[-1].split()
     assert float(rel_out) < 1e-4 and float(rel_state) < 1e-4
+
+
+@pytest.mark.parametrize("warps", ["1", "4"])
+def test_forward_cta_shapes_agree_with_the_oracle(warps, monkeypatch):
+    """The small-batch CTA shape (one scan warp + one helper warp, chosen automatically when the 4-warp grid would leave
+    most SMs empty -- B = 1 sliding-window tiles) and the training shape compute the same thing: both against the fp64
+    oracle on a ragged multi-tile shape, output, final state and checkpoints (through a backward pass)."""
+    from mlagg_unet_b200.selective_scan_interface import selective_scan_fn
+    from oracle.scan import scan_bwd_c, scan_fwd_c
+    monkeypatch.setenv("MLAGG_SCAN_WARPS", warps)
+    g = torch.Generator().manual_seed(17)
+    Bn, D, G, N, L = 1, 96, 4, 16, 333
+    u, dl = torch.randn(Bn, D, L, generator=g), 0.5 * torch.randn(Bn, D, L, generator=g)
+    A = -torch.rand(D, N, generator=g) * 4 - 0.1
+    Bm, Cm = torch.randn(Bn, G, N, L, generator=g), torch.randn(Bn, G, N, L, generator=g)
+    Dk, bias = torch.randn(D, generator=g), 0.3 * torch.randn(D, generator=g)
+    ref, last = scan_fwd_c(u, dl, A, Bm, Cm, Dk, bias, True, fp64=True, return_last_state=True)
+    dout = torch.randn(Bn, D, L, generator=g)
+    gref = scan_bwd_c(u, dl, A, Bm, Cm, Dk, bias, True, dout, fp64=True)
+    ts = [t.cuda().requires_grad_() for t in (u, dl, A, Bm, Cm, Dk, bias)]
+    out, st = selective_scan_fn(ts[0], ts[1], ts[2], ts[3], ts[4], ts[5], None, ts[6], True, return_last_state=True)
+    assert rel_err(out.cpu(), ref) < 1e-4 and rel_err(st.cpu(), last) < 1e-4
+    out.backward(dout.cuda())
+    for t, r in zip(ts, gref):
+        assert rel_err(t.grad.cpu(), r) < 1e-4
