@@ -79,9 +79,12 @@ def main():
         worst, worst_name, upd = 0.0, None, 0.0
         init = make(gplan, dev, False)
         p0 = dict(init.network.named_parameters())
+        num = den = 0.0
         for n, p in one.network.named_parameters():
             d = float((p.detach() - dp_params[n]).abs().max())
             upd = max(upd, float((p.detach() - p0[n].detach()).abs().max()))
+            num += float((p.detach() - dp_params[n]).double().pow(2).sum())
+            den += float((p.detach() - p0[n].detach()).double().pow(2).sum())
             if d > worst:
                 worst, worst_name = d, n
         res = {"world": world, "split": sizes, "size": a.size, "steps": a.steps, "graphs_per_step_dp": graphs,
@@ -89,6 +92,10 @@ def main():
                "loss_dp": dp_losses, "loss_single": sp_losses,
                "max_abs_loss_diff": max(abs(x - y) for x, y in zip(dp_losses, sp_losses)),
                "max_abs_param_diff": worst, "param_with_max_diff": worst_name, "max_abs_param_update": upd,
+               # AdamW's update is ~ lr * sign(g) for |g| >> eps: an element whose gradient is ~0 can step the other way
+               # when the bf16 conv-stage gradients are rounded per rank, so the element-wise maximum is one lr step;
+               # the meaningful figure is the distance between the two UPDATE VECTORS relative to their length
+               "rel_l2_update_diff": (num / max(den, 1e-30)) ** 0.5,
                "max_abs_diff_between_ranks": worst_rank_diff}
         os.makedirs(os.path.dirname(a.out), exist_ok=True)
         json.dump(res, open(a.out, "w"), indent=1)
@@ -99,7 +106,8 @@ def main():
         # bf16 compute with fp32 atomics: the two runs sum the same per-image gradients in a different order
         assert res["max_abs_diff_between_ranks"] == 0.0, res
         assert res["max_abs_loss_diff"] < 2e-3, res
-        assert res["max_abs_param_diff"] < 0.05 * res["max_abs_param_update"] + 1e-6, res
+        assert res["max_abs_param_diff"] <= 2.5 * res["max_abs_param_update"] / res["steps"], res   # <= ~2 lr steps
+        assert res["rel_l2_update_diff"] < 0.05, res
 
 
 if __name__ == "__main__":
