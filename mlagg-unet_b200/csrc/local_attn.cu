@@ -12,6 +12,9 @@
 //       d lambda and d subln_w are block-reduced then added atomically;
 //   p2: dk[i], dv[i] gathered from the <= 9 tokens that have i in their window.
 #include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -319,8 +322,436 @@ __global__ void __launch_bounds__(128) local_attn_bwd_p2_kernel(const LocalAttnP
     stv<T, 2 * HD>(static_cast<T *>(p.dv) + tok * p.lddkv + (long long)m * 2 * HD, dv);
 }
 
+// =====================================================================================================================
+// Tiled variants (round 2).  The thread-per-token kernels above read every neighbour row straight from global memory:
+// a warp's 64-bit load touches 32 different 128-byte lines (32 tokens, rows 2C elements apart), the L1 pipe retires one
+// line per cycle, and at stage 0 (256 000 tokens x 216 such loads) that alone is the kernel's run time -- 148 us forward,
+// 320 us backward for 100 MB of traffic (profiles/trace_r02_mid_summary.txt).  Here a CTA owns an 8 x 16 tile of tokens of
+// ONE (image, head pair): the k | v segments of the 10 x 18 halo, the q / dout rows of the tile and every per-token
+// result are staged through shared memory with 16-byte chunks (a warp instruction touches ~6 lines), and the threads
+// (still one per token, same arithmetic) read their 9 neighbours from shared memory; the per-token record stride is
+// padded so that 16 (8) consecutive tokens hit distinct banks with 64-bit (128-bit) loads.
+// =====================================================================================================================
+constexpr int kTR = 8, kTC = 16, kHC = kTC + 2, kHalo = (kTR + 2) * kHC, kTile = kTR * kTC;
+
+template <typename T, int V>
+__device__ __forceinline__ void ldv_s(const unsigned char *bp, float *dst) {   // shared-memory twin of ldv (V % 4 == 0)
+    const T *p = reinterpret_cast<const T *>(bp);
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+        if constexpr (sizeof(T) == 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(p + i);
+            dst[i] = t.x; dst[i + 1] = t.y; dst[i + 2] = t.z; dst[i + 3] = t.w;
+        } else {
+            const uint2 raw = *reinterpret_cast<const uint2 *>(p + i);
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.x));
+            const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&raw.y));
+            dst[i] = a.x; dst[i + 1] = a.y; dst[i + 2] = b.x; dst[i + 3] = b.y;
+        }
+    }
+}
+template <typename T, int V>
+__device__ __forceinline__ void stv_s(unsigned char *bp, const float *src) {
+    T *p = reinterpret_cast<T *>(bp);
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+        if constexpr (sizeof(T) == 4) {
+            *reinterpret_cast<float4 *>(p + i) = make_float4(src[i], src[i + 1], src[i + 2], src[i + 3]);
+        } else {
+            __nv_bfloat162 a = __floats2bfloat162_rn(src[i], src[i + 1]), b = __floats2bfloat162_rn(src[i + 2], src[i + 3]);
+            uint2 raw;
+            raw.x = *reinterpret_cast<uint32_t *>(&a);
+            raw.y = *reinterpret_cast<uint32_t *>(&b);
+            *reinterpret_cast<uint2 *>(p + i) = raw;
+        }
+    }
+}
+
+template <typename T, int HD>
+struct LT {
+    static constexpr int SEG = 2 * HD;                               // elements of one k / v / q / out segment
+    static constexpr int SEGB = SEG * (int)sizeof(T);                // its bytes (a multiple of 16 for the tiled path)
+    static constexpr int PAD = sizeof(T) == 2 ? 8 : 16;
+    static constexpr int CH = sizeof(T) == 2 ? 8 : 16;                // staging chunk of T-typed records
+    static constexpr int KVS = 2 * SEGB + PAD;                       // halo record: [k | v]
+    static constexpr int QS = SEGB + PAD;                            // tile record: q, later out / dq
+    static constexpr int FS = SEG * 4 + 16;                          // fp32 record (dO)
+};
+
+// stage `seg_bytes` of every token of a (rows x cols) window whose top-left token is (r0, c0) (may lie outside the image:
+// zero-filled) : smem record `rec` gets the bytes at dst_off.  src = first element of image b; tok_bytes = token stride.
+// CH = chunk bytes: 16 when the record stride is a multiple of 16 (fp32 records), else 8 (bf16 records, stride = 8 mod 16)
+template <int CH>
+__device__ __forceinline__ void stage_window(unsigned char *smem, int rec_stride, int dst_off, const unsigned char *src,
+                                             long long tok_bytes, int seg_off, int seg_bytes, int r0, int c0, int rows,
+                                             int cols, int H, int W) {
+    using V = typename std::conditional<CH == 16, uint4, uint2>::type;
+    const int nch = seg_bytes / CH;
+    for (int idx = threadIdx.x; idx < rows * cols * nch; idx += blockDim.x) {
+        const int ch = idx % nch, t = idx / nch;
+        const int rr = r0 + t / cols, cc = c0 + t % cols;
+        V v{};
+        if (rr >= 0 && rr < H && cc >= 0 && cc < W)
+            v = __ldg(reinterpret_cast<const V *>(src + ((long long)rr * W + cc) * tok_bytes + seg_off + CH * ch));
+        *reinterpret_cast<V *>(smem + t * rec_stride + dst_off + CH * ch) = v;
+    }
+}
+// the reverse: tile records -> global (only tokens inside the image)
+template <int CH>
+__device__ __forceinline__ void unstage_tile(const unsigned char *smem, int rec_stride, int src_off, unsigned char *dst,
+                                             long long tok_bytes, int seg_off, int seg_bytes, int r0, int c0, int H, int W) {
+    using V = typename std::conditional<CH == 16, uint4, uint2>::type;
+    const int nch = seg_bytes / CH;
+    for (int idx = threadIdx.x; idx < kTile * nch; idx += blockDim.x) {
+        const int ch = idx % nch, t = idx / nch;
+        const int rr = r0 + t / kTC, cc = c0 + t % kTC;
+        if (rr < H && cc < W)
+            *reinterpret_cast<V *>(dst + ((long long)rr * W + cc) * tok_bytes + seg_off + CH * ch) =
+                *reinterpret_cast<const V *>(smem + t * rec_stride + src_off + CH * ch);
+    }
+}
+
+// forward core on the staged halo: same arithmetic as local_core
+template <typename T, int HD>
+__device__ __forceinline__ float local_core_s(const LocalAttnParams &p, const unsigned char *kv, int tr, int tc,
+                                              const bool (&ok)[9], const float (&qv)[2][HD], float (&A)[2][9],
+                                              float (&abar)[9], float (&o)[2 * HD]) {
+    using L = LT<T, HD>;
+    float lg[2][9];
+#pragma unroll
+    for (int pp = 0; pp < 9; ++pp) {
+        lg[0][pp] = lg[1][pp] = -INFINITY;
+        if (ok[pp]) {
+            float kk[2 * HD];
+            ldv_s<T, 2 * HD>(kv + ((tr + pp / 3) * kHC + tc + pp % 3) * L::KVS, kk);
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < HD; ++c) {
+                d0 = fmaf(qv[0][c], kk[c], d0);
+                d1 = fmaf(qv[1][c], kk[HD + c], d1);
+            }
+            lg[0][pp] = d0 * p.scale;
+            lg[1][pp] = d1 * p.scale;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) mx = fmaxf(mx, lg[j][pp]);
+        float s = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) {
+            A[j][pp] = ok[pp] ? expf(lg[j][pp] - mx) : 0.f;
+            s += A[j][pp];
+        }
+        const float inv = 1.f / s;
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) A[j][pp] *= inv;
+    }
+    const float lam = __ldg(p.lamp);
+#pragma unroll
+    for (int c = 0; c < 2 * HD; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < 9; ++pp) {
+        abar[pp] = A[0][pp] - lam * A[1][pp];
+        if (ok[pp]) {
+            float vv[2 * HD];
+            ldv_s<T, 2 * HD>(kv + ((tr + pp / 3) * kHC + tc + pp % 3) * L::KVS + L::SEGB, vv);
+#pragma unroll
+            for (int c = 0; c < 2 * HD; ++c) o[c] = fmaf(abar[pp], vv[c], o[c]);
+        }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2 * HD; ++c) ss = fmaf(o[c], o[c], ss);
+    return 1.f / sqrtf(ss * (1.f / (2 * HD)) + p.eps);
+}
+
+struct TileIdx {
+    int b, m, r0, c0, tr, tc, hr, wc;
+    bool in;
+    long long tok;        // global token index (b * N + hr * W + wc), valid when `in`
+};
+__device__ __forceinline__ TileIdx tile_index(const LocalAttnParams &p) {
+    TileIdx t;
+    const int tcols = (p.W + kTC - 1) / kTC;
+    t.b = blockIdx.z; t.m = blockIdx.y;
+    t.r0 = (blockIdx.x / tcols) * kTR; t.c0 = (blockIdx.x % tcols) * kTC;
+    t.tr = threadIdx.x / kTC; t.tc = threadIdx.x % kTC;
+    t.hr = t.r0 + t.tr; t.wc = t.c0 + t.tc;
+    t.in = t.hr < p.H && t.wc < p.W;
+    t.tok = ((long long)t.b * p.H + t.hr) * p.W + t.wc;
+    return t;
+}
+__device__ __forceinline__ void window_mask(const LocalAttnParams &p, const TileIdx &t, bool (&ok)[9]) {
+#pragma unroll
+    for (int pp = 0; pp < 9; ++pp) {
+        const int rr = t.hr + pp / 3 - 1, cc = t.wc + pp % 3 - 1;
+        ok[pp] = t.in && rr >= 0 && rr < p.H && cc >= 0 && cc < p.W;
+    }
+}
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(kTile) local_attn_fwd_tiled_kernel(const LocalAttnParams p) {
+    using L = LT<T, HD>;
+    extern __shared__ __align__(16) unsigned char lsm[];
+    unsigned char *kv = lsm, *qs = lsm + kHalo * L::KVS;
+    const TileIdx t = tile_index(p);
+    const long long img = (long long)t.b * p.H * p.W;
+    const unsigned char *kb = reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.k) + img * p.ldkv);
+    const unsigned char *vb = reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.v) + img * p.ldkv);
+    const unsigned char *qb = reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq);
+    const int so = t.m * L::SEGB;
+    stage_window<L::CH>(kv, L::KVS, 0, kb, p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
+    stage_window<L::CH>(kv, L::KVS, L::SEGB, vb, p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
+    stage_window<L::CH>(qs, L::QS, 0, qb, p.ldq * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, kTR, kTC, p.H, p.W);
+    __syncthreads();
+    bool ok[9];
+    window_mask(p, t, ok);
+    float o[2 * HD];
+    if (t.in) {
+        float qv[2][HD];
+        ldv_s<T, HD>(qs + threadIdx.x * L::QS, qv[0]);
+        ldv_s<T, HD>(qs + threadIdx.x * L::QS + HD * sizeof(T), qv[1]);
+        float A[2][9], abar[9];
+        const float r = local_core_s<T, HD>(p, kv, t.tr, t.tc, ok, qv, A, abar, o);
+#pragma unroll
+        for (int c = 0; c < 2 * HD; ++c) o[c] = o[c] * r * __ldg(p.subln_w + c) * p.post;
+        stv_s<T, 2 * HD>(qs + threadIdx.x * L::QS, o);          // each thread overwrites its OWN q record
+    }
+    __syncthreads();
+    unstage_tile<L::CH>(qs, L::QS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.out) + img * p.ldo),
+                 p.ldo * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
+}
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(kTile) local_attn_bwd_p1_tiled_kernel(const LocalAttnParams p) {
+    using L = LT<T, HD>;
+    extern __shared__ __align__(16) unsigned char lsm[];
+    __shared__ float red[2 * HD + 1];
+    unsigned char *kv = lsm, *qs = lsm + kHalo * L::KVS, *gs = qs + kTile * L::QS;   // q -> dq ; dout
+    unsigned char *fs = gs + kTile * L::QS;                                          // fp32 staging: dO, then abar | dlog
+    for (int i = threadIdx.x; i < 2 * HD + 1; i += blockDim.x) red[i] = 0.f;
+    const TileIdx t = tile_index(p);
+    const long long img = (long long)t.b * p.H * p.W;
+    const int so = t.m * L::SEGB;
+    stage_window<L::CH>(kv, L::KVS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.k) + img * p.ldkv),
+                 p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
+    stage_window<L::CH>(kv, L::KVS, L::SEGB, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.v) + img * p.ldkv),
+                 p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
+    stage_window<L::CH>(qs, L::QS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq),
+                 p.ldq * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, kTR, kTC, p.H, p.W);
+    stage_window<L::CH>(gs, L::QS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.dout) + img * p.lddo),
+                 p.lddo * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, kTR, kTC, p.H, p.W);
+    __syncthreads();
+    bool ok[9];
+    window_mask(p, t, ok);
+    float dlam = 0.f;
+    float dw[2 * HD];
+#pragma unroll
+    for (int c = 0; c < 2 * HD; ++c) dw[c] = 0.f;
+    float wab[9], wdl[18];
+#pragma unroll
+    for (int pp = 0; pp < 9; ++pp) wab[pp] = wdl[pp] = wdl[9 + pp] = 0.f;
+    if (t.in) {
+        float qv[2][HD];
+        ldv_s<T, HD>(qs + threadIdx.x * L::QS, qv[0]);
+        ldv_s<T, HD>(qs + threadIdx.x * L::QS + HD * sizeof(T), qv[1]);
+        float A[2][9], abar[9], o[2 * HD];
+        const float r = local_core_s<T, HD>(p, kv, t.tr, t.tc, ok, qv, A, abar, o);
+        float g[2 * HD];
+        ldv_s<T, 2 * HD>(gs + threadIdx.x * L::QS, g);
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2 * HD; ++c) {
+            dw[c] = g[c] * p.post * o[c] * r;
+            g[c] *= p.post * __ldg(p.subln_w + c);
+            dot = fmaf(g[c], o[c], dot);
+        }
+        const float k3 = r * r * r * dot * (1.f / (2 * HD));
+        float dO[2 * HD];
+#pragma unroll
+        for (int c = 0; c < 2 * HD; ++c) dO[c] = r * g[c] - o[c] * k3;
+        stv_s<float, 2 * HD>(fs + threadIdx.x * L::FS, dO);
+        float dab[9];
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) {
+            dab[pp] = 0.f;
+            if (ok[pp]) {
+                float vv[2 * HD];
+                ldv_s<T, 2 * HD>(kv + ((t.tr + pp / 3) * kHC + t.tc + pp % 3) * L::KVS + L::SEGB, vv);
+                float d = 0.f;
+#pragma unroll
+                for (int c = 0; c < 2 * HD; ++c) d = fmaf(dO[c], vv[c], d);
+                dab[pp] = d;
+            }
+        }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) {
+            s0 = fmaf(A[0][pp], dab[pp], s0);
+            s1 = fmaf(A[1][pp], dab[pp], s1);
+        }
+        dlam = -s1;
+        const float lam = __ldg(p.lamp);
+        float dq[2 * HD];
+#pragma unroll
+        for (int c = 0; c < 2 * HD; ++c) dq[c] = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) {
+            const float a0 = A[0][pp] * (dab[pp] - s0) * p.scale, a1 = -lam * A[1][pp] * (dab[pp] - s1) * p.scale;
+            wab[pp] = abar[pp]; wdl[pp] = a0; wdl[9 + pp] = a1;
+            if (ok[pp]) {
+                float kk[2 * HD];
+                ldv_s<T, 2 * HD>(kv + ((t.tr + pp / 3) * kHC + t.tc + pp % 3) * L::KVS, kk);
+#pragma unroll
+                for (int c = 0; c < HD; ++c) {
+                    dq[c] = fmaf(a0, kk[c], dq[c]);
+                    dq[HD + c] = fmaf(a1, kk[HD + c], dq[HD + c]);
+                }
+            }
+        }
+        stv_s<T, 2 * HD>(qs + threadIdx.x * L::QS, dq);          // own record: q -> dq
+    }
+    __syncthreads();
+    // per-token results out: dq, dO (fp32), then abar | dlog through the same fp32 staging area
+    unstage_tile<L::CH>(qs, L::QS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dq) + img * p.lddq),
+                 p.lddq * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
+    unstage_tile<16>(fs, L::FS, 0, reinterpret_cast<unsigned char *>(p.ws_dO + img * p.h * 2 * HD), (long long)p.h * 2 * HD * 4,
+                 t.m * 2 * HD * 4, 2 * HD * 4, t.r0, t.c0, p.H, p.W);
+    if (t.in) {                                                   // 27 floats per token: contiguous per token, direct
+        float *wa = p.ws_abar + (t.tok * p.h + t.m) * 9;
+        float *wl = p.ws_dlog + (t.tok * p.h + t.m) * 18;
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) {
+            wa[pp] = wab[pp];
+            wl[pp] = wdl[pp];
+            wl[9 + pp] = wdl[9 + pp];
+        }
+    }
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) dlam += __shfl_xor_sync(0xffffffffu, dlam, o2);
+#pragma unroll
+    for (int c = 0; c < 2 * HD; ++c) {
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) dw[c] += __shfl_xor_sync(0xffffffffu, dw[c], o2);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&red[2 * HD], dlam);
+#pragma unroll
+        for (int c = 0; c < 2 * HD; ++c) atomicAdd(&red[c], dw[c]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * HD + 1; i += blockDim.x) {
+        if (i < 2 * HD) atomicAdd(p.d_subln_w + i, red[i]);
+        else atomicAdd(p.d_lambda, red[i]);
+    }
+}
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(kTile) local_attn_bwd_p2_tiled_kernel(const LocalAttnParams p) {
+    using L = LT<T, HD>;
+    extern __shared__ __align__(16) unsigned char lsm[];
+    constexpr int DOQ = 2 * HD * 4 + L::SEGB + 16;      // halo record: [dO fp32 | q], bank-spread
+    unsigned char *dq = lsm;                                   // [kHalo][DOQ]
+    float *sc = reinterpret_cast<float *>(lsm + kHalo * DOQ);  // [kHalo][28]: abar 9 | dlog 18 (+1 pad)
+    unsigned char *os = reinterpret_cast<unsigned char *>(sc + kHalo * 28);   // [kTile][2 * SEGB + PAD]: dk | dv
+    const TileIdx t = tile_index(p);
+    const long long img = (long long)t.b * p.H * p.W;
+    const int so = t.m * L::SEGB;
+    stage_window<16>(dq, DOQ, 0, reinterpret_cast<const unsigned char *>(p.ws_dO + img * p.h * 2 * HD), (long long)p.h * 2 * HD * 4,
+                 t.m * 2 * HD * 4, 2 * HD * 4, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
+    stage_window<16>(dq, DOQ, 2 * HD * 4, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq),
+                 p.ldq * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
+    for (int idx = threadIdx.x; idx < kHalo * 27; idx += blockDim.x) {
+        const int j = idx % 27, ht = idx / 27;
+        const int rr = t.r0 - 1 + ht / kHC, cc = t.c0 - 1 + ht % kHC;
+        float v = 0.f;
+        if (rr >= 0 && rr < p.H && cc >= 0 && cc < p.W) {
+            const long long n = (img + (long long)rr * p.W + cc) * p.h + t.m;
+            v = j < 9 ? __ldg(p.ws_abar + n * 9 + j) : __ldg(p.ws_dlog + n * 18 + (j - 9));
+        }
+        sc[ht * 28 + j] = v;
+    }
+    __syncthreads();
+    if (t.in) {
+        float dk[2 * HD], dv[2 * HD];
+#pragma unroll
+        for (int c = 0; c < 2 * HD; ++c) dk[c] = dv[c] = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < 9; ++pp) {
+            // token n = tok - off_p has this token as its pp-th neighbour
+            const int rr = t.hr - (pp / 3 - 1), cc = t.wc - (pp % 3 - 1);
+            if (rr >= 0 && rr < p.H && cc >= 0 && cc < p.W) {
+                const int ht = (t.tr + 1 - (pp / 3 - 1)) * kHC + (t.tc + 1 - (pp % 3 - 1));
+                const float ab = sc[ht * 28 + pp], l0 = sc[ht * 28 + 9 + pp], l1 = sc[ht * 28 + 18 + pp];
+                float dO[2 * HD], qn[2 * HD];
+                ldv_s<float, 2 * HD>(dq + ht * DOQ, dO);
+                ldv_s<T, 2 * HD>(dq + ht * DOQ + 2 * HD * 4, qn);
+#pragma unroll
+                for (int c = 0; c < 2 * HD; ++c) dv[c] = fmaf(ab, dO[c], dv[c]);
+#pragma unroll
+                for (int c = 0; c < HD; ++c) {
+                    dk[c] = fmaf(l0, qn[c], dk[c]);
+                    dk[HD + c] = fmaf(l1, qn[HD + c], dk[HD + c]);
+                }
+            }
+        }
+        stv_s<T, 2 * HD>(os + threadIdx.x * L::KVS, dk);
+        stv_s<T, 2 * HD>(os + threadIdx.x * L::KVS + L::SEGB, dv);
+    }
+    __syncthreads();
+    unstage_tile<L::CH>(os, L::KVS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dk) + img * p.lddkv),
+                 p.lddkv * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
+    unstage_tile<L::CH>(os, L::KVS, L::SEGB, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dv) + img * p.lddkv),
+                 p.lddkv * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
+}
+
+template <typename T, int HD>
+static bool local_tiled_ok(const LocalAttnParams &p, int which) {
+    using L = LT<T, HD>;
+    if (L::SEGB % 16 != 0 || HD % 4 != 0 || getenv("MLAGG_LOCAL_UNTILED")) return false;
+    auto a16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const long long e = sizeof(T);
+    bool ok = a16(p.q) && a16(p.k) && a16(p.v) && (p.ldq * e) % 16 == 0 && (p.ldkv * e) % 16 == 0 && p.Bn <= 65535 &&
+              p.h <= 65535;
+    if (which == 0) ok = ok && a16(p.out) && (p.ldo * e) % 16 == 0;
+    if (which == 1) ok = ok && a16(p.dout) && a16(p.dq) && a16(p.ws_dO) && (p.lddo * e) % 16 == 0 && (p.lddq * e) % 16 == 0;
+    if (which == 2) ok = ok && a16(p.dk) && a16(p.dv) && a16(p.ws_dO) && (p.lddkv * e) % 16 == 0;
+    return ok;
+}
+
+template <typename T, int HD>
+static cudaError_t local_launch_tiled(const LocalAttnParams &p, int which, cudaStream_t st) {
+    using L = LT<T, HD>;
+    const dim3 grid(((p.H + kTR - 1) / kTR) * ((p.W + kTC - 1) / kTC), p.h, p.Bn);
+    cudaError_t e;
+    if (which == 0) {
+        const size_t sm = (size_t)kHalo * L::KVS + (size_t)kTile * L::QS;
+        auto k = local_attn_fwd_tiled_kernel<T, HD>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return e;
+        k<<<grid, kTile, sm, st>>>(p);
+    } else if (which == 1) {
+        const size_t sm = (size_t)kHalo * L::KVS + 2 * (size_t)kTile * L::QS + (size_t)kTile * L::FS;
+        auto k = local_attn_bwd_p1_tiled_kernel<T, HD>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return e;
+        k<<<grid, kTile, sm, st>>>(p);
+    } else {
+        constexpr int DOQ = 2 * HD * 4 + L::SEGB + 16;
+        const size_t sm = (size_t)kHalo * DOQ + (size_t)kHalo * 28 * 4 + (size_t)kTile * L::KVS;
+        auto k = local_attn_bwd_p2_tiled_kernel<T, HD>;
+        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)) != cudaSuccess) return e;
+        k<<<grid, kTile, sm, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
 template <typename T, int HD>
 static cudaError_t local_launch(const LocalAttnParams &p, int which, cudaStream_t st) {
+    if constexpr ((2 * HD * sizeof(T)) % 16 == 0 && HD % 4 == 0) {
+        if (local_tiled_ok<T, HD>(p, which)) return local_launch_tiled<T, HD>(p, which, st);
+    }
     const long long total = (long long)p.Bn * p.H * p.W * p.h;
     const int blocks = (int)((total + 127) / 128);
     if (which == 0) local_attn_fwd_kernel<T, HD><<<blocks, 128, 0, st>>>(p);
