@@ -381,13 +381,15 @@ struct LT {
 // stage `seg_bytes` of every token of a (rows x cols) window whose top-left token is (r0, c0) (may lie outside the image:
 // zero-filled) : smem record `rec` gets the bytes at dst_off.  src = first element of image b; tok_bytes = token stride.
 // CH = chunk bytes: 16 when the record stride is a multiple of 16 (fp32 records), else 8 (bf16 records, stride = 8 mod 16)
-template <int CH>
+// (rows, cols, segment bytes are compile-time: the index arithmetic of these loops -- divisions by run-time values in the
+// first version -- cost as much as the attention arithmetic itself)
+template <int CH, int SEG_BYTES, int ROWS, int COLS>
 __device__ __forceinline__ void stage_window(unsigned char *smem, int rec_stride, int dst_off, const unsigned char *src,
-                                             long long tok_bytes, int seg_off, int seg_bytes, int r0, int c0, int rows,
-                                             int cols, int H, int W) {
+                                             long long tok_bytes, int seg_off, int r0, int c0, int H, int W) {
     using V = typename std::conditional<CH == 16, uint4, uint2>::type;
-    const int nch = seg_bytes / CH;
-    for (int idx = threadIdx.x; idx < rows * cols * nch; idx += blockDim.x) {
+    constexpr int nch = SEG_BYTES / CH, rows = ROWS, cols = COLS;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < rows * cols * nch; idx += kTile) {
         const int ch = idx % nch, t = idx / nch;
         const int rr = r0 + t / cols, cc = c0 + t % cols;
         V v{};
@@ -397,12 +399,13 @@ __device__ __forceinline__ void stage_window(unsigned char *smem, int rec_stride
     }
 }
 // the reverse: tile records -> global (only tokens inside the image)
-template <int CH>
+template <int CH, int SEG_BYTES>
 __device__ __forceinline__ void unstage_tile(const unsigned char *smem, int rec_stride, int src_off, unsigned char *dst,
-                                             long long tok_bytes, int seg_off, int seg_bytes, int r0, int c0, int H, int W) {
+                                             long long tok_bytes, int seg_off, int r0, int c0, int H, int W) {
     using V = typename std::conditional<CH == 16, uint4, uint2>::type;
-    const int nch = seg_bytes / CH;
-    for (int idx = threadIdx.x; idx < kTile * nch; idx += blockDim.x) {
+    constexpr int nch = SEG_BYTES / CH;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < kTile * nch; idx += kTile) {
         const int ch = idx % nch, t = idx / nch;
         const int rr = r0 + t / kTC, cc = c0 + t % kTC;
         if (rr < H && cc < W)
@@ -503,9 +506,9 @@ __global__ void __launch_bounds__(kTile) local_attn_fwd_tiled_kernel(const Local
     const unsigned char *vb = reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.v) + img * p.ldkv);
     const unsigned char *qb = reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq);
     const int so = t.m * L::SEGB;
-    stage_window<L::CH>(kv, L::KVS, 0, kb, p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
-    stage_window<L::CH>(kv, L::KVS, L::SEGB, vb, p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
-    stage_window<L::CH>(qs, L::QS, 0, qb, p.ldq * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, kTR, kTC, p.H, p.W);
+    stage_window<L::CH, L::SEGB, kTR + 2, kHC>(kv, L::KVS, 0, kb, p.ldkv * (long long)sizeof(T), so, t.r0 - 1, t.c0 - 1, p.H, p.W);
+    stage_window<L::CH, L::SEGB, kTR + 2, kHC>(kv, L::KVS, L::SEGB, vb, p.ldkv * (long long)sizeof(T), so, t.r0 - 1, t.c0 - 1, p.H, p.W);
+    stage_window<L::CH, L::SEGB, kTR, kTC>(qs, L::QS, 0, qb, p.ldq * (long long)sizeof(T), so, t.r0, t.c0, p.H, p.W);
     __syncthreads();
     bool ok[9];
     window_mask(p, t, ok);
@@ -521,8 +524,7 @@ __global__ void __launch_bounds__(kTile) local_attn_fwd_tiled_kernel(const Local
         stv_s<T, 2 * HD>(qs + threadIdx.x * L::QS, o);          // each thread overwrites its OWN q record
     }
     __syncthreads();
-    unstage_tile<L::CH>(qs, L::QS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.out) + img * p.ldo),
-                 p.ldo * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
+    unstage_tile<L::CH, L::SEGB>(qs, L::QS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.out) + img * p.ldo), p.ldo * (long long)sizeof(T), so, t.r0, t.c0, p.H, p.W);
 }
 
 template <typename T, int HD>
@@ -536,14 +538,10 @@ __global__ void __launch_bounds__(kTile) local_attn_bwd_p1_tiled_kernel(const Lo
     const TileIdx t = tile_index(p);
     const long long img = (long long)t.b * p.H * p.W;
     const int so = t.m * L::SEGB;
-    stage_window<L::CH>(kv, L::KVS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.k) + img * p.ldkv),
-                 p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
-    stage_window<L::CH>(kv, L::KVS, L::SEGB, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.v) + img * p.ldkv),
-                 p.ldkv * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
-    stage_window<L::CH>(qs, L::QS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq),
-                 p.ldq * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, kTR, kTC, p.H, p.W);
-    stage_window<L::CH>(gs, L::QS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.dout) + img * p.lddo),
-                 p.lddo * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, kTR, kTC, p.H, p.W);
+    stage_window<L::CH, L::SEGB, kTR + 2, kHC>(kv, L::KVS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.k) + img * p.ldkv), p.ldkv * (long long)sizeof(T), so, t.r0 - 1, t.c0 - 1, p.H, p.W);
+    stage_window<L::CH, L::SEGB, kTR + 2, kHC>(kv, L::KVS, L::SEGB, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.v) + img * p.ldkv), p.ldkv * (long long)sizeof(T), so, t.r0 - 1, t.c0 - 1, p.H, p.W);
+    stage_window<L::CH, L::SEGB, kTR, kTC>(qs, L::QS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq), p.ldq * (long long)sizeof(T), so, t.r0, t.c0, p.H, p.W);
+    stage_window<L::CH, L::SEGB, kTR, kTC>(gs, L::QS, 0, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.dout) + img * p.lddo), p.lddo * (long long)sizeof(T), so, t.r0, t.c0, p.H, p.W);
     __syncthreads();
     bool ok[9];
     window_mask(p, t, ok);
@@ -616,10 +614,8 @@ __global__ void __launch_bounds__(kTile) local_attn_bwd_p1_tiled_kernel(const Lo
     }
     __syncthreads();
     // per-token results out: dq, dO (fp32), then abar | dlog through the same fp32 staging area
-    unstage_tile<L::CH>(qs, L::QS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dq) + img * p.lddq),
-                 p.lddq * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
-    unstage_tile<16>(fs, L::FS, 0, reinterpret_cast<unsigned char *>(p.ws_dO + img * p.h * 2 * HD), (long long)p.h * 2 * HD * 4,
-                 t.m * 2 * HD * 4, 2 * HD * 4, t.r0, t.c0, p.H, p.W);
+    unstage_tile<L::CH, L::SEGB>(qs, L::QS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dq) + img * p.lddq), p.lddq * (long long)sizeof(T), so, t.r0, t.c0, p.H, p.W);
+    unstage_tile<16, 2 * HD * 4>(fs, L::FS, 0, reinterpret_cast<unsigned char *>(p.ws_dO + img * p.h * 2 * HD), (long long)p.h * 2 * HD * 4, t.m * 2 * HD * 4, t.r0, t.c0, p.H, p.W);
     if (t.in) {                                                   // 27 floats per token: contiguous per token, direct
         float *wa = p.ws_abar + (t.tok * p.h + t.m) * 9;
         float *wl = p.ws_dlog + (t.tok * p.h + t.m) * 18;
@@ -655,15 +651,13 @@ __global__ void __launch_bounds__(kTile) local_attn_bwd_p2_tiled_kernel(const Lo
     extern __shared__ __align__(16) unsigned char lsm[];
     constexpr int DOQ = 2 * HD * 4 + L::SEGB + 16;      // halo record: [dO fp32 | q], bank-spread
     unsigned char *dq = lsm;                                   // [kHalo][DOQ]
-    float *sc = reinterpret_cast<float *>(lsm + kHalo * DOQ);  // [kHalo][28]: abar 9 | dlog 18 (+1 pad)
+    float *sc = reinterpret_cast<float *>(lsm + kHalo * DOQ);  // [27 (+1)][kHalo]: abar 9 | dlog 18, token index fastest
     unsigned char *os = reinterpret_cast<unsigned char *>(sc + kHalo * 28);   // [kTile][2 * SEGB + PAD]: dk | dv
     const TileIdx t = tile_index(p);
     const long long img = (long long)t.b * p.H * p.W;
     const int so = t.m * L::SEGB;
-    stage_window<16>(dq, DOQ, 0, reinterpret_cast<const unsigned char *>(p.ws_dO + img * p.h * 2 * HD), (long long)p.h * 2 * HD * 4,
-                 t.m * 2 * HD * 4, 2 * HD * 4, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
-    stage_window<16>(dq, DOQ, 2 * HD * 4, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq),
-                 p.ldq * (long long)sizeof(T), so, L::SEGB, t.r0 - 1, t.c0 - 1, kTR + 2, kHC, p.H, p.W);
+    stage_window<16, 2 * HD * 4, kTR + 2, kHC>(dq, DOQ, 0, reinterpret_cast<const unsigned char *>(p.ws_dO + img * p.h * 2 * HD), (long long)p.h * 2 * HD * 4, t.m * 2 * HD * 4, t.r0 - 1, t.c0 - 1, p.H, p.W);
+    stage_window<16, L::SEGB, kTR + 2, kHC>(dq, DOQ, 2 * HD * 4, reinterpret_cast<const unsigned char *>(static_cast<const T *>(p.q) + img * p.ldq), p.ldq * (long long)sizeof(T), so, t.r0 - 1, t.c0 - 1, p.H, p.W);
     for (int idx = threadIdx.x; idx < kHalo * 27; idx += blockDim.x) {
         const int j = idx % 27, ht = idx / 27;
         const int rr = t.r0 - 1 + ht / kHC, cc = t.c0 - 1 + ht % kHC;
@@ -672,7 +666,7 @@ __global__ void __launch_bounds__(kTile) local_attn_bwd_p2_tiled_kernel(const Lo
             const long long n = (img + (long long)rr * p.W + cc) * p.h + t.m;
             v = j < 9 ? __ldg(p.ws_abar + n * 9 + j) : __ldg(p.ws_dlog + n * 18 + (j - 9));
         }
-        sc[ht * 28 + j] = v;
+        sc[j * kHalo + ht] = v;
     }
     __syncthreads();
     if (t.in) {
@@ -685,7 +679,7 @@ __global__ void __launch_bounds__(kTile) local_attn_bwd_p2_tiled_kernel(const Lo
             const int rr = t.hr - (pp / 3 - 1), cc = t.wc - (pp % 3 - 1);
             if (rr >= 0 && rr < p.H && cc >= 0 && cc < p.W) {
                 const int ht = (t.tr + 1 - (pp / 3 - 1)) * kHC + (t.tc + 1 - (pp % 3 - 1));
-                const float ab = sc[ht * 28 + pp], l0 = sc[ht * 28 + 9 + pp], l1 = sc[ht * 28 + 18 + pp];
+                const float ab = sc[pp * kHalo + ht], l0 = sc[(9 + pp) * kHalo + ht], l1 = sc[(18 + pp) * kHalo + ht];
                 float dO[2 * HD], qn[2 * HD];
                 ldv_s<float, 2 * HD>(dq + ht * DOQ, dO);
                 ldv_s<T, 2 * HD>(dq + ht * DOQ + 2 * HD * 4, qn);
@@ -702,10 +696,8 @@ __global__ void __launch_bounds__(kTile) local_attn_bwd_p2_tiled_kernel(const Lo
         stv_s<T, 2 * HD>(os + threadIdx.x * L::KVS + L::SEGB, dv);
     }
     __syncthreads();
-    unstage_tile<L::CH>(os, L::KVS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dk) + img * p.lddkv),
-                 p.lddkv * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
-    unstage_tile<L::CH>(os, L::KVS, L::SEGB, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dv) + img * p.lddkv),
-                 p.lddkv * (long long)sizeof(T), so, L::SEGB, t.r0, t.c0, p.H, p.W);
+    unstage_tile<L::CH, L::SEGB>(os, L::KVS, 0, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dk) + img * p.lddkv), p.lddkv * (long long)sizeof(T), so, t.r0, t.c0, p.H, p.W);
+    unstage_tile<L::CH, L::SEGB>(os, L::KVS, L::SEGB, reinterpret_cast<unsigned char *>(static_cast<T *>(p.dv) + img * p.lddkv), p.lddkv * (long long)sizeof(T), so, t.r0, t.c0, p.H, p.W);
 }
 
 template <typename T, int HD>
