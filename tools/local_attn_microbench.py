@@ -28,7 +28,10 @@ def t_us(fn, n=10):
     return ts[len(ts) // 2]
 
 
-for side, C in ((160, 48), (80, 96), (40, 192), (20, 384)):
+SHAPES = ((160, 48), (80, 96), (40, 192), (20, 384))
+if len(sys.argv) > 1:
+    SHAPES = tuple(sc for sc in SHAPES if sc[0] == int(sys.argv[1]))
+for side, C in SHAPES:
     h, hd, Bn, N = C // 48, 24, 10, side * side
     q = torch.randn(Bn, N, C, device="cuda").bfloat16().requires_grad_()
     kv = torch.randn(Bn, N, 2 * C, device="cuda").bfloat16().requires_grad_()
