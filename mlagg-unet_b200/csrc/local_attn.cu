@@ -704,6 +704,12 @@ template <typename T, int HD>
 static bool local_tiled_ok(const LocalAttnParams &p, int which) {
     using L = LT<T, HD>;
     if (L::SEGB % 16 != 0 || HD % 4 != 0 || getenv("MLAGG_LOCAL_UNTILED")) return false;
+    // Measured on B200 (tools/local_attn_microbench.py, profiles/local_attn_microbench_r02.txt): the tiled FORWARD is 2x
+    // faster on the large maps (160^2: 152 -> 76 us, 80^2: 78 -> 44 us) and slower on the small ones (tile quantisation:
+    // a 20 x 20 map fills 52 % of its 8 x 16 tiles); the tiled BACKWARD passes execute 40 % more instructions (staging)
+    // from a fully unrolled body that no longer fits the instruction cache (ncu: stall_no_instruction 2.0 per issue) and
+    // are not faster anywhere -- they stay available behind MLAGG_LOCAL_TILED_BWD=1 for the next round's work.
+    if (which == 0 ? (p.H < 64 || p.W < 64) : getenv("MLAGG_LOCAL_TILED_BWD") == nullptr) return false;
     auto a16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const long long e = sizeof(T);
     bool ok = a16(p.q) && a16(p.k) && a16(p.v) && (p.ldq * e) % 16 == 0 && (p.ldkv * e) % 16 == 0 && p.Bn <= 65535 &&
