@@ -22,7 +22,7 @@ import torch.nn.functional as F
 
 from . import attention as att
 from .mamba_skip import VSS_Conv_Layer
-from .ops import (Conv2dCL, ConvTranspose2dCL, GradContiguous, avgpool_tokens, dwconv3x3_tokens, layer_norm_fork, layer_norm_tokens, linear_tokens,
+from .ops import (Conv2dCL, ConvTranspose2dCL, GradContiguous, PadTopLeftAdd, SplitKV, avgpool_tokens, dwconv3x3_tokens, layer_norm_fork, layer_norm_tokens, linear_tokens,
                   mlp_gelu_tokens, residual_drop_path, silu_gate)
 from .thirdparty_shims import DropPath, UnetrBasicBlock, UnetrUpBlock, _inst_norm
 
@@ -118,8 +118,7 @@ class AggregatedAttention(nn.Module):
         assert N == H * W
         h, hd = self.num_heads, self.head_dim
         q = linear_tokens(x, self.q)
-        kv = linear_tokens(x, self.kv)
-        v_local = kv[..., C:]
+        kv, v_local = SplitKV.apply(linear_tokens(x, self.kv), C)      # v_local = kv[..., C:]; gradients re-joined in place
         lam = att.diff_lambda(self.lambda_q1, self.lambda_k1, self.lambda_q2, self.lambda_k2)
         if self.local:
             o = att.local_diff_attention(q, kv, lam, self.subln.weight, H, W, h, hd, self.scale)
@@ -365,10 +364,13 @@ class PatchExpand(nn.Module):
         self.norm = nn.GroupNorm(num_groups=in_channels, num_channels=in_channels)
 
     def forward(self, x, dummy_tensor=None):
-        y = F.pad(self.conv1(_inst_norm(self.norm, x)), (1, 0, 1, 0))
-        if self.resample_do_res:
-            y = y + F.pad(self.res_conv(x), (1, 0, 1, 0))
-        return y
+        y = self.conv1(_inst_norm(self.norm, x))
+        r = self.res_conv(x) if self.resample_do_res else None
+        if y.is_cuda and y.is_contiguous(memory_format=torch.channels_last) and (
+                r is None or (r.is_contiguous(memory_format=torch.channels_last) and r.dtype == y.dtype)):
+            return PadTopLeftAdd.apply(y, r)
+        y = F.pad(y, (1, 0, 1, 0))
+        return y if r is None else y + F.pad(r, (1, 0, 1, 0))
 
 
 class OutBlock(nn.Module):

@@ -836,6 +836,96 @@ class JoinLastDense(JoinLast):
         return ga, gb
 
 
+def _copy_rows_raw(src, src_off, ld_s, bs_s, dst, dst_off, ld_d, bs_d, batch, rows, cols):
+    """mlagg_copy_rows on explicit (element offset, row stride, batch stride) addressing of two same-dtype tensors"""
+    es = src.element_size()
+    with torch.cuda.device(src.device), _lib.timed("copy_rows"):
+        rc = _lib.lib().mlagg_copy_rows(src.data_ptr() + src_off * es, ld_s, bs_s, dst.data_ptr() + dst_off * es, ld_d, bs_d,
+                                        batch, rows, cols, _DT[src.dtype], _lib.stream_ptr())
+    _lib.check(rc, "mlagg_copy_rows")
+
+
+class UpShuffleJoin(torch.autograd.Function):
+    """Pixel-shuffle of a 2x2 / stride-2 transposed convolution computed as a per-token GEMM, joined with the skip map:
+         y    (B, H W, 4 Co)   columns ordered (di, dj, co) -- the GEMM output of `x . W[ci, co, di, dj]`
+         skip (B, 2H, 2W, Cs)  channels_last view
+         out  (B, 2H, 2W, Co + Cs):  out[b, 2i+di, 2j+dj, :Co] = y[b, i W + j, (2 di + dj) Co : ...],  out[..., Co:] = skip
+    Five strided row copies forward, five backward (dense gradients).  Replaces UnetrUpBlock's cuDNN transposed
+    convolution (an sm_75-era kernel with an NCHW result), the layout conversion of that result and torch.cat -- the
+    single largest piece of torch glue in the step (191 us forward, 3 x ~140 us backward at 10 x 96 x 320 x 320)."""
+
+    @staticmethod
+    def forward(ctx, y, skip, H, W):
+        Bn, Co, Cs = y.shape[0], y.shape[2] // 4, skip.shape[-1]
+        ld = Co + Cs
+        out = torch.empty(Bn, 2 * H, 2 * W, ld, device=y.device, dtype=y.dtype)
+        y = y.contiguous()
+        for di in range(2):
+            for dj in range(2):
+                _copy_rows_raw(y, (2 * di + dj) * Co, 4 * Co, W * 4 * Co, out, (di * 2 * W + dj) * ld, 2 * ld, 4 * W * ld,
+                               Bn * H, W, Co)
+        copy_rows_(out[..., Co:], skip.to(y.dtype))
+        ctx.meta = (H, W, Co, Cs, skip.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        H, W, Co, Cs, sdt = ctx.meta
+        g = g.contiguous()
+        Bn, ld = g.shape[0], Co + Cs
+        gy = torch.empty(Bn, H * W, 4 * Co, device=g.device, dtype=g.dtype)
+        for di in range(2):
+            for dj in range(2):
+                _copy_rows_raw(g, (di * 2 * W + dj) * ld, 2 * ld, 4 * W * ld, gy, (2 * di + dj) * Co, 4 * Co, W * 4 * Co,
+                               Bn * H, W, Co)
+        gs = torch.empty(Bn, 2 * H, 2 * W, Cs, device=g.device, dtype=g.dtype)
+        copy_rows_(gs, g[..., Co:])
+        return gy, gs.to(sdt), None, None
+
+
+class PadTopLeftAdd(torch.autograd.Function):
+    """F.pad(a, (1, 0, 1, 0)) + F.pad(b, (1, 0, 1, 0)) for two channels_last maps (PatchExpand, reference
+    nnUNetTrainer_MLAgg_2D_dt_MS.py:520-546): one zero fill and one add into the interior instead of two fills, two
+    strided copies and an add; the backward hands ONE dense copy of the interior gradient to both branches."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        Bn, C, H, W = a.shape
+        out = torch.zeros(Bn, C, H + 1, W + 1, device=a.device, dtype=a.dtype, memory_format=torch.channels_last)
+        if b is None:
+            out[:, :, 1:, 1:].copy_(a)
+        else:
+            torch.add(a, b, out=out[:, :, 1:, 1:])
+        ctx.two = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gi = g[:, :, 1:, 1:].contiguous(memory_format=torch.channels_last)
+        return gi, (gi if ctx.two else None)
+
+
+class SplitKV(torch.autograd.Function):
+    """kv -> (kv, v) with v = kv[..., C:] for the LePE branch (reference :690-691, :716, :759).  Both gradients arrive at
+    this node: the LePE gradient is added IN PLACE into the v half of the attention core's kv gradient (one half-size
+    add) instead of autograd's zero-filled full-size tensor + slice copy + full-size add."""
+
+    @staticmethod
+    def forward(ctx, kv, C):
+        ctx.C = C
+        return kv.view_as(kv), kv[..., C:]
+
+    @staticmethod
+    def backward(ctx, g_kv, g_v):
+        if g_kv is None:
+            g_kv = torch.zeros(g_v.shape[:-1] + (g_v.shape[-1] + ctx.C,), device=g_v.device, dtype=g_v.dtype)
+        if g_v is not None:
+            if not g_kv.is_contiguous():
+                g_kv = g_kv.contiguous()
+            g_kv[..., ctx.C:].add_(g_v.to(g_kv.dtype))
+        return g_kv, None
+
+
 class CatStages(torch.autograd.Function):
     """per-stage token maps (B, L_s, C) (row-strided views allowed) -> the stage-concatenated sequence (B, sum L_s, C);
     the gradients are views of the sequence gradient."""

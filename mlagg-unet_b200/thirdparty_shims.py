@@ -158,13 +158,24 @@ class UnetrUpBlock(nn.Module):
         self.conv_block = UnetResBlock2d(2 * out_channels, out_channels, kernel_size, 1)
 
     def forward(self, inp, skip):
-        up = self.transp_conv(inp)
-        a, b = up.permute(0, 2, 3, 1), skip.permute(0, 2, 3, 1)
-        if up.is_cuda and a.is_contiguous() and b.is_contiguous() and up.dtype == skip.dtype:
-            # channel concatenation of two channels_last maps == two row-strided copies (torch.cat falls onto its generic
-            # strided-copy kernel here: 191 us forward and 3 x ~130 us backward at 10 x 96 x 320 x 320)
-            from .ops import JoinLastDense
-            x = JoinLastDense.apply(a, b).permute(0, 3, 1, 2)
+        conv = self.transp_conv.conv
+        a, b = inp.permute(0, 2, 3, 1), skip.permute(0, 2, 3, 1)
+        if (inp.is_cuda and a.is_contiguous() and b.is_contiguous() and conv.kernel_size == (2, 2) and conv.stride == (2, 2)
+                and conv.padding == (0, 0) and conv.bias is None and conv.weight.shape[0] % 8 == 0
+                and conv.weight.shape[1] % 8 == 0 and skip.shape[-2:] == (2 * inp.shape[2], 2 * inp.shape[3])):
+            # kernel 2 / stride 2: every output pixel has ONE contributing input pixel -- a per-token GEMM against the
+            # (4 Co, Ci) matrix W[ci, co, di, dj] -> [(di, dj, co), ci], then a pixel shuffle fused with the skip concat
+            from .ops import UpShuffleJoin, _Linear
+            Bn, Ci, H, W = inp.shape
+            w4 = conv.weight.permute(2, 3, 1, 0).reshape(-1, Ci)
+            y = _Linear.apply(a.reshape(Bn, H * W, Ci), w4, None)
+            x = UpShuffleJoin.apply(y, b, H, W).permute(0, 3, 1, 2)
         else:
-            x = torch.cat((up, skip), dim=1)
+            up = self.transp_conv(inp)
+            a = up.permute(0, 2, 3, 1)
+            if up.is_cuda and a.is_contiguous() and b.is_contiguous() and up.dtype == skip.dtype:
+                from .ops import JoinLastDense
+                x = JoinLastDense.apply(a, b).permute(0, 3, 1, 2)
+            else:
+                x = torch.cat((up, skip), dim=1)
         return self.conv_block(x)

@@ -727,3 +727,48 @@ def test_layer_norm_fork_adds_the_shortcut_gradient_in_the_same_pass(dtype, tol)
     (torch.nn.functional.layer_norm(xr2, (C,), ln.weight.detach().cpu().double(), ln.bias.detach().cpu().double(), ln.eps)
      * w1.to(dtype).double()).sum().backward()
     assert rel_err(xc2.grad.float().cpu(), xr2.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_unetr_up_block_gemm_shuffle_matches_transposed_conv(dtype):
+    """UnetrUpBlock's 2x2 / stride-2 transposed convolution as a per-token GEMM + pixel shuffle + skip join
+    (ops.UpShuffleJoin) against torch's conv_transpose2d + cat, forward and all gradients."""
+    from mlagg_unet_b200.thirdparty_shims import UnetrUpBlock
+    torch.manual_seed(3)
+    blk = UnetrUpBlock(2, 16, 8, 3, 2, "instance", res_block=True).cuda()
+    x = torch.randn(2, 16, 5, 7, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    sk = torch.randn(2, 8, 10, 14, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    xr, sr = x.detach().clone().requires_grad_(), sk.detach().clone().requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        y = blk(x, sk)
+        ref = blk.conv_block(torch.cat((blk.transp_conv(xr), sr), dim=1))
+    tol = 1e-5 if dtype == torch.float32 else TOL16
+    assert rel_err(y.float(), ref.float()) < tol
+    g = torch.randn_like(ref)
+    y.backward(g.to(y.dtype))
+    gw = blk.transp_conv.conv.weight.grad.clone()
+    blk.zero_grad()
+    ref.backward(g.to(ref.dtype))
+    assert rel_err(x.grad, xr.grad) < tol and rel_err(sk.grad, sr.grad) < tol
+    assert rel_err(gw, blk.transp_conv.conv.weight.grad) < 2 * tol
+
+
+def test_pad_top_left_add_and_split_kv_gradients():
+    from mlagg_unet_b200.ops import PadTopLeftAdd, SplitKV
+    import torch.nn.functional as F
+    torch.manual_seed(5)
+    a = torch.randn(2, 8, 5, 6, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    b = torch.randn(2, 8, 5, 6, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    out = PadTopLeftAdd.apply(a, b)
+    ref = F.pad(a.detach(), (1, 0, 1, 0)) + F.pad(b.detach(), (1, 0, 1, 0))
+    assert torch.equal(out, ref)
+    g = torch.randn_like(out)
+    out.backward(g)
+    assert torch.equal(a.grad, g[:, :, 1:, 1:]) and torch.equal(b.grad, g[:, :, 1:, 1:])
+    kv = torch.randn(2, 9, 16, device="cuda", requires_grad=True)
+    full, v = SplitKV.apply(kv * 1.0, 8)
+    w1, w2 = torch.randn_like(full), torch.randn(2, 9, 8, device="cuda")
+    ((full * w1).sum() + (v * w2).sum()).backward()
+    want = w1.clone()
+    want[..., 8:] += w2
+    assert torch.allclose(kv.grad, want)
