@@ -734,8 +734,11 @@ cudaError_t gemm_tc_dispatch(const void *A, long long lda, int a_mn, const void 
     const int mt = (p.M + kBM - 1) / kBM, nt = (p.N + BN - 1) / BN;
     int splits = 1;
     if (p.reduce) {
-        // about one CTA per SM, at least 8 k-blocks each: every split pays an fp32 reduction of its whole tile
-        splits = max(1, min((sm_count() + mt * nt - 1) / (mt * nt), (kb_total + 7) / 8));
+        // about one CTA per SM, at least 8 k-blocks each; every split pays an fp32 atomic reduction of its whole tile, so
+        // the total number of reduced elements (splits x M x N) is capped as well -- at 768 x 1536 outputs five splits
+        // spent more time in red.global.add than in the MMAs
+        const long long cap = max(1LL, 3000000LL / ((long long)p.M * p.N));
+        splits = (int)max(1LL, min((long long)min((sm_count() + mt * nt - 1) / (mt * nt), (kb_total + 7) / 8), cap));
     }
     p.kblocks_per_split = (kb_total + splits - 1) / splits;
     splits = (kb_total + p.kblocks_per_split - 1) / p.kblocks_per_split;

@@ -891,7 +891,7 @@ class PadTopLeftAdd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):
         Bn, C, H, W = a.shape
-        out = torch.zeros(Bn, C, H + 1, W + 1, device=a.device, dtype=a.dtype, memory_format=torch.channels_last)
+        out = torch.empty(Bn, C, H + 1, W + 1, device=a.device, dtype=a.dtype, memory_format=torch.channels_last).zero_()
         if b is None:
             out[:, :, 1:, 1:].copy_(a)
         else:
