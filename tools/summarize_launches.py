@@ -15,9 +15,21 @@ for r in rows[1:]:
 tot = sum(v[1] for v in agg.values())
 OURS = ("scan_", "dwconv", "causal_conv1d", "pooled_attn", "local_attn", "layernorm_", "in_sums", "in_apply", "in_finalize",
         "in_param", "colsum", "avgpool", "linattn", "walk_", "residual_scale", "silu_gate", "diff_lambda", "copy_rows", "bias_add_cl")
-ours = {k: v for k, v in agg.items() if any(t in k for t in OURS) and "at::native" not in k}
-print(f"{sum(v[0] for v in agg.values())} launches, {tot:.2f} ms summed device time (cold-cache, serialised: compare SHARES)")
+ours = {k: v for k, v in agg.items() if ("mlagg::" in k or any(t in k for t in OURS)) and "at::native" not in k}
+GROUPS = (("tcgen05 projection GEMMs", ("gemm_tc",)), ("selective scan", ("scan_fwd", "scan_bwd")),
+          ("walk pack / unpack", ("walk_",)), ("depthwise conv", ("dwconv",)), ("local attention", ("local_attn",)),
+          ("pooled attention", ("pooled_attn", "avgpool")), ("LayerNorm", ("layernorm_",)),
+          ("instance norm", ("in_sums", "in_apply", "in_finalize", "in_param")),
+          ("element-wise seams / copies", ("residual_scale", "silu_gate", "diff_lambda", "copy_rows", "bias_add_cl", "colsum")))
+print(f"{sum(v[0] for v in agg.values())} launches, {tot:.2f} ms summed device time (ncu lists: cold-cache, serialised -- compare "
+      f"SHARES; CUPTI lists from bench.py --trace-step: in-stream durations)")
 print(f"libmlagg_b200.so kernels: {sum(v[0] for v in ours.values())} launches, {sum(v[1] for v in ours.values()):.2f} ms = "
       f"{100 * sum(v[1] for v in ours.values()) / tot:.1f} % of the step")
+for gname, pats in GROUPS:
+    sel = [v for k, v in ours.items() if any(t in k for t in pats)]
+    if sel:
+        print(f"   {gname:30s} {sum(v[0] for v in sel):5d}x {sum(v[1] for v in sel):7.3f} ms {100 * sum(v[1] for v in sel) / tot:5.1f} %")
+glue = [v for k, v in agg.items() if "at::native" in k and any(t in k for t in ("direct_copy", "CUDAFunctor_add", "FillFunctor", "CatArray"))]
+print(f"   {'torch copies / adds / fills / cat':30s} {sum(v[0] for v in glue):5d}x {sum(v[1] for v in glue):7.3f} ms {100 * sum(v[1] for v in glue) / tot:5.1f} %")
 for k, v in sorted(agg.items(), key=lambda x: -x[1][1])[:int(sys.argv[2]) if len(sys.argv) > 2 else 40]:
     print(f"{v[1]:8.3f} ms {v[0]:5d}x {100 * v[1] / tot:5.1f} %  {'*' if k in ours else ' '} {k[:110]}")
