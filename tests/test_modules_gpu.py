@@ -234,7 +234,8 @@ def test_full_network_logits_and_argmax_masks_identical():
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, TOL16)])
 @pytest.mark.parametrize("shape,silu", [((2, 7, 5, 8), True), ((1, 1, 1, 4), False), ((2, 5, 4, 21), True), ((3, 16, 12, 96), True),
-                                        ((2, 20, 20, 128), False)])
+                                        ((2, 20, 20, 128), False), ((2, 33, 37, 48), True), ((1, 40, 160, 32), True),
+                                        ((2, 9, 256, 32), False), ((1, 1, 3, 16), True), ((3, 2, 1, 64), True)])
 def test_dwconv3x3_tokens_matches_oracle(shape, silu, dtype, tol):
     from mlagg_unet_b200.ops import dwconv3x3_tokens
     from oracle.convs import dwconv3x3_tokens_act
@@ -556,7 +557,7 @@ def _dwconv_ref(x, w, b, H, W, silu):
     return y.flatten(2).transpose(1, 2)
 
 
-@pytest.mark.parametrize("C", [8, 6])
+@pytest.mark.parametrize("C", [8, 6, 16, 32])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_dwconv_strided_operands_and_residual(C, dtype):
     """mlagg_dwconv3x3_*_strided: the input and the residual are channel slices of wider activations (LePE on the v half
@@ -581,7 +582,7 @@ def test_dwconv_strided_operands_and_residual(C, dtype):
         assert rel_err(got.double(), want) < tol
 
 
-@pytest.mark.parametrize("C", [8, 6])
+@pytest.mark.parametrize("C", [8, 6, 32])
 def test_dwconv_stages_in_place_segments(C):
     """dwconv3x3_stages (MambaSkip.py:521-523) against per-stage fp64 torch convolutions: outputs, dx and every stage's
     parameter gradients."""
@@ -606,6 +607,33 @@ def test_dwconv_stages_in_place_segments(C):
     assert rel_err(y.double(), yd) < TOL32 and rel_err(x.grad.double(), xd.grad) < TOL32
     for cv, (ww, bb) in zip(convs, pd):
         assert rel_err(cv.weight.grad.double(), ww.grad) < TOL32 and rel_err(cv.bias.grad.double(), bb.grad) < TOL32
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 160, 96), (3, 20, 20, 768), (2, 50, 80, 48), (1, 130, 256, 32)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dwconv_ring_kernels_equal_the_strip_kernels(shape, dtype, monkeypatch):
+    """The shared-memory ring kernels (several row bands per image, both strip lengths, both chunk widths) against the
+    strip kernels they replace (MLAGG_DWCONV_STRIP=1): same operation order per output, so y and dx are bit-identical;
+    the weight / bias gradients differ only in summation order."""
+    from mlagg_unet_b200.ops import dwconv3x3_tokens
+    Bn, H, W, C = shape
+    torch.manual_seed(11)
+    x0 = torch.randn(Bn, H * W, C, device="cuda").to(dtype)
+    r0 = torch.randn(Bn, H * W, C, device="cuda").to(dtype)
+    w0 = 0.3 * torch.randn(C, 1, 3, 3, device="cuda")
+    b0 = 0.1 * torch.randn(C, device="cuda")
+    g = torch.randn(Bn, H * W, C, device="cuda").to(dtype)
+    outs = []
+    for strip in (False, True):
+        if strip:
+            monkeypatch.setenv("MLAGG_DWCONV_STRIP", "1")
+        x, r, w, b = (t.clone().requires_grad_() for t in (x0, r0, w0, b0))
+        y = dwconv3x3_tokens(x, w, b, H, W, silu=True, residual=r)
+        y.backward(g)
+        outs.append((y.detach(), x.grad, w.grad, b.grad))
+    (y1, dx1, dw1, db1), (y2, dx2, dw2, db2) = outs
+    assert torch.equal(y1, y2) and torch.equal(dx1, dx2)
+    assert rel_err(dw1, dw2) < 1e-5 and rel_err(db1, db2) < 1e-5
 
 
 @pytest.mark.parametrize("transposed", [False, True])
@@ -674,7 +702,7 @@ def test_strided_row_copies_and_split_join_functions(dtype):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("hid", [8, 7])
+@pytest.mark.parametrize("hid", [8, 7, 16, 64])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_glu_core_matches_torch(hid, dtype):
     """act(dwconv(h[..., :hid])) * h[..., hid:] (ConvolutionalGLU, MambaSkip.py:572-574) as one kernel with both halves of
