@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -184,6 +185,178 @@ __global__ void __launch_bounds__(256) in_apply_kernel(const T *__restrict__ x, 
     }
 }
 
+// ---------------------------------------------------------------- row-streaming kernels (C % (16 / sizeof(T)) == 0)
+// The kernels above spend two 64-bit divisions and twelve scalar loads on every 8-byte vector and keep one load per
+// thread in flight: 25 - 35 % of the HBM roofline at the full-resolution maps (tools/call_shapes.py).  Here a thread
+// owns ONE 16-byte channel vector (8 bf16 / 4 fp32 channels, per-channel constants in registers) and walks down the
+// rows of its CTA's row chunk, four rows per iteration with all loads issued before the arithmetic.
+template <typename T>
+struct InV {
+    static constexpr int N = 16 / (int)sizeof(T);
+};
+template <typename T>
+__device__ __forceinline__ uint4 in_ldraw(const T *p) {
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+}
+__device__ __forceinline__ void in_unpack(const uint4 &t, float (&v)[4]) {
+    v[0] = __uint_as_float(t.x), v[1] = __uint_as_float(t.y), v[2] = __uint_as_float(t.z), v[3] = __uint_as_float(t.w);
+}
+__device__ __forceinline__ void in_unpack(const uint4 &t, float (&v)[8]) {
+    const uint32_t r[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(r[i] << 16);
+        v[2 * i + 1] = __uint_as_float(r[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void in_stv(float *p, const float (&v)[4]) { in_st4(p, v); }
+__device__ __forceinline__ void in_stv(__nv_bfloat16 *p, const float (&v)[8]) {
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        r[i] = *reinterpret_cast<const uint32_t *>(&a);
+    }
+    *reinterpret_cast<uint4 *>(p) = make_uint4(r[0], r[1], r[2], r[3]);
+}
+constexpr int kInRows = 4;   // rows per thread and iteration
+
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(256) in_sums_rows_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+                                                           const float *__restrict__ stats_in,
+                                                           const float *__restrict__ w, const float *__restrict__ b,
+                                                           float *__restrict__ out, int N, int C, int rows_per_block,
+                                                           int act, float slope) {
+    constexpr int V = InV<T>::N;
+    extern __shared__ float red[];                  // [rpi][cvn][2 V]
+    const int cvn = C / V, rpi = 256 / cvn;
+    const int jc = threadIdx.x % cvn, jr = threadIdx.x / cvn;
+    const int bi = blockIdx.y;
+    const int n0 = blockIdx.x * rows_per_block, n1 = min(N, n0 + rows_per_block);
+    float a0[V], a1[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) a0[i] = a1[i] = 0.f;
+    if (jr < rpi) {
+        const int c0 = jc * V;
+        float mean[V], rstd[V], wv[V], bv[V];
+        if (kBwd) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                mean[i] = stats_in[((size_t)bi * C + c0 + i) * 2];
+                rstd[i] = stats_in[((size_t)bi * C + c0 + i) * 2 + 1];
+                wv[i] = w ? w[c0 + i] : 1.f;
+                bv[i] = b ? b[c0 + i] : 0.f;
+            }
+        }
+        const T *xb = x + (size_t)bi * N * C + c0;
+        const T *db = kBwd ? dy + (size_t)bi * N * C + c0 : nullptr;
+        for (int n = n0 + jr; n < n1; n += rpi * kInRows) {
+            uint4 rv[kInRows], rg[kInRows];
+#pragma unroll
+            for (int u = 0; u < kInRows; ++u) {
+                const int nn = n + u * rpi;
+                if (nn < n1) {
+                    rv[u] = in_ldraw(xb + (size_t)nn * C);
+                    if (kBwd) rg[u] = in_ldraw(db + (size_t)nn * C);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kInRows; ++u) {
+                if (n + u * rpi < n1) {
+                    float v[V], g[V];
+                    in_unpack(rv[u], v);
+                    if (kBwd) in_unpack(rg[u], g);
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        if (!kBwd) {
+                            a0[i] += v[i];
+                            a1[i] = fmaf(v[i], v[i], a1[i]);
+                        } else {
+                            const float xh = (v[i] - mean[i]) * rstd[i];
+                            const float dz = g[i] * in_dact(fmaf(xh, wv[i], bv[i]), act, slope);
+                            a0[i] += dz;
+                            a1[i] = fmaf(dz, xh, a1[i]);
+                        }
+                    }
+                }
+            }
+        }
+        float *mine = red + (size_t)threadIdx.x * 2 * V;
+#pragma unroll
+        for (int i = 0; i < V; ++i) mine[i] = a0[i], mine[V + i] = a1[i];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * C; o += blockDim.x) {
+        const int c = o >> 1, k = o & 1;
+        const int qc = c / V, qi = c - qc * V;
+        float sum = 0.f;
+        for (int r = 0; r < rpi; ++r) sum += red[((size_t)r * cvn + qc) * 2 * V + k * V + qi];
+        atomicAdd(out + ((size_t)bi * C + c) * 2 + k, sum);
+    }
+}
+
+template <typename T, bool kBwd>
+__global__ void __launch_bounds__(256) in_apply_rows_kernel(const T *__restrict__ x, const T *__restrict__ dy,
+                                                            const float *__restrict__ stats,
+                                                            const float *__restrict__ sums, const float *__restrict__ w,
+                                                            const float *__restrict__ b, T *__restrict__ out, int N,
+                                                            int C, int rows_per_block, int act, float slope, float invN) {
+    constexpr int V = InV<T>::N;
+    const int cvn = C / V, rpi = 256 / cvn;
+    const int jc = threadIdx.x % cvn, jr = threadIdx.x / cvn;
+    if (jr >= rpi) return;
+    const int bi = blockIdx.y;
+    const int n0 = blockIdx.x * rows_per_block, n1 = min(N, n0 + rows_per_block);
+    const int c0 = jc * V;
+    float mean[V], rstd[V], wv[V], bv[V], k1[V], k2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float2 st = __ldg(reinterpret_cast<const float2 *>(stats) + (size_t)bi * C + c0 + i);
+        mean[i] = st.x, rstd[i] = st.y;
+        wv[i] = w ? __ldg(w + c0 + i) : 1.f;
+        bv[i] = b ? __ldg(b + c0 + i) : 0.f;
+        if (kBwd) {
+            const float2 sm = __ldg(reinterpret_cast<const float2 *>(sums) + (size_t)bi * C + c0 + i);
+            k1[i] = sm.x * invN, k2[i] = sm.y * invN;
+        }
+    }
+    const T *xb = x + (size_t)bi * N * C + c0;
+    const T *db = kBwd ? dy + (size_t)bi * N * C + c0 : nullptr;
+    T *ob = out + (size_t)bi * N * C + c0;
+    for (int n = n0 + jr; n < n1; n += rpi * kInRows) {
+        uint4 rv[kInRows], rg[kInRows];
+#pragma unroll
+        for (int u = 0; u < kInRows; ++u) {
+            const int nn = n + u * rpi;
+            if (nn < n1) {
+                rv[u] = in_ldraw(xb + (size_t)nn * C);
+                if (kBwd) rg[u] = in_ldraw(db + (size_t)nn * C);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kInRows; ++u) {
+            const int nn = n + u * rpi;
+            if (nn < n1) {
+                float v[V], g[V], o[V];
+                in_unpack(rv[u], v);
+                if (kBwd) in_unpack(rg[u], g);
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const float xh = (v[i] - mean[i]) * rstd[i];
+                    const float z = fmaf(xh, wv[i], bv[i]);
+                    if (!kBwd) {
+                        o[i] = in_act(z, act, slope);
+                    } else {
+                        const float dz = g[i] * in_dact(z, act, slope);
+                        o[i] = rstd[i] * wv[i] * (dz - k1[i] - xh * k2[i]);
+                    }
+                }
+                in_stv(ob + (size_t)nn * C, o);
+            }
+        }
+    }
+}
+
 static void in_grid(int N, int C, int Bn, dim3 &gs, int &rpb) {
     const int gx = (C + 127) / 128;
     int by = (148 * 8 + gx * Bn - 1) / (gx * Bn);
@@ -203,6 +376,27 @@ static cudaError_t instnorm_run(const T *x, const T *dy, const float *w, const f
     const size_t per = (size_t)N * (C / 4);
     const dim3 ga((unsigned)std::min<size_t>((per + 255) / 256, 148 * 16), Bn);
     const float invN = 1.f / (float)N;
+    constexpr int V = InV<T>::N;
+    if (C % V == 0 && C / V <= 256 && !getenv("MLAGG_INSTNORM_OLD")) {
+        // ~8 CTAs per SM in total; a CTA's rows are a multiple of what its threads cover per iteration
+        const int rpi = 256 / (C / V);
+        int chunks = std::max(1, (148 * 8 + Bn - 1) / Bn);
+        int rpb = (N + chunks - 1) / chunks;
+        rpb = std::max(rpi * kInRows, (rpb + rpi * kInRows - 1) / (rpi * kInRows) * (rpi * kInRows));
+        chunks = (N + rpb - 1) / rpb;
+        const dim3 g2(chunks, Bn);
+        const size_t smem = (size_t)256 * 2 * V * sizeof(float);
+        if (!bwd) {
+            in_sums_rows_kernel<T, false><<<g2, 256, smem, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, N, C, rpb, act, slope);
+            in_finalize_kernel<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, Bn * C, invN, eps);
+            in_apply_rows_kernel<T, false><<<g2, 256, 0, st>>>(x, nullptr, stats, nullptr, w, b, out, N, C, rpb, act, slope, invN);
+        } else {
+            in_sums_rows_kernel<T, true><<<g2, 256, smem, st>>>(x, dy, stats, w, b, sums, N, C, rpb, act, slope);
+            if (dw || db) in_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dw, db, Bn, C);
+            in_apply_rows_kernel<T, true><<<g2, 256, 0, st>>>(x, dy, stats, sums, w, b, out, N, C, rpb, act, slope, invN);
+        }
+        return cudaGetLastError();
+    }
     if (!bwd) {
         in_sums_kernel<T, false><<<gs, 32 * kInWarps, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, N, C, rpb, act, slope);
         in_finalize_kernel<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, Bn * C, invN, eps);

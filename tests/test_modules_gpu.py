@@ -276,7 +276,7 @@ def test_causal_conv1d_matches_oracle(K, silu, L):
         assert rel_err(a.grad.cpu(), r_.grad) < 1e-5
 
 
-@pytest.mark.parametrize("C", [48, 96, 192, 768])
+@pytest.mark.parametrize("C", [48, 96, 192, 768, 8, 20, 144, 336, 384, 720, 1024])
 @pytest.mark.parametrize("din,dout,tol", [(torch.float32, torch.float32, 1e-5), (torch.bfloat16, torch.bfloat16, TOL16),
                                           (torch.float32, torch.bfloat16, TOL16)])
 def test_layer_norm_tokens_matches_torch(C, din, dout, tol):
