@@ -355,6 +355,27 @@ int mlagg_residual_scale(const void *x, const void *y, const float *scale, void 
  * gradients of both, without intermediate zero-filled tensors. */
 int mlagg_copy_rows(const void *src, long long ld_src, long long bs_src, void *dst, long long ld_dst, long long bs_dst,
                     int batch, long long rows, int cols, int dtype, mlagg_stream_t stream);
+/* dst[b][r][0:cols] += src[b][r][0:cols], same addressing: the LePE gradient joins the v half of the kv gradient
+ * (reference :716 / :759 `x + lepe(v)`, v = kv[..., C:]) without autograd's zero-filled kv-sized tensor and full-size add.
+ * cols, strides and bases must allow 8-byte vectors, cols * elsize <= 4096; MLAGG_ERR_UNSUPPORTED otherwise. */
+int mlagg_add_rows(const void *src, long long ld_src, long long bs_src, void *dst, long long ld_dst, long long bs_dst,
+                   int batch, long long rows, int cols, int dtype, mlagg_stream_t stream);
+
+/* ---- statistics of DC_and_CE_loss for one deep-supervision scale (reference training/loss/compound_losses.py
+ * DC_and_CE_loss, dice.py:58-112 MemoryEfficientSoftDiceLoss with softmax, robust_ce_loss.py; called once per scale by
+ * nnUNetTrainer.py:833-863).  logits (batch, K, npix) addressed through element strides (sb, sc, sn): NCHW heads have
+ * sc = npix, sn = 1, channels_last heads sc = 1, sn = K; dtype fp32 / bf16.  target (batch, npix) class indices, float
+ * (tdtype 0, rounded) or int64 (tdtype 1).  K <= 32.
+ *   fwd: stats (batch, K, 3) fp32 += (sum_n p_k [t = k], sum_n p_k, sum_n [t = k]) with p = softmax over K;
+ *        ce (1) += sum over every pixel of -log p_t.  Both accumulated into: zero-fill them.
+ *   bwd: dlogits (strides of logits) = d loss / d logits given g_stats (batch, K, 3) (the count component is ignored) and
+ *        g_ce (1) = d loss / d ce, softmax recomputed.
+ * The dice formula itself stays host-side arithmetic on `stats` (batch-dice, the DDP gather, the smoothing terms). */
+int mlagg_dice_ce_stats_fwd(const void *logits, const void *target, float *stats, float *ce, int batch, long long npix,
+                            int K, long long sb, long long sc, long long sn, int dtype, int tdtype, mlagg_stream_t stream);
+int mlagg_dice_ce_stats_bwd(const void *logits, const void *target, const float *g_stats, const float *g_ce, void *dlogits,
+                            int batch, long long npix, int K, long long sb, long long sc, long long sn, int dtype, int tdtype,
+                            mlagg_stream_t stream);
 /* y[pix][c] += bias[c] IN PLACE on a channels_last / tokens-major (pixels, C) map of n elements, C % 4 == 0 -- the bias of
  * the conv stages' nn.Conv2d / nn.ConvTranspose2d (nnUNetTrainer_MLAgg_2D_dt_MS.py:230-366, MambaSkip.py:712-716), which torch
  * adds after the cuDNN call with an un-vectorised broadcast kernel and differentiates with its generic reduction; the

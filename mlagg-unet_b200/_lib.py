@@ -26,6 +26,9 @@ SIGNATURES = {
     "mlagg_msmm_scan_bwd": (c_i, [c_p] * 17 + [c_i] * 5 + [c_p, c_i, c_p]),
     "mlagg_residual_scale": (c_i, [c_p] * 4 + [c_ll, c_ll, c_i, c_p]),
     "mlagg_copy_rows": (c_i, [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_i, c_ll, c_i, c_i, c_p]),
+    "mlagg_dice_ce_stats_fwd": (c_i, [c_p] * 4 + [c_i, c_ll, c_i, c_ll, c_ll, c_ll, c_i, c_i, c_p]),
+    "mlagg_dice_ce_stats_bwd": (c_i, [c_p] * 5 + [c_i, c_ll, c_i, c_ll, c_ll, c_ll, c_i, c_i, c_p]),
+    "mlagg_add_rows": (c_i, [c_p, c_ll, c_ll, c_p, c_ll, c_ll, c_i, c_ll, c_i, c_i, c_p]),
     "mlagg_bias_add_cl": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_p]),
     "mlagg_silu_gate_fwd": (c_i, [c_p] * 3 + [c_ll, c_i, c_p]),
     "mlagg_silu_gate_bwd": (c_i, [c_p] * 5 + [c_ll, c_i, c_p]),

@@ -13,8 +13,11 @@ cudaError_t scan_fwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStr
 cudaError_t scan_bwd_dispatch(const ScanParams &p, bool bulk, int warps, cudaStream_t st);
 cudaError_t residual_scale_dispatch(const void *x, const void *y, const float *s, void *out, long long n,
                                     long long per_sample, int dtype, cudaStream_t st);
+cudaError_t dice_ce_dispatch(const void *logits, const void *target, void *dlogits, float *stats, float *ce,
+                             const float *g_stats, const float *g_ce, long long sb, long long sc, long long sn,
+                             long long npix, int K, int Bn, int dtype, int tdtype, bool bwd, cudaStream_t st);
 cudaError_t copy_rows_dispatch(const void *src, long long ld_s, long long bs_s, void *dst, long long ld_d, long long bs_d,
-                               int batch, long long rows, int cols, int dtype, cudaStream_t st);
+                               int batch, long long rows, int cols, int dtype, bool add, cudaStream_t st);
 cudaError_t bias_add_cl_dispatch(void *y, const float *b, long long n, int C, int dtype, cudaStream_t st);
 cudaError_t silu_gate_dispatch(const void *t, const void *z, const void *g, void *o1, void *o2, long long n, int dtype,
                                bool bwd, cudaStream_t st);
@@ -509,8 +512,57 @@ extern "C" int mlagg_copy_rows(const void *src, long long ld_src, long long bs_s
     if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
     const size_t es = dtype == MLAGG_F32 ? 4 : 2;
     if (!aligned(src, es) || !aligned(dst, es)) return MLAGG_ERR_ALIGN;
-    cudaError_t e = copy_rows_dispatch(src, ld_src, bs_src, dst, ld_dst, bs_dst, batch, rows, cols, dtype,
+    cudaError_t e = copy_rows_dispatch(src, ld_src, bs_src, dst, ld_dst, bs_dst, batch, rows, cols, dtype, false,
                                        (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+// ------------------------------------------------------------------------------------------------ dice + CE statistics
+static int loss_check(const void *logits, const void *target, int batch, long long npix, int K, long long sb, long long sc,
+                      long long sn, int dtype, int tdtype) {
+    if (!logits || !target) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || npix <= 0 || K < 1 || sb < 0 || sc < 1 || sn < 1) return MLAGG_ERR_BAD_SHAPE;
+    if (K > 32) return MLAGG_ERR_UNSUPPORTED;
+    if ((dtype != MLAGG_F32 && dtype != MLAGG_BF16) || (tdtype != 0 && tdtype != 1)) return MLAGG_ERR_UNSUPPORTED;
+    return MLAGG_OK;
+}
+
+extern "C" int mlagg_dice_ce_stats_fwd(const void *logits, const void *target, float *stats, float *ce, int batch,
+                                       long long npix, int K, long long sb, long long sc, long long sn, int dtype,
+                                       int tdtype, mlagg_stream_t stream) {
+    int rc = loss_check(logits, target, batch, npix, K, sb, sc, sn, dtype, tdtype);
+    if (rc) return rc;
+    if (!stats || !ce) return MLAGG_ERR_NULL;
+    cudaError_t e = dice_ce_dispatch(logits, target, nullptr, stats, ce, nullptr, nullptr, sb, sc, sn, npix, K, batch, dtype,
+                                     tdtype, false, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_dice_ce_stats_bwd(const void *logits, const void *target, const float *g_stats, const float *g_ce,
+                                       void *dlogits, int batch, long long npix, int K, long long sb, long long sc,
+                                       long long sn, int dtype, int tdtype, mlagg_stream_t stream) {
+    int rc = loss_check(logits, target, batch, npix, K, sb, sc, sn, dtype, tdtype);
+    if (rc) return rc;
+    if (!g_stats || !g_ce || !dlogits) return MLAGG_ERR_NULL;
+    cudaError_t e = dice_ce_dispatch(logits, target, dlogits, nullptr, nullptr, g_stats, g_ce, sb, sc, sn, npix, K, batch, dtype,
+                                     tdtype, true, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_add_rows(const void *src, long long ld_src, long long bs_src, void *dst, long long ld_dst,
+                              long long bs_dst, int batch, long long rows, int cols, int dtype, mlagg_stream_t stream) {
+    if (!src || !dst) return MLAGG_ERR_NULL;
+    if (batch <= 0 || batch > 65535 || rows <= 0 || cols <= 0 || ld_src < cols || ld_dst < cols || bs_src < 0 || bs_dst < 0)
+        return MLAGG_ERR_BAD_SHAPE;
+    if (dtype != MLAGG_F32 && dtype != MLAGG_BF16) return MLAGG_ERR_UNSUPPORTED;
+    const size_t es = dtype == MLAGG_F32 ? 4 : 2;
+    // 8-byte vectors at least, at most 256 of them per row (the caller falls back to its own add otherwise)
+    const int v = (int)(8 / es);
+    if (cols % v || ld_src % v || ld_dst % v || bs_src % v || bs_dst % v || !aligned(src, 8) || !aligned(dst, 8)) return MLAGG_ERR_ALIGN;
+    if (cols / v > 512) return MLAGG_ERR_UNSUPPORTED;
+    cudaError_t e = copy_rows_dispatch(src, ld_src, bs_src, dst, ld_dst, bs_dst, batch, rows, cols, dtype, true,
+                                       (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported) return MLAGG_ERR_UNSUPPORTED;
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

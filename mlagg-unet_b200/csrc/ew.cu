@@ -7,6 +7,9 @@
 // per attention module for the scalar lambda and its gradient.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mlagg {
@@ -160,6 +163,55 @@ __global__ void __launch_bounds__(256) copy_rows_kernel(const T *__restrict__ sr
     }
 }
 
+// the same for <= 256 vectors per row without per-element index arithmetic: a thread owns one column vector and walks
+// down its CTA's rows four at a time (all loads first); ADD: dst += src (gradient joins of channel slices)
+template <typename T, int V, bool ADD>
+__global__ void __launch_bounds__(256) rows_walk_kernel(const T *__restrict__ src, long long ld_s, long long bs_s,
+                                                        T *__restrict__ dst, long long ld_d, long long bs_d,
+                                                        long long rows, int colsv, long long rows_per_block) {
+    using Vec = typename std::conditional<sizeof(T) * V == 16, uint4, uint2>::type;
+    const int rpi = 256 / colsv;
+    const int jc = threadIdx.x % colsv, jr = threadIdx.x / colsv;
+    if (jr >= rpi) return;
+    const T *sb = src + (long long)blockIdx.y * bs_s + jc * V;
+    T *db = dst + (long long)blockIdx.y * bs_d + jc * V;
+    const long long r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (long long r = r0 + jr; r < r1; r += 4 * rpi) {
+        Vec a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long rr = r + u * rpi;
+            if (rr < r1) {
+                a[u] = __ldg(reinterpret_cast<const Vec *>(sb + rr * ld_s));
+                if (ADD) b[u] = *reinterpret_cast<const Vec *>(db + rr * ld_d);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long rr = r + u * rpi;
+            if (rr < r1) {
+                if (ADD) {
+                    constexpr int NW = sizeof(Vec) / 4;
+                    uint32_t *pa = reinterpret_cast<uint32_t *>(&a[u]);
+                    const uint32_t *pb = reinterpret_cast<const uint32_t *>(&b[u]);
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        if (sizeof(T) == 4) {
+                            pa[k] = __float_as_uint(__uint_as_float(pa[k]) + __uint_as_float(pb[k]));
+                        } else {
+                            const float lo = __uint_as_float(pa[k] << 16) + __uint_as_float(pb[k] << 16);
+                            const float hi = __uint_as_float(pa[k] & 0xffff0000u) + __uint_as_float(pb[k] & 0xffff0000u);
+                            const __nv_bfloat162 o = __floats2bfloat162_rn(lo, hi);
+                            pa[k] = *reinterpret_cast<const uint32_t *>(&o);
+                        }
+                    }
+                }
+                *reinterpret_cast<Vec *>(db + rr * ld_d) = a[u];
+            }
+        }
+    }
+}
+
 static int ew_blocks(long long n4) {
     long long b = (n4 + 255) / 256;
     const long long cap = 148LL * 16;
@@ -184,7 +236,7 @@ cudaError_t bias_add_cl_dispatch(void *y, const float *b, long long n, int C, in
 }
 
 cudaError_t copy_rows_dispatch(const void *src, long long ld_s, long long bs_s, void *dst, long long ld_d, long long bs_d,
-                               int batch, long long rows, int cols, int dtype, cudaStream_t st) {
+                               int batch, long long rows, int cols, int dtype, bool add, cudaStream_t st) {
     const size_t es = dtype == 0 ? 4 : 2;
     // widest vector (in elements) that divides cols and every stride and keeps both bases aligned
     int V = (int)(16 / es);
@@ -195,6 +247,28 @@ cudaError_t copy_rows_dispatch(const void *src, long long ld_s, long long bs_s, 
     };
     while (V > 1 && !ok(V)) V /= 2;
     if (V * es < 8) V = 1;                                   // 8- and 16-byte vectors, else scalar
+    if (V * es >= 8 && cols / V <= 256) {
+        const int rpi = 256 / (cols / V);
+        long long chunks = std::max<long long>(1, (148LL * 8 + batch - 1) / batch);
+        long long rpb = (rows + chunks - 1) / chunks;
+        rpb = std::max<long long>(4LL * rpi, (rpb + 4LL * rpi - 1) / (4LL * rpi) * (4LL * rpi));
+        const dim3 g2((unsigned)((rows + rpb - 1) / rpb), (unsigned)batch);
+#define MLAGG_WALK(T_, V_) \
+    do { \
+        if (add) rows_walk_kernel<T_, V_, true><<<g2, 256, 0, st>>>(static_cast<const T_ *>(src), ld_s, bs_s, static_cast<T_ *>(dst), ld_d, bs_d, rows, cols / V_, rpb); \
+        else rows_walk_kernel<T_, V_, false><<<g2, 256, 0, st>>>(static_cast<const T_ *>(src), ld_s, bs_s, static_cast<T_ *>(dst), ld_d, bs_d, rows, cols / V_, rpb); \
+    } while (0)
+        if (dtype == 0) {
+            if (V == 4) MLAGG_WALK(float, 4);
+            else MLAGG_WALK(float, 2);
+        } else {
+            if (V == 8) MLAGG_WALK(__nv_bfloat16, 8);
+            else MLAGG_WALK(__nv_bfloat16, 4);
+        }
+#undef MLAGG_WALK
+        return cudaGetLastError();
+    }
+    if (add) return cudaErrorNotSupported;
     const long long n = rows * (cols / V);
     long long bx = (n + 255) / 256;
     const long long cap = (148LL * 16 + batch - 1) / batch;

@@ -103,28 +103,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
            (1ull << 46) | (2ull << 61);
 }
 
-// exact-GELU pieces for the epilogues.  erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far inside the bf16
-// output rounding) on ONE exponential shared with the density: libm's erff + expf cost ~40 instructions per element, which
-// made the 8 epilogue warps -- not HBM -- the limiter of the fused fc2-data-gradient GEMM (87 us at stage 0).
-__device__ __forceinline__ void gelu_parts(float x, float &cdf, float &pdf_x) {
-    const float e = ex2_approx(-0.72134752044f * x * x);              // exp(-x^2 / 2)
-    const float z = fabsf(x) * 0.70710678118654752f;
-    const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
-    const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-    const float erfa = fmaf(-poly, e, 1.f);                            // erf(|x| / sqrt 2)
-    cdf = 0.5f * (1.f + copysignf(erfa, x));
-    pdf_x = x * e * 0.3989422804014327f;
-}
-__device__ __forceinline__ float gelu_f(float x) {
-    float cdf, px;
-    gelu_parts(x, cdf, px);
-    return x * cdf;
-}
-__device__ __forceinline__ float gelu_grad(float x) {
-    float cdf, px;
-    gelu_parts(x, cdf, px);
-    return cdf + px;
-}
+// gelu_parts / gelu_f / gelu_grad: common.cuh (Abramowitz-Stegun erf on one exponential shared with the density)
 __device__ __forceinline__ float silu_grad(float x) {
     const float s = 1.f / (1.f + __expf(-x));
     return s * (1.f + x * (1.f - s));

@@ -789,6 +789,21 @@ def copy_rows_(dst, src):
     return dst
 
 
+def add_rows_(dst, src):
+    """dst[...] += src[...] for two equally shaped row-strided views (C ABI: mlagg_add_rows); Tensor.add_ for anything the
+    kernel does not address."""
+    a, b = _rows3(dst), _rows3(src)
+    if (a is not None and b is not None and dst.is_cuda and dst.dtype in _DT and src.dtype == dst.dtype and a[1:4] == b[1:4]
+            and dst.numel() > 0 and min(a[4], b[4]) >= a[3]):
+        with torch.cuda.device(dst.device), _lib.timed("add_rows"):
+            rc = _lib.lib().mlagg_add_rows(src.data_ptr(), b[4], b[5], dst.data_ptr(), a[4], a[5], a[1], a[2], a[3],
+                                           _DT[dst.dtype], _lib.stream_ptr())
+        if rc == 0:
+            return dst
+    dst.add_(src)
+    return dst
+
+
 class SplitLast(torch.autograd.Function):
     """x[..., :k], x[..., k:] as views; the backward assembles ONE gradient with two strided row copies.  Autograd's own
     slice gradients are two zero-filled full-size tensors (contiguous in the logical NCHW order, which then drags every
@@ -922,7 +937,7 @@ class SplitKV(torch.autograd.Function):
         if g_v is not None:
             if not g_kv.is_contiguous():
                 g_kv = g_kv.contiguous()
-            g_kv[..., ctx.C:].add_(g_v.to(g_kv.dtype))
+            add_rows_(g_kv[..., ctx.C:], g_v.to(g_kv.dtype))
         return g_kv, None
 
 

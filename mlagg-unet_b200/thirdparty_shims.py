@@ -112,6 +112,10 @@ class _Conv(nn.Module):
             self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=(k - 1) // 2, bias=False)
 
     def forward(self, x):
+        if x.dim() == 4 and x.shape[1] == 1 and x.is_cuda and x.is_contiguous():
+            # a one-channel map has ambiguous strides and torch reads them as NCHW: cuDNN then returns an NCHW result that
+            # every channels_last consumer (and the gradient coming back) has to re-lay out.  Spell the NHWC strides out.
+            x = x.as_strided(x.size(), (x.stride(0), 1, x.stride(2), x.stride(3)))
         return self.conv(x)
 
 

@@ -65,6 +65,65 @@ def soft_dice_loss(logits, target, batch_dice=True, do_bg=False, smooth=1e-5, dd
     return -((2 * inter + smooth) / torch.clip(sgt + spred + smooth, 1e-8)).mean()
 
 
+class _DiceCEStats(torch.autograd.Function):
+    """C ABI: mlagg_dice_ce_stats_fwd / _bwd (csrc/loss.cu).  (logits (B, K, H, W), target (B, 1, H, W)) ->
+    (stats (B, K, 3) = per-image, per-class (sum p [t = k], sum p, sum [t = k]) with p = softmax(logits), ce_sum (1))."""
+
+    @staticmethod
+    def addressable(logits, target):
+        if not (logits.is_cuda and logits.dim() == 4 and logits.dtype in (torch.float32, torch.bfloat16)
+                and target.dtype in (torch.float32, torch.int64) and logits.shape[1] <= 32 and target.shape[1] == 1):
+            return False
+        W = logits.shape[3]
+        return logits.stride(2) == W * logits.stride(3) and logits.stride(3) >= 1 and logits.stride(1) >= 1
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        from . import _lib
+        Bn, K, H, W = logits.shape
+        tgt = target.contiguous()
+        stats, ce = _lib.zeros((Bn, K, 3), logits.device), _lib.zeros(1, logits.device)
+        dt, tdt = (0 if logits.dtype == torch.float32 else 1), (0 if tgt.dtype == torch.float32 else 1)
+        with torch.cuda.device(logits.device), _lib.timed("dice_ce_fwd"):
+            rc = _lib.lib().mlagg_dice_ce_stats_fwd(logits.data_ptr(), tgt.data_ptr(), stats.data_ptr(), ce.data_ptr(), Bn,
+                                                    H * W, K, logits.stride(0), logits.stride(1), logits.stride(3), dt, tdt,
+                                                    _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dice_ce_stats_fwd")
+        ctx.save_for_backward(logits, tgt)
+        ctx.meta = (dt, tdt)
+        return stats, ce
+
+    @staticmethod
+    def backward(ctx, g_stats, g_ce):
+        from . import _lib
+        logits, tgt = ctx.saved_tensors
+        dt, tdt = ctx.meta
+        Bn, K, H, W = logits.shape
+        g_stats = torch.zeros(Bn, K, 3, device=logits.device) if g_stats is None else g_stats.float().contiguous()
+        g_ce = torch.zeros(1, device=logits.device) if g_ce is None else g_ce.float().contiguous()
+        dl = torch.empty_strided(logits.shape, logits.stride(), device=logits.device, dtype=logits.dtype)
+        with torch.cuda.device(logits.device), _lib.timed("dice_ce_bwd"):
+            rc = _lib.lib().mlagg_dice_ce_stats_bwd(logits.data_ptr(), tgt.data_ptr(), g_stats.data_ptr(), g_ce.data_ptr(),
+                                                    dl.data_ptr(), Bn, H * W, K, logits.stride(0), logits.stride(1),
+                                                    logits.stride(3), dt, tdt, _lib.stream_ptr())
+        _lib.check(rc, "mlagg_dice_ce_stats_bwd")
+        return dl, None
+
+
+def dice_ce_loss_fused(logits, target, batch_dice=True, do_bg=False, smooth=1e-5, ddp=False):
+    """cross_entropy + soft_dice_loss of one scale from one pass over the logits (same formulas as the two functions it
+    replaces; the dice arithmetic runs on the (B, K, 3) statistics)."""
+    stats, ce = _DiceCEStats.apply(logits, target)
+    k0 = 0 if do_bg else 1
+    inter, spred, sgt = stats[:, k0:, 0], stats[:, k0:, 1], stats[:, k0:, 2].detach()
+    if ddp and batch_dice:
+        inter, spred, sgt = _AllGatherGrad.apply(torch.stack((inter, spred, sgt), dim=0)).sum(0).unbind(0)
+    if batch_dice:
+        inter, spred, sgt = inter.sum(0), spred.sum(0), sgt.sum(0)
+    dice = -((2 * inter + smooth) / torch.clip(sgt + spred + smooth, 1e-8)).mean()
+    return ce[0] / (logits.shape[0] * logits.shape[2] * logits.shape[3]) + dice
+
+
 class DeepSupervisionDiceCE(nn.Module):
     """DeepSupervisionWrapper(DC_and_CE_loss(weight_ce=1, weight_dice=1)) with weights 1/2**i, normalised."""
 
@@ -75,6 +134,8 @@ class DeepSupervisionDiceCE(nn.Module):
         self.batch_dice, self.ddp = batch_dice, ddp
 
     def one(self, logits, target):
+        if _DiceCEStats.addressable(logits, target) and os.environ.get("MLAGG_LOSS_TORCH") is None:
+            return dice_ce_loss_fused(logits, target, self.batch_dice, False, 1e-5, self.ddp)
         ce = F.cross_entropy(logits.float(), target[:, 0].long())
         return ce + soft_dice_loss(logits, target, self.batch_dice, False, 1e-5, self.ddp)
 

@@ -71,3 +71,45 @@ def test_validation_step_counts_match_a_direct_evaluation():
         assert abs(out["fn_hard"][c - 1] - int(((pred != c) & (gt == c)).sum())) <= 8
     assert out["tp_hard"].sum() + out["fn_hard"].sum() == int((gt > 0).sum())          # every foreground pixel counted once
     assert np.isfinite(out["loss"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,cl,dtype,tdtype,batch_dice", [(14, True, torch.bfloat16, torch.float32, True),
+                                                          (14, False, torch.float32, torch.float32, True),
+                                                          (5, True, torch.float32, torch.int64, False),
+                                                          (3, False, torch.bfloat16, torch.int64, True),
+                                                          (20, True, torch.float32, torch.float32, True)])
+def test_fused_dice_ce_matches_the_torch_formulation(K, cl, dtype, tdtype, batch_dice):
+    """mlagg_dice_ce_stats_* + the dice arithmetic on the statistics against cross_entropy + soft_dice_loss (the
+    restatement of the reference's DC_and_CE_loss) evaluated in float64 on the same logits: value and d loss / d logits,
+    NCHW and channels_last heads, float and int64 labels, ragged pixel count."""
+    from mlagg_unet_b200.trainer import DeepSupervisionDiceCE, soft_dice_loss
+    torch.manual_seed(K)
+    Bn, H, W = 3, 37, 29
+    logits = (2 * torch.randn(Bn, K, H, W, device="cuda")).to(dtype)
+    if cl:
+        logits = logits.contiguous(memory_format=torch.channels_last)
+    target = torch.randint(0, K, (Bn, 1, H, W), device="cuda").to(tdtype)
+    lf = DeepSupervisionDiceCE(1, batch_dice=batch_dice)
+    x = logits.clone().requires_grad_()
+    loss = lf.one(x, target)
+    loss.backward()
+    xd = logits.double().requires_grad_()
+    ref = torch.nn.functional.cross_entropy(xd, target[:, 0].long()) + soft_dice_loss_f64(xd, target, batch_dice)
+    ref.backward()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert x.grad.dtype == dtype and x.grad.stride() == x.stride()
+    err = float((x.grad.double() - xd.grad).abs().max() / xd.grad.abs().max())
+    assert err < tol, err
+
+
+def soft_dice_loss_f64(x64, target, batch_dice, smooth=1e-5):
+    """trainer.soft_dice_loss without its .float() casts"""
+    x = torch.softmax(x64, dim=1)
+    onehot = torch.zeros_like(x, dtype=torch.bool).scatter_(1, target.long(), 1)
+    x, onehot = x[:, 1:], onehot[:, 1:]
+    inter, spred, sgt = (x * onehot).sum((2, 3)), x.sum((2, 3)), onehot.sum((2, 3)).double()
+    if batch_dice:
+        inter, spred, sgt = inter.sum(0), spred.sum(0), sgt.sum(0)
+    return -((2 * inter + smooth) / torch.clip(sgt + spred + smooth, 1e-8)).mean()
