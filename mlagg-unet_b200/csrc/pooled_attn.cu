@@ -519,6 +519,45 @@ constexpr int kMmaKS = 40;                                       // K row stride
 constexpr int kMmaVS = kMmaPmax + 8;                             // V^T row stride (bf16)
 constexpr int kMmaTok = 256;                                     // query tokens per block (4 warps x 4 tiles of 16)
 
+// K (both maps) / V of one (image, head pair) into the shared-memory layouts the mma kernels read, from 16-byte loads
+// (one per 8 channels of a pooled token).  The first version moved one bf16 per loop iteration with three index
+// divisions each: 37 % of the forward kernel's instructions and 40 % of its stall samples sat in front of the first
+// barrier (ncu source page, stage-1 shape).  The caller zero-fills the arrays (padding rows / channels) and
+// synchronises before this runs.  sK [2][kMmaPmax][kMmaKS]; optional sKt [2][HD][kMmaVS], sV [kMmaPmax][2 HD + 8],
+// sVt [2 HD][kMmaVS].
+template <int HD>
+__device__ __forceinline__ void pooled_stage_kv(const __nv_bfloat16 *kb, const __nv_bfloat16 *vb, long long ldkv, int P,
+                                                __nv_bfloat16 *sK, __nv_bfloat16 *sKt, __nv_bfloat16 *sV,
+                                                __nv_bfloat16 *sVt) {
+    constexpr int VPR = 2 * HD / 8, VR = 2 * HD + 8;
+    for (int i = threadIdx.x; i < P * VPR; i += blockDim.x) {
+        const int pp = i / VPR, v = i - pp * VPR;
+        const uint4 kq = __ldg(reinterpret_cast<const uint4 *>(kb + (long long)pp * ldkv + v * 8));
+        const uint4 vq = __ldg(reinterpret_cast<const uint4 *>(vb + (long long)pp * ldkv + v * 8));
+        const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = v * 8 + 2 * e;
+            const int j = c >= HD ? 1 : 0, d = c - j * HD;
+            *reinterpret_cast<uint32_t *>(sK + ((size_t)j * kMmaPmax + pp) * kMmaKS + d) = kw[e];
+            if (sKt) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&kw[e]);
+                sKt[((size_t)j * HD + d) * kMmaVS + pp] = h2.x;
+                sKt[((size_t)j * HD + d + 1) * kMmaVS + pp] = h2.y;
+            }
+            if (sVt) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&vw[e]);
+                sVt[(size_t)c * kMmaVS + pp] = h2.x;
+                sVt[(size_t)(c + 1) * kMmaVS + pp] = h2.y;
+            }
+        }
+        if (sV) *reinterpret_cast<uint4 *>(sV + (size_t)pp * VR + v * 8) = vq;
+    }
+}
+__device__ __forceinline__ void smem_zero16(void *ptr, int bytes) {
+    for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(static_cast<unsigned char *>(ptr) + i) = make_uint4(0, 0, 0, 0);
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAttnParams p) {
     constexpr int NC = 2 * HD / 8;      // n8 tiles over the 2hd output channels
@@ -529,15 +568,10 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
     {   // stage K (both maps, zero-padded to 32 channels / 112 rows) and V^T
         const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
         const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
-        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
-        for (int i = threadIdx.x; i < 2 * kMmaPmax * kMmaKS; i += blockDim.x) {
-            const int j = i / (kMmaPmax * kMmaKS), pp = (i / kMmaKS) % kMmaPmax, d = i % kMmaKS;
-            sK[j][pp][d] = (pp < p.P && d < HD) ? kb[(long long)pp * p.ldkv + j * HD + d] : z;
-        }
-        for (int i = threadIdx.x; i < 2 * HD * kMmaVS; i += blockDim.x) {
-            const int pp = i / (2 * HD), c = i % (2 * HD);         // coalesced read of a V row, transposed store
-            if (pp < kMmaVS) sVt[c][pp] = pp < p.P ? vb[(long long)pp * p.ldkv + c] : z;
-        }
+        smem_zero16(sK, sizeof(sK));
+        smem_zero16(sVt, sizeof(sVt));
+        __syncthreads();
+        pooled_stage_kv<HD>(kb, vb, p.ldkv, p.P, &sK[0][0][0], nullptr, nullptr, &sVt[0][0]);
     }
     __syncthreads();
     const float qs = p.scale2 * kLog2e;
@@ -682,19 +716,9 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
     {
         const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
         const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
-        const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
-        for (int i = threadIdx.x; i < 2 * kMmaPmax * kMmaKS; i += blockDim.x) {
-            const int j = i / (kMmaPmax * kMmaKS), pp = (i / kMmaKS) % kMmaPmax, d = i % kMmaKS;
-            sK[j][pp][d] = (pp < p.P && d < HD) ? kb[(long long)pp * p.ldkv + j * HD + d] : z;
-        }
-        for (int i = threadIdx.x; i < kMmaVS * 2 * HD; i += blockDim.x) {
-            const int pp = i / (2 * HD), c = i % (2 * HD);                // c = j * HD + d
-            sKt[c / HD][c % HD][pp] = pp < p.P ? kb[(long long)pp * p.ldkv + c] : z;
-        }
-        for (int i = threadIdx.x; i < kMmaPmax * kMmaVR; i += blockDim.x) {
-            const int pp = i / kMmaVR, c = i % kMmaVR;
-            sV[pp][c] = (pp < p.P && c < 2 * HD) ? vb[(long long)pp * p.ldkv + c] : z;
-        }
+        smem_zero16(bq_smem, (int)(sizeof(__nv_bfloat16) * (2 * kMmaPmax * kMmaKS + 2 * HD * kMmaVS + kMmaPmax * kMmaVR)));
+        __syncthreads();
+        pooled_stage_kv<HD>(kb, vb, p.ldkv, p.P, &sK[0][0][0], &sKt[0][0][0], &sV[0][0], nullptr);
         for (int i = threadIdx.x; i < 2 * HD + 1; i += blockDim.x) red[i] = 0.f;
     }
     __syncthreads();
@@ -1070,6 +1094,11 @@ static bool pooled_use_mma() {
     return !(e && e[0] == '0');
 }
 
+// the vectorised K / V staging of the mma kernels: 16-byte aligned rows and head-pair offsets
+static bool pooled_kv16(const PooledAttnParams &p) {
+    return p.ldkv % 8 == 0 && reinterpret_cast<uintptr_t>(p.kp) % 16 == 0 && reinterpret_cast<uintptr_t>(p.vp) % 16 == 0;
+}
+
 template <typename T, int HD>
 static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStream_t st) {
     const size_t smem = (size_t)p.P * HD * 16;   // kI (P x hd float2) + V (P x 2hd float)
@@ -1077,14 +1106,14 @@ static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStrea
     constexpr bool kMmaHd = HD == 24 || HD == 32;
     constexpr int MH = kMmaHd ? HD : 24;   // instantiate the tensor-core kernels only for the head sizes they support
     if (which == 0 && std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
-        p.ldq % 2 == 0 && p.ldkv % 2 == 0 && p.ldo % 2 == 0) {
+        p.ldq % 2 == 0 && pooled_kv16(p) && p.ldo % 2 == 0) {
         pooled_attn_fwd_mma_kernel<MH><<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, 0, st>>>(p);
     } else if (which == 0) {
         auto k = pooled_attn_fwd_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);
     } else if (which == 1 && std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
-               p.ldq % 2 == 0 && p.ldkv % 2 == 0 && p.lddo % 2 == 0 && p.lddq % 2 == 0) {
+               p.ldq % 2 == 0 && pooled_kv16(p) && p.lddo % 2 == 0 && p.lddq % 2 == 0) {
         const size_t bq = sizeof(__nv_bfloat16) * (2 * kMmaPmax * kMmaKS + 2 * MH * kMmaVS + kMmaPmax * (2 * MH + 8));
         auto k = pooled_attn_bwd_q_mma_kernel<MH>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bq)) != cudaSuccess) return e;

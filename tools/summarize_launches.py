@@ -17,7 +17,7 @@ OURS = ("scan_", "dwconv", "causal_conv1d", "pooled_attn", "local_attn", "layern
         "in_param", "colsum", "avgpool", "linattn", "walk_", "residual_scale", "silu_gate", "diff_lambda", "copy_rows", "bias_add_cl")
 ours = {k: v for k, v in agg.items() if ("mlagg::" in k or any(t in k for t in OURS)) and "at::native" not in k}
 GROUPS = (("tcgen05 projection GEMMs", ("gemm_tc",)), ("selective scan", ("scan_fwd", "scan_bwd")),
-          ("walk pack / unpack", ("walk_",)), ("depthwise conv", ("dwconv", "dw3x3_")), ("local attention", ("local_attn",)),
+          ("walk pack / unpack", ("walk_pack", "walk_unpack")), ("depthwise conv", ("dwconv", "dw3x3_")), ("local attention", ("local_attn",)),
           ("pooled attention", ("pooled_attn", "avgpool")), ("LayerNorm", ("layernorm_",)),
           ("instance norm", ("in_sums", "in_apply", "in_finalize", "in_param")),
           ("element-wise seams / copies", ("residual_scale", "silu_gate", "diff_lambda", "copy_rows", "bias_add_cl", "colsum")))
