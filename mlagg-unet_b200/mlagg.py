@@ -304,8 +304,18 @@ def _conv1x1_cl(conv, x):
     wgt = conv.weight.view(conv.weight.shape[0], conv.weight.shape[1])
     if isinstance(conv, nn.ConvTranspose2d):
         wgt = wgt.t()                                        # (in, out, 1, 1) -> (out, in)
-    y = _Linear.apply(t.reshape(Bn, H * W, C), wgt, conv.bias)
-    return y.reshape(Bn, H, W, -1).permute(0, 3, 1, 2)
+    Co, bias = wgt.shape[0], conv.bias
+    if Co % 8 != 0 and C % 8 == 0 and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16:
+        # the 14-class segmentation heads: an output width that is not a multiple of 8 sends all three GEMMs to cuBLAS'
+        # 2-byte-aligned kernels (0.9 ms per step for the two largest heads, tools/glue_sites.py / the launch list).
+        # Zero rows up to the next multiple of 8 keep them on the tcgen05 kernels; the logits are the first Co columns of
+        # the padded result (a strided view the loss kernel reads in place), and autograd's slice / pad gradients put
+        # zeros into the padding on the way back.
+        pad = 8 - Co % 8
+        wgt = F.pad(wgt, (0, 0, 0, pad))
+        bias = None if bias is None else F.pad(bias, (0, pad))
+    y = _Linear.apply(t.reshape(Bn, H * W, C), wgt, bias)
+    return y.reshape(Bn, H, W, -1)[..., :Co].permute(0, 3, 1, 2)
 
 
 class MedNeXtBlock(nn.Module):

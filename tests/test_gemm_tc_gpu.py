@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 SHAPES = [  # (M, N, K)
     (300, 96, 96), (25600, 96, 96), (1000, 48, 48), (6400, 192, 96), (4000, 1536, 768), (4000, 768, 1536),
-    (3400, 144, 96), (777, 96, 48), (129, 256, 128), (128, 8, 8), (5000, 384, 192), (1111, 200, 72), (4100, 768, 384),
+    (3400, 144, 96), (777, 96, 48), (129, 256, 128), (128, 8, 8), (20480, 16, 48), (1600, 16, 384), (5000, 384, 192), (1111, 200, 72), (4100, 768, 384),
 ]
 
 

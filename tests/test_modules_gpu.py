@@ -800,3 +800,28 @@ def test_pad_top_left_add_and_split_kv_gradients():
     want = w1.clone()
     want[..., 8:] += w2
     assert torch.allclose(kv.grad, want)
+
+
+def test_segmentation_head_padded_to_the_tensor_core_gemm():
+    """OutBlock with 14 classes under bf16 autocast: the width is padded to 16 so that all three GEMMs take the tcgen05
+    kernels; logits, input gradient, weight and bias gradients against the fp64 1x1 convolution."""
+    from mlagg_unet_b200 import _lib
+    from mlagg_unet_b200.mlagg import OutBlock
+    torch.manual_seed(3)
+    head = OutBlock(48, 14, "2d").cuda()
+    x = torch.randn(2, 48, 20, 24, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    g = torch.randn(2, 14, 20, 24, device="cuda")
+    n0 = _lib.STATS["launches"]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = head(x)
+    assert y.shape == (2, 14, 20, 24) and y.dtype == torch.bfloat16
+    (y.float() * g).sum().backward()
+    assert _lib.STATS["launches"] - n0 >= 3                       # forward, data gradient, weight gradient: own kernels
+    xd = x.detach().double().requires_grad_()
+    wd, bd = head.conv_out.weight.detach().double().requires_grad_(), head.conv_out.bias.detach().double().requires_grad_()
+    yd = torch.nn.functional.conv_transpose2d(xd, wd, bd)
+    (yd * g.double()).sum().backward()
+    assert rel_err(y.double(), yd) < TOL16
+    assert rel_err(x.grad.double(), xd.grad) < TOL16
+    assert rel_err(head.conv_out.weight.grad.double(), wd.grad) < TOL16
+    assert rel_err(head.conv_out.bias.grad.double(), bd.grad) < TOL16
