@@ -136,6 +136,66 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- side stream for work nothing downstream waits for.  The weight-gradient GEMMs feed only the optimizer, are mostly
+# latency-bound (small grids, split-K atomics, 10 - 20 us each, 120 per step) and read the same dy as the data-gradient GEMM
+# that follows them: they run on a second stream next to the main backward chain and are joined before the gradients
+# are gathered.  Operands are kept referenced until the join so that the caching allocator cannot hand their memory to a
+# later main-stream kernel while the side kernel still reads it.  Only active inside a trainer step (side_begin()).
+_SIDE = {"stream": None, "on": False, "keep": [], "pending": 0}
+
+
+def side_begin(device):
+    import os
+    import torch
+    if os.environ.get("MLAGG_SIDE_STREAM", "1") == "0":
+        _SIDE["on"] = False
+        return
+    if _SIDE["stream"] is None or _SIDE["stream"].device != torch.device(device):
+        _SIDE["stream"] = torch.cuda.Stream(device=device)
+    _SIDE["on"] = True
+
+
+class side_launch:
+    """with side_launch(t1, t2, ...) as on_side: ...   -- the body runs on the side stream behind everything already queued
+    on the current stream; the tensors stay referenced until side_join().  A no-op outside a trainer step."""
+
+    def __init__(self, *tensors):
+        self.tensors = tensors
+
+    def __enter__(self):
+        import torch
+        self.active = _SIDE["on"]
+        if not self.active:
+            return False
+        if _SIDE["pending"] >= 24:                 # bound the memory held for pending launches
+            side_join(final=False)
+        st = _SIDE["stream"]
+        ev = torch.cuda.Event()
+        ev.record()
+        st.wait_event(ev)
+        _SIDE["keep"].append(self.tensors)
+        _SIDE["pending"] += 1
+        self.ctx = torch.cuda.stream(st)
+        self.ctx.__enter__()
+        return True
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.ctx.__exit__(*exc)
+        return False
+
+
+def side_join(final=True):
+    """the current stream waits for everything launched through side_launch"""
+    import torch
+    if _SIDE["pending"]:
+        torch.cuda.current_stream().wait_stream(_SIDE["stream"])
+        _SIDE["keep"].clear()
+        _SIDE["pending"] = 0
+    if final:
+        _SIDE["on"] = False
+
+
 # ---- per-step arena of zero-initialised fp32 scratch.  Every backward wrapper needs small zero-filled accumulators (bias /
 # weight gradients, column sums, scalar sums): ~350 separate fill kernels per train step.  While a trainer step is running
 # they are carved out of one buffer that is cleared by a single memset at the start of the step; outside a step (tests,

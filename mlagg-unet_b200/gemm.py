@@ -57,10 +57,11 @@ def linear_bwd_weight(dy2, x2, want_db=False):
     """dw (N, K) fp32 = dy2.T @ x2 [, db (N,) fp32 = dy2.sum(0) from the same pass]; dy2 (M, N), x2 (M, K)"""
     M, N = dy2.shape
     K = x2.shape[1]
-    dw = _lib.zeros((N, K), dy2.device)
-    db = _lib.zeros((N,), dy2.device) if want_db else None
-    with torch.cuda.device(dy2.device), _lib.timed("linear_bwd_weight"):
-        rc = _lib.lib().mlagg_linear_bwd_weight(dy2.data_ptr(), dy2.stride(0), x2.data_ptr(), x2.stride(0), dw.data_ptr(),
-                                                dw.stride(0), _lib.ptr(db), M, N, K, _lib.stream_ptr())
+    with _lib.side_launch(dy2, x2):          # inside a trainer step: next to the main backward chain (see _lib)
+        dw = _lib.zeros((N, K), dy2.device)
+        db = _lib.zeros((N,), dy2.device) if want_db else None
+        with torch.cuda.device(dy2.device), _lib.timed("linear_bwd_weight"):
+            rc = _lib.lib().mlagg_linear_bwd_weight(dy2.data_ptr(), dy2.stride(0), x2.data_ptr(), x2.stride(0), dw.data_ptr(),
+                                                    dw.stride(0), _lib.ptr(db), M, N, K, _lib.stream_ptr())
     _lib.check(rc, "mlagg_linear_bwd_weight")
     return (dw, db) if want_db else dw

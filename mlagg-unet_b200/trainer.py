@@ -429,7 +429,10 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         self._drop_grads()
         from . import _lib, ops
         l = self._forward_loss(data, target)
+        if self.device.type == "cuda":
+            _lib.side_begin(self.device)      # weight-gradient GEMMs run next to the main backward chain
         l.backward()
+        _lib.side_join()
         ops.release_cast_cache()
         self._reduce_clip_step()
         _lib.arena_end()
@@ -498,7 +501,9 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             st["douts"] = [torch.zeros_like(o) for o in outs]
             self._drop_grads()
             with torch.cuda.graph(gb, pool=ga.pool()):
+                _lib.side_begin(self.device)
                 torch.autograd.backward(outs, grad_tensors=st["douts"])
+                _lib.side_join()
             ops.release_cast_cache()
             _lib.arena_end()
             st["grads"] = [p.grad for p in self._params]     # written in place by every replay of graph B
