@@ -743,13 +743,51 @@ def _conv_bias_cl(y, bias):
     return y if bias is None else y + bias.to(y.dtype).view(1, -1, 1, 1)
 
 
+class _Conv2dSplit(torch.autograd.Function):
+    """Bias-free cuDNN conv2d (the conv stages, off the named path) whose backward is issued as TWO library calls: the
+    input gradient on the current stream -- the rest of the backward pass waits for it -- and the weight gradient, which
+    only the optimizer reads, on the side stream of `_lib.side_launch` next to it."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding, dilation, groups):
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        xc, wc = x.to(cdt), _cast_param(weight, cdt)
+        with torch.autocast("cuda", enabled=False):
+            y = torch.nn.functional.conv2d(xc, wc, None, stride, padding, dilation, groups)
+        ctx.save_for_backward(xc, wc)
+        ctx.conf = (tuple(stride), tuple(padding), tuple(dilation), groups, x.dtype, weight.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, wc = ctx.saved_tensors
+        stride, padding, dilation, groups, xdt, wdt = ctx.conf
+        dy = dy.to(wc.dtype)
+        bwd = torch.ops.aten.convolution_backward
+        dx = dw = None
+        if ctx.needs_input_grad[1]:
+            with _lib.side_launch(dy, xc, wc):
+                dw = bwd(dy, xc, wc, None, stride, padding, dilation, False, [0, 0], groups, [False, True, False])[1].to(wdt)
+        if ctx.needs_input_grad[0]:
+            dx = bwd(dy, xc, wc, None, stride, padding, dilation, False, [0, 0], groups, [True, False, False])[0].to(xdt)
+        return dx, dw, None, None, None, None
+
+
+def conv2d_split(conv, x):
+    """conv(x) without its bias for an nn.Conv2d with zero padding; plain `_conv_forward` when gradients are off / on CPU"""
+    if (x.is_cuda and torch.is_grad_enabled() and conv.padding_mode == "zeros" and not isinstance(conv.padding, str)
+            and (x.requires_grad or conv.weight.requires_grad)):
+        return _Conv2dSplit.apply(x, conv.weight, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return conv._conv_forward(x, conv.weight, None)
+
+
 class Conv2dCL(torch.nn.Conv2d):
     """nn.Conv2d (same parameters / state_dict) whose bias is applied by `_conv_bias_cl` after a bias-free cuDNN call."""
 
     def forward(self, x):
         if self.bias is None or not x.is_cuda:
             return super().forward(x)
-        return _conv_bias_cl(self._conv_forward(x, self.weight, None), self.bias)
+        return _conv_bias_cl(conv2d_split(self, x), self.bias)
 
 
 class ConvTranspose2dCL(torch.nn.ConvTranspose2d):
