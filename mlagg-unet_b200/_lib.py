@@ -141,7 +141,11 @@ def stream_ptr():
 # that follows them: they run on a second stream next to the main backward chain and are joined before the gradients
 # are gathered.  Operands are kept referenced until the join so that the caching allocator cannot hand their memory to a
 # later main-stream kernel while the side kernel still reads it.  Only active inside a trainer step (side_begin()).
-_SIDE = {"stream": None, "on": False, "keep": [], "pending": 0}
+# A tensor produced on the side stream must not travel through autograd (AccumulateGrad may clone it, a view's backward
+# may copy it -- kernels on the main stream that the engine would not order behind the side stream): the autograd
+# wrappers hand such gradients over with stash_grad(parameter, tensor), return None to autograd, and the trainer attaches
+# them to .grad after side_join().
+_SIDE = {"stream": None, "on": False, "keep": [], "pending": 0, "grads": []}
 
 
 def side_begin(device):
@@ -183,6 +187,32 @@ class side_launch:
         if self.active:
             self.ctx.__exit__(*exc)
         return False
+
+
+def side_active():
+    return _SIDE["on"]
+
+
+def leaf_param(t):
+    """the leaf Parameter a gradient for `t` ends up in, if `t` is one or a same-size dense view of one; else None"""
+    import torch
+    if t is None:
+        return None
+    base = t if t._base is None else t._base
+    if not (isinstance(base, torch.nn.Parameter) and base.is_leaf and base.requires_grad and base.numel() == t.numel()):
+        return None
+    if t is not base and not (t.is_contiguous() and (base.is_contiguous() or (base.dim() == 4 and base.shape[2] == base.shape[3] == 1))):
+        return None
+    return base
+
+
+def stash_grad(param, g):
+    _SIDE["grads"].append((param, g.view(param.shape) if g.shape != param.shape else g))
+
+
+def take_stashed_grads():
+    out, _SIDE["grads"] = _SIDE["grads"], []
+    return out
 
 
 def side_join(final=True):

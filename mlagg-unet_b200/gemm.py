@@ -53,11 +53,21 @@ def linear_bwd_data(dy2, w, aux=None, act=None, out_dtype=torch.bfloat16):
     return dx
 
 
-def linear_bwd_weight(dy2, x2, want_db=False):
-    """dw (N, K) fp32 = dy2.T @ x2 [, db (N,) fp32 = dy2.sum(0) from the same pass]; dy2 (M, N), x2 (M, K)"""
+class _Here:
+    def __enter__(self):
+        return False
+
+    def __exit__(self, *exc):
+        return False
+
+
+def linear_bwd_weight(dy2, x2, want_db=False, side=False):
+    """dw (N, K) fp32 = dy2.T @ x2 [, db (N,) fp32 = dy2.sum(0) from the same pass]; dy2 (M, N), x2 (M, K).
+    side=True (only with _lib.side_active(), and only when the results go to _lib.stash_grad, never through autograd):
+    the launch goes to the side stream, next to the main backward chain."""
     M, N = dy2.shape
     K = x2.shape[1]
-    with _lib.side_launch(dy2, x2):          # inside a trainer step: next to the main backward chain (see _lib)
+    with (_lib.side_launch(dy2, x2) if side else _Here()):
         dw = _lib.zeros((N, K), dy2.device)
         db = _lib.zeros((N,), dy2.device) if want_db else None
         with torch.cuda.device(dy2.device), _lib.timed("linear_bwd_weight"):

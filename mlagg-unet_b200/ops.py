@@ -454,6 +454,8 @@ class _Linear(torch.autograd.Function):
                     y = (torch.mm(x2, wc.t()) if bc is None else torch.addmm(bc, x2, wc.t())).view(*xc.shape[:-1], wc.shape[0])
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        # parameters whose gradients may be produced on the side stream and handed to the trainer directly (_lib.stash_grad)
+        ctx.leaves = (_lib.leaf_param(weight), _lib.leaf_param(bias))
         return y
 
     @staticmethod
@@ -465,6 +467,19 @@ class _Linear(torch.autograd.Function):
         dy2 = _rows2d(dy2) if _rows2d(dy2) is not None else dy2.reshape(-1, Cout)
         x2 = _rows2d(xc) if _rows2d(xc) is not None else xc.reshape(-1, Cin)
         if ctx.tc and gemm.rows_ok(dy2) and gemm.rows_ok(x2):
+            wleaf, bleaf = ctx.leaves
+            if (_lib.side_active() and ctx.needs_input_grad[1] and wleaf is not None and wleaf.dtype == torch.float32
+                    and (bdt is None or (bleaf is not None and ctx.needs_input_grad[2] and bleaf.dtype == torch.float32))):
+                # weight (and bias) gradient on the side stream, handed to the trainer; the data gradient -- which the rest
+                # of the backward pass waits for -- on this stream, next to it
+                if bdt is None:
+                    _lib.stash_grad(wleaf, gemm.linear_bwd_weight(dy2, x2, side=True))
+                else:
+                    dw, db = gemm.linear_bwd_weight(dy2, x2, want_db=True, side=True)
+                    _lib.stash_grad(wleaf, dw)
+                    _lib.stash_grad(bleaf, db)
+                dx = gemm.linear_bwd_data(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
+                return dx, None, None
             dx = gemm.linear_bwd_data(dy2, wc).view(xc.shape).to(xdt) if ctx.needs_input_grad[0] else None
             if ctx.needs_input_grad[1] and bdt is not None and ctx.needs_input_grad[2]:
                 dw, db = gemm.linear_bwd_weight(dy2, x2, want_db=True)      # bias gradient from the same operand tiles
@@ -492,6 +507,7 @@ class _MlpFused(torch.autograd.Function):
         y, _ = gemm.linear_fwd(h, w2c, b2)
         ctx.save_for_backward(x2, pre, h, w1c, w2c)
         ctx.meta = (x.dtype, x.shape, w1.dtype, w2.dtype, None if b1 is None else b1.dtype, None if b2 is None else b2.dtype)
+        ctx.leaves = tuple(_lib.leaf_param(t) for t in (w1, b1, w2, b2))
         return y.view(*x.shape[:-1], w2c.shape[0])
 
     @staticmethod
@@ -503,10 +519,16 @@ class _MlpFused(torch.autograd.Function):
         if not gemm.rows_ok(dy2):
             dy2 = dy2.contiguous()
         need = ctx.needs_input_grad
+        l1, lb1, l2, lb2 = ctx.leaves
+        side = (_lib.side_active() and all(t is not None and t.dtype == torch.float32 for t in ctx.leaves) and all(need[1:]))
         dpre = gemm.linear_bwd_data(dy2, w2c, aux=pre, act="gelu")            # (dy W2) * gelu'(pre)
-        dw2, db2 = gemm.linear_bwd_weight(dy2, h, want_db=True)
+        dw2, db2 = gemm.linear_bwd_weight(dy2, h, want_db=True, side=side)
         dx = gemm.linear_bwd_data(dpre, w1c).view(xshape).to(xdt) if need[0] else None
-        dw1, db1 = gemm.linear_bwd_weight(dpre, x2, want_db=True)
+        dw1, db1 = gemm.linear_bwd_weight(dpre, x2, want_db=True, side=side)
+        if side:    # weight / bias gradients were produced on the side stream: handed to the trainer, not to autograd
+            for leaf, gten in ((l1, dw1), (lb1, db1), (l2, dw2), (lb2, db2)):
+                _lib.stash_grad(leaf, gten)
+            return dx, None, None, None, None
         return (dx, dw1.to(w1dt), None if b1dt is None else db1.to(b1dt), dw2.to(w2dt), None if b2dt is None else db2.to(b2dt))
 
 
@@ -756,6 +778,7 @@ class _Conv2dSplit(torch.autograd.Function):
             y = torch.nn.functional.conv2d(xc, wc, None, stride, padding, dilation, groups)
         ctx.save_for_backward(xc, wc)
         ctx.conf = (tuple(stride), tuple(padding), tuple(dilation), groups, x.dtype, weight.dtype)
+        ctx.wleaf = _lib.leaf_param(weight)
         return y
 
     @staticmethod
@@ -766,7 +789,11 @@ class _Conv2dSplit(torch.autograd.Function):
         bwd = torch.ops.aten.convolution_backward
         dx = dw = None
         if ctx.needs_input_grad[1]:
-            with _lib.side_launch(dy, xc, wc):
+            if _lib.side_active() and ctx.wleaf is not None and ctx.wleaf.dtype == wdt:
+                with _lib.side_launch(dy, xc, wc):   # handed to the trainer directly: never through autograd (see _lib)
+                    _lib.stash_grad(ctx.wleaf, bwd(dy, xc, wc, None, stride, padding, dilation, False, [0, 0], groups,
+                                                   [False, True, False])[1].to(wdt))
+            else:
                 dw = bwd(dy, xc, wc, None, stride, padding, dilation, False, [0, 0], groups, [False, True, False])[1].to(wdt)
         if ctx.needs_input_grad[0]:
             dx = bwd(dy, xc, wc, None, stride, padding, dilation, False, [0, 0], groups, [True, False, False])[0].to(xdt)

@@ -398,6 +398,14 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         for p in self._params:        # undefined .grad: autograd hands its gradient tensors over instead of adding
             p.grad = None
 
+    @staticmethod
+    def _attach_side_grads():
+        """join the side stream and attach the parameter gradients that were produced on it (`_lib.stash_grad`)"""
+        from . import _lib
+        _lib.side_join()
+        for p, g in _lib.take_stashed_grads():
+            p.grad = g if p.grad is None else p.grad + g
+
     def _reduce_clip_step(self, grads=None):
         """Gather the per-parameter gradients into ONE flat fp32 buffer (a handful of batched-copy launches), all-reduce
         it once over NCCL / NVSwitch (108 MB: well under a millisecond, no DDP hooks or buckets), clip the global norm to
@@ -432,7 +440,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         if self.device.type == "cuda":
             _lib.side_begin(self.device)      # weight-gradient GEMMs run next to the main backward chain
         l.backward()
-        _lib.side_join()
+        self._attach_side_grads()
         ops.release_cast_cache()
         self._reduce_clip_step()
         _lib.arena_end()
@@ -503,7 +511,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             with torch.cuda.graph(gb, pool=ga.pool()):
                 _lib.side_begin(self.device)
                 torch.autograd.backward(outs, grad_tensors=st["douts"])
-                _lib.side_join()
+                self._attach_side_grads()
             ops.release_cast_cache()
             _lib.arena_end()
             st["grads"] = [p.grad for p in self._params]     # written in place by every replay of graph B

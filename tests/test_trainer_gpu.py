@@ -113,3 +113,33 @@ def soft_dice_loss_f64(x64, target, batch_dice, smooth=1e-5):
     if batch_dice:
         inter, spred, sgt = inter.sum(0), spred.sum(0), sgt.sum(0)
     return -((2 * inter + smooth) / torch.clip(sgt + spred + smooth, 1e-8)).mean()
+
+
+def test_side_stream_gradients_equal_the_single_stream_step(monkeypatch):
+    """Weight gradients produced on the side stream (tcgen05 dW GEMMs, cuDNN wgrad) and attached by the trainer give the
+    same training trajectory as the single-stream step (MLAGG_SIDE_STREAM=0): losses and parameters over four steps,
+    three eager and one graph replay, stochastic depth off.  (Float atomics reorder sums between runs: tolerance, not
+    equality.)"""
+    from mlagg_unet_b200.thirdparty_shims import DropPath
+    from mlagg_unet_b200.trainer import SyntheticPlan, nnUNetTrainer_MLAgg_2D_dt_MS
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MLAGG_SIDE_STREAM", mode)
+        torch.manual_seed(0)
+        tr = nnUNetTrainer_MLAgg_2D_dt_MS(SyntheticPlan(patch_size=(128, 128), batch_size=2, num_classes=14)).initialize()
+        for m in tr.network.modules():
+            if isinstance(m, DropPath):
+                m.drop_prob = 0.0
+        batch = tr.synthetic_batch(2, seed=1)
+        losses = [float(tr.train_step(batch)["loss"]) for _ in range(5)]
+        res[mode] = (losses, [p.detach().clone() for p in tr.network.parameters()])
+        assert tr._graph is not None
+    (l1, p1), (l0, p0) = res["1"], res["0"]
+    assert max(abs(a - b) for a, b in zip(l1, l0)) < 2e-3, (l1, l0)
+    # AdamW moves every element by ~lr per step whatever the gradient's size: compare with the total movement
+    num = sum(float((a - b).pow(2).sum()) for a, b in zip(p1, p0)) ** 0.5
+    tr0 = nnUNetTrainer_MLAgg_2D_dt_MS(SyntheticPlan(patch_size=(128, 128), batch_size=2, num_classes=14))
+    torch.manual_seed(0)
+    tr0.initialize()
+    den = sum(float((a - b.detach()).pow(2).sum()) for a, b in zip(p0, tr0.network.parameters())) ** 0.5
+    assert num < 0.05 * den, (num, den)
