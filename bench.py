@@ -273,7 +273,7 @@ def main():
                 # profiles/mufu_bench_r01.txt) puts the exponential floor above the HBM floor -- report both
                 "xu_floor": {"exp_per_launch": a.batch_per_gpu * D * N * Lcat * (2 if dom == "scan_bwd" else 1),
                              "floor_ms": a.batch_per_gpu * D * N * Lcat * (2 if dom == "scan_bwd" else 1)
-                                         / (16.0 * 148 * (clocks or {}).get("sm_mhz", 1965.0) * 1e6) * 1e3 if clocks else None,
+                                         / (16.0 * 148 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) * 1e3,
                              "note": "backward recomputes a_t from the 16-step checkpoints: 1 exponential per update "
                                      "in the recompute sweep, reused by the adjoint sweep; counted 2x with the "
                                      "softplus / sigmoid helpers"},
