@@ -525,11 +525,11 @@ constexpr int kMmaTok = 256;                                     // query tokens
 // barrier (ncu source page, stage-1 shape).  The caller zero-fills the arrays (padding rows / channels) and
 // synchronises before this runs.  sK [2][kMmaPmax][kMmaKS]; optional sKt [2][HD][kMmaVS], sV [kMmaPmax][2 HD + 8],
 // sVt [2 HD][kMmaVS].
-template <int HD>
+template <int HD, int PM>
 __device__ __forceinline__ void pooled_stage_kv(const __nv_bfloat16 *kb, const __nv_bfloat16 *vb, long long ldkv, int P,
                                                 __nv_bfloat16 *sK, __nv_bfloat16 *sKt, __nv_bfloat16 *sV,
                                                 __nv_bfloat16 *sVt) {
-    constexpr int VPR = 2 * HD / 8, VR = 2 * HD + 8;
+    constexpr int VPR = 2 * HD / 8, VR = 2 * HD + 8, VS = PM + 8;   // PM: pooled-token capacity of the shared-memory arrays
     for (int i = threadIdx.x; i < P * VPR; i += blockDim.x) {
         const int pp = i / VPR, v = i - pp * VPR;
         const uint4 kq = __ldg(reinterpret_cast<const uint4 *>(kb + (long long)pp * ldkv + v * 8));
@@ -539,16 +539,16 @@ __device__ __forceinline__ void pooled_stage_kv(const __nv_bfloat16 *kb, const _
         for (int e = 0; e < 4; ++e) {
             const int c = v * 8 + 2 * e;
             const int j = c >= HD ? 1 : 0, d = c - j * HD;
-            *reinterpret_cast<uint32_t *>(sK + ((size_t)j * kMmaPmax + pp) * kMmaKS + d) = kw[e];
+            *reinterpret_cast<uint32_t *>(sK + ((size_t)j * PM + pp) * kMmaKS + d) = kw[e];
             if (sKt) {
                 const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&kw[e]);
-                sKt[((size_t)j * HD + d) * kMmaVS + pp] = h2.x;
-                sKt[((size_t)j * HD + d + 1) * kMmaVS + pp] = h2.y;
+                sKt[((size_t)j * HD + d) * VS + pp] = h2.x;
+                sKt[((size_t)j * HD + d + 1) * VS + pp] = h2.y;
             }
             if (sVt) {
                 const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162 *>(&vw[e]);
-                sVt[(size_t)c * kMmaVS + pp] = h2.x;
-                sVt[(size_t)(c + 1) * kMmaVS + pp] = h2.y;
+                sVt[(size_t)c * VS + pp] = h2.x;
+                sVt[(size_t)(c + 1) * VS + pp] = h2.y;
             }
         }
         if (sV) *reinterpret_cast<uint4 *>(sV + (size_t)pp * VR + v * 8) = vq;
@@ -558,20 +558,24 @@ __device__ __forceinline__ void smem_zero16(void *ptr, int bytes) {
     for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) *reinterpret_cast<uint4 *>(static_cast<unsigned char *>(ptr) + i) = make_uint4(0, 0, 0, 0);
 }
 
-template <int HD>
+// NT n8-tiles of pooled tokens per chunk, NCH chunks: (14, 1) covers P <= 112 in one piece (the shipped P = 100); (16, 2)
+// covers P <= 256 (config 5) with an online softmax across the two chunks -- the running maximum and sum of a row are
+// rescaled once per chunk, so the S tile in registers stays NT x 4 floats.
+template <int HD, int NT, int NCH>
 __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAttnParams p) {
     constexpr int NC = 2 * HD / 8;      // n8 tiles over the 2hd output channels
-    __shared__ __align__(16) __nv_bfloat16 sK[2][kMmaPmax][kMmaKS];
-    __shared__ __align__(16) __nv_bfloat16 sVt[2 * HD][kMmaVS];
+    constexpr int PM = NT * 8 * NCH, VS = PM + 8;
+    extern __shared__ __align__(16) unsigned char fw_smem[];
+    auto sK = reinterpret_cast<__nv_bfloat16 (*)[PM][kMmaKS]>(fw_smem);                                   // K_j[p][d]
+    auto sVt = reinterpret_cast<__nv_bfloat16 (*)[VS]>(fw_smem + sizeof(__nv_bfloat16) * 2 * PM * kMmaKS);   // V^T[c][p]
     const int b = blockIdx.z, m = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     {   // stage K (both maps, zero-padded to 32 channels / 112 rows) and V^T
         const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
         const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
-        smem_zero16(sK, sizeof(sK));
-        smem_zero16(sVt, sizeof(sVt));
+        smem_zero16(fw_smem, (int)(sizeof(__nv_bfloat16) * (2 * PM * kMmaKS + 2 * HD * VS)));
         __syncthreads();
-        pooled_stage_kv<HD>(kb, vb, p.ldkv, p.P, &sK[0][0][0], nullptr, nullptr, &sVt[0][0]);
+        pooled_stage_kv<HD, PM>(kb, vb, p.ldkv, p.P, &sK[0][0][0], nullptr, nullptr, &sVt[0][0]);
     }
     __syncthreads();
     const float qs = p.scale2 * kLog2e;
@@ -602,57 +606,74 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
                 qa[1][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 16 + 2 * t) : 0u;
                 qa[1][2 + r] = (HD > 24 && ok[r]) ? *reinterpret_cast<const uint32_t *>(qp + 24 + 2 * t) : 0u;
             }
-            // ---- S_j = Q_j K_j^T
-            float S[kMmaNT][4];
+            float mx0 = -INFINITY, mx1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 #pragma unroll
-            for (int nt = 0; nt < kMmaNT; ++nt) {
-                S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
-                const __nv_bfloat16 *kr = &sK[j][nt * 8 + g][2 * t];
-                mma_bf16_16816(S[nt], qa[0], *reinterpret_cast<const uint32_t *>(kr), *reinterpret_cast<const uint32_t *>(kr + 8));
-                mma_bf16_16816(S[nt], qa[1], *reinterpret_cast<const uint32_t *>(kr + 16), *reinterpret_cast<const uint32_t *>(kr + 24));
-            }
-            // ---- softmax over the P valid columns (exp2 domain)
-            float mx0 = -INFINITY, mx1 = -INFINITY;
+            for (int nc = 0; nc < NC; ++nc) O[j][nc][0] = O[j][nc][1] = O[j][nc][2] = O[j][nc][3] = 0.f;
 #pragma unroll
-            for (int nt = 0; nt < kMmaNT; ++nt) {
-                const int c0 = nt * 8 + 2 * t;
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int pbase = ch * NT * 8;
+                // ---- S_j = Q_j K_j^T (this chunk's pooled tokens)
+                float S[NT][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    S[nt][e] = (c0 + (e & 1) < p.P) ? S[nt][e] * qs : -INFINITY;
+                for (int nt = 0; nt < NT; ++nt) {
+                    S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+                    const __nv_bfloat16 *kr = &sK[j][pbase + nt * 8 + g][2 * t];
+                    mma_bf16_16816(S[nt], qa[0], *reinterpret_cast<const uint32_t *>(kr), *reinterpret_cast<const uint32_t *>(kr + 8));
+                    mma_bf16_16816(S[nt], qa[1], *reinterpret_cast<const uint32_t *>(kr + 16), *reinterpret_cast<const uint32_t *>(kr + 24));
                 }
-                mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
-                mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
-            }
-            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-            float l0 = 0.f, l1 = 0.f;
+                // ---- softmax over the P valid columns (exp2 domain); across chunks: running maximum, rescaled sum and O
+                float c0m = -INFINITY, c1m = -INFINITY;
 #pragma unroll
-            for (int nt = 0; nt < kMmaNT; ++nt) {
-                S[nt][0] = ex2_approx(S[nt][0] - mx0); S[nt][1] = ex2_approx(S[nt][1] - mx0);
-                S[nt][2] = ex2_approx(S[nt][2] - mx1); S[nt][3] = ex2_approx(S[nt][3] - mx1);
-                l0 += S[nt][0] + S[nt][1];
-                l1 += S[nt][2] + S[nt][3];
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int c0 = pbase + nt * 8 + 2 * t;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        S[nt][e] = (c0 + (e & 1) < p.P) ? S[nt][e] * qs : -INFINITY;
+                    }
+                    c0m = fmaxf(c0m, fmaxf(S[nt][0], S[nt][1]));
+                    c1m = fmaxf(c1m, fmaxf(S[nt][2], S[nt][3]));
+                }
+                c0m = fmaxf(c0m, __shfl_xor_sync(0xffffffffu, c0m, 1)); c0m = fmaxf(c0m, __shfl_xor_sync(0xffffffffu, c0m, 2));
+                c1m = fmaxf(c1m, __shfl_xor_sync(0xffffffffu, c1m, 1)); c1m = fmaxf(c1m, __shfl_xor_sync(0xffffffffu, c1m, 2));
+                if (NCH == 1) {
+                    mx0 = c0m, mx1 = c1m;
+                } else {
+                    const float n0 = fmaxf(mx0, c0m), n1 = fmaxf(mx1, c1m);      // finite from the first chunk on (P >= 1)
+                    const float s0 = ex2_approx(mx0 - n0), s1 = ex2_approx(mx1 - n1);
+                    mx0 = n0, mx1 = n1;
+                    l0 *= s0, l1 *= s1;
+#pragma unroll
+                    for (int nc = 0; nc < NC; ++nc) {
+                        O[j][nc][0] *= s0; O[j][nc][1] *= s0;
+                        O[j][nc][2] *= s1; O[j][nc][3] *= s1;
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    S[nt][0] = ex2_approx(S[nt][0] - mx0); S[nt][1] = ex2_approx(S[nt][1] - mx0);
+                    S[nt][2] = ex2_approx(S[nt][2] - mx1); S[nt][3] = ex2_approx(S[nt][3] - mx1);
+                    l0 += S[nt][0] + S[nt][1];
+                    l1 += S[nt][2] + S[nt][3];
+                }
+                // ---- O_j += P V  (probabilities: accumulator layout -> A operand)
+#pragma unroll
+                for (int kk = 0; kk < NT / 2; ++kk) {
+                    uint32_t pa[4];
+                    pa[0] = pack_bf16(S[2 * kk][0], S[2 * kk][1]);
+                    pa[1] = pack_bf16(S[2 * kk][2], S[2 * kk][3]);
+                    pa[2] = pack_bf16(S[2 * kk + 1][0], S[2 * kk + 1][1]);
+                    pa[3] = pack_bf16(S[2 * kk + 1][2], S[2 * kk + 1][3]);
+#pragma unroll
+                    for (int nc = 0; nc < NC; ++nc) {
+                        const __nv_bfloat16 *vr = &sVt[nc * 8 + g][pbase + kk * 16 + 2 * t];
+                        mma_bf16_16816(O[j][nc], pa, *reinterpret_cast<const uint32_t *>(vr), *reinterpret_cast<const uint32_t *>(vr + 8));
+                    }
+                }
             }
             l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
             l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
             lsev[j][0] = mx0 + lg2_approx(l0);
             lsev[j][1] = mx1 + lg2_approx(l1);
-            // ---- O_j = P V  (probabilities: accumulator layout -> A operand)
-#pragma unroll
-            for (int nc = 0; nc < NC; ++nc) O[j][nc][0] = O[j][nc][1] = O[j][nc][2] = O[j][nc][3] = 0.f;
-#pragma unroll
-            for (int kk = 0; kk < kMmaNT / 2; ++kk) {
-                uint32_t pa[4];
-                pa[0] = pack_bf16(S[2 * kk][0], S[2 * kk][1]);
-                pa[1] = pack_bf16(S[2 * kk][2], S[2 * kk][3]);
-                pa[2] = pack_bf16(S[2 * kk + 1][0], S[2 * kk + 1][1]);
-                pa[3] = pack_bf16(S[2 * kk + 1][2], S[2 * kk + 1][3]);
-#pragma unroll
-                for (int nc = 0; nc < NC; ++nc) {
-                    const __nv_bfloat16 *vr = &sVt[nc * 8 + g][kk * 16 + 2 * t];
-                    mma_bf16_16816(O[j][nc], pa, *reinterpret_cast<const uint32_t *>(vr), *reinterpret_cast<const uint32_t *>(vr + 8));
-                }
-            }
             const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
             for (int nc = 0; nc < NC; ++nc) {
@@ -703,22 +724,23 @@ __global__ void __launch_bounds__(128) pooled_attn_fwd_mma_kernel(const PooledAt
 // (B operands: V row-major, K_j row-major for S, K_j^T for dq).  Also writes dO / D_j for the dK, dV kernel and
 // accumulates d lambda and d subln_w.
 
-template <int HD>
+template <int HD, int NT, int NCH>
 __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const PooledAttnParams p) {
     constexpr int NC = 2 * HD / 8, KC = 2 * HD / 16, ND = HD / 8, kMmaVR = 2 * HD + 8;
+    constexpr int PM = NT * 8 * NCH, VS = PM + 8;       // pooled-token capacity: NCH chunks of NT n8-tiles (see the forward kernel)
     extern __shared__ __align__(16) unsigned char bq_smem[];
-    auto sK = reinterpret_cast<__nv_bfloat16 (*)[kMmaPmax][kMmaKS]>(bq_smem);                                  // K_j[p][d]
-    auto sKt = reinterpret_cast<__nv_bfloat16 (*)[HD][kMmaVS]>(bq_smem + sizeof(__nv_bfloat16) * 2 * kMmaPmax * kMmaKS);   // K_j^T[d][p]
-    auto sV = reinterpret_cast<__nv_bfloat16 (*)[kMmaVR]>(bq_smem + sizeof(__nv_bfloat16) * (2 * kMmaPmax * kMmaKS + 2 * HD * kMmaVS));   // V[p][c]
+    auto sK = reinterpret_cast<__nv_bfloat16 (*)[PM][kMmaKS]>(bq_smem);                                  // K_j[p][d]
+    auto sKt = reinterpret_cast<__nv_bfloat16 (*)[HD][VS]>(bq_smem + sizeof(__nv_bfloat16) * 2 * PM * kMmaKS);   // K_j^T[d][p]
+    auto sV = reinterpret_cast<__nv_bfloat16 (*)[kMmaVR]>(bq_smem + sizeof(__nv_bfloat16) * (2 * PM * kMmaKS + 2 * HD * VS));   // V[p][c]
     __shared__ float red[2 * HD + 1];
     const int b = blockIdx.z, m = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     {
         const __nv_bfloat16 *kb = static_cast<const __nv_bfloat16 *>(p.kp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
         const __nv_bfloat16 *vb = static_cast<const __nv_bfloat16 *>(p.vp) + (long long)b * p.P * p.ldkv + (long long)m * 2 * HD;
-        smem_zero16(bq_smem, (int)(sizeof(__nv_bfloat16) * (2 * kMmaPmax * kMmaKS + 2 * HD * kMmaVS + kMmaPmax * kMmaVR)));
+        smem_zero16(bq_smem, (int)(sizeof(__nv_bfloat16) * (2 * PM * kMmaKS + 2 * HD * VS + PM * kMmaVR)));
         __syncthreads();
-        pooled_stage_kv<HD>(kb, vb, p.ldkv, p.P, &sK[0][0][0], &sKt[0][0][0], &sV[0][0], nullptr);
+        pooled_stage_kv<HD, PM>(kb, vb, p.ldkv, p.P, &sK[0][0][0], &sKt[0][0][0], &sV[0][0], nullptr);
         for (int i = threadIdx.x; i < 2 * HD + 1; i += blockDim.x) red[i] = 0.f;
     }
     __syncthreads();
@@ -795,8 +817,9 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                 }
             }
         }
+        if constexpr (NCH == 1) {
         // ---- dab = dO V^T  (k = 48 channels = 3 steps; dO: accumulator layout -> A operand)
-        float dab[kMmaNT][4];
+        float dab[NT][4];
         {
             uint32_t da[KC][4];
 #pragma unroll
@@ -807,7 +830,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                 da[kc][3] = pack_bf16(dO[2 * kc + 1][2], dO[2 * kc + 1][3]);
             }
 #pragma unroll
-            for (int nt = 0; nt < kMmaNT; ++nt) {
+            for (int nt = 0; nt < NT; ++nt) {
                 dab[nt][0] = dab[nt][1] = dab[nt][2] = dab[nt][3] = 0.f;
 #pragma unroll
                 for (int kc = 0; kc < KC; ++kc) {
@@ -838,7 +861,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
             // tests/test_parity_shipped_gpu.py.)
             float Dj[2] = {0.f, 0.f};
 #pragma unroll
-            for (int nt = 0; nt < kMmaNT; ++nt) {
+            for (int nt = 0; nt < NT; ++nt) {
                 float S[4] = {0.f, 0.f, 0.f, 0.f};
                 const __nv_bfloat16 *kr = &sK[j][nt * 8 + g][2 * t];
                 mma_bf16_16816(S, qa[0], *reinterpret_cast<const uint32_t *>(kr), *reinterpret_cast<const uint32_t *>(kr + 8));
@@ -861,7 +884,7 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
 #pragma unroll
             for (int nd = 0; nd < ND; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.f;
 #pragma unroll
-            for (int kk = 0; kk < kMmaNT / 2; ++kk) {
+            for (int kk = 0; kk < NT / 2; ++kk) {
                 uint32_t sa[4];
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -898,6 +921,124 @@ __global__ void __launch_bounds__(128) pooled_attn_bwd_q_mma_kernel(const Pooled
                         pack_bf16(dq[nd][2 * r] * p.scale2, dq[nd][2 * r + 1] * p.scale2);
             }
         }
+        } else
+        {
+            // ---- NCH > 1: two sweeps over the chunks.  Sweep 1 forms D_j = sum_p A_j[p] dab[p] over ALL pooled tokens, sweep 2
+            // dS_j = A_j (dab - D_j) and dq_j += dS_j K_j; dab = dO V^T of a chunk is recomputed in each sweep (NT x 4 floats
+            // in registers instead of NT x NCH x 4), from the same bf16 operands both times.
+            uint32_t da[KC][4];
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+                da[kc][0] = pack_bf16(dO[2 * kc][0], dO[2 * kc][1]);
+                da[kc][1] = pack_bf16(dO[2 * kc][2], dO[2 * kc][3]);
+                da[kc][2] = pack_bf16(dO[2 * kc + 1][0], dO[2 * kc + 1][1]);
+                da[kc][3] = pack_bf16(dO[2 * kc + 1][2], dO[2 * kc + 1][3]);
+            }
+            uint32_t qa[2][2][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const __nv_bfloat16 *qp = static_cast<const __nv_bfloat16 *>(p.q) + ((long long)b * p.N + (ok[r] ? nr[r] : 0)) * p.ldq +
+                                              (long long)m * 2 * HD + j * HD;
+                    qa[j][0][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 2 * t) : 0u;
+                    qa[j][0][2 + r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 8 + 2 * t) : 0u;
+                    qa[j][1][r] = ok[r] ? *reinterpret_cast<const uint32_t *>(qp + 16 + 2 * t) : 0u;
+                    qa[j][1][2 + r] = (HD > 24 && ok[r]) ? *reinterpret_cast<const uint32_t *>(qp + 24 + 2 * t) : 0u;
+                }
+            auto dab_chunk = [&](int pbase, float (&dab)[NT][4]) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    dab[nt][0] = dab[nt][1] = dab[nt][2] = dab[nt][3] = 0.f;
+#pragma unroll
+                    for (int kc = 0; kc < KC; ++kc) {
+                        const __nv_bfloat16 *vr = &sV[pbase + nt * 8 + g][kc * 16 + 2 * t];
+                        mma_bf16_16816(dab[nt], da[kc], *reinterpret_cast<const uint32_t *>(vr), *reinterpret_cast<const uint32_t *>(vr + 8));
+                    }
+                }
+            };
+            auto probs = [&](int j, int pbase, int nt, float (&a)[4]) {       // A_j of one n8 tile from the saved lse
+                float S[4] = {0.f, 0.f, 0.f, 0.f};
+                const __nv_bfloat16 *kr = &sK[j][pbase + nt * 8 + g][2 * t];
+                mma_bf16_16816(S, qa[j][0], *reinterpret_cast<const uint32_t *>(kr), *reinterpret_cast<const uint32_t *>(kr + 8));
+                mma_bf16_16816(S, qa[j][1], *reinterpret_cast<const uint32_t *>(kr + 16), *reinterpret_cast<const uint32_t *>(kr + 24));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = e >> 1;
+                    const bool in = pbase + nt * 8 + 2 * t + (e & 1) < p.P;
+                    a[e] = in ? ex2_approx(S[e] * qs - (j == 0 ? lse0[r] : lse1[r])) : 0.f;
+                }
+            };
+            float Dj[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ++ch) {
+                float dab[NT][4];
+                dab_chunk(ch * NT * 8, dab);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        float a[4];
+                        probs(j, ch * NT * 8, nt, a);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) Dj[j][e >> 1] = fmaf(a[e], dab[nt][e], Dj[j][e >> 1]);
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    Dj[j][r] += __shfl_xor_sync(0xffffffffu, Dj[j][r], 1);
+                    Dj[j][r] += __shfl_xor_sync(0xffffffffu, Dj[j][r], 2);
+                    if (p.ws_D && ok[r] && t == 0) p.ws_D[(((long long)b * p.N + nr[r]) * p.h + m) * 2 + j] = Dj[j][r];
+                }
+            float dq[2][ND][4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int nd = 0; nd < ND; ++nd) dq[j][nd][0] = dq[j][nd][1] = dq[j][nd][2] = dq[j][nd][3] = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ++ch) {
+                float dab[NT][4];
+                dab_chunk(ch * NT * 8, dab);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float sgn = j == 0 ? 1.f : -lam;
+#pragma unroll
+                    for (int kk = 0; kk < NT / 2; ++kk) {
+                        uint32_t sa[4];
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int nt = 2 * kk + hf;
+                            float a[4], ds[4];
+                            probs(j, ch * NT * 8, nt, a);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) ds[e] = sgn * a[e] * (dab[nt][e] - Dj[j][e >> 1]);
+                            sa[2 * hf] = pack_bf16(ds[0], ds[1]);
+                            sa[2 * hf + 1] = pack_bf16(ds[2], ds[3]);
+                        }
+#pragma unroll
+                        for (int nd = 0; nd < ND; ++nd) {
+                            const __nv_bfloat16 *kt = &sKt[j][nd * 8 + g][ch * NT * 8 + kk * 16 + 2 * t];
+                            mma_bf16_16816(dq[j][nd], sa, *reinterpret_cast<const uint32_t *>(kt), *reinterpret_cast<const uint32_t *>(kt + 8));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (!ok[r]) continue;
+                    __nv_bfloat16 *dqp = static_cast<__nv_bfloat16 *>(p.dq) + ((long long)b * p.N + nr[r]) * p.lddq +
+                                         (long long)m * 2 * HD + j * HD;
+#pragma unroll
+                    for (int nd = 0; nd < ND; ++nd)
+                        *reinterpret_cast<uint32_t *>(dqp + nd * 8 + 2 * t) =
+                            pack_bf16(dq[j][nd][2 * r] * p.scale2, dq[j][nd][2 * r + 1] * p.scale2);
+                }
+        }
+
     }
     // ---- d subln_w (column sums over the block's tokens) and d lambda
 #pragma unroll
@@ -937,11 +1078,12 @@ __global__ void __launch_bounds__(224) pooled_attn_bwd_kv_mma_kernel(const Poole
     __shared__ __align__(16) __nv_bfloat16 sG[kKvChunk][kMmaVR];         // dO[tok][c]
     __shared__ __align__(16) __nv_bfloat16 sGt[2 * HD][kKvTS];           // dO^T[c][tok]
     __shared__ float sl[kKvChunk][4];                                    // lse0, lse1, D0, D1
-    const int b = blockIdx.z, m = blockIdx.y;
+    // blockIdx.y = (chunk of 112 pooled tokens) * h + head pair: P > 112 (config 5: 256) takes several CTAs per slab
+    const int b = blockIdx.z, m = blockIdx.y % p.h, p0 = (blockIdx.y / p.h) * kMmaPmax;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int prow[2] = {warp * 16 + g, warp * 16 + g + 8};
+    const int prow[2] = {p0 + warp * 16 + g, p0 + warp * 16 + g + 8};
     const bool pok[2] = {prow[0] < p.P, prow[1] < p.P};
-    const bool warp_on = warp * 16 < p.P;
+    const bool warp_on = p0 + warp * 16 < p.P;
     // ---- A operands: K_j rows (k = 32 channels, 24..31 zero) and V rows (k = 48 channels) of this warp's pooled tokens
     uint32_t ka[2][2][4], va[KC][4];
     {
@@ -1105,26 +1247,36 @@ static cudaError_t pooled_launch(const PooledAttnParams &p, int which, cudaStrea
     cudaError_t e;
     constexpr bool kMmaHd = HD == 24 || HD == 32;
     constexpr int MH = kMmaHd ? HD : 24;   // instantiate the tensor-core kernels only for the head sizes they support
-    if (which == 0 && std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
-        p.ldq % 2 == 0 && pooled_kv16(p) && p.ldo % 2 == 0) {
-        pooled_attn_fwd_mma_kernel<MH><<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, 0, st>>>(p);
+    constexpr int kBigNT = 16, kBigNCH = 2;                 // P <= 256 in two chunks of 128
+    const bool mma_ok = std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kBigNT * 8 * kBigNCH && pooled_use_mma() &&
+                        p.ldq % 2 == 0 && pooled_kv16(p);
+    const bool big = p.P > kMmaPmax;
+    auto fw_bytes = [](int pm) { return sizeof(__nv_bfloat16) * (size_t)(2 * pm * kMmaKS + 2 * MH * (pm + 8)); };
+    auto bq_bytes = [](int pm) { return sizeof(__nv_bfloat16) * (size_t)(2 * pm * kMmaKS + 2 * MH * (pm + 8) + pm * (2 * MH + 8)); };
+    auto go = [&](auto k, dim3 grid, int threads, size_t bytes) -> cudaError_t {
+        cudaError_t e2 = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e2 != cudaSuccess) return e2;
+        k<<<grid, threads, bytes, st>>>(p);
+        return cudaSuccess;
+    };
+    const dim3 gq((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn);
+    if (which == 0 && mma_ok && p.ldo % 2 == 0) {
+        if ((e = big ? go(pooled_attn_fwd_mma_kernel<MH, kBigNT, kBigNCH>, gq, 128, fw_bytes(kBigNT * 8 * kBigNCH))
+                     : go(pooled_attn_fwd_mma_kernel<MH, kMmaNT, 1>, gq, 128, fw_bytes(kMmaPmax))) != cudaSuccess) return e;
     } else if (which == 0) {
         auto k = pooled_attn_fwd_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);
-    } else if (which == 1 && std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
-               p.ldq % 2 == 0 && pooled_kv16(p) && p.lddo % 2 == 0 && p.lddq % 2 == 0) {
-        const size_t bq = sizeof(__nv_bfloat16) * (2 * kMmaPmax * kMmaKS + 2 * MH * kMmaVS + kMmaPmax * (2 * MH + 8));
-        auto k = pooled_attn_bwd_q_mma_kernel<MH>;
-        if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bq)) != cudaSuccess) return e;
-        k<<<dim3((p.N + kMmaTok - 1) / kMmaTok, p.h, p.Bn), 128, bq, st>>>(p);
+    } else if (which == 1 && mma_ok && p.lddo % 2 == 0 && p.lddq % 2 == 0) {
+        if ((e = big ? go(pooled_attn_bwd_q_mma_kernel<MH, kBigNT, kBigNCH>, gq, 128, bq_bytes(kBigNT * 8 * kBigNCH))
+                     : go(pooled_attn_bwd_q_mma_kernel<MH, kMmaNT, 1>, gq, 128, bq_bytes(kMmaPmax))) != cudaSuccess) return e;
     } else if (which == 1) {
         auto k = pooled_attn_bwd_q_kernel<T, HD>;
         if ((e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         k<<<dim3((p.N + kPTok - 1) / kPTok, p.h, p.Bn), kPTok, smem, st>>>(p);
-    } else if (std::is_same<T, __nv_bfloat16>::value && kMmaHd && p.P <= kMmaPmax && pooled_use_mma() &&
-               p.ldq % 2 == 0 && p.ldkv % 2 == 0) {
-        pooled_attn_bwd_kv_mma_kernel<MH><<<dim3((p.N + kKvSlab - 1) / kKvSlab, p.h, p.Bn), 224, 0, st>>>(p);
+    } else if (mma_ok) {
+        const int pchunks = (p.P + kMmaPmax - 1) / kMmaPmax;
+        pooled_attn_bwd_kv_mma_kernel<MH><<<dim3((p.N + kKvSlab - 1) / kKvSlab, p.h * pchunks, p.Bn), 224, 0, st>>>(p);
     } else {
         if (HD % 4 == 0 && 2 * p.P <= 256) {
             const int threads = ((2 * p.P + 31) / 32) * 32;

@@ -486,12 +486,14 @@ def test_cuda_graph_train_step_matches_eager():
 
 
 def test_pooled_attention_tensor_core_forward_matches_fp32_path():
-    """bf16 / hd 24 or 32 / P <= 112 takes the mma.sync kernels: output and (through the shared saved tensors) all
-    gradients agree with the fp32 FMA kernels at the bf16 tolerance; ragged token count, P = 100 (not a multiple of 16),
-    and P = 7 (a single, mostly masked k-step)."""
+    """bf16 / hd 24 or 32 / P <= 256 takes the mma.sync kernels (P <= 112 in one piece; up to 256 -- config 5 -- in two
+    chunks of 128 with an online softmax forward and a two-sweep backward): output and (through the shared saved
+    tensors) all gradients agree with the fp32 FMA kernels at the bf16 tolerance; ragged token count, P = 100 (not a
+    multiple of 16), P = 7 (a single, mostly masked k-step), P = 113 / 129 (second chunk almost empty), 200, 256."""
     from mlagg_unet_b200 import attention as att
     g = torch.Generator().manual_seed(23)
-    for Bn, N, h, P, hd in [(2, 700, 2, 100, 24), (1, 37, 1, 7, 24), (1, 256, 3, 112, 24), (2, 333, 2, 64, 32)]:
+    for Bn, N, h, P, hd in [(2, 700, 2, 100, 24), (1, 37, 1, 7, 24), (1, 256, 3, 112, 24), (2, 333, 2, 64, 32),
+                            (2, 700, 2, 256, 24), (1, 333, 1, 200, 24), (1, 100, 3, 113, 24), (2, 300, 2, 129, 32)]:
         C = 2 * h * hd
         q0 = torch.randn(Bn, N, C, generator=g).cuda()
         kv0 = torch.randn(Bn, P, 2 * C, generator=g).cuda()
@@ -504,9 +506,17 @@ def test_pooled_attention_tensor_core_forward_matches_fp32_path():
             w = w0.clone().requires_grad_()
             o = att.pooled_diff_attention(q, kv, lam, w, h, hd, hd ** -0.5)
             outs[dt] = (o.detach().float(),) + tuple(t.float() for t in torch.autograd.grad(o, [q, kv, lam, w], do.to(dt)))
-        for a, b in zip(outs[torch.float32], outs[torch.bfloat16]):
+        # d lambda = - sum over tokens of dO' . O1, and every TERM is itself a cancelling inner product (the RMSNorm backward
+        # projects dO' off the direction of O0 - lambda O1, which random K / V make nearly parallel to O1): its bf16 error is
+        # bounded against the sum of the factor magnitudes, not against the cancelled sum (the fp32 / fp64 core tests
+        # check the value itself)
+        lam_scale = float((do.abs() * outs[torch.float32][0].abs()).sum())
+        for i, (a, b) in enumerate(zip(outs[torch.float32], outs[torch.bfloat16])):
             assert torch.isfinite(b).all()
-            assert rel_err(b.cpu(), a.cpu()) < TOL16, (N, P)
+            if i == 3:
+                assert abs(float(b) - float(a)) < max(5 * TOL16 * abs(float(a)), TOL16 * lam_scale / 10), (N, P)
+            else:
+                assert rel_err(b.cpu(), a.cpu()) < TOL16, (N, P)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
