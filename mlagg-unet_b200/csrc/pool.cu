@@ -32,7 +32,19 @@ __device__ __forceinline__ void pl4_st(__nv_bfloat16 *p, const float (&v)[4]) {
     raw.y = *reinterpret_cast<const uint32_t *>(&b);
     *reinterpret_cast<uint2 *>(p) = raw;
 }
-__device__ __forceinline__ float dgelu_f(float x) { return gelu_grad(x); }   // common.cuh: fast erf, |error| <= 1.5e-7
+// GELU of the pooled branch.  bf16 storage: the Abramowitz-Stegun erf of common.cuh (|error| <= 1.5e-7, far inside the
+// output rounding).  fp32 storage is the 1e-4 parity path: libm's erff / expf -- the pooled tokens feed d lambda, a sum
+// over every token that cancels to ~1e-5 of its terms, and a systematic 1e-7 in them showed up as 2e-2 there.
+template <typename T>
+__device__ __forceinline__ float pool_gelu(float x) {
+    if (sizeof(T) == 4) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    return gelu_f(x);
+}
+template <typename T>
+__device__ __forceinline__ float pool_dgelu(float x) {
+    if (sizeof(T) == 4) return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+    return gelu_grad(x);
+}
 __device__ __forceinline__ int bin_lo(int i, int n, int pn) { return (int)(((long long)i * n) / pn); }
 __device__ __forceinline__ int bin_hi(int i, int n, int pn) { return (int)((((long long)(i + 1)) * n + pn - 1) / pn); }
 
@@ -58,7 +70,7 @@ __global__ void __launch_bounds__(kPoolThreads) avgpool_fwd_kernel(const T *__re
                 float v[4];
                 pl4_ld(xb + ((size_t)rr * W + cc) * C + 4 * cb, v);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] += gelu ? gelu_f(v[i]) : v[i];
+                for (int i = 0; i < 4; ++i) acc[i] += gelu ? pool_gelu<T>(v[i]) : v[i];
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) red[ty * C + 4 * cb + i] = acc[i];
@@ -121,7 +133,7 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const T *__restrict__ 
             float v[4];
             pl4_ld(x + off, v);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) g[k] *= dgelu_f(v[k]);
+            for (int k = 0; k < 4; ++k) g[k] *= pool_dgelu<T>(v[k]);
         }
         pl4_st(dx + off, g);
     }
