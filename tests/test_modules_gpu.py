@@ -235,7 +235,8 @@ def test_full_network_logits_and_argmax_masks_identical():
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, TOL16)])
 @pytest.mark.parametrize("shape,silu", [((2, 7, 5, 8), True), ((1, 1, 1, 4), False), ((2, 5, 4, 21), True), ((3, 16, 12, 96), True),
                                         ((2, 20, 20, 128), False), ((2, 33, 37, 48), True), ((1, 40, 160, 32), True),
-                                        ((2, 9, 256, 32), False), ((1, 1, 3, 16), True), ((3, 2, 1, 64), True)])
+                                        ((2, 9, 256, 32), False), ((1, 1, 3, 16), True), ((3, 2, 1, 64), True), ((1, 5, 300, 16), True),
+                                        ((2, 3, 7, 32), False), ((1, 130, 11, 48), True)])
 def test_dwconv3x3_tokens_matches_oracle(shape, silu, dtype, tol):
     from mlagg_unet_b200.ops import dwconv3x3_tokens
     from oracle.convs import dwconv3x3_tokens_act
@@ -404,7 +405,7 @@ def test_colsum_and_linear_tokens_match_torch():
     assert rel_err(lin.weight.grad.cpu(), ga[1].cpu()) < TOL16
 
 
-@pytest.mark.parametrize("C", [20, 48, 160])       # 6 rows / 2 rows per warp (narrow maps), two block columns
+@pytest.mark.parametrize("C", [20, 48, 160, 768])       # 6 rows / 2 rows per warp (narrow maps), two block columns
 @pytest.mark.parametrize("act", [None, "leaky_relu", "silu"])
 @pytest.mark.parametrize("affine", [False, True])
 def test_instance_norm_channels_last_matches_torch(act, affine, C):
@@ -437,8 +438,17 @@ def test_instance_norm_channels_last_matches_torch(act, affine, C):
         with torch.no_grad():
             gn.weight.copy_(w); gn.bias.copy_(b)
         assert rel_err(ops.instance_norm_cl(xc.detach(), gn.weight, gn.bias, gn.eps).cpu(), gn(xc.detach()).cpu()) < TOL32
-    y16 = ops.instance_norm_cl(xc.detach().bfloat16(), w, b, 1e-5, act, 0.01)
+    x16 = xc.detach().bfloat16().requires_grad_()
+    y16 = ops.instance_norm_cl(x16, w, b, 1e-5, act, 0.01)
     assert y16.dtype == torch.bfloat16 and rel_err(y16.float().cpu(), ref.detach()) < TOL16
+    # bf16 storage, backward: the reference evaluated on the bf16-rounded input
+    x64b = x16.detach().double().cpu().requires_grad_()
+    (f(ref_m(x64b)) * wgt.double()).sum().backward()
+    if affine:
+        w.grad = None
+        b.grad = None
+    (y16.float() * wgt.cuda()).sum().backward()
+    assert rel_err(x16.grad.float().cpu(), x64b.grad) < TOL16
 
 
 @pytest.mark.parametrize("H,W,pH,pW,C,gelu", [(32, 48, 4, 6, 48, True), (37, 23, 5, 4, 20, True), (20, 20, 10, 10, 384, False),
