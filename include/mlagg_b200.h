@@ -365,7 +365,9 @@ int mlagg_add_rows(const void *src, long long ld_src, long long bs_src, void *ds
  * DC_and_CE_loss, dice.py:58-112 MemoryEfficientSoftDiceLoss with softmax, robust_ce_loss.py; called once per scale by
  * nnUNetTrainer.py:833-863).  logits (batch, K, npix) addressed through element strides (sb, sc, sn): NCHW heads have
  * sc = npix, sn = 1, channels_last heads sc = 1, sn = K; dtype fp32 / bf16.  target (batch, npix) class indices, float
- * (tdtype 0, rounded) or int64 (tdtype 1).  K <= 32.
+ * (tdtype 0, rounded) or int64 (tdtype 1).  K <= 32.  dtype | 2: the caller states that every pixel row of logits (and of
+ * dlogits) owns 16 contiguous elements (heads padded to 16 channels): bf16 rows are then read / written as two 16-byte
+ * vectors, and the gradient's padding columns receive zeros.
  *   fwd: stats (batch, K, 3) fp32 += (sum_n p_k [t = k], sum_n p_k, sum_n [t = k]) with p = softmax over K;
  *        ce (1) += sum over every pixel of -log p_t.  Both accumulated into: zero-fill them.
  *   bwd: dlogits (strides of logits) = d loss / d logits given g_stats (batch, K, 3) (the count component is ignored) and

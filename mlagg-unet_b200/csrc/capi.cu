@@ -523,7 +523,7 @@ static int loss_check(const void *logits, const void *target, int batch, long lo
     if (!logits || !target) return MLAGG_ERR_NULL;
     if (batch <= 0 || batch > 65535 || npix <= 0 || K < 1 || sb < 0 || sc < 1 || sn < 1) return MLAGG_ERR_BAD_SHAPE;
     if (K > 32) return MLAGG_ERR_UNSUPPORTED;
-    if ((dtype != MLAGG_F32 && dtype != MLAGG_BF16) || (tdtype != 0 && tdtype != 1)) return MLAGG_ERR_UNSUPPORTED;
+    if (((dtype & 1) != MLAGG_F32 && (dtype & 1) != MLAGG_BF16) || dtype < 0 || dtype > 3 || (tdtype != 0 && tdtype != 1)) return MLAGG_ERR_UNSUPPORTED;
     return MLAGG_OK;
 }
 

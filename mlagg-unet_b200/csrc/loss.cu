@@ -44,19 +44,36 @@ struct LossParams {
     const float *g_stats, *g_ce;         // backward: (B, K, 3) (third component ignored), (1)
     long long sb, sc, sn;                // logits strides in elements: batch, class, pixel
     long long npix;                      // pixels per image
-    int K;
+    int K, rows16;
     long long pix_per_block;
 };
 
+// the logits of one pixel.  VEC: bf16 rows of exactly 16 elements, 32-byte aligned (the segmentation heads padded to 16
+// output channels, classes contiguous): two 16-byte loads instead of K strided 2-byte ones (each warp instruction of the
+// scalar form touches 32 different sectors, 14 times over)
+template <typename T, int KP, bool VEC>
+__device__ __forceinline__ void ls_row(const T *lp, long long sc, int K, float (&p)[KP]) {
+    if constexpr (VEC) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(lp)), b = __ldg(reinterpret_cast<const uint4 *>(lp) + 1);
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            p[2 * i] = 2 * i < K ? __uint_as_float(w[i] << 16) : -3.0e38f;
+            p[2 * i + 1] = 2 * i + 1 < K ? __uint_as_float(w[i] & 0xffff0000u) : -3.0e38f;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) p[k] = k < K ? ls_ld<T>(lp + k * sc) : -3.0e38f;
+    }
+}
+
 // softmax of one pixel in registers; returns max and sum
-template <typename T, int KP>
+template <typename T, int KP, bool VEC>
 __device__ __forceinline__ void ls_softmax(const T *lp, long long sc, int K, float (&p)[KP], float &mx, float &sum) {
+    ls_row<T, KP, VEC>(lp, sc, K, p);
     mx = -3.0e38f;
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-        p[k] = k < K ? ls_ld<T>(lp + k * sc) : -3.0e38f;
-        mx = fmaxf(mx, p[k]);
-    }
+    for (int k = 0; k < KP; ++k) mx = fmaxf(mx, p[k]);
     sum = 0.f;
 #pragma unroll
     for (int k = 0; k < KP; ++k) {
@@ -68,7 +85,7 @@ __device__ __forceinline__ void ls_softmax(const T *lp, long long sc, int K, flo
     for (int k = 0; k < KP; ++k) p[k] *= inv;
 }
 
-template <typename T, typename TT, int KP>
+template <typename T, typename TT, int KP, bool VEC>
 __global__ void __launch_bounds__(256) dice_ce_fwd_kernel(const LossParams q) {
     __shared__ float red[8][3 * KP + 1];
     const int K = q.K, bi = blockIdx.y;
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(256) dice_ce_fwd_kernel(const LossParams q) {
         float p[KP], mx, sum;
         // the logit of the label, before the exponentials overwrite the registers
         const float lt = (t >= 0 && t < K) ? ls_ld<T>(lp + t * q.sc) : 0.f;
-        ls_softmax<T, KP>(lp, q.sc, K, p, mx, sum);
+        ls_softmax<T, KP, VEC>(lp, q.sc, K, p, mx, sum);
         if (t >= 0 && t < K) ce += logf(sum) - (lt - mx);
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
@@ -119,7 +136,7 @@ __global__ void __launch_bounds__(256) dice_ce_fwd_kernel(const LossParams q) {
     }
 }
 
-template <typename T, typename TT, int KP>
+template <typename T, typename TT, int KP, bool VEC>
 __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(const LossParams q) {
     __shared__ float gi[KP], gp[KP];
     const int K = q.K, bi = blockIdx.y;
@@ -138,18 +155,31 @@ __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(const LossParams q) {
         const T *lp = lb + n * q.sn;
         const int t = ls_label<TT>(tb + n);
         float p[KP], mx, sum;
-        ls_softmax<T, KP>(lp, q.sc, K, p, mx, sum);
+        ls_softmax<T, KP, VEC>(lp, q.sc, K, p, mx, sum);
         float dot = 0.f;
 #pragma unroll
         for (int k = 0; k < KP; ++k) dot = fmaf(p[k], gp[k] + (k == t ? gi[k] : 0.f), dot);
         const float cev = (t >= 0 && t < K) ? gce : 0.f;     // labels outside [0, K) contribute no cross-entropy term
+        float v[KP];
 #pragma unroll
         for (int k = 0; k < KP; ++k) {
-            if (k < K) {
-                const float G = gp[k] + (k == t ? gi[k] : 0.f);
-                const float v = p[k] * (G - dot) + cev * (p[k] - (k == t ? 1.f : 0.f));
-                ls_st<T>(db + n * q.sn + k * q.sc, v);
+            const float G = gp[k] + (k == t ? gi[k] : 0.f);
+            v[k] = k < K ? p[k] * (G - dot) + cev * (p[k] - (k == t ? 1.f : 0.f)) : 0.f;
+        }
+        if constexpr (VEC) {            // the row's padding columns receive zeros
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<const uint32_t *>(&h2);
             }
+            uint4 *dp = reinterpret_cast<uint4 *>(db + n * q.sn);
+            dp[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dp[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) ls_st<T>(db + n * q.sn + k * q.sc, v[k]);
         }
     }
 }
@@ -163,9 +193,19 @@ static cudaError_t loss_launch(const LossParams &q, int Bn, bool bwd, cudaStream
     const dim3 grid((unsigned)((q.npix + p.pix_per_block - 1) / p.pix_per_block), (unsigned)Bn);
 #define MLAGG_LOSS(KP) \
     do { \
-        if (bwd) dice_ce_bwd_kernel<T, TT, KP><<<grid, 256, 0, st>>>(p); \
-        else dice_ce_fwd_kernel<T, TT, KP><<<grid, 256, 0, st>>>(p); \
+        if (bwd) dice_ce_bwd_kernel<T, TT, KP, false><<<grid, 256, 0, st>>>(p); \
+        else dice_ce_fwd_kernel<T, TT, KP, false><<<grid, 256, 0, st>>>(p); \
     } while (0)
+    if constexpr (sizeof(T) == 2) {
+        // rows of 16 bf16 (padded heads), classes contiguous, everything 32-byte aligned: vector row access.  `rows16` is the
+        // caller's statement that each pixel row owns all 16 elements (the gradient's padding columns are written).
+        if (q.rows16 && q.sc == 1 && q.sn == 16 && q.K <= 16 && q.K > 8 && q.sb % 16 == 0 &&
+            reinterpret_cast<uintptr_t>(q.logits) % 32 == 0 && (!bwd || reinterpret_cast<uintptr_t>(q.dlogits) % 32 == 0)) {
+            if (bwd) dice_ce_bwd_kernel<T, TT, 16, true><<<grid, 256, 0, st>>>(p);
+            else dice_ce_fwd_kernel<T, TT, 16, true><<<grid, 256, 0, st>>>(p);
+            return cudaGetLastError();
+        }
+    }
     if (q.K <= 4) MLAGG_LOSS(4);
     else if (q.K <= 8) MLAGG_LOSS(8);
     else if (q.K <= 16) MLAGG_LOSS(16);
@@ -179,6 +219,8 @@ cudaError_t dice_ce_dispatch(const void *logits, const void *target, void *dlogi
                              const float *g_stats, const float *g_ce, long long sb, long long sc, long long sn,
                              long long npix, int K, int Bn, int dtype, int tdtype, bool bwd, cudaStream_t st) {
     LossParams q{};
+    q.rows16 = (dtype & 2) ? 1 : 0;      // bit 1 of dtype: rows of 16 elements owned by the tensor (see loss_launch)
+    dtype &= 1;
     q.logits = logits, q.target = target, q.dlogits = dlogits, q.stats = stats, q.ce = ce, q.g_stats = g_stats, q.g_ce = g_ce;
     q.sb = sb, q.sc = sc, q.sn = sn, q.npix = npix, q.K = K;
     if (dtype == 0) return tdtype == 0 ? loss_launch<float, float>(q, Bn, bwd, st) : loss_launch<float, long long>(q, Bn, bwd, st);

@@ -84,6 +84,10 @@ class _DiceCEStats(torch.autograd.Function):
         tgt = target.contiguous()
         stats, ce = _lib.zeros((Bn, K, 3), logits.device), _lib.zeros(1, logits.device)
         dt, tdt = (0 if logits.dtype == torch.float32 else 1), (0 if tgt.dtype == torch.float32 else 1)
+        # heads padded to 16 channels (mlagg._conv1x1_cl): every pixel row owns 16 contiguous bf16 -> vector row access
+        rows16 = (dt == 1 and K <= 16 and logits.stride() == (H * W * 16, 1, W * 16, 16) and logits.data_ptr() % 32 == 0
+                  and logits.untyped_storage().nbytes() >= (logits.storage_offset() + Bn * H * W * 16) * 2)
+        dt |= 2 if rows16 else 0
         with torch.cuda.device(logits.device), _lib.timed("dice_ce_fwd"):
             rc = _lib.lib().mlagg_dice_ce_stats_fwd(logits.data_ptr(), tgt.data_ptr(), stats.data_ptr(), ce.data_ptr(), Bn,
                                                     H * W, K, logits.stride(0), logits.stride(1), logits.stride(3), dt, tdt,
@@ -101,7 +105,10 @@ class _DiceCEStats(torch.autograd.Function):
         Bn, K, H, W = logits.shape
         g_stats = torch.zeros(Bn, K, 3, device=logits.device) if g_stats is None else g_stats.float().contiguous()
         g_ce = torch.zeros(1, device=logits.device) if g_ce is None else g_ce.float().contiguous()
-        dl = torch.empty_strided(logits.shape, logits.stride(), device=logits.device, dtype=logits.dtype)
+        if dt & 2:      # same strides as the logits, with the 16-wide rows owned by the gradient tensor (padding <- zeros)
+            dl = torch.empty(Bn, H, W, 16, device=logits.device, dtype=logits.dtype)[..., :K].permute(0, 3, 1, 2)
+        else:
+            dl = torch.empty_strided(logits.shape, logits.stride(), device=logits.device, dtype=logits.dtype)
         with torch.cuda.device(logits.device), _lib.timed("dice_ce_bwd"):
             rc = _lib.lib().mlagg_dice_ce_stats_bwd(logits.data_ptr(), tgt.data_ptr(), g_stats.data_ptr(), g_ce.data_ptr(),
                                                     dl.data_ptr(), Bn, H * W, K, logits.stride(0), logits.stride(1),
