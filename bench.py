@@ -181,6 +181,7 @@ def main():
         barrier()
         _lib.STATS["launches"] = 0
         _lib.STATS["events"] = {} if events else None
+        _lib.STATS["bytes"] = {}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -249,6 +250,7 @@ def main():
     for name, pairs in (ev or {}).items():
         ts = [p[0].elapsed_time(p[1]) for p in pairs]
         kern[name] = {"launches": len(ts), "ms_avg": sum(ts) / len(ts), "ms_total": sum(ts)}
+    fam_bytes = dict(_lib.STATS.get("bytes") or {})       # algorithmic bytes per family over the eager K steps
     dom = "scan_bwd"
     roof = None
     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel (the newest committed
@@ -277,8 +279,16 @@ def main():
                              "note": "backward recomputes a_t from the 16-step checkpoints: 1 exponential per update "
                                      "in the recompute sweep, reused by the adjoint sweep; counted 2x with the "
                                      "softplus / sigmoid helpers"},
+                # every kernel family of the library: ms per step, and -- where the wrapper states the algorithmic bytes of
+                # its calls -- achieved GB/s over all of a step's calls and its fraction of the same HBM peak
                 "also": {k: {"ms_avg": v["ms_avg"], "launches_per_step": v["launches"] / a.steps,
-                             **({"achieved_GBps": alg[k] / (v["ms_avg"] * 1e-3) / 1e9} if k in alg else {})}
+                             "ms_per_step": v["ms_total"] / a.steps,
+                             **({"achieved_GBps": alg[k] / (v["ms_avg"] * 1e-3) / 1e9,
+                                 "frac": alg[k] / (v["ms_avg"] * 1e-3) / 1e9 / peak} if k in alg else {}),
+                             **({"achieved_GBps": fam_bytes[k] / (v["ms_total"] * 1e-3) / 1e9,
+                                 "frac": fam_bytes[k] / (v["ms_total"] * 1e-3) / 1e9 / peak,
+                                 "algorithmic_bytes_per_step": fam_bytes[k] / a.steps}
+                                if (k not in alg and fam_bytes.get(k)) else {})}
                          for k, v in kern.items()}}
     line = {
         "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": a.steps,

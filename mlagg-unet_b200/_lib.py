@@ -102,15 +102,15 @@ def check(rc: int, what: str):
 
 
 # ---- bookkeeping for bench.py: how many of OUR kernels were launched, and (optionally) per-kernel CUDA-event timing
-STATS = {"launches": 0, "events": None}
+STATS = {"launches": 0, "events": None, "bytes": {}}
 
 
 class timed:
     """with timed("scan_bwd", n_kernels): ...  -- counts launches; records CUDA events on the current stream when
     STATS["events"] is a dict (bench.py turns that on for the timed region)."""
 
-    def __init__(self, name, n_kernels=1):
-        self.name, self.n = name, n_kernels
+    def __init__(self, name, n_kernels=1, nbytes=0):
+        self.name, self.n, self.nbytes = name, n_kernels, nbytes      # nbytes: ALGORITHMIC HBM bytes of the call (bench roofline)
 
     def __enter__(self):
         STATS["launches"] += self.n
@@ -124,6 +124,7 @@ class timed:
         if STATS["events"] is not None:
             self.e1.record()
             STATS["events"].setdefault(self.name, []).append((self.e0, self.e1))
+            STATS["bytes"][self.name] = STATS["bytes"].get(self.name, 0) + self.nbytes
         return False
 
 

@@ -32,7 +32,7 @@ def linear_fwd(x2, w, bias=None, act=None, out_dtype=torch.bfloat16, want_pre=Fa
     y = torch.empty(M, N, device=x2.device, dtype=out_dtype) if out is None else out
     pre = torch.empty(M, N, device=x2.device, dtype=torch.bfloat16) if want_pre else None
     b = None if bias is None else bias.detach().float().contiguous()
-    with torch.cuda.device(x2.device), _lib.timed("linear_fwd"):
+    with torch.cuda.device(x2.device), _lib.timed("linear_fwd", 1, 2 * (M * K + N * K + M * N * (2 if pre is not None else 1))):
         rc = _lib.lib().mlagg_linear_fwd(x2.data_ptr(), x2.stride(0), w.data_ptr(), w.stride(0), _lib.ptr(b), y.data_ptr(),
                                          y.stride(0), _lib.ptr(pre), 0 if pre is None else pre.stride(0), M, N, K, ACT[act],
                                          _DT[y.dtype], _lib.stream_ptr())
@@ -45,7 +45,7 @@ def linear_bwd_data(dy2, w, aux=None, act=None, out_dtype=torch.bfloat16):
     M, N = dy2.shape
     K = w.shape[1]
     dx = torch.empty(M, K, device=dy2.device, dtype=out_dtype)
-    with torch.cuda.device(dy2.device), _lib.timed("linear_bwd_data"):
+    with torch.cuda.device(dy2.device), _lib.timed("linear_bwd_data", 1, 2 * (M * N + N * K + M * K * (2 if aux is not None else 1))):
         rc = _lib.lib().mlagg_linear_bwd_data(dy2.data_ptr(), dy2.stride(0), w.data_ptr(), w.stride(0), _lib.ptr(aux),
                                               0 if aux is None else aux.stride(0), ACT[act], dx.data_ptr(), dx.stride(0),
                                               M, N, K, _DT[out_dtype], _lib.stream_ptr())
@@ -70,7 +70,7 @@ def linear_bwd_weight(dy2, x2, want_db=False, side=False):
     with (_lib.side_launch(dy2, x2) if side else _Here()):
         dw = _lib.zeros((N, K), dy2.device)
         db = _lib.zeros((N,), dy2.device) if want_db else None
-        with torch.cuda.device(dy2.device), _lib.timed("linear_bwd_weight"):
+        with torch.cuda.device(dy2.device), _lib.timed("linear_bwd_weight", 1, 2 * M * (N + K) + 4 * N * K):
             rc = _lib.lib().mlagg_linear_bwd_weight(dy2.data_ptr(), dy2.stride(0), x2.data_ptr(), x2.stride(0), dw.data_ptr(),
                                                     dw.stride(0), _lib.ptr(db), M, N, K, _lib.stream_ptr())
     _lib.check(rc, "mlagg_linear_bwd_weight")

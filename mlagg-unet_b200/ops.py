@@ -56,7 +56,7 @@ class _DWConv3x3(torch.autograd.Function):
             assert residual.shape == x.shape
             res, (ldr, bsr) = _tok_operand(residual.to(xin.dtype), C)
         y = torch.empty(Bn, N, C, device=x.device, dtype=xin.dtype)
-        with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd"):
+        with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd", 1, (2 + (res is not None)) * y.numel() * y.element_size()):
             rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(res),
                                                         _lib.ptr(y), Bn, H, W, C, ldx, bsx, ldr, bsr, C, N * C, int(silu),
                                                         0, _DT[xin.dtype], _lib.stream_ptr())
@@ -76,7 +76,7 @@ class _DWConv3x3(torch.autograd.Function):
         dx = torch.empty_like(dz)
         dw = _lib.zeros((C, 9), xin.device)
         db = _lib.zeros(C, xin.device) if b32 is not None else None
-        with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2):
+        with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2, 6 * dz.numel() * dz.element_size()):
             rc = _lib.lib().mlagg_dwconv3x3_bwd_strided(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy),
                                                         _lib.ptr(dz), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), Bn, H, W,
                                                         C, ldx, bsx, ldg, bsg, C, N * C, None, None, 0, 0, int(silu),
@@ -110,7 +110,7 @@ class _ConvGLUCore(torch.autograd.Function):
         b32 = None if bias is None else bias.detach().float().contiguous()
         y = torch.empty(Bn, N, C, device=h.device, dtype=hin.dtype)
         es = hin.element_size()
-        with torch.cuda.device(h.device), _lib.timed("dwconv3x3_fwd"):
+        with torch.cuda.device(h.device), _lib.timed("dwconv3x3_fwd", 1, 3 * y.numel() * es):
             rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(hin.data_ptr(), _lib.ptr(w32), _lib.ptr(b32), hin.data_ptr() + C * es,
                                                         _lib.ptr(y), Bn, H, W, C, C2, N * C2, C2, N * C2, C, N * C,
                                                         int(silu), 1, _DT[hin.dtype], _lib.stream_ptr())
@@ -131,7 +131,7 @@ class _ConvGLUCore(torch.autograd.Function):
         dw = _lib.zeros((C, 9), hin.device)
         db = _lib.zeros(C, hin.device) if b32 is not None else None
         es = hin.element_size()
-        with torch.cuda.device(hin.device), _lib.timed("dwconv3x3_bwd", 2):
+        with torch.cuda.device(hin.device), _lib.timed("dwconv3x3_bwd", 2, 8 * dz.numel() * es):
             rc = _lib.lib().mlagg_dwconv3x3_bwd_strided(hin.data_ptr(), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(dy),
                                                         _lib.ptr(dz), dh.data_ptr(), _lib.ptr(dw), _lib.ptr(db), Bn, H, W,
                                                         C, C2, N * C2, ldg, bsg, C2, N * C2, hin.data_ptr() + C * es,
@@ -164,7 +164,7 @@ class _DWConv3x3Stages(torch.autograd.Function):
         w32 = [w.detach().float().contiguous() for w in ws]
         b32 = [None if b is None else b.detach().float().contiguous() for b in bs_]
         es, off = xin.element_size(), 0
-        with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd", ns):
+        with torch.cuda.device(x.device), _lib.timed("dwconv3x3_fwd", ns, 2 * y.numel() * es):
             for s, (h, w) in enumerate(hw):
                 rc = _lib.lib().mlagg_dwconv3x3_fwd_strided(xin.data_ptr() + off * C * es, _lib.ptr(w32[s]),
                                                             _lib.ptr(b32[s]), None, y.data_ptr() + off * C * es, Bn, h, w,
@@ -190,7 +190,7 @@ class _DWConv3x3Stages(torch.autograd.Function):
         dx = torch.empty_like(xin)
         es, off = xin.element_size(), 0
         dws, dbs = [], []
-        with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2 * ns):
+        with torch.cuda.device(xin.device), _lib.timed("dwconv3x3_bwd", 2 * ns, 6 * dx.numel() * es):
             for s, (h, w) in enumerate(hw):
                 dz = torch.empty(Bn, h * w, C, device=xin.device, dtype=xin.dtype)
                 dw = _lib.zeros((C, 9), xin.device)
@@ -270,7 +270,7 @@ def _ln_forward(ctx, x, weight, bias, eps, out_dtype):
     y = torch.empty(xin.shape, device=x.device, dtype=odt)
     mean = torch.empty(M, device=x.device, dtype=torch.float32)
     rstd = torch.empty(M, device=x.device, dtype=torch.float32)
-    with torch.cuda.device(x.device), _lib.timed("layernorm_fwd"):
+    with torch.cuda.device(x.device), _lib.timed("layernorm_fwd", 1, xin.numel() * xin.element_size() + y.numel() * y.element_size() + 8 * M):
         rc = _lib.lib().mlagg_layernorm_fwd(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), _lib.ptr(mean),
                                             _lib.ptr(rstd), M, C, float(eps), _DT[xin.dtype], _DT[odt],
                                             _lib.stream_ptr())
@@ -291,7 +291,8 @@ def _ln_backward(ctx, dy, dres):
     dx = torch.empty_like(xin)
     dw = _lib.zeros(C, xin.device)
     db = _lib.zeros(C, xin.device) if bdt is not None else None
-    with torch.cuda.device(xin.device), _lib.timed("layernorm_bwd"):
+    with torch.cuda.device(xin.device), _lib.timed("layernorm_bwd", 1, (2 + (dres is not None)) * xin.numel() * xin.element_size()
+                                                       + dy.numel() * dy.element_size() + 8 * M):
         rc = _lib.lib().mlagg_layernorm_bwd_res(_lib.ptr(xin), _lib.ptr(w32), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(dy),
                                                 _lib.ptr(dres), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), M, C,
                                                 _DT[xin.dtype], _DT[odt], _lib.stream_ptr())
@@ -568,7 +569,7 @@ class _InstNorm(torch.autograd.Function):
         b32 = None if bias is None else bias.detach().float().contiguous()
         y = torch.empty_like(xt)
         stats = torch.empty(Bn, C, 2, device=x.device, dtype=torch.float32)
-        with torch.cuda.device(x.device), _lib.timed("instnorm_fwd", 3):
+        with torch.cuda.device(x.device), _lib.timed("instnorm_fwd", 3, 3 * y.numel() * y.element_size()):
             rc = _lib.lib().mlagg_instnorm_fwd(_lib.ptr(xt), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(y), _lib.ptr(stats),
                                                Bn, H * W, C, float(eps), act, float(slope), _DT[xt.dtype], _lib.stream_ptr())
         _lib.check(rc, "mlagg_instnorm_fwd")
@@ -588,7 +589,7 @@ class _InstNorm(torch.autograd.Function):
         sums = torch.empty(Bn, C, 2, device=xt.device, dtype=torch.float32)
         dw = _lib.zeros(C, xt.device) if w32 is not None else None
         db = _lib.zeros(C, xt.device) if b32 is not None else None
-        with torch.cuda.device(xt.device), _lib.timed("instnorm_bwd", 3):
+        with torch.cuda.device(xt.device), _lib.timed("instnorm_bwd", 3, 5 * dx.numel() * dx.element_size()):
             rc = _lib.lib().mlagg_instnorm_bwd(_lib.ptr(xt), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(stats), _lib.ptr(dyt),
                                                _lib.ptr(dx), _lib.ptr(sums), _lib.ptr(dw), _lib.ptr(db), Bn, H * W, C, act,
                                                slope, _DT[xt.dtype], _lib.stream_ptr())
