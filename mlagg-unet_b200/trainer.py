@@ -149,7 +149,33 @@ class DeepSupervisionDiceCE(nn.Module):
     def forward(self, outputs, targets):
         if not isinstance(outputs, (list, tuple)):
             return self.one(outputs, targets[0] if isinstance(targets, (list, tuple)) else targets)
+        if (os.environ.get("MLAGG_LOSS_TORCH") is None and len(outputs) > 1
+                and all(_DiceCEStats.addressable(o, t) for o, t in zip(outputs, targets))
+                and len({(o.shape[0], o.shape[1]) for o in outputs}) == 1):
+            return self.all_scales(outputs, targets)
         return sum(w * self.one(o, t) for w, o, t in zip(self.weights, outputs, targets))
+
+    def all_scales(self, outputs, targets, smooth=1e-5):
+        """The same loss with the dice arithmetic of ALL scales done at once on the stacked (S, B, K, 3) statistics:
+        one set of tiny element-wise kernels (and, data parallel, ONE packed all-gather) per step instead of one per
+        scale -- ~150 fewer launches.  Per scale the formulas are exactly those of `dice_ce_loss_fused`."""
+        pairs = [_DiceCEStats.apply(o, t) for o, t in zip(outputs, targets)]
+        stats = torch.stack([st for st, _ in pairs], dim=0)                       # (S, B, K, 3)
+        ce = torch.cat([c for _, c in pairs], dim=0)                              # (S,)
+        key = (ce.device, tuple(tuple(o.shape) for o in outputs))
+        if getattr(self, "_consts", (None,))[0] != key:      # built from device-side fills: safe inside a graph capture
+            mk = lambda vals: torch.stack([torch.full((), float(v), device=ce.device) for v in vals])
+            self._consts = (key, mk([o.shape[0] * o.shape[2] * o.shape[3] for o in outputs]), mk(self.weights[:len(outputs)]))
+        _, npix, w = self._consts
+        inter, spred, sgt = stats[:, :, 1:, 0], stats[:, :, 1:, 1], stats[:, :, 1:, 2].detach()
+        if self.ddp and self.batch_dice:
+            inter, spred, sgt = _AllGatherGrad.apply(torch.stack((inter, spred, sgt), dim=0)).sum(0).unbind(0)
+        if self.batch_dice:
+            inter, spred, sgt = inter.sum(1), spred.sum(1), sgt.sum(1)            # (S, K - 1)
+            dice = -((2 * inter + smooth) / torch.clip(sgt + spred + smooth, 1e-8)).mean(1)
+        else:
+            dice = -((2 * inter + smooth) / torch.clip(sgt + spred + smooth, 1e-8)).mean((1, 2))
+        return (w * (ce / npix + dice)).sum()
 
 
 # ------------------------------------------------------------------ synthetic plans (SURVEY.md F9, 8d)

@@ -151,3 +151,23 @@ def test_side_stream_gradients_equal_the_single_stream_step(monkeypatch):
     tr0.initialize()
     den = sum(float((a - b.detach()).pow(2).sum()) for a, b in zip(p0, tr0.network.parameters())) ** 0.5
     assert num < 0.05 * den, (num, den)
+
+
+@pytest.mark.parametrize("batch_dice", [True, False])
+def test_deep_supervision_loss_all_scales_at_once_equals_the_per_scale_sum(batch_dice):
+    """DeepSupervisionDiceCE.all_scales (stacked statistics, one set of tiny kernels) == sum_i w_i * one(scale i): value and
+    the gradient of every scale's logits."""
+    from mlagg_unet_b200.trainer import DeepSupervisionDiceCE
+    torch.manual_seed(5)
+    K, Bn = 14, 2
+    outs = [torch.randn(Bn, K, 64 >> i, 48 >> i, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+            for i in range(5)]
+    tgts = [torch.randint(0, K, (Bn, 1, 64 >> i, 48 >> i), device="cuda").float() for i in range(5)]
+    lf = DeepSupervisionDiceCE(5, batch_dice=batch_dice)
+    l1 = lf(outs, tgts)
+    g1 = torch.autograd.grad(l1, outs)
+    l2 = sum(w * lf.one(o, t) for w, o, t in zip(lf.weights, outs, tgts))
+    g2 = torch.autograd.grad(l2, outs)
+    assert abs(float(l1) - float(l2)) < 1e-6 * max(1.0, abs(float(l2)))
+    for a, b in zip(g1, g2):
+        assert float((a - b).abs().max()) <= 1e-6 * float(b.abs().max()) + 1e-12
