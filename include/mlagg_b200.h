@@ -322,6 +322,15 @@ int mlagg_instnorm_fwd(const void *x, const float *w, const float *b, void *y, f
 int mlagg_instnorm_bwd(const void *x, const float *w, const float *b, const float *stats, const void *dy, void *dx,
                        float *sums, float *dw, float *db, int batch, int N, int C, int act, float slope, int dtype,
                        mlagg_stream_t stream);
+/* The residual form, y = act(norm(x) + residual) with act 0 | 1: the tail of monai's UnetResBlock,
+ * `lrelu(norm2(conv2(.)) + residual)` (reference network: encoder0 / decoder stages, nnUNetTrainer_MLAgg_2D_dt_MS.py:1339-1357),
+ * in the apply pass instead of an add and an activation kernel.  The backward takes the saved OUTPUT y (the LeakyReLU
+ * slope is read off its sign), stores dx and d residual = dy * act'.  C % 8 == 0 (bf16) / % 4 (fp32), 16-byte aligned. */
+int mlagg_instnorm_res_fwd(const void *x, const float *w, const float *b, const void *residual, void *y, float *stats,
+                           int batch, int N, int C, float eps, int act, float slope, int dtype, mlagg_stream_t stream);
+int mlagg_instnorm_res_bwd(const void *x, const float *w, const float *b, const float *stats, const void *y, const void *dy,
+                           void *dx, void *dresidual, float *sums, float *dw, float *db, int batch, int N, int C, int act,
+                           float slope, int dtype, mlagg_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * Adaptive average pooling of a tokens-major map, optional exact GELU applied to x on the fly:

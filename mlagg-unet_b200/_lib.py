@@ -44,6 +44,8 @@ SIGNATURES = {
     "mlagg_linattn_bwd": (c_i, [c_p] * 10 + [c_i] * 5 + [c_ll] * 7 + [c_f, c_i, c_p]),
     "mlagg_instnorm_fwd": (c_i, [c_p] * 5 + [c_i] * 3 + [c_f, c_i, c_f, c_i, c_p]),
     "mlagg_instnorm_bwd": (c_i, [c_p] * 9 + [c_i] * 3 + [c_i, c_f, c_i, c_p]),
+    "mlagg_instnorm_res_fwd": (c_i, [c_p] * 6 + [c_i] * 3 + [c_f, c_i, c_f, c_i, c_p]),
+    "mlagg_instnorm_res_bwd": (c_i, [c_p] * 11 + [c_i] * 3 + [c_i, c_f, c_i, c_p]),
     "mlagg_avgpool_tokens_fwd": (c_i, [c_p] * 2 + [c_i] * 8 + [c_p]),
     "mlagg_avgpool_tokens_bwd": (c_i, [c_p] * 3 + [c_i] * 8 + [c_p]),
     "mlagg_colsum": (c_i, [c_p, c_p, c_ll, c_i, c_ll, c_i, c_p]),

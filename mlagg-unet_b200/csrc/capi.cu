@@ -87,7 +87,7 @@ cudaError_t colsum_dispatch(const void *x, float *out, long long M, int C, long 
 
 cudaError_t instnorm_dispatch(const void *x, const void *dy, const float *w, const float *b, void *out, float *stats,
                               float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
-                              int dtype, bool bwd, cudaStream_t st);
+                              int dtype, bool bwd, cudaStream_t st, const void *res = nullptr, void *dres = nullptr);
 
 cudaError_t avgpool_dispatch(const void *x, const void *dy, void *out, int Bn, int H, int W, int C, int pH, int pW,
                              int gelu, int dtype, bool bwd, cudaStream_t st);
@@ -808,6 +808,39 @@ extern "C" int mlagg_instnorm_bwd(const void *x, const float *w, const float *b,
     if (e == cudaSuccess)
         e = instnorm_dispatch(x, dy, w, b, dx, const_cast<float *>(stats), sums, dw, db, batch, N, C, 0.f, act, slope,
                               dtype, true, (cudaStream_t)stream);
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+// y = act(norm(x) + residual): the tail of monai's UnetResBlock (`lrelu(norm2(conv2(.)) + residual)`) in the apply pass
+extern "C" int mlagg_instnorm_res_fwd(const void *x, const float *w, const float *b, const void *residual, void *y,
+                                      float *stats, int batch, int N, int C, float eps, int act, float slope, int dtype,
+                                      mlagg_stream_t stream) {
+    int rc = instnorm_check(x, y, stats, batch, N, C, dtype);
+    if (rc) return rc;
+    if (!residual) return MLAGG_ERR_NULL;
+    if (act < 0 || act > 1 || C % (dtype == MLAGG_F32 ? 4 : 8) != 0 || C / (dtype == MLAGG_F32 ? 4 : 8) > 256) return MLAGG_ERR_UNSUPPORTED;
+    if (!aligned(x, 16) || !aligned(y, 16) || !aligned(residual, 16)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = cudaMemsetAsync(stats, 0, (size_t)batch * C * 2 * sizeof(float), (cudaStream_t)stream);
+    if (e == cudaSuccess)
+        e = instnorm_dispatch(x, nullptr, w, b, y, stats, nullptr, nullptr, nullptr, batch, N, C, eps, act, slope, dtype, false,
+                              (cudaStream_t)stream, residual, nullptr);
+    if (e == cudaErrorNotSupported) return MLAGG_ERR_UNSUPPORTED;
+    return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
+}
+
+extern "C" int mlagg_instnorm_res_bwd(const void *x, const float *w, const float *b, const float *stats, const void *y,
+                                      const void *dy, void *dx, void *dresidual, float *sums, float *dw, float *db,
+                                      int batch, int N, int C, int act, float slope, int dtype, mlagg_stream_t stream) {
+    int rc = instnorm_check(x, dx, stats, batch, N, C, dtype);
+    if (rc) return rc;
+    if (!dy || !sums || !y || !dresidual) return MLAGG_ERR_NULL;
+    if (act < 0 || act > 1 || C % (dtype == MLAGG_F32 ? 4 : 8) != 0 || C / (dtype == MLAGG_F32 ? 4 : 8) > 256) return MLAGG_ERR_UNSUPPORTED;
+    if (!aligned(x, 16) || !aligned(y, 16) || !aligned(dy, 16) || !aligned(dx, 16) || !aligned(dresidual, 16)) return MLAGG_ERR_ALIGN;
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)batch * C * 2 * sizeof(float), (cudaStream_t)stream);
+    if (e == cudaSuccess)
+        e = instnorm_dispatch(x, dy, w, b, dx, const_cast<float *>(stats), sums, dw, db, batch, N, C, 0.f, act, slope,
+                              dtype, true, (cudaStream_t)stream, y, dresidual);
+    if (e == cudaErrorNotSupported) return MLAGG_ERR_UNSUPPORTED;
     return e == cudaSuccess ? MLAGG_OK : fail_cuda(e);
 }
 

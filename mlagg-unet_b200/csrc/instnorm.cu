@@ -221,12 +221,14 @@ __device__ __forceinline__ void in_stv(__nv_bfloat16 *p, const float (&v)[8]) {
 }
 constexpr int kInRows = 4;   // rows per thread and iteration
 
-template <typename T, bool kBwd>
+// RES (backward only): the forward was y = lrelu(xhat w + b + residual) -- the slope of the activation is read off the
+// sign of the saved OUTPUT y (a LeakyReLU keeps the sign of its argument) instead of recomputing z without the residual
+template <typename T, bool kBwd, bool RES = false>
 __global__ void __launch_bounds__(256) in_sums_rows_kernel(const T *__restrict__ x, const T *__restrict__ dy,
                                                            const float *__restrict__ stats_in,
                                                            const float *__restrict__ w, const float *__restrict__ b,
                                                            float *__restrict__ out, int N, int C, int rows_per_block,
-                                                           int act, float slope) {
+                                                           int act, float slope, const T *__restrict__ yout = nullptr) {
     constexpr int V = InV<T>::N;
     extern __shared__ float red[];                  // [rpi][cvn][2 V]
     const int cvn = C / V, rpi = 256 / cvn;
@@ -250,22 +252,25 @@ __global__ void __launch_bounds__(256) in_sums_rows_kernel(const T *__restrict__
         }
         const T *xb = x + (size_t)bi * N * C + c0;
         const T *db = kBwd ? dy + (size_t)bi * N * C + c0 : nullptr;
+        const T *yb = RES ? yout + (size_t)bi * N * C + c0 : nullptr;
         for (int n = n0 + jr; n < n1; n += rpi * kInRows) {
-            uint4 rv[kInRows], rg[kInRows];
+            uint4 rv[kInRows], rg[kInRows], ry[kInRows];
 #pragma unroll
             for (int u = 0; u < kInRows; ++u) {
                 const int nn = n + u * rpi;
                 if (nn < n1) {
                     rv[u] = in_ldraw(xb + (size_t)nn * C);
                     if (kBwd) rg[u] = in_ldraw(db + (size_t)nn * C);
+                    if (RES) ry[u] = in_ldraw(yb + (size_t)nn * C);
                 }
             }
 #pragma unroll
             for (int u = 0; u < kInRows; ++u) {
                 if (n + u * rpi < n1) {
-                    float v[V], g[V];
+                    float v[V], g[V], yv[V];
                     in_unpack(rv[u], v);
                     if (kBwd) in_unpack(rg[u], g);
+                    if (RES) in_unpack(ry[u], yv);
 #pragma unroll
                     for (int i = 0; i < V; ++i) {
                         if (!kBwd) {
@@ -273,7 +278,8 @@ __global__ void __launch_bounds__(256) in_sums_rows_kernel(const T *__restrict__
                             a1[i] = fmaf(v[i], v[i], a1[i]);
                         } else {
                             const float xh = (v[i] - mean[i]) * rstd[i];
-                            const float dz = g[i] * in_dact(fmaf(xh, wv[i], bv[i]), act, slope);
+                            const float dz = RES ? g[i] * (act == 1 && !(yv[i] > 0.f) ? slope : 1.f)
+                                                 : g[i] * in_dact(fmaf(xh, wv[i], bv[i]), act, slope);
                             a0[i] += dz;
                             a1[i] = fmaf(dz, xh, a1[i]);
                         }
@@ -295,12 +301,16 @@ __global__ void __launch_bounds__(256) in_sums_rows_kernel(const T *__restrict__
     }
 }
 
-template <typename T, bool kBwd>
+// RES forward: y = act(xhat w + b + res).  RES backward: dz from the sign of the saved output `res` (= y), dx as always,
+// and dz itself -- the gradient of the residual input -- stored to `dres`.
+template <typename T, bool kBwd, bool RES = false>
 __global__ void __launch_bounds__(256) in_apply_rows_kernel(const T *__restrict__ x, const T *__restrict__ dy,
                                                             const float *__restrict__ stats,
                                                             const float *__restrict__ sums, const float *__restrict__ w,
                                                             const float *__restrict__ b, T *__restrict__ out, int N,
-                                                            int C, int rows_per_block, int act, float slope, float invN) {
+                                                            int C, int rows_per_block, int act, float slope, float invN,
+                                                            const T *__restrict__ res = nullptr,
+                                                            T *__restrict__ dres = nullptr) {
     constexpr int V = InV<T>::N;
     const int cvn = C / V, rpi = 256 / cvn;
     const int jc = threadIdx.x % cvn, jr = threadIdx.x / cvn;
@@ -323,35 +333,41 @@ __global__ void __launch_bounds__(256) in_apply_rows_kernel(const T *__restrict_
     const T *xb = x + (size_t)bi * N * C + c0;
     const T *db = kBwd ? dy + (size_t)bi * N * C + c0 : nullptr;
     T *ob = out + (size_t)bi * N * C + c0;
+    const T *rb = RES ? res + (size_t)bi * N * C + c0 : nullptr;
+    T *drb = (RES && kBwd) ? dres + (size_t)bi * N * C + c0 : nullptr;
     for (int n = n0 + jr; n < n1; n += rpi * kInRows) {
-        uint4 rv[kInRows], rg[kInRows];
+        uint4 rv[kInRows], rg[kInRows], rr[kInRows];
 #pragma unroll
         for (int u = 0; u < kInRows; ++u) {
             const int nn = n + u * rpi;
             if (nn < n1) {
                 rv[u] = in_ldraw(xb + (size_t)nn * C);
                 if (kBwd) rg[u] = in_ldraw(db + (size_t)nn * C);
+                if (RES) rr[u] = in_ldraw(rb + (size_t)nn * C);
             }
         }
 #pragma unroll
         for (int u = 0; u < kInRows; ++u) {
             const int nn = n + u * rpi;
             if (nn < n1) {
-                float v[V], g[V], o[V];
+                float v[V], g[V], o[V], rvv[V], dzv[V];
                 in_unpack(rv[u], v);
                 if (kBwd) in_unpack(rg[u], g);
+                if (RES) in_unpack(rr[u], rvv);
 #pragma unroll
                 for (int i = 0; i < V; ++i) {
                     const float xh = (v[i] - mean[i]) * rstd[i];
-                    const float z = fmaf(xh, wv[i], bv[i]);
+                    const float z = fmaf(xh, wv[i], bv[i]) + (RES && !kBwd ? rvv[i] : 0.f);
                     if (!kBwd) {
                         o[i] = in_act(z, act, slope);
                     } else {
-                        const float dz = g[i] * in_dact(z, act, slope);
+                        const float dz = RES ? g[i] * (act == 1 && !(rvv[i] > 0.f) ? slope : 1.f) : g[i] * in_dact(z, act, slope);
+                        dzv[i] = dz;
                         o[i] = rstd[i] * wv[i] * (dz - k1[i] - xh * k2[i]);
                     }
                 }
                 in_stv(ob + (size_t)nn * C, o);
+                if (RES && kBwd) in_stv(drb + (size_t)nn * C, dzv);
             }
         }
     }
@@ -369,7 +385,7 @@ static void in_grid(int N, int C, int Bn, dim3 &gs, int &rpb) {
 template <typename T>
 static cudaError_t instnorm_run(const T *x, const T *dy, const float *w, const float *b, T *out, float *stats,
                                 float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
-                                bool bwd, cudaStream_t st) {
+                                bool bwd, cudaStream_t st, const T *res = nullptr, T *dres = nullptr) {
     dim3 gs;
     int rpb;
     in_grid(N, C, Bn, gs, rpb);
@@ -386,6 +402,18 @@ static cudaError_t instnorm_run(const T *x, const T *dy, const float *w, const f
         chunks = (N + rpb - 1) / rpb;
         const dim3 g2(chunks, Bn);
         const size_t smem = (size_t)256 * 2 * V * sizeof(float);
+        if (res != nullptr) {      // residual form: forward res = the residual input; backward res = the saved output y
+            if (!bwd) {
+                in_sums_rows_kernel<T, false><<<g2, 256, smem, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, N, C, rpb, act, slope);
+                in_finalize_kernel<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, Bn * C, invN, eps);
+                in_apply_rows_kernel<T, false, true><<<g2, 256, 0, st>>>(x, nullptr, stats, nullptr, w, b, out, N, C, rpb, act, slope, invN, res, nullptr);
+            } else {
+                in_sums_rows_kernel<T, true, true><<<g2, 256, smem, st>>>(x, dy, stats, w, b, sums, N, C, rpb, act, slope, res);
+                if (dw || db) in_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dw, db, Bn, C);
+                in_apply_rows_kernel<T, true, true><<<g2, 256, 0, st>>>(x, dy, stats, sums, w, b, out, N, C, rpb, act, slope, invN, res, dres);
+            }
+            return cudaGetLastError();
+        }
         if (!bwd) {
             in_sums_rows_kernel<T, false><<<g2, 256, smem, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, N, C, rpb, act, slope);
             in_finalize_kernel<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, Bn * C, invN, eps);
@@ -397,6 +425,7 @@ static cudaError_t instnorm_run(const T *x, const T *dy, const float *w, const f
         }
         return cudaGetLastError();
     }
+    if (res != nullptr) return cudaErrorNotSupported;      // the residual form exists for the row-streaming kernels only
     if (!bwd) {
         in_sums_kernel<T, false><<<gs, 32 * kInWarps, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, stats, N, C, rpb, act, slope);
         in_finalize_kernel<<<(Bn * C + 255) / 256, 256, 0, st>>>(stats, Bn * C, invN, eps);
@@ -411,12 +440,14 @@ static cudaError_t instnorm_run(const T *x, const T *dy, const float *w, const f
 
 cudaError_t instnorm_dispatch(const void *x, const void *dy, const float *w, const float *b, void *out, float *stats,
                               float *sums, float *dw, float *db, int Bn, int N, int C, float eps, int act, float slope,
-                              int dtype, bool bwd, cudaStream_t st) {
+                              int dtype, bool bwd, cudaStream_t st, const void *res, void *dres) {
     if (dtype == 0)
         return instnorm_run<float>(static_cast<const float *>(x), static_cast<const float *>(dy), w, b,
-                                   static_cast<float *>(out), stats, sums, dw, db, Bn, N, C, eps, act, slope, bwd, st);
+                                   static_cast<float *>(out), stats, sums, dw, db, Bn, N, C, eps, act, slope, bwd, st,
+                                   static_cast<const float *>(res), static_cast<float *>(dres));
     return instnorm_run<__nv_bfloat16>(static_cast<const __nv_bfloat16 *>(x), static_cast<const __nv_bfloat16 *>(dy), w, b,
-                                       static_cast<__nv_bfloat16 *>(out), stats, sums, dw, db, Bn, N, C, eps, act, slope, bwd, st);
+                                       static_cast<__nv_bfloat16 *>(out), stats, sums, dw, db, Bn, N, C, eps, act, slope, bwd, st,
+                                       static_cast<const __nv_bfloat16 *>(res), static_cast<__nv_bfloat16 *>(dres));
 }
 
 }  // namespace mlagg

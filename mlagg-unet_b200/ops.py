@@ -598,6 +598,61 @@ class _InstNorm(torch.autograd.Function):
                 None, None, None)
 
 
+class _InstNormRes(torch.autograd.Function):
+    """C ABI: mlagg_instnorm_res_fwd / _bwd.  y = act(instance_norm(x) + residual) on channels_last (B, C, H, W) maps,
+    act None | 'leaky_relu': the add and the activation of monai's UnetResBlock tail inside the normalisation's apply pass;
+    the backward reads the activation's slope off the sign of the saved output."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, eps, act, slope):
+        Bn, C, H, W = x.shape
+        xt, rt = x.permute(0, 2, 3, 1), residual.permute(0, 2, 3, 1)
+        w32 = None if weight is None else weight.detach().float().contiguous()
+        b32 = None if bias is None else bias.detach().float().contiguous()
+        y = torch.empty_like(xt)
+        stats = torch.empty(Bn, C, 2, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device), _lib.timed("instnorm_fwd", 3, 4 * y.numel() * y.element_size()):
+            rc = _lib.lib().mlagg_instnorm_res_fwd(_lib.ptr(xt), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(rt), _lib.ptr(y),
+                                                   _lib.ptr(stats), Bn, H * W, C, float(eps), act, float(slope),
+                                                   _DT[xt.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_instnorm_res_fwd")
+        ctx.save_for_backward(xt, y, w32, b32, stats)
+        ctx.meta = (act, float(slope), None if weight is None else weight.dtype, None if bias is None else bias.dtype)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xt, y, w32, b32, stats = ctx.saved_tensors
+        act, slope, wdt, bdt = ctx.meta
+        Bn, H, W, C = xt.shape
+        dyt = dy.to(xt.dtype).permute(0, 2, 3, 1)
+        if not dyt.is_contiguous():
+            dyt = dyt.contiguous()
+        dx, dres = torch.empty_like(xt), torch.empty_like(xt)
+        sums = torch.empty(Bn, C, 2, device=xt.device, dtype=torch.float32)
+        dw = _lib.zeros(C, xt.device) if w32 is not None else None
+        db = _lib.zeros(C, xt.device) if b32 is not None else None
+        with torch.cuda.device(xt.device), _lib.timed("instnorm_bwd", 3, 8 * dx.numel() * dx.element_size()):
+            rc = _lib.lib().mlagg_instnorm_res_bwd(_lib.ptr(xt), _lib.ptr(w32), _lib.ptr(b32), _lib.ptr(stats), _lib.ptr(y),
+                                                   _lib.ptr(dyt), _lib.ptr(dx), _lib.ptr(dres), _lib.ptr(sums), _lib.ptr(dw),
+                                                   _lib.ptr(db), Bn, H * W, C, act, slope, _DT[xt.dtype], _lib.stream_ptr())
+        _lib.check(rc, "mlagg_instnorm_res_bwd")
+        return (dx.permute(0, 3, 1, 2), dres.permute(0, 3, 1, 2), None if dw is None else dw.to(wdt),
+                None if db is None else db.to(bdt), None, None, None)
+
+
+def instance_norm_res_cl(x, residual, weight=None, bias=None, eps=1e-5, act="leaky_relu", slope=0.01):
+    """act(instance_norm(x) + residual) as one node when the row-streaming kernels take the shape (channels_last CUDA maps
+    of one dtype, C a multiple of the 16-byte vector); None otherwise -- the caller then adds and activates itself."""
+    if not (supports_instance_norm_cl(x) and residual.shape == x.shape and residual.dtype == x.dtype and act in (None, "leaky_relu")):
+        return None
+    C = x.shape[1]
+    v = 16 // x.element_size()
+    if C % v or C // v > 256 or not x.permute(0, 2, 3, 1).is_contiguous() or not residual.permute(0, 2, 3, 1).is_contiguous():
+        return None
+    return _InstNormRes.apply(x, residual, weight, bias, eps, _ACT[act], slope)
+
+
 def instance_norm_cl(x, weight=None, bias=None, eps=1e-5, act=None, slope=0.01):
     """Per-(image, channel) normalisation of a (B, C, H, W) map kept in channels_last memory, optional affine and a
     fused activation (None | 'leaky_relu' | 'silu').  Equals nn.InstanceNorm2d (training statistics) and

@@ -140,10 +140,15 @@ class UnetResBlock2d(nn.Module):
     def forward(self, x):
         res = x
         y = _inst_norm(self.norm1, self.conv1(x), "leaky_relu")
-        y = _inst_norm(self.norm2, self.conv2(y))
         if self.downsample:
             res = _inst_norm(self.norm3, self.conv3(res))
-        return self.lrelu(y + res)
+        c2 = self.conv2(y)
+        if not getattr(self.norm2, "track_running_stats", False) and self.lrelu.negative_slope == 0.01:
+            from .ops import instance_norm_res_cl
+            out = instance_norm_res_cl(c2, res, self.norm2.weight, self.norm2.bias, self.norm2.eps, "leaky_relu", 0.01)
+            if out is not None:           # lrelu(norm2(.) + res): add and activation inside the normalisation's apply pass
+                return out
+        return self.lrelu(_inst_norm(self.norm2, c2) + res)
 
 
 class UnetrBasicBlock(nn.Module):

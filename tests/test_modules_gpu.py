@@ -845,3 +845,35 @@ def test_segmentation_head_padded_to_the_tensor_core_gemm():
     assert rel_err(x.grad.double(), xd.grad) < TOL16
     assert rel_err(head.conv_out.weight.grad.double(), wd.grad) < TOL16
     assert rel_err(head.conv_out.bias.grad.double(), bd.grad) < TOL16
+
+
+@pytest.mark.parametrize("C,affine", [(48, False), (96, True), (20, False)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_instance_norm_with_residual_and_activation(C, affine, dtype):
+    """mlagg_instnorm_res_*: lrelu(instance_norm(x) + residual) as one node (the tail of monai's UnetResBlock) against the
+    float64 torch expression: output, dx, d residual and the affine gradients; C = 20 in bf16 is outside the 16-byte
+    vectors and must report None (the caller's own add + activation)."""
+    from mlagg_unet_b200 import ops
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    g = torch.Generator().manual_seed(31)
+    Bn, H, W = 2, 19, 23
+    x = (torch.randn(Bn, C, H, W, generator=g) * 2 + 0.5).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    r = torch.randn(Bn, C, H, W, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_()
+    wgt = torch.randn(Bn, C, H, W, generator=g).cuda()
+    w = (torch.randn(C, generator=g).cuda()).requires_grad_() if affine else None
+    b = (torch.randn(C, generator=g).cuda()).requires_grad_() if affine else None
+    y = ops.instance_norm_res_cl(x, r, w, b, 1e-5, "leaky_relu", 0.01)
+    if dtype == torch.bfloat16 and C % 8:
+        assert y is None
+        return
+    assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    (y.float() * wgt).sum().backward()
+    xd, rd = x.detach().double().requires_grad_(), r.detach().double().requires_grad_()
+    wd = w.detach().double().requires_grad_() if affine else None
+    bd = b.detach().double().requires_grad_() if affine else None
+    yd = torch.nn.functional.leaky_relu(torch.nn.functional.instance_norm(xd, weight=wd, bias=bd, eps=1e-5) + rd, 0.01)
+    (yd * wgt.double()).sum().backward()
+    assert rel_err(y.double(), yd) < tol
+    assert rel_err(x.grad.double(), xd.grad) < tol and rel_err(r.grad.double(), rd.grad) < tol
+    if affine:
+        assert rel_err(w.grad.double(), wd.grad) < tol and rel_err(b.grad.double(), bd.grad) < tol
