@@ -6,6 +6,8 @@ round trips around nn.Conv2d are needed.  CUDA only; no CPU p
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, gemm
@@ -858,6 +860,10 @@ class _Conv2dSplit(torch.autograd.Function):
 
 def conv2d_split(conv, x):
     """conv(x) without its bias for an nn.Conv2d with zero padding; plain `_conv_forward` when gradients are off / on CPU"""
+    if x.dim() == 4 and x.shape[1] == 1 and x.is_cuda and x.is_contiguous():
+        # a one-channel map has ambiguous strides and torch reads them as NCHW: cuDNN then returns an NCHW result that every
+        # channels_last consumer (and the gradient coming back) has to re-lay out.  Spell the NHWC strides out (a view).
+        x = x.as_strided(x.size(), (x.stride(0), 1, x.stride(2), x.stride(3)))
     if (x.is_cuda and torch.is_grad_enabled() and conv.padding_mode == "zeros" and not isinstance(conv.padding, str)
             and (x.requires_grad or conv.weight.requires_grad)):
         return _Conv2dSplit.apply(x, conv.weight, conv.stride, conv.padding, conv.dilation, conv.groups)

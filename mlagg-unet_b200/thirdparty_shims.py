@@ -112,13 +112,9 @@ class _Conv(nn.Module):
             self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=(k - 1) // 2, bias=False)
 
     def forward(self, x):
-        if x.dim() == 4 and x.shape[1] == 1 and x.is_cuda and x.is_contiguous():
-            # a one-channel map has ambiguous strides and torch reads them as NCHW: cuDNN then returns an NCHW result that
-            # every channels_last consumer (and the gradient coming back) has to re-lay out.  Spell the NHWC strides out.
-            x = x.as_strided(x.size(), (x.stride(0), 1, x.stride(2), x.stride(3)))
         if isinstance(self.conv, nn.Conv2d) and self.conv.bias is None and x.is_cuda:
             from .ops import conv2d_split
-            return conv2d_split(self.conv, x)        # weight gradient on the side stream (ops._Conv2dSplit)
+            return conv2d_split(self.conv, x)        # NHWC strides for one-channel inputs; weight gradient on the side stream
         return self.conv(x)
 
 
