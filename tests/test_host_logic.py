@@ -247,3 +247,35 @@ def test_training_logger_and_epoch_bookkeeping_follow_the_reference():
     assert len(lg.my_fantastic_logging["mean_fg_dice"]) == 3 and lg.my_fantastic_logging["mean_fg_dice"][2] == 0.5
     with pytest.raises(AssertionError):
         lg.log("train_losses", 1.0, 5)                   # exactly one value per epoch
+
+
+def test_leaf_param_resolves_parameters_and_dense_views_only():
+    """_lib.leaf_param decides which weight gradients may be produced on the side stream and handed to the trainer
+    (never through autograd): the Parameter itself or a same-size dense view of it; not a padded / permuted copy, not a
+    frozen parameter, not a slice."""
+    import torch
+    from mlagg_unet_b200 import _lib
+    lin = torch.nn.Linear(6, 4)
+    conv = torch.nn.Conv2d(6, 4, 1).to(memory_format=torch.channels_last)
+    assert _lib.leaf_param(lin.weight) is lin.weight and _lib.leaf_param(lin.bias) is lin.bias
+    assert _lib.leaf_param(lin.weight.view(24)) is lin.weight
+    assert _lib.leaf_param(conv.weight.view(4, 6)) is conv.weight
+    assert _lib.leaf_param(None) is None
+    assert _lib.leaf_param(torch.nn.functional.pad(lin.weight, (0, 0, 0, 4))) is None      # the padded segmentation head
+    assert _lib.leaf_param(lin.weight.t().reshape(24)) is None                              # a copy
+    assert _lib.leaf_param(lin.weight[:2]) is None                                          # a slice
+    assert _lib.leaf_param(lin.weight.detach()) is None
+    lin.weight.requires_grad_(False)
+    assert _lib.leaf_param(lin.weight) is None
+
+
+def test_side_stream_helpers_are_inert_outside_a_trainer_step():
+    import torch
+    from mlagg_unet_b200 import _lib
+    assert not _lib.side_active()
+    with _lib.side_launch(torch.zeros(1)) as on_side:
+        assert on_side is False
+    p = torch.nn.Parameter(torch.zeros(2, 3))
+    _lib.stash_grad(p, torch.ones(6))
+    (q, g), = _lib.take_stashed_grads()
+    assert q is p and g.shape == p.shape and _lib.take_stashed_grads() == []
