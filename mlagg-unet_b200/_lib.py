@@ -218,6 +218,21 @@ def take_stashed_grads():
     return out
 
 
+_BRANCH = {"stream": None}
+
+
+def branch_stream(device):
+    """a (default = lowest priority) stream for an independent sub-graph of the forward pass; autograd replays the
+    sub-graph's backward nodes on the same stream.  Only with MLAGG_BRANCH_STREAM=1 (experimental)."""
+    import os
+    import torch
+    if os.environ.get("MLAGG_SIDE_STREAM", "1") == "0" or os.environ.get("MLAGG_BRANCH_STREAM", "0") != "1":
+        return None
+    if _BRANCH["stream"] is None or _BRANCH["stream"].device != torch.device(device):
+        _BRANCH["stream"] = torch.cuda.Stream(device=device)
+    return _BRANCH["stream"]
+
+
 def side_join(final=True):
     """the current stream waits for everything launched through side_launch"""
     import torch

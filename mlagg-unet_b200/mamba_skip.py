@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
 from .ops import CatStages, Conv2dCL, JoinLast, SplitLast, SplitStages, _Linear, conv_glu_core, dwconv3x3_stages, dwconv3x3_tokens, layer_norm_fork, layer_norm_tokens, linear_tokens, residual_drop_path
 from .selective_scan_interface import msmm_scan, msmm_scan_tokens, selective_scan_fn, xdbl_pad
 from .thirdparty_shims import DropPath, _inst_norm
@@ -272,6 +273,20 @@ class VSS_Conv_Block(nn.Module):
         # NHWC views of the inputs (free when they are channels_last), split into the first hd channels -> tokens-major
         # (B, L, hd) for the scan branch, and the rest -> conv branch
         halves = [SplitLast.apply(t.permute(0, 2, 3, 1), hd) for t in inputs]
+
+        def conv_branch(s):                                                            # Conv2d, InstanceNorm2d, SiLU
+            br = self.conv_branches[s]
+            return _inst_norm(br[1], br[0](halves[s][1].permute(0, 3, 1, 2)), "silu").permute(0, 2, 3, 1)   # NHWC view
+
+        # MLAGG_BRANCH_STREAM=1 (experimental): the conv branches do not depend on the scan path and can run on a second,
+        # lower-priority stream next to it (the scan kernels occupy 120 of the 148 SMs)
+        side = _lib.branch_stream(inputs[0].device) if (inputs[0].is_cuda and self.training) else None
+        cbs = None
+        if side is not None:
+            main = torch.cuda.current_stream(inputs[0].device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                cbs = [conv_branch(s) for s in range(len(inputs))]
         m = CatStages.apply(*[a.flatten(1, 2) for a, _ in halves])         # (B, H, W, hd) -> (B, H W, hd): views
         n1, m = layer_norm_fork(m, self.ln_1)                # m's residual-path gradient is added inside ln_1's backward
         m = residual_drop_path(m, self.self_attention(n1, Bn, H, W, L_split), self.drop_path)
@@ -279,11 +294,12 @@ class VSS_Conv_Block(nn.Module):
         # one-pass kernel, and the Linear backward needs no re-pack of its saved input
         stage_tokens = SplitStages.apply(layer_norm_tokens(m, self.norm2), tuple(L_split))
         outs = []
+        if side is not None:
+            torch.cuda.current_stream(inputs[0].device).wait_stream(side)
         for s, t in enumerate(inputs):
             ms = stage_tokens[s]
             ms = residual_drop_path(ms, self.mlps[s](ms, H[s], W[s]), self.drop_path)
-            br = self.conv_branches[s]                                                 # Conv2d, InstanceNorm2d, SiLU
-            cb = _inst_norm(br[1], br[0](halves[s][1].permute(0, 3, 1, 2)), "silu").permute(0, 2, 3, 1)   # NHWC view
+            cb = cbs[s] if cbs is not None else conv_branch(s)
             outs.append(JoinLast.apply(ms.reshape(Bn, H[s], W[s], hd), cb).permute(0, 3, 1, 2))      # channels_last
         return outs
 

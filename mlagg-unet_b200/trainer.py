@@ -499,6 +499,16 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         for d, t in zip(self._static["target"], batch["target"]):
             d.copy_(t)
 
+    def _capture_stream_kw(self):
+        """The graphs are captured on a high-priority stream: the kernel nodes of the main chain then carry a higher
+        priority than the side-stream nodes (weight gradients, default = lowest priority) and the block scheduler places
+        their CTAs first -- measured +0.3 .. 0.6 ms per step on top of the side stream itself.  MLAGG_HP_STREAM=0: off."""
+        if os.environ.get("MLAGG_HP_STREAM", "1") == "0":
+            return {}
+        if getattr(self, "_hp_stream", None) is None:
+            self._hp_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        return {"stream": self._hp_stream}
+
     def _side_stream_warmup(self, fn, n=2):
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -524,7 +534,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
         if not self.is_ddp:
             self._side_stream_warmup(lambda: self._step_math(st["data"], st["target"]))
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, **self._capture_stream_kw()):
                 st["loss"] = self._step_math(st["data"], st["target"])
             self._graph = (graph,)
         else:
@@ -532,7 +542,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             from . import ops
             from . import _lib
-            with torch.cuda.graph(ga):
+            with torch.cuda.graph(ga, **self._capture_stream_kw()):
                 _lib.arena_begin(self.device)
                 ops.refresh_cast_cache()
                 with torch.autocast("cuda", dtype=self.amp_dtype):
@@ -541,7 +551,7 @@ class nnUNetTrainer_MLAgg_2D_dt_MS:
             st["outs"] = outs
             st["douts"] = [torch.zeros_like(o) for o in outs]
             self._drop_grads()
-            with torch.cuda.graph(gb, pool=ga.pool()):
+            with torch.cuda.graph(gb, pool=ga.pool(), **self._capture_stream_kw()):
                 _lib.side_begin(self.device)
                 torch.autograd.backward(outs, grad_tensors=st["douts"])
                 self._attach_side_grads()
